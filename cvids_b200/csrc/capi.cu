@@ -1,0 +1,1145 @@
+// capi.cu -- map lifecycle, capacity management and the C ABI declared in include/chisel_b200.h.
+//
+// Host orchestration of one frame (replaces Chisel::IntegrateDepthScan[Color], OC Chisel.h:59-213):
+//   host:   frustum -> candidate ID box (host_geometry.h, exact)       [Chisel.h:64-68 / :119-123]
+//   device: frame_prepare -> chunk_candidates -> integrate             [Chisel.h:70-107 / :133-207]
+// Chunks that the reference would create and immediately garbage-collect are never materialised, so there
+// is no erase path; the pool is a bump allocator and the hash table is insert-only between resets.
+// Capacities are grown on the host BEFORE a frame from conservative upper bounds (candidate count), using
+// the stream-ordered allocator, so no kernel can overflow a table and no per-frame host sync is needed.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/chisel_b200.h"
+#include "device_map.cuh"
+#include "host_geometry.h"
+#include "kernels.h"
+
+namespace chs
+{
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CHS_CUDA(expr)                                                                                      \
+    do                                                                                                      \
+    {                                                                                                       \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(CHS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+__global__ void fill_u64_kernel(unsigned long long *p, size_t n, unsigned long long v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st)
+{
+    if (n == 0)
+        return;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    fill_u64_kernel<<<grid, 256, 0, st>>>(p, n, v);
+}
+
+// Re-insert every pool slot into a freshly emptied (larger) table.
+__global__ void rebuild_hash_kernel(DeviceMap map)
+{
+    const int n = map.ctr->n_chunks;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+        hash_insert_new(map, pack_id(map.slot_ids[3 * s], map.slot_ids[3 * s + 1], map.slot_ids[3 * s + 2]), s);
+}
+void launch_rebuild_hash(const DeviceMap &map, int, cudaStream_t st) { rebuild_hash_kernel<<<148, 256, 0, st>>>(map); }
+
+__global__ void rebuild_dirty_kernel(DeviceMap map)
+{
+    const int n = min(map.ctr->n_dirty, map.dirty_cap);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    {
+        const unsigned long long key = map.dirty_list[s];
+        unsigned i = (unsigned)mix64(key) & map.dirty_mask;
+        while (atomicCAS(&map.dirty_keys[i], kEmptyKey, key) != kEmptyKey)
+            i = (i + 1) & map.dirty_mask;
+    }
+}
+void launch_rebuild_dirty(const DeviceMap &map, int, cudaStream_t st) { rebuild_dirty_kernel<<<148, 256, 0, st>>>(map); }
+
+struct InFlight
+{
+    cudaEvent_t ev;
+    long long newBound;     // upper bound of chunks this frame may add
+    long long dirtyBound;   // upper bound of dirty IDs this frame may add
+    int slot;               // index into the pinned counter ring
+};
+
+} // namespace chs
+
+using namespace chs;
+
+struct chs_map
+{
+    chs_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    DeviceMap dm{};
+    std::vector<float2 *> distSlabs;
+    std::vector<uchar4 *> colorSlabs;
+    size_t hashSize = 0, dirtySize = 0;
+    // frame staging
+    float *dDepth = nullptr, *dTrunc = nullptr;
+    uint8_t *dColor = nullptr;
+    float2 *dHiz = nullptr;
+    int4 *dWork = nullptr;
+    size_t depthCap = 0, truncCap = 0, colorCap = 0, hizCap = 0, workCap = 0;
+    cudaEvent_t h2dDone = nullptr;
+    // counters
+    Counters *dCtr = nullptr;
+    Counters *hCtr = nullptr;           // pinned ring
+    static constexpr int kRing = 8;
+    int ringNext = 0;
+    std::deque<InFlight> inflight;
+    std::vector<cudaEvent_t> eventPool;
+    long long knownChunks = 0, knownDirty = 0;
+    Counters lastFrame{};
+    bool haveFrame = false;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t evt[8] = {};
+    bool frameTimed = false, meshTimed = false;
+    // host mirror of slot -> id (extended lazily; slots are never recycled between resets)
+    std::vector<int32_t> hostIds;
+    std::unordered_map<unsigned long long, int> hostIndex;
+    // meshing
+    int *dMeshSlots = nullptr, *dTriCounts = nullptr, *dGridCounts = nullptr;
+    long long *dVertOffsets = nullptr, *dGridOffsets = nullptr;
+    size_t meshChunkCap = 0;
+    float *dVerts = nullptr, *dNormals = nullptr, *dColors = nullptr, *dGrids = nullptr;
+    long long vertCap = 0, gridCap = 0;
+    chs_mesh_counts lastMesh{};
+    int lastMeshChunks = 0;
+};
+
+namespace chs
+{
+
+static int alloc_async(void **p, size_t bytes, cudaStream_t st)
+{
+    CHS_CUDA(cudaMallocAsync(p, std::max<size_t>(bytes, 256), st));
+    return CHS_OK;
+}
+
+template <typename T>
+static int grow_buffer(T **buf, size_t *cap, size_t need, cudaStream_t st)
+{
+    if (need <= *cap)
+        return CHS_OK;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    if (*buf)
+        CHS_CUDA(cudaFreeAsync(*buf, st));
+    void *p = nullptr;
+    int rc = alloc_async(&p, ncap * sizeof(T), st);
+    if (rc)
+        return rc;
+    *buf = (T *)p;
+    *cap = ncap;
+    return CHS_OK;
+}
+
+static size_t pow2_at_least(size_t n)
+{
+    size_t p = 1024;
+    while (p < n)
+        p <<= 1;
+    return p;
+}
+
+// Add slabs until the pool holds `chunks`; grows the slot->id array alongside.
+static int ensure_pool(chs_map *m, long long chunks)
+{
+    if (chunks <= m->dm.capacity)
+        return CHS_OK;
+    const int V = m->dm.V;
+    const size_t needSlabs = (size_t)((chunks + kSlabChunks - 1) / kSlabChunks);
+    if (needSlabs > (size_t)kMaxSlabs)
+        return fail(CHS_ERR_CAPACITY, "chunk pool would exceed kMaxSlabs");
+    const size_t oldSlabs = m->distSlabs.size();
+    for (size_t s = oldSlabs; s < needSlabs; s++)
+    {
+        void *p = nullptr;
+        int rc = alloc_async(&p, sizeof(float2) * (size_t)kSlabChunks * V, m->stream);
+        if (rc)
+            return rc;
+        m->distSlabs.push_back((float2 *)p);
+        if (m->cfg.use_color)
+        {
+            rc = alloc_async(&p, sizeof(uchar4) * (size_t)kSlabChunks * V, m->stream);
+            if (rc)
+                return rc;
+            m->colorSlabs.push_back((uchar4 *)p);
+        }
+    }
+    CHS_CUDA(cudaMemcpyAsync(m->dm.dist_slabs + oldSlabs, m->distSlabs.data() + oldSlabs, sizeof(float2 *) * (needSlabs - oldSlabs),
+                             cudaMemcpyHostToDevice, m->stream));
+    if (m->cfg.use_color)
+        CHS_CUDA(cudaMemcpyAsync(m->dm.color_slabs + oldSlabs, m->colorSlabs.data() + oldSlabs, sizeof(uchar4 *) * (needSlabs - oldSlabs),
+                                 cudaMemcpyHostToDevice, m->stream));
+    // the pageable source vectors must outlive the copy: cudaMemcpyAsync from pageable memory stages before returning
+    const long long newCap = (long long)needSlabs * kSlabChunks;
+    void *ids = nullptr;
+    int rc = alloc_async(&ids, sizeof(int) * 3 * (size_t)newCap, m->stream);
+    if (rc)
+        return rc;
+    if (m->dm.slot_ids)
+    {
+        CHS_CUDA(cudaMemcpyAsync(ids, m->dm.slot_ids, sizeof(int) * 3 * (size_t)m->dm.capacity, cudaMemcpyDeviceToDevice, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.slot_ids, m->stream));
+    }
+    m->dm.slot_ids = (int *)ids;
+    m->dm.capacity = (int)newCap;
+    return CHS_OK;
+}
+
+static int ensure_hash(chs_map *m, long long chunks)
+{
+    const size_t need = pow2_at_least((size_t)chunks * 2);
+    if (need <= m->hashSize)
+        return CHS_OK;
+    if (m->dm.keys)
+    {
+        CHS_CUDA(cudaFreeAsync(m->dm.keys, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.vals, m->stream));
+    }
+    void *k = nullptr, *v = nullptr;
+    int rc = alloc_async(&k, sizeof(unsigned long long) * need, m->stream);
+    if (rc)
+        return rc;
+    rc = alloc_async(&v, sizeof(int) * need, m->stream);
+    if (rc)
+        return rc;
+    m->dm.keys = (unsigned long long *)k;
+    m->dm.vals = (int *)v;
+    m->dm.mask = (unsigned)(need - 1);
+    m->hashSize = need;
+    launch_fill_u64(m->dm.keys, need, kEmptyKey, m->stream);
+    launch_rebuild_hash(m->dm, 0, m->stream);
+    CHS_CUDA(cudaGetLastError());
+    return CHS_OK;
+}
+
+static int ensure_dirty(chs_map *m, long long ids)
+{
+    const size_t need = pow2_at_least((size_t)ids * 2);
+    if (need <= m->dirtySize)
+        return CHS_OK;
+    void *k = nullptr, *l = nullptr;
+    int rc = alloc_async(&k, sizeof(unsigned long long) * need, m->stream);
+    if (rc)
+        return rc;
+    rc = alloc_async(&l, sizeof(unsigned long long) * (need / 2), m->stream);
+    if (rc)
+        return rc;
+    if (m->dm.dirty_list)
+    {
+        CHS_CUDA(cudaMemcpyAsync(l, m->dm.dirty_list, sizeof(unsigned long long) * (size_t)m->dm.dirty_cap, cudaMemcpyDeviceToDevice, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.dirty_list, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.dirty_keys, m->stream));
+    }
+    m->dm.dirty_keys = (unsigned long long *)k;
+    m->dm.dirty_list = (unsigned long long *)l;
+    m->dm.dirty_mask = (unsigned)(need - 1);
+    m->dm.dirty_cap = (int)(need / 2);
+    m->dirtySize = need;
+    launch_fill_u64(m->dm.dirty_keys, need, kEmptyKey, m->stream);
+    launch_rebuild_dirty(m->dm, 0, m->stream);
+    CHS_CUDA(cudaGetLastError());
+    return CHS_OK;
+}
+
+// Retire completed counter snapshots; `block` waits for all of them.
+static int poll_inflight(chs_map *m, bool block)
+{
+    while (!m->inflight.empty())
+    {
+        InFlight &f = m->inflight.front();
+        cudaError_t q = block ? cudaEventSynchronize(f.ev) : cudaEventQuery(f.ev);
+        if (q == cudaErrorNotReady)
+            break;
+        if (q != cudaSuccess)
+            return fail(CHS_ERR_CUDA, std::string("counter event: ") + cudaGetErrorString(q));
+        const Counters &c = m->hCtr[f.slot];
+        m->knownChunks = c.n_chunks;
+        m->knownDirty = c.n_dirty;
+        m->lastFrame = c;
+        m->eventPool.push_back(f.ev);
+        m->inflight.pop_front();
+    }
+    return CHS_OK;
+}
+
+static int snapshot_counters(chs_map *m, long long newBound, long long dirtyBound)
+{
+    if ((int)m->inflight.size() >= chs_map::kRing)
+    {
+        // ring full: wait for the oldest snapshot
+        CHS_CUDA(cudaEventSynchronize(m->inflight.front().ev));
+        int rc = poll_inflight(m, false);
+        if (rc)
+            return rc;
+    }
+    InFlight f;
+    if (m->eventPool.empty())
+        CHS_CUDA(cudaEventCreateWithFlags(&f.ev, cudaEventDisableTiming));
+    else
+    {
+        f.ev = m->eventPool.back();
+        m->eventPool.pop_back();
+    }
+    f.slot = m->ringNext;
+    m->ringNext = (m->ringNext + 1) % chs_map::kRing;
+    f.newBound = newBound;
+    f.dirtyBound = dirtyBound;
+    CHS_CUDA(cudaMemcpyAsync(&m->hCtr[f.slot], m->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    CHS_CUDA(cudaEventRecord(f.ev, m->stream));
+    m->inflight.push_back(f);
+    return CHS_OK;
+}
+
+static bool finite12(const float *p)
+{
+    for (int i = 0; i < 12; i++)
+        if (!std::isfinite(p[i]))
+            return false;
+    return true;
+}
+
+static void fill_camera(CameraDev *c, const float pose[12], const chs_camera &cam)
+{
+    for (int r = 0; r < 3; r++)
+    {
+        for (int k = 0; k < 3; k++)
+            c->R[r * 3 + k] = pose[r * 4 + k];
+        c->t[r] = pose[r * 4 + 3];
+    }
+    c->fx = cam.fx; c->fy = cam.fy; c->cx = cam.cx; c->cy = cam.cy;
+    c->W = cam.width; c->H = cam.height;
+    c->Wf = (float)cam.width; c->Hf = (float)cam.height;
+}
+
+static int integrate_common(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12],
+                            const chs_camera *cam, const uint8_t *color, int channels, const float cpose[12],
+                            const chs_camera *ccam, bool colorPath)
+{
+    if (!m || !integ || !depth || !pose || !cam)
+        return fail(CHS_ERR_INVALID, "null argument");
+    if (cam->width <= 0 || cam->height <= 0 || !finite12(pose))
+        return fail(CHS_ERR_INVALID, "bad camera size or non-finite pose (quirk Q14: rejected at the boundary)");
+    if (colorPath && (!color || !cpose || !ccam || channels < 1 || channels > 4 || !finite12(cpose) || ccam->width <= 0 || ccam->height <= 0))
+        return fail(CHS_ERR_INVALID, "bad colour arguments");
+    if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !integ->trunc_per_pixel)
+        return fail(CHS_ERR_INVALID, "CHS_TRUNC_PER_PIXEL without trunc_per_pixel");
+    CHS_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+
+    FrustumGeom fg;
+    build_frustum(pose, *cam, &fg);
+    CandidateBox box;
+    if (!candidate_box(fg, m->cfg.chunk_size, m->cfg.resolution, &box))
+        return fail(CHS_ERR_INVALID, "frustum is not finite or lies outside the packable chunk-ID range");
+    for (int k = 0; k < 3; k++)
+        if (box.lo[k] - 1 < -kIdBias || box.hi[k] + 1 >= kIdBias)
+            return fail(CHS_ERR_INVALID, "chunk IDs outside [-2^20, 2^20)");
+    const long long cand = box.count();
+    if (cand > (1ll << 26))
+        return fail(CHS_ERR_CAPACITY, "candidate box larger than 2^26 chunks");
+    long long dirtyBound = 1;
+    for (int k = 0; k < 3; k++)
+        dirtyBound *= (long long)(box.hi[k] - box.lo[k] + 3);
+
+    // capacity: known counts + bounds of frames whose counters have not come back yet + this frame
+    int rc = poll_inflight(m, false);
+    if (rc)
+        return rc;
+    long long chunkUb = m->knownChunks + cand, dirtyUb = m->knownDirty + dirtyBound;
+    for (const InFlight &f : m->inflight)
+    {
+        chunkUb += f.newBound;
+        dirtyUb += f.dirtyBound;
+    }
+    if (chunkUb > m->dm.capacity || (size_t)chunkUb * 2 > m->hashSize || (size_t)dirtyUb * 2 > m->dirtySize)
+    {
+        // tighten the bound before growing: wait for outstanding counters
+        if ((rc = poll_inflight(m, true)))
+            return rc;
+        chunkUb = m->knownChunks + cand;
+        dirtyUb = m->knownDirty + dirtyBound;
+        if ((rc = ensure_pool(m, chunkUb + chunkUb / 4)) || (rc = ensure_hash(m, chunkUb + chunkUb / 4)) ||
+            (rc = ensure_dirty(m, dirtyUb + dirtyUb / 4)))
+            return rc;
+    }
+    if ((rc = grow_buffer(&m->dWork, &m->workCap, (size_t)cand, st)))
+        return rc;
+
+    const size_t npx = (size_t)cam->width * cam->height;
+    FrameParams fp{};
+    fill_camera(&fp.cam, pose, *cam);
+    if (colorPath)
+        fill_camera(&fp.ccam, cpose, *ccam);
+    else
+        fp.ccam = fp.cam;
+    // inputs
+    bool copied = false;
+    if (mem == CHS_MEM_HOST)
+    {
+        if ((rc = grow_buffer(&m->dDepth, &m->depthCap, npx, st)))
+            return rc;
+        CHS_CUDA(cudaMemcpyAsync(m->dDepth, depth, npx * sizeof(float), cudaMemcpyHostToDevice, st));
+        fp.depth = m->dDepth;
+        copied = true;
+    }
+    else
+        fp.depth = depth;
+    fp.trunc_img = nullptr;
+    if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL)
+    {
+        if (mem == CHS_MEM_HOST)
+        {
+            if ((rc = grow_buffer(&m->dTrunc, &m->truncCap, npx, st)))
+                return rc;
+            CHS_CUDA(cudaMemcpyAsync(m->dTrunc, integ->trunc_per_pixel, npx * sizeof(float), cudaMemcpyHostToDevice, st));
+            fp.trunc_img = m->dTrunc;
+        }
+        else
+            fp.trunc_img = integ->trunc_per_pixel;
+    }
+    else if (integ->trunc_kind != CHS_TRUNC_CONSTANT)
+    {
+        if ((rc = grow_buffer(&m->dTrunc, &m->truncCap, npx, st)))
+            return rc;
+        fp.trunc_img = m->dTrunc;                                   // written by frame_prepare
+    }
+    if (colorPath)
+    {
+        const size_t nb = (size_t)ccam->width * ccam->height * channels;
+        if (mem == CHS_MEM_HOST)
+        {
+            if ((rc = grow_buffer(&m->dColor, &m->colorCap, nb, st)))
+                return rc;
+            CHS_CUDA(cudaMemcpyAsync(m->dColor, color, nb, cudaMemcpyHostToDevice, st));
+            fp.color = m->dColor;
+        }
+        else
+            fp.color = color;
+    }
+    if (copied)
+        CHS_CUDA(cudaEventRecord(m->h2dDone, st));
+    fp.channels = channels;
+    fp.color_path = colorPath ? 1 : 0;
+    fp.trunc_kind = integ->trunc_kind;
+    fp.trunc_param = integ->trunc_param;
+    // ProjectionIntegrator.h:59 / :108 -- double expression, narrowed once
+    fp.diag = (float)(2.0 * std::sqrt((double)3.0f) * (double)m->cfg.resolution);
+    fp.carve_dist = integ->carving_dist;
+    fp.carve = integ->carving_enabled ? 1 : 0;
+    fp.weight = integ->weight;
+    fp.depth_cutoff = colorPath ? 100.0f : 50.0f;
+    {
+        float T = (float)1e-5;
+        if ((double)T < 1e-5)
+            T = std::nextafterf(T, INFINITY);
+        fp.sdf_carve_max = T;
+    }
+    for (int k = 0; k < 3; k++)
+    {
+        fp.lo[k] = box.lo[k];
+        fp.n[k] = box.hi[k] - box.lo[k] + 1;
+    }
+    for (int p = 0; p < 6; p++)
+    {
+        for (int k = 0; k < 3; k++)
+            fp.planes[p][k] = fg.plane[p].n[k];
+        fp.planes[p][3] = fg.plane[p].d;
+    }
+    size_t hizTotal = 0;
+    for (int l = 0; l < kHizLevels; l++)
+    {
+        const int tile = 8 << l;
+        fp.hizW[l] = (cam->width + tile - 1) / tile;
+        fp.hizH[l] = (cam->height + tile - 1) / tile;
+        hizTotal += (size_t)fp.hizW[l] * fp.hizH[l];
+    }
+    if ((rc = grow_buffer(&m->dHiz, &m->hizCap, hizTotal, st)))
+        return rc;
+    {
+        size_t off = 0;
+        for (int l = 0; l < kHizLevels; l++)
+        {
+            fp.hiz[l] = m->dHiz + off;
+            off += (size_t)fp.hizW[l] * fp.hizH[l];
+        }
+    }
+    fp.work = m->dWork;
+    fp.work_cap = (int)std::min<size_t>(m->workCap, 0x7fffffff);
+
+    if (m->profiling)
+        CHS_CUDA(cudaEventRecord(m->evt[0], st));
+    launch_frame_prepare(fp, m->dm, st);
+    if (m->profiling)
+        CHS_CUDA(cudaEventRecord(m->evt[1], st));
+    launch_chunk_candidates(fp, m->dm, st);
+    if (m->profiling)
+        CHS_CUDA(cudaEventRecord(m->evt[2], st));
+    // persistent-style grid: CTAs stride over the work list, whose length is only known on the device
+    const int grid = (int)std::min<long long>(cand, 148ll * 8);
+    launch_integrate(fp, m->dm, std::max(grid, 1), st);
+    if (m->profiling)
+    {
+        CHS_CUDA(cudaEventRecord(m->evt[3], st));
+        m->frameTimed = true;
+    }
+    CHS_CUDA(cudaGetLastError());
+    if ((rc = snapshot_counters(m, cand, dirtyBound)))
+        return rc;
+    m->haveFrame = true;
+    // the caller may reuse its host buffers as soon as we return (chisel_ros does: CR ChiselServer.cpp:285-295)
+    if (copied)
+        CHS_CUDA(cudaEventSynchronize(m->h2dDone));
+    return CHS_OK;
+}
+
+static int refresh_host_ids(chs_map *m, long long n)
+{
+    const long long have = (long long)m->hostIds.size() / 3;
+    if (n > have)
+    {
+        m->hostIds.resize((size_t)n * 3);
+        CHS_CUDA(cudaMemcpyAsync(m->hostIds.data() + have * 3, m->dm.slot_ids + have * 3, sizeof(int) * 3 * (size_t)(n - have),
+                                 cudaMemcpyDeviceToHost, m->stream));
+        CHS_CUDA(cudaStreamSynchronize(m->stream));
+        for (long long s = have; s < n; s++)
+            m->hostIndex[pack_id(m->hostIds[3 * s], m->hostIds[3 * s + 1], m->hostIds[3 * s + 2])] = (int)s;
+    }
+    return CHS_OK;
+}
+
+static int sync_counts(chs_map *m)
+{
+    CHS_CUDA(cudaSetDevice(m->device));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    int rc = poll_inflight(m, true);
+    if (rc)
+        return rc;
+    // counters may have changed outside integrate (reset, update_meshes): read them directly
+    Counters c;
+    CHS_CUDA(cudaMemcpyAsync(&m->hCtr[chs_map::kRing], m->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    c = m->hCtr[chs_map::kRing];
+    m->knownChunks = c.n_chunks;
+    m->knownDirty = c.n_dirty;
+    if (c.error_flags)
+        return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(c.error_flags));
+    return CHS_OK;
+}
+
+} // namespace chs
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+
+extern "C"
+{
+
+const char *chs_last_error_string(void) { return g_last_error.c_str(); }
+int chs_abi_version(void) { return CHS_ABI_VERSION; }
+
+int chs_create(const chs_config *cfg, chs_map **out)
+{
+    if (!cfg || !out)
+        return fail(CHS_ERR_INVALID, "null argument");
+    if (cfg->chunk_size != 8 && cfg->chunk_size != 16 && cfg->chunk_size != 32)
+        return fail(CHS_ERR_INVALID, "chunk_size must be 8, 16 or 32 (cubic chunks only, quirk Q12)");
+    if (!(cfg->resolution > 0.0f) || !std::isfinite(cfg->resolution))
+        return fail(CHS_ERR_INVALID, "resolution must be positive");
+    int count = 0;
+    CHS_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0)
+        return fail(CHS_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    chs_map *m = new chs_map();
+    m->cfg = *cfg;
+    if (m->cfg.world < 1)
+        m->cfg.world = 1;
+    if (m->cfg.rank < 0 || m->cfg.rank >= m->cfg.world)
+    {
+        delete m;
+        return fail(CHS_ERR_INVALID, "rank outside [0, world)");
+    }
+    if (cfg->device >= 0)
+        m->device = cfg->device;
+    else
+        CHS_CUDA(cudaGetDevice(&m->device));
+    CHS_CUDA(cudaSetDevice(m->device));
+    if (cfg->stream)
+        m->stream = (cudaStream_t)cfg->stream;
+    else
+    {
+        CHS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->ownStream = true;
+    }
+    // keep freed stream-ordered memory cached in the pool instead of returning it to the OS at every sync
+    {
+        cudaMemPool_t pool;
+        CHS_CUDA(cudaDeviceGetDefaultMemPool(&pool, m->device));
+        unsigned long long thr = ~0ull;
+        CHS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
+    DeviceMap &d = m->dm;
+    d.cs = cfg->chunk_size;
+    d.V = d.cs * d.cs * d.cs;
+    d.res = cfg->resolution;
+    d.half = cfg->resolution * 0.5f;
+    d.use_color = cfg->use_color ? 1 : 0;
+    d.rank = m->cfg.rank;
+    d.world = m->cfg.world;
+    CHS_CUDA(cudaMalloc((void **)&d.dist_slabs, sizeof(float2 *) * kMaxSlabs));
+    CHS_CUDA(cudaMalloc((void **)&d.color_slabs, sizeof(uchar4 *) * kMaxSlabs));
+    CHS_CUDA(cudaMalloc((void **)&m->dCtr, sizeof(Counters)));
+    CHS_CUDA(cudaMemsetAsync(m->dCtr, 0, sizeof(Counters), m->stream));
+    d.ctr = m->dCtr;
+    CHS_CUDA(cudaHostAlloc((void **)&m->hCtr, sizeof(Counters) * (chs_map::kRing + 1), cudaHostAllocDefault));
+    std::memset(m->hCtr, 0, sizeof(Counters) * (chs_map::kRing + 1));
+    CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
+    for (int i = 0; i < 8; i++)
+        CHS_CUDA(cudaEventCreate(&m->evt[i]));
+    const long long initial = cfg->initial_chunks > 0 ? cfg->initial_chunks : 4096;
+    int rc;
+    if ((rc = ensure_pool(m, initial)) || (rc = ensure_hash(m, initial)) || (rc = ensure_dirty(m, initial * 2)))
+    {
+        chs_destroy(m);
+        return rc;
+    }
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    *out = m;
+    return CHS_OK;
+}
+
+int chs_destroy(chs_map *m)
+{
+    if (!m)
+        return CHS_OK;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    for (float2 *p : m->distSlabs)
+        cudaFreeAsync(p, m->stream);
+    for (uchar4 *p : m->colorSlabs)
+        cudaFreeAsync(p, m->stream);
+    void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dHiz,
+                    m->dWork, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
+                    m->dColors, m->dGrids};
+    for (void *p : bufs)
+        if (p)
+            cudaFreeAsync(p, m->stream);
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->dm.dist_slabs);
+    cudaFree(m->dm.color_slabs);
+    cudaFree(m->dCtr);
+    cudaFreeHost(m->hCtr);
+    for (InFlight &f : m->inflight)
+        cudaEventDestroy(f.ev);
+    for (cudaEvent_t e : m->eventPool)
+        cudaEventDestroy(e);
+    if (m->h2dDone)
+        cudaEventDestroy(m->h2dDone);
+    for (int i = 0; i < 8; i++)
+        if (m->evt[i])
+            cudaEventDestroy(m->evt[i]);
+    if (m->ownStream)
+        cudaStreamDestroy(m->stream);
+    delete m;
+    return CHS_OK;
+}
+
+// Chisel::Reset (OC Chisel.cpp:44-48): drop every chunk, mesh and dirty flag; keep the allocations.
+int chs_reset(chs_map *m)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    CHS_CUDA(cudaSetDevice(m->device));
+    int rc = poll_inflight(m, true);
+    if (rc)
+        return rc;
+    launch_fill_u64(m->dm.keys, m->hashSize, kEmptyKey, m->stream);
+    launch_fill_u64(m->dm.dirty_keys, m->dirtySize, kEmptyKey, m->stream);
+    CHS_CUDA(cudaMemsetAsync(m->dCtr, 0, sizeof(Counters), m->stream));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    m->knownChunks = m->knownDirty = 0;
+    m->hostIds.clear();
+    m->hostIndex.clear();
+    m->lastMesh = chs_mesh_counts{};
+    m->lastMeshChunks = 0;
+    m->haveFrame = false;
+    return CHS_OK;
+}
+
+int chs_synchronize(chs_map *m)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    CHS_CUDA(cudaSetDevice(m->device));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    return CHS_OK;
+}
+
+int chs_set_stream(chs_map *m, void *stream)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    CHS_CUDA(cudaSetDevice(m->device));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->ownStream)
+    {
+        cudaStreamDestroy(m->stream);
+        m->ownStream = false;
+    }
+    if (stream)
+        m->stream = (cudaStream_t)stream;
+    else
+    {
+        CHS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->ownStream = true;
+    }
+    return CHS_OK;
+}
+
+int chs_set_profiling(chs_map *m, int enabled)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    m->profiling = enabled != 0;
+    m->frameTimed = m->meshTimed = false;
+    return CHS_OK;
+}
+
+int chs_integrate_depth(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12], const chs_camera *cam)
+{
+    return integrate_common(m, integ, depth, mem, pose, cam, nullptr, 0, nullptr, nullptr, false);
+}
+
+int chs_integrate_depth_color(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12],
+                              const chs_camera *cam, const uint8_t *color, int channels, const float cpose[12], const chs_camera *ccam)
+{
+    return integrate_common(m, integ, depth, mem, pose, cam, color, channels, cpose, ccam, true);
+}
+
+int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
+{
+    if (!m || !out)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    int rc = poll_inflight(m, true);
+    if (rc)
+        return rc;
+    const Counters &c = m->lastFrame;
+    out->candidates = c.candidates;
+    out->processed_chunks = c.work_count;
+    out->n_upd = (int64_t)c.n_upd;
+    out->n_carve = (int64_t)c.n_carve;
+    out->n_col = (int64_t)c.n_col;
+    out->n_new = c.n_new;
+    out->updated_chunks = c.updated_chunks;
+    out->total_chunks = c.n_chunks;
+    out->dirty_chunks = c.n_dirty;
+    out->error_flags = c.error_flags;
+    if (c.error_flags)
+        return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(c.error_flags));
+    return CHS_OK;
+}
+
+int chs_get_timings(chs_map *m, chs_timings *out)
+{
+    if (!m || !out)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    std::memset(out, 0, sizeof(*out));
+    if (m->frameTimed)
+    {
+        CHS_CUDA(cudaEventElapsedTime(&out->prepare_ms, m->evt[0], m->evt[1]));
+        CHS_CUDA(cudaEventElapsedTime(&out->candidates_ms, m->evt[1], m->evt[2]));
+        CHS_CUDA(cudaEventElapsedTime(&out->integrate_ms, m->evt[2], m->evt[3]));
+        CHS_CUDA(cudaEventElapsedTime(&out->frame_ms, m->evt[0], m->evt[3]));
+    }
+    if (m->meshTimed)
+    {
+        CHS_CUDA(cudaEventElapsedTime(&out->mesh_count_ms, m->evt[4], m->evt[5]));
+        CHS_CUDA(cudaEventElapsedTime(&out->mesh_emit_ms, m->evt[5], m->evt[6]));
+        CHS_CUDA(cudaEventElapsedTime(&out->mesh_ms, m->evt[4], m->evt[6]));
+    }
+    return CHS_OK;
+}
+
+int chs_num_chunks(chs_map *m, int64_t *n)
+{
+    if (!m || !n)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    *n = m->knownChunks;
+    return CHS_OK;
+}
+
+int chs_chunk_ids(chs_map *m, int32_t *ids, int64_t cap)
+{
+    if (!m || !ids)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    const int64_t n = std::min<int64_t>(cap, m->knownChunks);
+    std::memcpy(ids, m->hostIds.data(), sizeof(int32_t) * 3 * (size_t)n);
+    return CHS_OK;
+}
+
+static int download_slot(chs_map *m, int slot, float *sdf, float *weight, uint8_t *rgbw)
+{
+    const int V = m->dm.V;
+    std::vector<float2> tmp((size_t)V);
+    const float2 *src = m->distSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
+    CHS_CUDA(cudaMemcpyAsync(tmp.data(), src, sizeof(float2) * V, cudaMemcpyDeviceToHost, m->stream));
+    if (rgbw && m->cfg.use_color)
+    {
+        const uchar4 *cs = m->colorSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
+        CHS_CUDA(cudaMemcpyAsync(rgbw, cs, 4 * (size_t)V, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CHS_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < V; i++)
+    {
+        if (sdf)
+            sdf[i] = tmp[i].x;
+        if (weight)
+            weight[i] = tmp[i].y;
+    }
+    return CHS_OK;
+}
+
+int chs_download_chunk(chs_map *m, const int32_t id[3], float *sdf, float *weight, uint8_t *rgbw)
+{
+    if (!m || !id)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    if (id[0] < -kIdBias || id[0] >= kIdBias || id[1] < -kIdBias || id[1] >= kIdBias || id[2] < -kIdBias || id[2] >= kIdBias)
+        return fail(CHS_ERR_NOT_FOUND, "no such chunk");
+    auto it = m->hostIndex.find(pack_id(id[0], id[1], id[2]));
+    if (it == m->hostIndex.end())
+        return fail(CHS_ERR_NOT_FOUND, "no such chunk");
+    return download_slot(m, it->second, sdf, weight, rgbw);
+}
+
+int chs_download_all(chs_map *m, int64_t cap, int32_t *ids, float *sdf, float *weight, uint8_t *rgbw)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    const int64_t n = std::min<int64_t>(cap, m->knownChunks);
+    const int V = m->dm.V;
+    if (ids)
+        std::memcpy(ids, m->hostIds.data(), sizeof(int32_t) * 3 * (size_t)n);
+    std::vector<float2> tmp;
+    for (int64_t s0 = 0; s0 < n; s0 += kSlabChunks)
+    {
+        const int64_t cnt = std::min<int64_t>(kSlabChunks, n - s0);
+        const size_t slab = (size_t)(s0 >> kSlabChunksLog2);
+        if (sdf || weight)
+        {
+            tmp.resize((size_t)cnt * V);
+            CHS_CUDA(cudaMemcpyAsync(tmp.data(), m->distSlabs[slab], sizeof(float2) * (size_t)cnt * V, cudaMemcpyDeviceToHost, m->stream));
+        }
+        if (rgbw && m->cfg.use_color)
+            CHS_CUDA(cudaMemcpyAsync(rgbw + (size_t)s0 * V * 4, m->colorSlabs[slab], 4 * (size_t)cnt * V, cudaMemcpyDeviceToHost, m->stream));
+        CHS_CUDA(cudaStreamSynchronize(m->stream));
+        if (sdf || weight)
+            for (size_t i = 0; i < (size_t)cnt * V; i++)
+            {
+                if (sdf)
+                    sdf[(size_t)s0 * V + i] = tmp[i].x;
+                if (weight)
+                    weight[(size_t)s0 * V + i] = tmp[i].y;
+            }
+    }
+    return CHS_OK;
+}
+
+int chs_num_dirty(chs_map *m, int64_t *n)
+{
+    if (!m || !n)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    *n = m->knownDirty;
+    return CHS_OK;
+}
+
+int chs_dirty_ids(chs_map *m, int32_t *ids, int64_t cap)
+{
+    if (!m || !ids)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    const int64_t n = std::min<int64_t>(cap, m->knownDirty);
+    std::vector<unsigned long long> keys((size_t)n);
+    if (n)
+    {
+        CHS_CUDA(cudaMemcpyAsync(keys.data(), m->dm.dirty_list, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+        CHS_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    for (int64_t i = 0; i < n; i++)
+        unpack_id(keys[(size_t)i], &ids[3 * i], &ids[3 * i + 1], &ids[3 * i + 2]);
+    return CHS_OK;
+}
+
+// Chisel::UpdateMeshes without its every-10th gate (OC Chisel.cpp:50-59): RecomputeMeshes(meshesToUpdate), clear.
+int chs_update_meshes(chs_map *m)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    cudaStream_t st = m->stream;
+    const long long nd = m->knownDirty;
+    m->lastMesh = chs_mesh_counts{};
+    m->lastMesh.has_colors = m->cfg.use_color ? 1 : 0;
+    m->lastMeshChunks = 0;
+    if (nd == 0)
+        return CHS_OK;
+    if ((size_t)nd > m->meshChunkCap)
+    {
+        const size_t want = (size_t)nd + (size_t)nd / 2;
+        size_t c0 = m->meshChunkCap, c1 = m->meshChunkCap, c2 = m->meshChunkCap;
+        if ((rc = grow_buffer(&m->dMeshSlots, &c0, want, st)) || (rc = grow_buffer(&m->dTriCounts, &c1, want, st)) ||
+            (rc = grow_buffer(&m->dGridCounts, &c2, want, st)))
+            return rc;
+        size_t o0 = m->meshChunkCap ? m->meshChunkCap + 1 : 0, o1 = o0;
+        if ((rc = grow_buffer(&m->dVertOffsets, &o0, want + 1, st)) || (rc = grow_buffer(&m->dGridOffsets, &o1, want + 1, st)))
+            return rc;
+        m->meshChunkCap = want;
+    }
+    MeshParams mp{};
+    mp.dirty_list = m->dm.dirty_list;
+    mp.n_dirty = (int)nd;
+    mp.mesh_slots = m->dMeshSlots;
+    mp.tri_counts = m->dTriCounts;
+    mp.grid_counts = m->dGridCounts;
+    mp.vert_offsets = m->dVertOffsets;
+    mp.grid_offsets = m->dGridOffsets;
+    {
+        float T = (float)1e-12;
+        if ((double)T > 1e-12)
+            T = std::nextafterf(T, -INFINITY);
+        mp.w_observed_min = T;                                  // weight > 1e-12 (double)  <=>  weight > T
+    }
+    CHS_CUDA(cudaMemsetAsync(&m->dCtr->mesh_chunks, 0, sizeof(int), st));
+    if (m->profiling)
+        CHS_CUDA(cudaEventRecord(m->evt[4], st));
+    launch_mesh_select(mp, m->dm, st);
+    launch_mesh_count(mp, m->dm, (int)nd, st);
+    launch_mesh_scan(mp, m->dm, (int)nd, st);
+    if (m->profiling)
+        CHS_CUDA(cudaEventRecord(m->evt[5], st));
+    CHS_CUDA(cudaGetLastError());
+    CHS_CUDA(cudaMemcpyAsync(&m->hCtr[chs_map::kRing], m->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CHS_CUDA(cudaStreamSynchronize(st));
+    const Counters c = m->hCtr[chs_map::kRing];
+    const long long nv = (long long)c.mesh_verts, ng = (long long)c.mesh_grids;
+    if (nv > m->vertCap)
+    {
+        size_t a = (size_t)m->vertCap * 3, b = a, cc = a;
+        const size_t want = (size_t)(nv + nv / 4) * 3;
+        if ((rc = grow_buffer(&m->dVerts, &a, want, st)) || (rc = grow_buffer(&m->dNormals, &b, want, st)))
+            return rc;
+        if (m->cfg.use_color && (rc = grow_buffer(&m->dColors, &cc, want, st)))
+            return rc;
+        m->vertCap = (long long)(want / 3);
+    }
+    if (ng > m->gridCap)
+    {
+        size_t a = (size_t)m->gridCap * 3;
+        const size_t want = (size_t)(ng + ng / 4) * 3;
+        if ((rc = grow_buffer(&m->dGrids, &a, want, st)))
+            return rc;
+        m->gridCap = (long long)(want / 3);
+    }
+    mp.vertices = m->dVerts;
+    mp.normals = m->dNormals;
+    mp.colors = m->cfg.use_color ? m->dColors : nullptr;
+    mp.grids = m->dGrids;
+    mp.cap_vertices = m->vertCap;
+    mp.cap_grids = m->gridCap;
+    if (c.mesh_chunks > 0)
+        launch_mesh_emit(mp, m->dm, c.mesh_chunks, st);
+    if (m->profiling)
+    {
+        CHS_CUDA(cudaEventRecord(m->evt[6], st));
+        m->meshTimed = true;
+    }
+    // meshesToUpdate.clear() (Chisel.cpp:57)
+    launch_fill_u64(m->dm.dirty_keys, m->dirtySize, kEmptyKey, st);
+    CHS_CUDA(cudaMemsetAsync(&m->dCtr->n_dirty, 0, sizeof(int), st));
+    CHS_CUDA(cudaGetLastError());
+    m->knownDirty = 0;
+    m->lastMesh.n_chunks = c.mesh_chunks;
+    m->lastMesh.n_vertices = nv;
+    m->lastMesh.n_grids = ng;
+    m->lastMeshChunks = c.mesh_chunks;
+    return CHS_OK;
+}
+
+int chs_mesh_counts_last(chs_map *m, chs_mesh_counts *out)
+{
+    if (!m || !out)
+        return fail(CHS_ERR_INVALID, "null argument");
+    *out = m->lastMesh;
+    return CHS_OK;
+}
+
+int chs_download_meshes(chs_map *m, int32_t *ids, int64_t *vertOffsets, int64_t *gridOffsets, float *vertices, float *normals,
+                        float *colors, float *grids)
+{
+    if (!m)
+        return fail(CHS_ERR_INVALID, "null map");
+    CHS_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const int n = m->lastMeshChunks;
+    const long long nv = m->lastMesh.n_vertices, ng = m->lastMesh.n_grids;
+    std::vector<int> slots((size_t)n);
+    if (n)
+    {
+        CHS_CUDA(cudaMemcpyAsync(slots.data(), m->dMeshSlots, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+        if (vertOffsets)
+            CHS_CUDA(cudaMemcpyAsync(vertOffsets, m->dVertOffsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        if (gridOffsets)
+            CHS_CUDA(cudaMemcpyAsync(gridOffsets, m->dGridOffsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    }
+    else
+    {
+        if (vertOffsets)
+            vertOffsets[0] = 0;
+        if (gridOffsets)
+            gridOffsets[0] = 0;
+    }
+    if (nv)
+    {
+        if (vertices)
+            CHS_CUDA(cudaMemcpyAsync(vertices, m->dVerts, sizeof(float) * 3 * (size_t)nv, cudaMemcpyDeviceToHost, st));
+        if (normals)
+            CHS_CUDA(cudaMemcpyAsync(normals, m->dNormals, sizeof(float) * 3 * (size_t)nv, cudaMemcpyDeviceToHost, st));
+        if (colors && m->cfg.use_color)
+            CHS_CUDA(cudaMemcpyAsync(colors, m->dColors, sizeof(float) * 3 * (size_t)nv, cudaMemcpyDeviceToHost, st));
+    }
+    if (ng && grids)
+        CHS_CUDA(cudaMemcpyAsync(grids, m->dGrids, sizeof(float) * 3 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+    CHS_CUDA(cudaStreamSynchronize(st));
+    if (ids && n)
+    {
+        int rc = refresh_host_ids(m, m->knownChunks);
+        if (rc)
+            return rc;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++)
+                ids[3 * i + k] = m->hostIds[3 * (size_t)slots[i] + k];
+    }
+    return CHS_OK;
+}
+
+int chs_frustum(const float pose[12], const chs_camera *cam, float corners[24], float lines[72], float planes[24])
+{
+    if (!pose || !cam)
+        return fail(CHS_ERR_INVALID, "null argument");
+    FrustumGeom g;
+    build_frustum(pose, *cam, &g);
+    if (corners)
+        for (int i = 0; i < 8; i++)
+            for (int k = 0; k < 3; k++)
+                corners[3 * i + k] = g.corner[i][k];
+    if (lines)
+        frustum_lines(g, lines);
+    if (planes)
+        for (int p = 0; p < 6; p++)
+        {
+            for (int k = 0; k < 3; k++)
+                planes[4 * p + k] = g.plane[p].n[k];
+            planes[4 * p + 3] = g.plane[p].d;
+        }
+    return CHS_OK;
+}
+
+// ChunkManager::GetChunkIDsIntersecting(Frustum) on the host (OC ChunkManager.cpp:182-212), for the facade and tests.
+int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], const chs_camera *cam, int32_t *ids, int64_t cap, int64_t *n)
+{
+    if (!pose || !cam || !n)
+        return fail(CHS_ERR_INVALID, "null argument");
+    FrustumGeom g;
+    build_frustum(pose, *cam, &g);
+    CandidateBox box;
+    if (!candidate_box(g, chunk_size, resolution, &box))
+        return fail(CHS_ERR_INVALID, "frustum is not finite or out of range");
+    int64_t count = 0;
+    const float ext = (float)chunk_size * resolution;
+    for (int x = box.lo[0]; x <= box.hi[0]; x++)
+        for (int y = box.lo[1]; y <= box.hi[1]; y++)
+            for (int z = box.lo[2]; z <= box.hi[2]; z++)
+            {
+                const F3 bmin = f3((float)(x * chunk_size) * resolution, (float)(y * chunk_size) * resolution, (float)(z * chunk_size) * resolution);
+                const F3 bmax = f3(bmin[0] + ext, bmin[1] + ext, bmin[2] + ext);
+                bool hit = false;
+                for (int p = 0; p < 6 && !hit; p++)
+                {
+                    const PlaneEq &pl = g.plane[p];
+                    const F3 a = f3(pl.n[0] < 0.0f ? bmin[0] : bmax[0], pl.n[1] < 0.0f ? bmin[1] : bmax[1], pl.n[2] < 0.0f ? bmin[2] : bmax[2]);
+                    hit = dot3(a, pl.n) + pl.d > 0.0f;
+                }
+                if (hit)
+                {
+                    if (ids && count < cap)
+                    {
+                        ids[3 * count] = x;
+                        ids[3 * count + 1] = y;
+                        ids[3 * count + 2] = z;
+                    }
+                    count++;
+                }
+            }
+    *n = count;
+    return CHS_OK;
+}
+
+float chs_truncation(int kind, float param, float depth) { return host_truncation(kind, param, depth); }
+uint32_t chs_owner(int32_t x, int32_t y, int32_t z) { return owner_hash(x, y, z); }
+
+} // extern "C"

@@ -1,0 +1,602 @@
+// mesh.cu -- incremental marching cubes over the dirty chunk set (sm_100a).
+//
+//   mesh_select_kernel  dirty ID list -> pool slots of the IDs that exist (warp-ballot compaction)
+//   mesh_count_kernel   per chunk: halo tile in shared memory, cube configuration per cell, triangle / grid counts
+//   mesh_scan_kernel    exclusive prefix sums over chunks -> vertex and grid offsets
+//   mesh_emit_kernel    per chunk: same classification, block prefix sum in the REFERENCE'S cell order, emission of
+//                       vertices + flat normals + grids, then gradient normals and colours per vertex
+//
+// Replaces ChunkManager::RecomputeMeshes / RecomputeMesh / GenerateMesh / Extract{Inside,Border}VoxelMesh
+// (OC ChunkManager.cpp:91-169, 259-447), MarchingCubes::MeshCube & friends (OC MarchingCubes.h:73-146),
+// ComputeNormalsFromGradients / GetSDFAndGradient / GetSDF (ChunkManager.cpp:449-499, 609-626) and
+// ColorizeMesh / InterpolateColor / GetColorVoxel / Chunk::GetColorAt (ChunkManager.cpp:501-607, 628-639,
+// Chunk.cpp:118-136). Emission rank = the reference's traversal order (interior z,y,x; +X face; +Y face; +Z face),
+// so vertex arrays match the reference index for index. Arithmetic that produces output follows the
+// reference's binary32 operation order with __f*_rn intrinsics.
+#include "device_map.cuh"
+#include "kernels.h"
+
+#include "mc_table.inc"
+
+namespace chs
+{
+
+__constant__ unsigned long long cTriPacked[256] = MC_TRI_PACKED_INIT;
+__constant__ unsigned char cTriCount[256] = MC_TRI_COUNT_INIT;
+__constant__ unsigned char cEdgePairs[12] = MC_EDGE_PAIRS_INIT;
+
+__global__ void mesh_select_kernel(MeshParams mp, DeviceMap map)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = -1;
+    if (i < mp.n_dirty)
+        slot = hash_lookup(map, mp.dirty_list[i]);          // RecomputeMesh skips IDs without a chunk (ChunkManager.cpp:94-98)
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, slot >= 0);
+    int base = 0;
+    if (lane == 0 && mask)
+        base = atomicAdd(&map.ctr->mesh_chunks, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (slot >= 0)
+        mp.mesh_slots[base + __popc(mask & ((1u << lane) - 1))] = slot;
+}
+
+// Cell k of the reference's traversal (ChunkManager.cpp:393-441) -> voxel index of the cell's corner 0.
+template <int CS>
+__device__ __forceinline__ void cell_of_rank(int k, int *x, int *y, int *z)
+{
+    constexpr int M = CS - 1;
+    constexpr int nInterior = M * M * M, nX = M * CS, nY = M * M;
+    if (k < nInterior)
+    {
+        *z = k / (M * M);
+        *y = (k / M) % M;
+        *x = k % M;
+    }
+    else if (k < nInterior + nX)
+    {
+        const int j = k - nInterior;
+        *x = M;
+        *z = j / CS;
+        *y = j % CS;
+    }
+    else if (k < nInterior + nX + nY)
+    {
+        const int j = k - nInterior - nX;
+        *y = M;
+        *z = j / M;
+        *x = j % M;
+    }
+    else
+    {
+        const int j = k - nInterior - nX - nY;
+        *z = M;
+        *y = j / CS;
+        *x = j % CS;
+    }
+}
+
+// Halo tile: (CS+1)^3 SDF values; NaN marks a corner that makes the cell unmeshable (weight <= 0.5 or the
+// neighbour chunk is missing: ChunkManager.cpp:274-278, 311-314, 336-367).
+template <int CS>
+__device__ void load_halo(const DeviceMap &map, int slot, float *tile, int *nbrSlots)
+{
+    constexpr int H = CS + 1;
+    const int t = threadIdx.x;
+    const int idx = map.slot_ids[3 * slot], idy = map.slot_ids[3 * slot + 1], idz = map.slot_ids[3 * slot + 2];
+    if (t < 8)
+        nbrSlots[t] = (t == 0) ? slot : hash_lookup(map, pack_id(idx + (t & 1), idy + ((t >> 1) & 1), idz + (t >> 2)));
+    __syncthreads();
+    for (int i = t; i < H * H * H; i += blockDim.x)
+    {
+        const int x = i % H, y = (i / H) % H, z = i / (H * H);
+        const int n = (x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0);
+        const int s = nbrSlots[n];
+        float v = __int_as_float(0x7fc00000);
+        if (s >= 0)
+        {
+            const int vx = x == CS ? 0 : x, vy = y == CS ? 0 : y, vz = z == CS ? 0 : z;
+            const float2 d = dist_ptr(map, s)[(vz * CS + vy) * CS + vx];
+            if (!(d.y <= 0.5f))
+                v = d.x;
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+}
+
+// cube corner offsets, ChunkManager.cpp:67-69: x 0 1 1 0 0 1 1 0 ; y 0 0 1 1 0 0 1 1 ; z 0 0 0 0 1 1 1 1
+__device__ __forceinline__ int corner_dx(int i) { return (0x66 >> i) & 1; }
+__device__ __forceinline__ int corner_dy(int i) { return (0xCC >> i) & 1; }
+__device__ __forceinline__ int corner_dz(int i) { return (0xF0 >> i) & 1; }
+
+// returns the cube configuration, or -1 if any corner is unobserved
+template <int CS>
+__device__ __forceinline__ int cell_config(const float *tile, int x, int y, int z, float *sdf)
+{
+    constexpr int H = CS + 1;
+    int cfg = 0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        const float v = tile[((z + corner_dz(i)) * H + (y + corner_dy(i))) * H + (x + corner_dx(i))];
+        sdf[i] = v;
+        ok &= (v == v);
+        cfg |= (v < 0.0f) ? (1 << i) : 0;                   // MarchingCubes::CalculateVertexConfiguration (MarchingCubes.h:106-116)
+    }
+    return ok ? cfg : -1;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(256) mesh_count_kernel(MeshParams mp, DeviceMap map)
+{
+    extern __shared__ float tile[];
+    __shared__ int nbr[8];
+    __shared__ int red[2][8];
+    constexpr int V = CS * CS * CS, CPT = V / 256;
+    const int n = map.ctr->mesh_chunks;
+    for (int c = blockIdx.x; c < n; c += gridDim.x)
+    {
+        load_halo<CS>(map, mp.mesh_slots[c], tile, nbr);
+        int tris = 0, grids = 0;
+        for (int j = 0; j < CPT; j++)
+        {
+            int x, y, z;
+            float sdf[8];
+            cell_of_rank<CS>(threadIdx.x * CPT + j, &x, &y, &z);
+            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            if (cfg >= 0)
+            {
+                const int nt = cTriCount[cfg];
+                tris += nt;
+                grids += nt > 0;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            tris += __shfl_xor_sync(0xffffffffu, tris, o);
+            grids += __shfl_xor_sync(0xffffffffu, grids, o);
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            red[0][threadIdx.x >> 5] = tris;
+            red[1][threadIdx.x >> 5] = grids;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2)
+        {
+            int s = 0;
+            for (int k = 0; k < 8; k++)
+                s += red[threadIdx.x][k];
+            (threadIdx.x == 0 ? mp.tri_counts : mp.grid_counts)[c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// one block; exclusive scans of 3*tri_counts and grid_counts over the remeshed chunks
+__global__ void __launch_bounds__(1024) mesh_scan_kernel(MeshParams mp, DeviceMap map)
+{
+    __shared__ long long warpSum[2][32];
+    __shared__ long long carry[2];
+    const int n = map.ctr->mesh_chunks;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0)
+        carry[0] = carry[1] = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024)
+    {
+        const int i = base + t;
+        long long v[2] = {i < n ? 3ll * mp.tri_counts[i] : 0, i < n ? (long long)mp.grid_counts[i] : 0};
+        long long inc[2] = {v[0], v[1]};
+        for (int o = 1; o < 32; o <<= 1)
+            for (int q = 0; q < 2; q++)
+            {
+                const long long up = __shfl_up_sync(0xffffffffu, inc[q], o);
+                if (lane >= o)
+                    inc[q] += up;
+            }
+        if (lane == 31)
+        {
+            warpSum[0][warp] = inc[0];
+            warpSum[1][warp] = inc[1];
+        }
+        __syncthreads();
+        if (warp == 0)
+            for (int q = 0; q < 2; q++)
+            {
+                long long s = warpSum[q][lane];
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const long long up = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane >= o)
+                        s += up;
+                }
+                warpSum[q][lane] = s;                           // inclusive over warps
+            }
+        __syncthreads();
+        for (int q = 0; q < 2; q++)
+        {
+            const long long before = carry[q] + (warp ? warpSum[q][warp - 1] : 0) + inc[q] - v[q];
+            if (i < n)
+                (q == 0 ? mp.vert_offsets : mp.grid_offsets)[i] = before;
+        }
+        __syncthreads();
+        if (t == 0)
+        {
+            carry[0] += warpSum[0][31];
+            carry[1] += warpSum[1][31];
+        }
+        __syncthreads();
+    }
+    if (t == 0)
+    {
+        mp.vert_offsets[n] = carry[0];
+        mp.grid_offsets[n] = carry[1];
+        map.ctr->mesh_verts = (unsigned long long)carry[0];
+        map.ctr->mesh_grids = (unsigned long long)carry[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exact helpers
+
+struct P3
+{
+    float x, y, z;
+};
+
+// ChunkManager::GetIDAt (OC ChunkManager.h:136-145): floor(pos * 1/(chunkSize*res)) per axis
+__device__ __forceinline__ int lookup_chunk_at(const DeviceMap &map, float rfChunk, P3 pos)
+{
+    const float fx = floorf(__fmul_rn(pos.x, rfChunk)), fy = floorf(__fmul_rn(pos.y, rfChunk)), fz = floorf(__fmul_rn(pos.z, rfChunk));
+    // outside the packable range (or NaN) there is no chunk
+    if (!(fabsf(fx) < (float)(kIdBias - 1)) || !(fabsf(fy) < (float)(kIdBias - 1)) || !(fabsf(fz) < (float)(kIdBias - 1)))
+        return -1;
+    return hash_lookup(map, pack_id((int)fx, (int)fy, (int)fz));
+}
+
+// Chunk::GetVoxelID(const Vec3&) (OC Chunk.cpp:72-86): floor(rel * (1/res)), then (z*N + y)*N + x
+__device__ __forceinline__ int voxel_id_of_rel(const DeviceMap &map, float rfVoxel, P3 rel)
+{
+    const int x = (int)floorf(__fmul_rn(rel.x, rfVoxel)), y = (int)floorf(__fmul_rn(rel.y, rfVoxel)), z = (int)floorf(__fmul_rn(rel.z, rfVoxel));
+    return (z * map.cs + y) * map.cs + x;
+}
+
+__device__ __forceinline__ P3 chunk_origin(const DeviceMap &map, int slot)
+{
+    P3 o;
+    o.x = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot]), map.res);
+    o.y = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot + 1]), map.res);
+    o.z = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot + 2]), map.res);
+    return o;
+}
+
+// ChunkManager::GetSDF (ChunkManager.cpp:476-499)
+__device__ __forceinline__ bool get_sdf(const DeviceMap &map, float rfChunk, float rfVoxel, float wMin, P3 pos, float *out)
+{
+    const int slot = lookup_chunk_at(map, rfChunk, pos);
+    if (slot < 0)
+        return false;
+    const P3 o = chunk_origin(map, slot);
+    P3 rel = {__fsub_rn(pos.x, o.x), __fsub_rn(pos.y, o.y), __fsub_rn(pos.z, o.z)};
+    const int id = voxel_id_of_rel(map, rfVoxel, rel);
+    if (id < 0 || id >= map.V)
+        return false;
+    const float2 d = dist_ptr(map, slot)[id];
+    if (!(d.y > wMin))                                      // weight > 1e-12
+        return false;
+    *out = d.x;
+    return true;
+}
+
+// ChunkManager::GetSDFAndGradient + ComputeNormalsFromGradients (ChunkManager.cpp:449-474, 609-626)
+__device__ bool gradient_normal(const DeviceMap &map, float rfChunk, float rfVoxel, float wMin, P3 v, P3 *n)
+{
+    const float r = map.res, h = __fdiv_rn(r, 2.0f);
+    P3 p = {__fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.x, r)), r), h), __fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.y, r)), r), h),
+            __fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.z, r)), r), h)};
+    float c, xp, yp, zp, xm, ym, zm;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, p, &c))
+        return false;
+    // posf +/- Vector3f(res, 0, 0): the untouched components add 0.0f (identity for non-zero values)
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, r), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, 0.0f)}, &xp)) return false;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, r), __fadd_rn(p.z, 0.0f)}, &yp)) return false;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, r)}, &zp)) return false;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, r), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, 0.0f)}, &xm)) return false;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, r), __fsub_rn(p.z, 0.0f)}, &ym)) return false;
+    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, r)}, &zm)) return false;
+    // Eigen::Vector3f(double, double, double): differences in double, narrowed once
+    float gx = (float)((double)xp - (double)xm), gy = (float)((double)yp - (double)ym), gz = (float)((double)zp - (double)zm);
+    float z2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+    if (z2 > 0.0f)                                          // grad->normalize()
+    {
+        const float s = __fsqrt_rn(z2);
+        gx = __fdiv_rn(gx, s);
+        gy = __fdiv_rn(gy, s);
+        gz = __fdiv_rn(gz, s);
+    }
+    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz))));
+    if (!((double)mag > 1e-12))
+        return false;
+    const float inv = __fdiv_rn(1.0f, mag);
+    n->x = __fmul_rn(gx, inv);
+    n->y = __fmul_rn(gy, inv);
+    n->z = __fmul_rn(gz, inv);
+    return true;
+}
+
+// ChunkManager::GetColorVoxel (ChunkManager.cpp:588-607)
+__device__ __forceinline__ bool get_color_voxel(const DeviceMap &map, float rfChunk, float rfVoxel, P3 pos, uchar4 *out)
+{
+    const int slot = lookup_chunk_at(map, rfChunk, pos);
+    if (slot < 0)
+        return false;
+    const P3 o = chunk_origin(map, slot);
+    P3 rel = {__fsub_rn(pos.x, o.x), __fsub_rn(pos.y, o.y), __fsub_rn(pos.z, o.z)};
+    const int id = voxel_id_of_rel(map, rfVoxel, rel);
+    if (id < 0 || id >= map.V)
+        return false;
+    *out = color_ptr(map, slot)[id];
+    return true;
+}
+
+__device__ __forceinline__ float lerp_channel(float a000, float a100, float a010, float a110, float a001, float a101, float a011, float a111,
+                                              float xd, float yd, float zd)
+{
+    const float ix = __fsub_rn(1.0f, xd), iy = __fsub_rn(1.0f, yd), iz = __fsub_rn(1.0f, zd);
+    const float c00 = __fadd_rn(__fmul_rn(a000, ix), __fmul_rn(a100, xd));
+    const float c10 = __fadd_rn(__fmul_rn(a010, ix), __fmul_rn(a110, xd));
+    const float c01 = __fadd_rn(__fmul_rn(a001, ix), __fmul_rn(a101, xd));
+    const float c11 = __fadd_rn(__fmul_rn(a011, ix), __fmul_rn(a111, xd));
+    const float c0 = __fadd_rn(__fmul_rn(c00, iy), __fmul_rn(c10, yd));
+    const float c1 = __fadd_rn(__fmul_rn(c01, iy), __fmul_rn(c11, yd));
+    const float c = __fadd_rn(__fmul_rn(c0, iz), __fmul_rn(c1, zd));
+    return __fdiv_rn(c, 255.0f);
+}
+
+// ChunkManager::InterpolateColor (ChunkManager.cpp:501-573), bug-compatible (quirk Q9: the eight lookups pass voxel
+// INDICES where GetColorVoxel expects metres), with the Chunk::GetColorAt fallback (Chunk.cpp:118-136).
+__device__ P3 interpolate_color(const DeviceMap &map, float rfChunk, float rfVoxel, P3 p)
+{
+    const float r = map.res;
+    const float fx0 = floorf(__fdiv_rn(p.x, r)), fy0 = floorf(__fdiv_rn(p.y, r)), fz0 = floorf(__fdiv_rn(p.z, r));
+    // static_cast<int>(floor(.)) then back to float inside Vec3(int, int, int); exact for |value| < 2^24
+    const float x0 = (float)(int)fx0, y0 = (float)(int)fy0, z0 = (float)(int)fz0;
+    const float x1 = (float)((int)fx0 + 1), y1 = (float)((int)fy0 + 1), z1 = (float)((int)fz0 + 1);
+    uchar4 v000, v001, v011, v111, v110, v100, v010, v101;
+    bool all = get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y0, z0}, &v000);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y0, z1}, &v001);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y1, z1}, &v011);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y1, z1}, &v111);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y1, z0}, &v110);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y0, z0}, &v100);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y1, z0}, &v010);
+    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y0, z1}, &v101);
+    if (!all)
+    {
+        const int slot = lookup_chunk_at(map, rfChunk, p);
+        P3 zero = {0.0f, 0.0f, 0.0f};
+        if (slot < 0)
+            return zero;
+        const P3 o = chunk_origin(map, slot);
+        const float ext = __fmul_rn((float)map.cs, r);
+        const P3 mx = {__fadd_rn(o.x, ext), __fadd_rn(o.y, ext), __fadd_rn(o.z, ext)};
+        if (!(p.x >= o.x && p.y >= o.y && p.z >= o.z && p.x <= mx.x && p.y <= mx.y && p.z <= mx.z))
+            return zero;
+        const int cx = (int)__fdiv_rn(__fsub_rn(p.x, o.x), r), cy = (int)__fdiv_rn(__fsub_rn(p.y, o.y), r), cz = (int)__fdiv_rn(__fsub_rn(p.z, o.z), r);
+        if (!(cx >= 0 && cx < map.cs && cy >= 0 && cy < map.cs && cz >= 0 && cz < map.cs))
+            return zero;
+        const uchar4 c = color_ptr(map, slot)[(cz * map.cs + cy) * map.cs + cx];
+        P3 out = {__fdiv_rn((float)c.x, 255.0f), __fdiv_rn((float)c.y, 255.0f), __fdiv_rn((float)c.z, 255.0f)};
+        return out;
+    }
+    const float xd = __fdiv_rn(__fsub_rn(p.x, x0), 1.0f), yd = __fdiv_rn(__fsub_rn(p.y, y0), 1.0f), zd = __fdiv_rn(__fsub_rn(p.z, z0), 1.0f);
+    P3 out;
+    out.x = lerp_channel(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, xd, yd, zd);
+    out.y = lerp_channel(v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y, xd, yd, zd);
+    out.z = lerp_channel(v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z, xd, yd, zd);
+    return out;
+}
+
+// MarchingCubes::InterpolateVertex (MarchingCubes.h:134-146), incl. the v1 + 0.5*v2 branch (quirk Q8)
+__device__ __forceinline__ P3 interpolate_vertex(P3 a, P3 b, float s1, float s2)
+{
+    const float diff = __fsub_rn(s1, s2);
+    P3 o;
+    if (fabsf(diff) < 1e-6f)
+    {
+        o.x = __fadd_rn(a.x, __fmul_rn(0.5f, b.x));
+        o.y = __fadd_rn(a.y, __fmul_rn(0.5f, b.y));
+        o.z = __fadd_rn(a.z, __fmul_rn(0.5f, b.z));
+        return o;
+    }
+    const float t = __fdiv_rn(s1, diff);
+    o.x = __fadd_rn(a.x, __fmul_rn(t, __fsub_rn(b.x, a.x)));
+    o.y = __fadd_rn(a.y, __fmul_rn(t, __fsub_rn(b.y, a.y)));
+    o.z = __fadd_rn(a.z, __fmul_rn(t, __fsub_rn(b.z, a.z)));
+    return o;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap map)
+{
+    extern __shared__ float tile[];
+    __shared__ int nbr[8];
+    __shared__ int warpTot[2][8];
+    constexpr int V = CS * CS * CS, CPT = V / 256;
+    const int n = map.ctr->mesh_chunks;
+    const float rfChunk = __fdiv_rn(1.0f, __fmul_rn((float)CS, map.res));
+    const float rfVoxel = __fdiv_rn(1.0f, map.res);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = blockIdx.x; c < n; c += gridDim.x)
+    {
+        const int slot = mp.mesh_slots[c];
+        load_halo<CS>(map, slot, tile, nbr);
+        // pass 1: this thread's triangle / grid totals over its CPT consecutive cells
+        int tris = 0, grids = 0;
+        for (int j = 0; j < CPT; j++)
+        {
+            int x, y, z;
+            float sdf[8];
+            cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
+            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            if (cfg >= 0)
+            {
+                const int nt = cTriCount[cfg];
+                tris += nt;
+                grids += nt > 0;
+            }
+        }
+        // block-wide exclusive prefix sums (warp shuffles, then across the 8 warps)
+        int incT = tris, incG = grids;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int a = __shfl_up_sync(0xffffffffu, incT, o), b = __shfl_up_sync(0xffffffffu, incG, o);
+            if (lane >= o)
+            {
+                incT += a;
+                incG += b;
+            }
+        }
+        if (lane == 31)
+        {
+            warpTot[0][warp] = incT;
+            warpTot[1][warp] = incG;
+        }
+        __syncthreads();
+        int baseT = incT - tris, baseG = incG - grids;
+        for (int w = 0; w < warp; w++)
+        {
+            baseT += warpTot[0][w];
+            baseG += warpTot[1][w];
+        }
+        long long vOut = mp.vert_offsets[c] + 3ll * baseT;
+        long long gOut = mp.grid_offsets[c] + baseG;
+        const P3 org = chunk_origin(map, slot);
+        // pass 2: emit
+        for (int j = 0; j < CPT; j++)
+        {
+            int x, y, z;
+            float sdf[8];
+            cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
+            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            if (cfg < 0)
+                continue;
+            const int nt = cTriCount[cfg];
+            if (nt == 0)
+                continue;
+            // coords = centroid + origin (ChunkManager.cpp:400 etc.), centroid_k = float(k)*res + res/2 (:61)
+            const P3 c0 = {__fadd_rn(__fadd_rn(__fmul_rn((float)x, map.res), map.half), org.x),
+                           __fadd_rn(__fadd_rn(__fmul_rn((float)y, map.res), map.half), org.y),
+                           __fadd_rn(__fadd_rn(__fmul_rn((float)z, map.res), map.half), org.z)};
+            if (gOut < mp.cap_grids)
+            {
+                mp.grids[3 * gOut] = c0.x;
+                mp.grids[3 * gOut + 1] = c0.y;
+                mp.grids[3 * gOut + 2] = c0.z;
+            }
+            gOut++;
+            const unsigned long long row = cTriPacked[cfg];
+            for (int tri = 0; tri < nt; tri++)
+            {
+                P3 p[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                {
+                    // vertices are pushed in the order col+2, col+1, col (MarchingCubes.h:88-90)
+                    const int e = (int)((row >> (4 * (3 * tri + 2 - k))) & 0xF);
+                    const int a = cEdgePairs[e] >> 3, b = cEdgePairs[e] & 7;
+                    // cornerCoords = coords + float(offset) * res (ChunkManager.cpp:262,278)
+                    const P3 pa = {__fadd_rn(c0.x, __fmul_rn((float)corner_dx(a), map.res)), __fadd_rn(c0.y, __fmul_rn((float)corner_dy(a), map.res)),
+                                   __fadd_rn(c0.z, __fmul_rn((float)corner_dz(a), map.res))};
+                    const P3 pb = {__fadd_rn(c0.x, __fmul_rn((float)corner_dx(b), map.res)), __fadd_rn(c0.y, __fmul_rn((float)corner_dy(b), map.res)),
+                                   __fadd_rn(c0.z, __fmul_rn((float)corner_dz(b), map.res))};
+                    p[k] = interpolate_vertex(pa, pb, sdf[a], sdf[b]);
+                }
+                // flat normal: (p1 - p0) x (p2 - p0), normalised (MarchingCubes.h:94-99)
+                const P3 u = {__fsub_rn(p[1].x, p[0].x), __fsub_rn(p[1].y, p[0].y), __fsub_rn(p[1].z, p[0].z)};
+                const P3 w = {__fsub_rn(p[2].x, p[0].x), __fsub_rn(p[2].y, p[0].y), __fsub_rn(p[2].z, p[0].z)};
+                P3 nf = {__fsub_rn(__fmul_rn(u.y, w.z), __fmul_rn(u.z, w.y)), __fsub_rn(__fmul_rn(u.z, w.x), __fmul_rn(u.x, w.z)),
+                         __fsub_rn(__fmul_rn(u.x, w.y), __fmul_rn(u.y, w.x))};
+                const float z2 = __fadd_rn(__fmul_rn(nf.x, nf.x), __fadd_rn(__fmul_rn(nf.y, nf.y), __fmul_rn(nf.z, nf.z)));
+                if (z2 > 0.0f)
+                {
+                    const float s = __fsqrt_rn(z2);
+                    nf.x = __fdiv_rn(nf.x, s);
+                    nf.y = __fdiv_rn(nf.y, s);
+                    nf.z = __fdiv_rn(nf.z, s);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                {
+                    if (vOut < mp.cap_vertices)
+                    {
+                        P3 nn = nf;
+                        gradient_normal(map, rfChunk, rfVoxel, mp.w_observed_min, p[k], &nn);   // overwrites the flat normal when all 7 taps exist
+                        mp.vertices[3 * vOut] = p[k].x;
+                        mp.vertices[3 * vOut + 1] = p[k].y;
+                        mp.vertices[3 * vOut + 2] = p[k].z;
+                        mp.normals[3 * vOut] = nn.x;
+                        mp.normals[3 * vOut + 1] = nn.y;
+                        mp.normals[3 * vOut + 2] = nn.z;
+                        if (mp.colors)
+                        {
+                            const P3 col = interpolate_color(map, rfChunk, rfVoxel, p[k]);
+                            mp.colors[3 * vOut] = col.x;
+                            mp.colors[3 * vOut + 1] = col.y;
+                            mp.colors[3 * vOut + 2] = col.z;
+                        }
+                    }
+                    vOut++;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+
+void launch_mesh_select(const MeshParams &mp, const DeviceMap &map, cudaStream_t st)
+{
+    if (mp.n_dirty > 0)
+        mesh_select_kernel<<<(mp.n_dirty + 255) / 256, 256, 0, st>>>(mp, map);
+}
+
+template <int CS>
+static void mesh_launch_cs(const MeshParams &mp, const DeviceMap &map, int grid, cudaStream_t st, bool emit)
+{
+    const size_t smem = sizeof(float) * (CS + 1) * (CS + 1) * (CS + 1);
+    if (emit)
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(mesh_emit_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mesh_emit_kernel<CS><<<grid, 256, smem, st>>>(mp, map);
+    }
+    else
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(mesh_count_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mesh_count_kernel<CS><<<grid, 256, smem, st>>>(mp, map);
+    }
+}
+
+static void mesh_dispatch(const MeshParams &mp, const DeviceMap &map, int nChunks, cudaStream_t st, bool emit)
+{
+    const int grid = nChunks < 148 * 8 ? (nChunks > 0 ? nChunks : 1) : 148 * 8;
+    switch (map.cs)
+    {
+    case 8: mesh_launch_cs<8>(mp, map, grid, st, emit); break;
+    case 16: mesh_launch_cs<16>(mp, map, grid, st, emit); break;
+    case 32: mesh_launch_cs<32>(mp, map, grid, st, emit); break;
+    default: break;
+    }
+}
+
+void launch_mesh_count(const MeshParams &mp, const DeviceMap &map, int nChunks, cudaStream_t st) { mesh_dispatch(mp, map, nChunks, st, false); }
+void launch_mesh_scan(const MeshParams &mp, const DeviceMap &map, int, cudaStream_t st) { mesh_scan_kernel<<<1, 1024, 0, st>>>(mp, map); }
+void launch_mesh_emit(const MeshParams &mp, const DeviceMap &map, int nChunks, cudaStream_t st) { mesh_dispatch(mp, map, nChunks, st, true); }
+
+} // namespace chs

@@ -1,0 +1,164 @@
+/* chisel_b200.h -- C ABI of the B200-native OpenChisel hot path (TSDF integration + incremental
+ * marching cubes). This is the drop-in boundary: the open_chisel C++ facade under
+ * cvids_b200/include/open_chisel/ and the Python harness (cvids_b200/capi.py) both call ONLY these
+ * entry points. Plain pointers and sizes; no C++ or torch types; int status codes; no exceptions.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference's
+ * OpenChisel/open_chisel/, "OC/"; callers in OpenChisel/chisel_ros/, "CR/"):
+ *
+ *   chs_create               chisel::Chisel::Chisel(chunkSize, res, useColor)       OC/src/Chisel.cpp:34-37, CR/src/ChiselServer.cpp:189
+ *   chs_destroy              chisel::Chisel::~Chisel                                 OC/src/Chisel.cpp:39-42
+ *   chs_reset                chisel::Chisel::Reset                                   OC/src/Chisel.cpp:44-48, CR/src/ChiselServer.cpp:200
+ *   chs_integrate_depth      chisel::Chisel::IntegrateDepthScan<float>               OC/include/open_chisel/Chisel.h:59-112, CR/src/ChiselServer.cpp:501
+ *   chs_integrate_depth_color chisel::Chisel::IntegrateDepthScanColor<float,uint8_t> OC/include/open_chisel/Chisel.h:114-213, CR/src/ChiselServer.cpp:497
+ *   chs_update_meshes        ChunkManager::RecomputeMeshes(meshesToUpdate) + clear    OC/src/ChunkManager.cpp:130-169, OC/src/Chisel.cpp:55-57
+ *                            (the every-10th-call gate of Chisel::UpdateMeshes, Chisel.cpp:50-59, lives in the facade)
+ *   chs_num_dirty/_dirty_ids chisel::Chisel::GetMeshesToUpdate                       OC/include/open_chisel/Chisel.h:221-224, CR/src/ChiselServer.cpp:346,554
+ *   chs_num_chunks/_chunk_ids/_download_chunk  ChunkManager::GetChunks, HasChunk, GetChunk, Chunk::GetVoxels/GetColorVoxels
+ *                                                                                    OC/include/open_chisel/ChunkManager.h:69-87, CR/include/chisel_ros/Serialization.h:31-84
+ *   chs_mesh_counts/_download_meshes  ChunkManager::GetAllMeshes / Mesh fields       OC/include/open_chisel/ChunkManager.h:163-182, OC/include/open_chisel/mesh/Mesh.h:52-57
+ *   chs_frustum              PinholeCamera::SetupFrustum, Frustum::GetLines/GetCorners OC/src/camera/PinholeCamera.cpp:55-59, OC/src/geometry/Frustum.cpp:143-219
+ *   chs_candidate_ids        ChunkManager::GetChunkIDsIntersecting(Frustum)          OC/src/ChunkManager.cpp:182-212
+ *   chs_truncation           Truncator::GetTruncationDistance (3 shipped subclasses) OC/include/open_chisel/truncation/ (all three headers)
+ *
+ * Threading: one caller thread per map (the reference's ChiselNode is a single-threaded ros::spin,
+ * CR/src/ChiselNode.cpp:135). Host buffers are caller-owned; device memory is library-owned.
+ * All work of a map runs on one CUDA stream; calls return after ENQUEUEING unless stated otherwise.
+ * There is no CPU fallback: every entry point that computes fails with CHS_ERR_CUDA without a device.
+ */
+#ifndef CHISEL_B200_H
+#define CHISEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHS_ABI_VERSION 1
+
+typedef struct chs_map chs_map; /* opaque */
+
+enum
+{
+    CHS_OK = 0,
+    CHS_ERR_INVALID = 1,   /* bad argument (null, non-cubic chunk, non-finite pose, ID out of the packable range) */
+    CHS_ERR_CUDA = 2,      /* a CUDA call failed; see chs_last_error_string */
+    CHS_ERR_CAPACITY = 3,  /* a device table overflowed (should not happen: capacities are grown ahead of need) */
+    CHS_ERR_NOT_FOUND = 4
+};
+
+enum { CHS_TRUNC_CONSTANT = 0, CHS_TRUNC_QUADRATIC = 1, CHS_TRUNC_INVERSE = 2, CHS_TRUNC_PER_PIXEL = 3 };
+enum { CHS_MEM_HOST = 0, CHS_MEM_DEVICE = 1 };
+
+typedef struct
+{
+    int chunk_size;              /* voxels per chunk edge; cubic chunks only (8, 16 or 32), see DESIGN.md Q12 */
+    float resolution;            /* voxel edge in metres */
+    int use_color;
+    int device;                  /* CUDA ordinal; -1 = current device */
+    int rank, world;             /* chunk-ownership shard: this map keeps chunk IDs with chs_owner(id) % world == rank; world <= 1: all */
+    int64_t initial_chunks;      /* initial pool capacity in chunks; 0 = default */
+    void *stream;                /* cudaStream_t to enqueue on; NULL = the library creates a non-blocking stream */
+} chs_config;
+
+typedef struct
+{
+    float fx, fy, cx, cy;
+    int width, height;
+    float near_plane, far_plane;
+} chs_camera;
+
+/* ProjectionIntegrator state (OC/include/open_chisel/ProjectionIntegrator.h:185-229) */
+typedef struct
+{
+    int trunc_kind;              /* CHS_TRUNC_* */
+    float trunc_param;           /* constant: metres; quadratic / inverse: scale */
+    const float *trunc_per_pixel;/* CHS_TRUNC_PER_PIXEL: W*H truncation distances evaluated by the caller (any Truncator subclass), same memory space as the depth image */
+    float weight;                /* ConstantWeighter(weight); colour path only (the depth path integrates with 1.0f, quirk Q7) */
+    int carving_enabled;
+    float carving_dist;
+} chs_integrator;
+
+/* Counters of the last integrated frame (SURVEY.md section 8(d) definitions). */
+typedef struct
+{
+    int64_t candidates;          /* chunk IDs the reference would iterate (box passing Frustum::Intersects), owned by this rank */
+    int64_t processed_chunks;    /* candidates that survived the conservative depth-range cull */
+    int64_t n_upd;               /* voxels on which DistVoxel::Integrate ran */
+    int64_t n_carve;             /* voxels reset or decremented by carving */
+    int64_t n_col;               /* voxels whose colour was written */
+    int64_t n_new;               /* chunks created this frame (all survive: untouched ones are never materialised) */
+    int64_t updated_chunks;      /* chunks whose integrate returned true */
+    int64_t total_chunks;        /* chunks in the map after the frame */
+    int64_t dirty_chunks;        /* size of the dirty set after the frame */
+    int64_t error_flags;         /* non-zero: a device table overflowed */
+} chs_frame_stats;
+
+typedef struct
+{
+    int64_t n_chunks;            /* remeshed chunks in the last chs_update_meshes (existing dirty chunks, incl. those with no triangle) */
+    int64_t n_vertices;          /* total vertices (3 per triangle) */
+    int64_t n_grids;             /* total occupied-cell centres (Mesh::grids) */
+    int has_colors;
+} chs_mesh_counts;
+
+/* Device time of the phases of the last frame / last re-mesh, from CUDA events on the map's stream
+ * (recorded only while profiling is enabled; chs_get_timings synchronises). Milliseconds. */
+typedef struct
+{
+    float prepare_ms, candidates_ms, integrate_ms, frame_ms;
+    float mesh_count_ms, mesh_emit_ms, mesh_ms;
+} chs_timings;
+
+const char *chs_last_error_string(void);
+int chs_abi_version(void);
+
+int chs_create(const chs_config *cfg, chs_map **out);
+int chs_destroy(chs_map *map);
+int chs_reset(chs_map *map);
+int chs_synchronize(chs_map *map);
+int chs_set_stream(chs_map *map, void *cuda_stream);
+int chs_set_profiling(chs_map *map, int enabled);
+
+/* pose: row-major 3x4 [R|t], camera -> world. depth: width*height float metres (NaN = invalid).
+ * mem: CHS_MEM_HOST (copied H2D on the map's stream) or CHS_MEM_DEVICE (used in place). */
+int chs_integrate_depth(chs_map *map, const chs_integrator *integ, const float *depth, int mem,
+                        const float pose[12], const chs_camera *cam);
+/* color: cam.width*cam.height*channels uint8, channels 1 (mono), 3 (BGR) or 4 (BGRA) (OC ColorImage.h:61-101) */
+int chs_integrate_depth_color(chs_map *map, const chs_integrator *integ, const float *depth, int mem,
+                              const float pose[12], const chs_camera *cam, const uint8_t *color, int channels,
+                              const float color_pose[12], const chs_camera *color_cam);
+int chs_get_frame_stats(chs_map *map, chs_frame_stats *out);   /* synchronises */
+int chs_get_timings(chs_map *map, chs_timings *out);           /* synchronises */
+
+/* Re-mesh every chunk of the dirty set that exists, then clear the dirty set. Synchronises (the vertex
+ * count decides the output allocation). Results stay on the device until downloaded. */
+int chs_update_meshes(chs_map *map);
+int chs_mesh_counts_last(chs_map *map, chs_mesh_counts *out);
+/* ids [3*n_chunks]; vert_offsets, grid_offsets [n_chunks+1] (prefix sums, in vertices / grid points);
+ * vertices, normals, colors [3*n_vertices] (colors may be NULL); grids [3*n_grids]. Any pointer may be NULL. */
+int chs_download_meshes(chs_map *map, int32_t *ids, int64_t *vert_offsets, int64_t *grid_offsets,
+                        float *vertices, float *normals, float *colors, float *grids);
+
+int chs_num_chunks(chs_map *map, int64_t *n);                  /* synchronises */
+int chs_chunk_ids(chs_map *map, int32_t *ids, int64_t cap);    /* pool order */
+/* sdf, weight [V]; rgbw [4V] (r, g, b, colour weight) or NULL. CHS_ERR_NOT_FOUND if the chunk is absent. */
+int chs_download_chunk(chs_map *map, const int32_t id[3], float *sdf, float *weight, uint8_t *rgbw);
+/* Whole map in one transfer, pool order: ids [3n], sdf/weight [n*V], rgbw [n*4V] or NULL. */
+int chs_download_all(chs_map *map, int64_t cap_chunks, int32_t *ids, float *sdf, float *weight, uint8_t *rgbw);
+int chs_num_dirty(chs_map *map, int64_t *n);                   /* synchronises */
+int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
+
+/* Host-side exact restatements the facade needs (no device work). */
+int chs_frustum(const float pose[12], const chs_camera *cam, float corners[24], float lines[72], float planes[24]);
+int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], const chs_camera *cam,
+                      int32_t *ids, int64_t cap, int64_t *n);
+float chs_truncation(int trunc_kind, float trunc_param, float depth);
+uint32_t chs_owner(int32_t x, int32_t y, int32_t z);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHISEL_B200_H */

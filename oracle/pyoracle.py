@@ -222,3 +222,90 @@ class RefChisel(_Base):
         out = np.zeros(3, np.int64)
         self._lib.ref_last_counts(self._h, out)
         return dict(candidates=int(out[0]), new=int(out[1]), garbage=int(out[2]))
+
+
+_oracle_lib = None
+
+
+def _load_oracle():
+    global _oracle_lib
+    if _oracle_lib is None:
+        src = os.path.join(HERE, "chisel_oracle.c")
+        if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+            build("oracle")
+        lib = C.CDLL(ORACLE_SO)
+        _declare(lib, "orc_")
+        lib.orc_frame_counters.argtypes = [C.c_void_p, _i64p]
+        _oracle_lib = lib
+    return _oracle_lib
+
+
+COUNTER_NAMES = ("candidates", "visited", "n_upd", "n_carve", "n_col", "n_new", "updated_chunks", "garbage")
+
+
+class OracleChisel(RefChisel):
+    """The plain-C restatement (oracle/chisel_oracle.c). Same methods as RefChisel."""
+    _prefix = "orc_"
+    kind = "port"
+
+    def __init__(self, chunk: int, resolution: float, use_color: bool):
+        self.chunk, self.resolution, self.use_color = chunk, float(np.float32(resolution)), use_color
+        self._lib = _load_oracle()
+        self._h = self._lib.orc_create(chunk, resolution, int(use_color))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.orc_destroy(self._h)
+            self._h = None
+
+    def setup_integrator(self, trunc_kind, trunc_param, weight, carve, carve_dist):
+        self._lib.orc_setup_integrator(self._h, trunc_kind, trunc_param, weight, int(carve), carve_dist)
+
+    def truncation(self, kind, param, depth):
+        return self._lib.orc_truncation(kind, param, depth)
+
+    def integrate_depth(self, depth, pose, cam):
+        H, W = depth.shape
+        self._lib.orc_integrate_depth(self._h, np.ascontiguousarray(depth, np.float32), W, H, _as_pose(pose),
+                                      np.ascontiguousarray(cam, np.float32))
+
+    def integrate_color(self, depth, pose, cam, color, cpose=None, ccam=None, as_is=False):
+        H, W = depth.shape
+        cH, cW, ch = color.shape
+        cpose = pose if cpose is None else cpose
+        ccam = cam if ccam is None else ccam
+        self._lib.orc_integrate_color(self._h, np.ascontiguousarray(depth, np.float32), W, H, _as_pose(pose),
+                                      np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(color), cW, cH, ch,
+                                      _as_pose(cpose), np.ascontiguousarray(ccam, np.float32), 0)
+
+    def candidate_ids(self, pose, cam) -> np.ndarray:
+        cap = 1 << 16
+        while True:
+            out = np.zeros((cap, 3), np.int32)
+            n = self._lib.orc_candidate_ids(self._h, _as_pose(pose), np.ascontiguousarray(cam, np.float32), out, cap)
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def frustum(self, pose, cam):
+        corners = np.zeros((8, 3), np.float32)
+        lines = np.zeros((24, 3), np.float32)
+        planes = np.zeros((6, 4), np.float32)
+        self._lib.orc_frustum(_as_pose(pose), np.ascontiguousarray(cam, np.float32), corners, lines, planes)
+        return corners, lines, planes
+
+    def update_meshes(self, as_is=False):
+        self._lib.orc_update_meshes(self._h, 0)
+
+    def reset(self):
+        self._lib.orc_reset(self._h)
+
+    def last_counts(self):
+        out = np.zeros(3, np.int64)
+        self._lib.orc_last_counts(self._h, out)
+        return dict(candidates=int(out[0]), new=int(out[1]), garbage=int(out[2]))
+
+    def frame_counters(self):
+        out = np.zeros(8, np.int64)
+        self._lib.orc_frame_counters(self._h, out)
+        return dict(zip(COUNTER_NAMES, (int(x) for x in out)))

@@ -1,0 +1,94 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/chisel_b200.h declares, its host-side exact
+geometry agrees bit for bit with the oracle, and it fails loudly (no fallback) without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cvids_b200 import capi, scenes
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "chisel_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(chs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    names = _declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libchisel_b200.so does not export %s" % n
+    assert sorted(capi.EXPORTS) == names
+    assert lib.chs_abi_version() == 1
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_frustum_candidates_truncation_match_oracle():
+    from oracle.pyoracle import OracleChisel
+    o = OracleChisel(16, 0.02, False)
+    for f in range(0, 50, 9):
+        pose = scenes.orbit_pose(f, 50, 0.2)
+        for cam in (scenes.KINECT_640.as_array(), scenes.EUROC_752.as_array()):
+            for x, y in zip(capi.frustum(pose, cam), o.frustum(pose, cam)):
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+            assert np.array_equal(capi.candidate_ids(16, 0.02, pose, cam), o.candidate_ids(pose, cam))
+    rng = np.random.RandomState(1)
+    for d in rng.uniform(0.05, 20, 100).astype(np.float32):
+        for kind, p in ((0, 0.2), (1, 2.0), (2, 8.0)):
+            x, y = np.float32(capi.truncation(kind, p, float(d))), np.float32(o.truncation(kind, p, float(d)))
+            assert x.view(np.uint32) == y.view(np.uint32)
+
+
+def test_owner_hash_is_stable_and_balanced():
+    ids = [(x, y, z) for x in range(-8, 8) for y in range(-8, 8) for z in range(-4, 4)]
+    for world in (2, 4, 8):
+        counts = np.bincount([capi.owner(*i) % world for i in ids], minlength=world)
+        assert counts.min() > 0.8 * len(ids) / world, counts
+    assert capi.owner(1, -2, 3) == capi.owner(1, -2, 3)
+
+
+def test_argument_validation_needs_no_device():
+    lib = capi.load_library()
+    assert lib.chs_create(None, None) == capi.CHS_ERR_INVALID
+    cfg = capi.chs_config(12, 0.05, 0, -1, 0, 1, 0, None)
+    h = ctypes.c_void_p()
+    assert lib.chs_create(ctypes.byref(cfg), ctypes.byref(h)) == capi.CHS_ERR_INVALID
+    assert b"chunk_size" in lib.chs_last_error_string()
+
+
+def test_no_cpu_fallback():
+    """Without a device, creating a map must fail with CHS_ERR_CUDA; with one, this test is a no-op."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.ChiselError) as e:
+        capi.Chisel(16, 0.05, False)
+    assert e.value.code == capi.CHS_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (the checker) in any way."""
+    pkg = os.path.join(ROOT, "cvids_b200")
+    bad = re.compile(r"^\s*(from\s+oracle|import\s+oracle)|pyoracle|chisel_oracle|libchisel_ref|#\s*include\s*[<\"][^>\"]*oracle", re.M)
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dp, f)).read()
+                assert not bad.search(text), os.path.join(dp, f)
