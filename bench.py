@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native OpenChisel hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] -- the single-agent EuRoC-shape 752x480 synthetic depth+colour
+stream of the analytic room, 2 cm voxels, 16^3 chunks, truncation 4 voxels, ConstantWeighter(1), carving on;
+one STEP = one frame through IntegrateDepthScanColor (chs_integrate_depth_color). Frames W .. W+K-1 of the 200-frame
+orbit are timed after W warm-up frames from an empty map.
+
+Metric: TSDF voxel updates per second (GVox/s; a "voxel update" is one DistVoxel::Integrate), with
+frames/s alongside. `value`: inputs resident in HBM, device time from CUDA events per step, L2 flushed between
+steps (flush excluded). `e2e`: the same call with pinned HOST frames (H2D inside) plus the D2H read of the frame's
+counters, wall clock per step. `roofline`: algorithmic bytes of the integrate kernel / its event-timed duration,
+against MEASURED_PEAKS.json. `cpu_baseline`: the reference CPU OpenChisel (oracle/_ref, else the C port) on a
+bounded sample of the same frames on this box's host cores.
+
+N > 1: one process per GPU; the chunk-ID hash space is partitioned (owner = chs_owner(id) % N), rank 0 holds the
+stream and broadcasts each frame with NCCL, every rank integrates the chunks it owns. Total work is fixed =>
+"scaling": "strong". Time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from cvids_b200 import scenes  # noqa: E402
+
+METRIC = "tsdf_voxel_updates_per_s"
+UNIT = "GVox/s"
+CFG = scenes.CONFIG2
+WORKLOAD = "configs[1]: single-agent EuRoC-shape 752x480 depth+colour stream, analytic room, 2 cm voxels, 16^3 chunks, " \
+           "trunc 4 voxels, IntegrateDepthScanColor; step = 1 frame"
+
+
+def frames_for(lo: int, hi: int):
+    out = []
+    for f in range(lo, hi):
+        depth, col, pose = scenes.stream_frame(CFG, f % CFG.n_frames)
+        out.append((depth, col, pose))
+    return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+def algorithmic_bytes(st: dict, cam: scenes.Camera, channels: int, use_color: bool) -> int:
+    """B_int of SURVEY.md 8(d) / BASELINE.md section 4 for one frame."""
+    V = CFG.chunk ** 3
+    px = cam.width * cam.height
+    return (16 * (st["n_upd"] + st["n_carve"]) + 8 * st["n_col"] + V * (8 + 4 * int(use_color)) * st["n_new"]
+            + 4 * px + channels * px * int(use_color))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm and CPU baseline
+
+def cpu_arm(frames, warm, steps, budget_s):
+    """Reference CPU OpenChisel on the host cores: oracle/_ref (as-is, 16 threads: Chisel.h:150) when it was built,
+    else the single-threaded C port. Returns dict(value GVox/s, fps, kind, cores, steps_done, seconds)."""
+    from oracle import pyoracle
+    use_ref = pyoracle.ref_available()
+    cls = pyoracle.RefChisel if use_ref else pyoracle.OracleChisel
+    ref = cls(CFG.chunk, CFG.resolution, True)
+    ref.setup_integrator(pyoracle.TRUNC_CONSTANT, CFG.truncation, CFG.weight, CFG.carve, CFG.carve_dist)
+    counter = pyoracle.OracleChisel(CFG.chunk, CFG.resolution, True)       # untimed: counts N_upd for the same frames
+    counter.setup_integrator(pyoracle.TRUNC_CONSTANT, CFG.truncation, CFG.weight, CFG.carve, CFG.carve_dist)
+    cam = CFG.cam.as_array()
+    t_total, upd, done = 0.0, 0, 0
+    t_begin = time.perf_counter()
+    for i, (depth, col, pose) in enumerate(frames[:warm + steps]):
+        t0 = time.perf_counter()
+        ref.integrate_color(depth, pose, cam, col, as_is=True)
+        dt = time.perf_counter() - t0
+        if use_ref:
+            counter.integrate_color(depth, pose, cam, col)              # untimed
+            n = counter.frame_counters()["n_upd"]
+        else:
+            n = ref.frame_counters()["n_upd"]
+        if i >= warm:
+            t_total += dt
+            upd += n
+            done += 1
+            if time.perf_counter() - t_begin > budget_s:
+                break
+    cores = os.cpu_count() or 1
+    return dict(value=upd / t_total / 1e9 if t_total else 0.0, fps=done / t_total if t_total else 0.0,
+                kind="reference" if use_ref else "port", cores=min(16, cores) if use_ref else 1, host_cores=cores,
+                steps_done=done, seconds=t_total, updates=upd)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm, steps = args.warmup, args.steps
+    frames = frames_for(0, warm + steps)
+    r = cpu_arm(frames, warm, steps, budget_s=args.cpu_budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_done"],
+        "warmup": warm, "ms_per_step": 1000.0 * r["seconds"] / max(r["steps_done"], 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_s": r["fps"],
+        "config": {"workload": WORKLOAD, "threads": "16 std::threads hard-coded by the reference (Chisel.h:150)" if r["kind"] == "reference" else "1 (C port)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
+                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames" % (r["steps_done"], warm)},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA arm
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from cvids_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm, steps = args.warmup, args.steps
+    cam = CFG.cam
+    camv = cam.as_array()
+    channels = 3
+    H, W = cam.height, cam.width
+
+    # rank 0 owns the stream; other ranks receive frames by NCCL broadcast
+    frames = frames_for(0, warm + steps) if rank == 0 else None
+    poses = np.zeros((warm + steps, 12), np.float32)
+    if rank == 0:
+        for i, fr in enumerate(frames):
+            poses[i] = fr[2].reshape(12)
+    if world > 1:
+        pt = torch.from_numpy(poses).to(dev)
+        dist.broadcast(pt, 0)
+        poses = pt.cpu().numpy()
+
+    nfr = warm + steps
+    d_depth = torch.empty((nfr, H, W), dtype=torch.float32, device=dev)
+    d_color = torch.empty((nfr, H, W, channels), dtype=torch.uint8, device=dev)
+    h_depth = h_color = None
+    if rank == 0:
+        h_depth = torch.empty((nfr, H, W), dtype=torch.float32).pin_memory()
+        h_color = torch.empty((nfr, H, W, channels), dtype=torch.uint8).pin_memory()
+        for i, fr in enumerate(frames):
+            h_depth[i].copy_(torch.from_numpy(fr[0]))
+            h_color[i].copy_(torch.from_numpy(fr[1]))
+        d_depth.copy_(h_depth)
+        d_color.copy_(h_color)
+    recv_depth = torch.empty((H, W), dtype=torch.float32, device=dev)
+    recv_color = torch.empty((H, W, channels), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
+    stream = torch.cuda.current_stream(dev)
+    integ = capi.ProjectionIntegrator(capi.TRUNC_CONSTANT, CFG.truncation, CFG.weight, CFG.carve, CFG.carve_dist)
+
+    def new_map():
+        return capi.Chisel(CFG.chunk, CFG.resolution, True, device=local, rank=rank, world=world, stream=stream.cuda_stream,
+                           initial_chunks=16384)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device(m, i):
+        """inputs resident in HBM (rank 0) -> [NCCL broadcast] -> integrate"""
+        if world > 1:
+            src_d = d_depth[i] if rank == 0 else recv_depth
+            src_c = d_color[i] if rank == 0 else recv_color
+            dist.broadcast(src_d, 0)
+            dist.broadcast(src_c, 0)
+        else:
+            src_d, src_c = d_depth[i], d_color[i]
+        m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(src_d.data_ptr(), src_c.data_ptr()), channels=channels)
+
+    # ---------------- leg A: device-resident inputs, CUDA events per step, L2 flushed between steps -------------
+    m = new_map()
+    for i in range(warm):
+        step_device(m, i)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        step_device(m, warm + k)
+        ev[k][1].record(stream)
+    barrier()
+    wall_a = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1000.0
+    m.close()
+
+    # ---------------- leg C: per-frame counters and integrate-kernel time (profiling events inside the library) --
+    m = new_map()
+    m.set_profiling(True)
+    upd_local = 0
+    bytes_alg = 0
+    t_integrate = t_prepare = t_cand = 0.0
+    per_frame = []
+    for i in range(warm + steps):
+        if flush is not None and i >= warm:
+            flush.fill_(i & 0xFF)
+        step_device(m, i)
+        if i >= warm:
+            st = m.frame_stats()
+            tm = m.timings()
+            upd_local += st["n_upd"]
+            b = algorithmic_bytes(st, cam, channels, True)
+            bytes_alg += b
+            t_integrate += tm["integrate_ms"] / 1000.0
+            t_prepare += tm["prepare_ms"] / 1000.0
+            t_cand += tm["candidates_ms"] / 1000.0
+            per_frame.append((st["n_upd"], st["processed_chunks"], st["candidates"], tm["integrate_ms"]))
+    total_chunks = m.frame_stats()["total_chunks"]
+    m.close()
+
+    # ---------------- leg B: end to end through the C ABI with pinned HOST frames + D2H counters ----------------
+    m = new_map()
+
+    def step_host(i):
+        if world > 1:
+            if rank == 0:
+                recv_depth.copy_(h_depth[i], non_blocking=True)
+                recv_color.copy_(h_color[i], non_blocking=True)
+            dist.broadcast(recv_depth, 0)
+            dist.broadcast(recv_color, 0)
+            m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(recv_depth.data_ptr(), recv_color.data_ptr()), channels=channels)
+        else:
+            lib_d = h_depth[i].numpy()
+            lib_c = h_color[i].numpy()
+            m.integrate_depth_scan_color(integ, lib_d, poses[i], camv, lib_c)
+        return m.frame_stats()["n_upd"]
+
+    for i in range(warm):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    upd_e2e = 0
+    for k in range(steps):
+        upd_e2e += step_host(warm + k)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    m.close()
+
+    # ---------------- reduce over ranks -------------------------------------------------------------------------
+    vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(upd_local), float(upd_e2e), float(bytes_alg), float(total_chunks)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    t_dev, t_e2e, wall_a, t_int_max = vals.tolist()
+    upd_total, upd_e2e_total, bytes_total, chunks_total = sums.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # roofline of the dominant kernel on THIS rank (rank 0): algorithmic bytes it processed / its event time
+        achieved = bytes_alg / t_integrate / 1e9 if t_integrate > 0 else 0.0
+        h2d = 4 * W * H + channels * W * H
+        line = {
+            "metric": METRIC, "value": upd_total / t_dev / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1000.0 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "frames_per_s": steps / t_dev,
+            "config": {"workload": WORKLOAD, "parallelism": "chunk-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "1 GPU",
+                       "l2": "256 MiB write between steps, excluded from the step time" if flush is not None else
+                             "no flush: frame stream (%d MB) > L2, map working set stays in L2" % ((h2d * nfr) >> 20),
+                       "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total},
+            "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88, "timing": "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
+            "gpu_launches": 3 * steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "integrate_kernel<16,color>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_integrate / steps,
+                         "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps},
+            "wall_s_timed_region": wall_a,
+        }
+        if world == 1 and not args.no_cpu:
+            n_cpu = min(steps, args.cpu_frames)
+            r = cpu_arm(frames, 0, n_cpu, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
+                                    "frames_per_s": r["fps"],
+                                    "sample": "first %d frames of the same stream from an empty map, whole frames, %.1f s" % (r["steps_done"], r["seconds"])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--cpu-budget", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -224,9 +224,9 @@ def test_sharded_union_equals_single_map():
 
 def test_full_size_properties_config2():
     """BASELINE config 2 at full size (752x480, 2 cm, colour): size-independent properties instead of the oracle.
-    (1) integer-valued weights: with ConstantWeighter(1) and trunc 4 voxels the update weight is 1/(5*0.08) = 2.5, so
-        every weight is a multiple of 2.5; (2) colour weights never exceed 8 (ProjectionIntegrator.h:153);
-        (3) idempotent re-mesh; (4) sum over voxels of weight/2.5 == sum of per-frame N_upd (no carving in a static scene)."""
+    (1) with ConstantWeighter(1) and trunc 4 voxels the update weight is 1/(5*0.08f) ~ 2.5, so every weight is a
+        whole multiple of it; (2) colour weights never exceed 8 (ProjectionIntegrator.h:153);
+        (3) idempotent re-mesh; (4) sum over voxels of weight/wu == sum of per-frame N_upd (no carving in a static scene)."""
     cfg = scenes.CONFIG2
     setup = Setup(cfg.chunk, cfg.resolution, True)
     a = common.Driver(setup, "cuda")
@@ -239,9 +239,11 @@ def test_full_size_properties_config2():
         total_upd += st["n_upd"]
     ids, sdf, w, rgbw = a.state()
     assert len(np.unique(ids, axis=0)) == len(ids)
-    q = w / np.float32(2.5)
-    assert np.array_equal(q, np.round(q))
-    assert int(q.astype(np.float64).sum()) == total_upd
+    # update weight exactly as the kernel forms it: weight / (5 * trunc) in binary32 (ConstantWeighter.h:43-46)
+    wu = np.float32(1.0) / (np.float32(5.0) * np.float32(setup.trunc))
+    k = np.round(w / wu)
+    assert np.all(np.abs(w - k * wu) <= 1e-5 * np.maximum(w, 1)), "weights are not multiples of the update weight"
+    assert int(k.astype(np.float64).sum()) == total_upd
     assert rgbw[..., 3].max() <= 8
     assert np.all(np.abs(sdf[w > 0]) < 0.08 + 2 * np.sqrt(3) * 0.02 + 1e-6)
     a.remesh()
