@@ -178,6 +178,11 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # a real (non-default) stream for everything: handle 0 would make the library create its own stream and the
+    # CUDA events of the timed region would then bracket nothing
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm, steps = args.warmup, args.steps
@@ -211,13 +216,20 @@ def run_cuda(args):
         d_color.copy_(h_color)
     recv_depth = torch.empty((H, W), dtype=torch.float32, device=dev)
     recv_color = torch.empty((H, W, channels), dtype=torch.uint8, device=dev)
+    # L2 flush between timed steps: write a 256 MiB buffer, then read another one, so that L2 ends up full of CLEAN
+    # foreign lines (a write-only flush leaves ~126 MB of dirty lines whose write-back would be charged to the step)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
-    stream = torch.cuda.current_stream(dev)
+    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev) if args.flush_l2 else None
+
+    def flush_l2(k):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+            flush_rd.max()
     integ = capi.ProjectionIntegrator(capi.TRUNC_CONSTANT, CFG.truncation, CFG.weight, CFG.carve, CFG.carve_dist)
 
     def new_map():
         return capi.Chisel(CFG.chunk, CFG.resolution, True, device=local, rank=rank, world=world, stream=stream.cuda_stream,
-                           initial_chunks=16384)
+                           initial_chunks=args.pool_chunks)
 
     def barrier():
         if world > 1:
@@ -246,8 +258,7 @@ def run_cuda(args):
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(steps):
-        if flush is not None:
-            flush.fill_(k & 0xFF)
+        flush_l2(k)
         ev[k][0].record(stream)
         step_device(m, warm + k)
         ev[k][1].record(stream)
@@ -257,16 +268,30 @@ def run_cuda(args):
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1000.0
     m.close()
 
+    # ---------------- leg A': same, no flush (the map working set stays in L2 as it does in a live stream) -------
+    m = new_map()
+    for i in range(warm):
+        step_device(m, i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        step_device(m, warm + k)
+    e1.record(stream)
+    barrier()
+    t_warm = e0.elapsed_time(e1) / 1000.0
+    m.close()
+
     # ---------------- leg C: per-frame counters and integrate-kernel time (profiling events inside the library) --
     m = new_map()
     m.set_profiling(True)
     upd_local = 0
     bytes_alg = 0
-    t_integrate = t_prepare = t_cand = 0.0
+    t_integrate = t_prepare = t_cand = t_new = 0.0
     per_frame = []
     for i in range(warm + steps):
-        if flush is not None and i >= warm:
-            flush.fill_(i & 0xFF)
+        if i >= warm:
+            flush_l2(i)
         step_device(m, i)
         if i >= warm:
             st = m.frame_stats()
@@ -277,7 +302,8 @@ def run_cuda(args):
             t_integrate += tm["integrate_ms"] / 1000.0
             t_prepare += tm["prepare_ms"] / 1000.0
             t_cand += tm["candidates_ms"] / 1000.0
-            per_frame.append((st["n_upd"], st["processed_chunks"], st["candidates"], tm["integrate_ms"]))
+            t_new += tm["new_chunks_ms"] / 1000.0
+            per_frame.append((st["n_upd"], st["brick_units"], st["candidates"], tm["integrate_ms"], st["updated_chunks"], st["n_new"], st["new_candidates"]))
     total_chunks = m.frame_stats()["total_chunks"]
     m.close()
 
@@ -310,12 +336,12 @@ def run_cuda(args):
     m.close()
 
     # ---------------- reduce over ranks -------------------------------------------------------------------------
-    vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate], dtype=torch.float64, device=dev)
+    vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate, t_warm], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(upd_local), float(upd_e2e), float(bytes_alg), float(total_chunks)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_dev, t_e2e, wall_a, t_int_max = vals.tolist()
+    t_dev, t_e2e, wall_a, t_int_max, t_warm = vals.tolist()
     upd_total, upd_e2e_total, bytes_total, chunks_total = sums.tolist()
 
     if rank == 0:
@@ -328,18 +354,26 @@ def run_cuda(args):
             "ms_per_step": 1000.0 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "frames_per_s": steps / t_dev,
+            "l2_warm": {"value": upd_total / t_warm / 1e9, "unit": UNIT, "frames_per_s": steps / t_warm, "ms_per_step": 1000.0 * t_warm / steps,
+                        "note": "same steps back to back without the L2 flush; includes host launch gaps"},
             "config": {"workload": WORKLOAD, "parallelism": "chunk-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "1 GPU",
-                       "l2": "256 MiB write between steps, excluded from the step time" if flush is not None else
+                       "l2": "256 MiB write + 256 MiB read between steps, excluded from the step time" if flush is not None else
                              "no flush: frame stream (%d MB) > L2, map working set stays in L2" % ((h2d * nfr) >> 20),
-                       "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total},
+                       "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
+                       "rank0_per_step": {"candidate_chunks": float(np.mean([p[2] for p in per_frame])),
+                                          "brick_units": float(np.mean([p[1] for p in per_frame])),
+                                          "new_chunk_candidates": float(np.mean([p[6] for p in per_frame])),
+                                          "updated_chunks": float(np.mean([p[4] for p in per_frame])),
+                                          "new_chunks": float(np.mean([p[5] for p in per_frame]))}},
             "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88, "timing": "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
-            "gpu_launches": 3 * steps,
+            "gpu_launches": 4 * steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "integrate_kernel<16,color>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "integrate_bricks_kernel<16,color>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_integrate / steps,
-                         "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps},
+                         "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps,
+                         "new_chunks_ms_per_launch": 1000.0 * t_new / steps},
             "wall_s_timed_region": wall_a,
         }
         if world == 1 and not args.no_cpu:
@@ -362,6 +396,8 @@ def main():
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--pool-chunks", type=int, default=98304,
+                    help="pre-sized chunk pool (chunks) so that no slab / hash growth lands inside the timed region")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,7 +52,7 @@ class chs_integrator(C.Structure):
 
 
 class chs_frame_stats(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("candidates", "processed_chunks", "n_upd", "n_carve", "n_col", "n_new",
+    _fields_ = [(n, C.c_int64) for n in ("candidates", "new_candidates", "brick_units", "n_upd", "n_carve", "n_col", "n_new",
                                          "updated_chunks", "total_chunks", "dirty_chunks", "error_flags")]
 
 
@@ -61,7 +61,7 @@ class chs_mesh_counts(C.Structure):
 
 
 class chs_timings(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("prepare_ms", "candidates_ms", "integrate_ms", "frame_ms",
+    _fields_ = [(n, C.c_float) for n in ("prepare_ms", "candidates_ms", "new_chunks_ms", "integrate_ms", "frame_ms",
                                          "mesh_count_ms", "mesh_emit_ms", "mesh_ms")]
 
 

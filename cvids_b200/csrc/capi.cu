@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -79,7 +80,7 @@ void launch_rebuild_dirty(const DeviceMap &map, int, cudaStream_t st) { rebuild_
 
 struct InFlight
 {
-    cudaEvent_t ev;
+    int frameId;            // the snapshot kernel writes this id into the ring slot when the frame is done
     long long newBound;     // upper bound of chunks this frame may add
     long long dirtyBound;   // upper bound of dirty IDs this frame may add
     int slot;               // index into the pinned counter ring
@@ -103,16 +104,17 @@ struct chs_map
     float *dDepth = nullptr, *dTrunc = nullptr;
     uint8_t *dColor = nullptr;
     float2 *dHiz = nullptr;
-    int4 *dWork = nullptr;
-    size_t depthCap = 0, truncCap = 0, colorCap = 0, hizCap = 0, workCap = 0;
+    int4 *dUnits = nullptr, *dNews = nullptr;
+    size_t depthCap = 0, truncCap = 0, colorCap = 0, hizCap = 0, unitsCap = 0, newsCap = 0;
+    int frameId = 0;
     cudaEvent_t h2dDone = nullptr;
     // counters
     Counters *dCtr = nullptr;
     Counters *hCtr = nullptr;           // pinned ring
-    static constexpr int kRing = 8;
+    static constexpr int kRing = 16;
     int ringNext = 0;
     std::deque<InFlight> inflight;
-    std::vector<cudaEvent_t> eventPool;
+    FrameGraph *frameGraph = nullptr;
     long long knownChunks = 0, knownDirty = 0;
     Counters lastFrame{};
     bool haveFrame = false;
@@ -209,6 +211,26 @@ static int ensure_pool(chs_map *m, long long chunks)
         CHS_CUDA(cudaFreeAsync(m->dm.slot_ids, m->stream));
     }
     m->dm.slot_ids = (int *)ids;
+    void *flags = nullptr;
+    rc = alloc_async(&flags, sizeof(unsigned long long) * (size_t)newCap, m->stream);
+    if (rc)
+        return rc;
+    if (m->dm.brick_flags)
+    {
+        CHS_CUDA(cudaMemcpyAsync(flags, m->dm.brick_flags, sizeof(unsigned long long) * (size_t)m->dm.capacity, cudaMemcpyDeviceToDevice, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.brick_flags, m->stream));
+    }
+    m->dm.brick_flags = (unsigned long long *)flags;
+    void *epoch = nullptr;
+    rc = alloc_async(&epoch, sizeof(int) * (size_t)newCap, m->stream);
+    if (rc)
+        return rc;
+    if (m->dm.slot_epoch)
+    {
+        CHS_CUDA(cudaMemcpyAsync(epoch, m->dm.slot_epoch, sizeof(int) * (size_t)m->dm.capacity, cudaMemcpyDeviceToDevice, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dm.slot_epoch, m->stream));
+    }
+    m->dm.slot_epoch = (int *)epoch;
     m->dm.capacity = (int)newCap;
     return CHS_OK;
 }
@@ -269,52 +291,51 @@ static int ensure_dirty(chs_map *m, long long ids)
     return CHS_OK;
 }
 
-// Retire completed counter snapshots; `block` waits for all of them.
+// Retire completed counter snapshots (the frame graph's last node writes them into the pinned ring); `block` waits
+// for all of them.
 static int poll_inflight(chs_map *m, bool block)
 {
+    if (block && !m->inflight.empty())
+        CHS_CUDA(cudaStreamSynchronize(m->stream));
     while (!m->inflight.empty())
     {
         InFlight &f = m->inflight.front();
-        cudaError_t q = block ? cudaEventSynchronize(f.ev) : cudaEventQuery(f.ev);
-        if (q == cudaErrorNotReady)
+        const volatile Counters *c = &m->hCtr[f.slot];
+        if (c->frame_id != f.frameId)
+        {
+            if (block)
+                return fail(CHS_ERR_CUDA, "counter snapshot missing after synchronisation");
             break;
-        if (q != cudaSuccess)
-            return fail(CHS_ERR_CUDA, std::string("counter event: ") + cudaGetErrorString(q));
-        const Counters &c = m->hCtr[f.slot];
-        m->knownChunks = c.n_chunks;
-        m->knownDirty = c.n_dirty;
-        m->lastFrame = c;
-        m->eventPool.push_back(f.ev);
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        m->lastFrame = m->hCtr[f.slot];
+        m->knownChunks = m->lastFrame.n_chunks;
+        m->knownDirty = m->lastFrame.n_dirty;
         m->inflight.pop_front();
     }
     return CHS_OK;
 }
 
-static int snapshot_counters(chs_map *m, long long newBound, long long dirtyBound)
+// Reserve a ring slot for the frame about to be launched.
+static int reserve_snapshot(chs_map *m, int frameId, long long newBound, long long dirtyBound, Counters **slotOut)
 {
     if ((int)m->inflight.size() >= chs_map::kRing)
     {
-        // ring full: wait for the oldest snapshot
-        CHS_CUDA(cudaEventSynchronize(m->inflight.front().ev));
         int rc = poll_inflight(m, false);
         if (rc)
             return rc;
+        if ((int)m->inflight.size() >= chs_map::kRing && (rc = poll_inflight(m, true)))
+            return rc;
     }
     InFlight f;
-    if (m->eventPool.empty())
-        CHS_CUDA(cudaEventCreateWithFlags(&f.ev, cudaEventDisableTiming));
-    else
-    {
-        f.ev = m->eventPool.back();
-        m->eventPool.pop_back();
-    }
+    f.frameId = frameId;
     f.slot = m->ringNext;
     m->ringNext = (m->ringNext + 1) % chs_map::kRing;
     f.newBound = newBound;
     f.dirtyBound = dirtyBound;
-    CHS_CUDA(cudaMemcpyAsync(&m->hCtr[f.slot], m->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
-    CHS_CUDA(cudaEventRecord(f.ev, m->stream));
+    m->hCtr[f.slot].frame_id = -1;
     m->inflight.push_back(f);
+    *slotOut = &m->hCtr[f.slot];
     return CHS_OK;
 }
 
@@ -386,12 +407,17 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
             return rc;
         chunkUb = m->knownChunks + cand;
         dirtyUb = m->knownDirty + dirtyBound;
-        if ((rc = ensure_pool(m, chunkUb + chunkUb / 4)) || (rc = ensure_hash(m, chunkUb + chunkUb / 4)) ||
-            (rc = ensure_dirty(m, dirtyUb + dirtyUb / 4)))
+        // head-room for several frames in flight: the bound per frame is the candidate count
+        const long long wantChunks = m->knownChunks + 4 * cand + m->knownChunks / 4;
+        const long long wantDirty = m->knownDirty + 4 * dirtyBound + m->knownDirty / 4;
+        if ((rc = ensure_pool(m, wantChunks)) || (rc = ensure_hash(m, wantChunks)) || (rc = ensure_dirty(m, wantDirty)))
             return rc;
     }
-    if ((rc = grow_buffer(&m->dWork, &m->workCap, (size_t)cand, st)))
-        return rc;
+    {
+        const int bpa = m->cfg.chunk_size / 8;
+        if ((rc = grow_buffer(&m->dUnits, &m->unitsCap, (size_t)cand * bpa * bpa * bpa, st)) || (rc = grow_buffer(&m->dNews, &m->newsCap, (size_t)cand, st)))
+            return rc;
+    }
 
     const size_t npx = (size_t)cam->width * cam->height;
     FrameParams fp{};
@@ -456,6 +482,8 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
     fp.carve = integ->carving_enabled ? 1 : 0;
     fp.weight = integ->weight;
     fp.depth_cutoff = colorPath ? 100.0f : 50.0f;
+    fp.same_cam = (colorPath && std::memcmp(&fp.cam, &fp.ccam, sizeof(CameraDev)) == 0) ? 1 : 0;
+    fp.wu_const = integ->weight / (5 * integ->trunc_param);            // ConstantWeighter.h:43-46 (binary32, used for the constant truncator)
     {
         float T = (float)1e-5;
         if ((double)T < 1e-5)
@@ -491,28 +519,28 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
             off += (size_t)fp.hizW[l] * fp.hizH[l];
         }
     }
-    fp.work = m->dWork;
-    fp.work_cap = (int)std::min<size_t>(m->workCap, 0x7fffffff);
-
-    if (m->profiling)
-        CHS_CUDA(cudaEventRecord(m->evt[0], st));
-    launch_frame_prepare(fp, m->dm, st);
-    if (m->profiling)
-        CHS_CUDA(cudaEventRecord(m->evt[1], st));
-    launch_chunk_candidates(fp, m->dm, st);
-    if (m->profiling)
-        CHS_CUDA(cudaEventRecord(m->evt[2], st));
-    // persistent-style grid: CTAs stride over the work list, whose length is only known on the device
-    const int grid = (int)std::min<long long>(cand, 148ll * 8);
-    launch_integrate(fp, m->dm, std::max(grid, 1), st);
-    if (m->profiling)
+    fp.units = m->dUnits;
+    fp.units_cap = (int)std::min<size_t>(m->unitsCap, 0x1fffffff);
+    fp.news = m->dNews;
+    fp.news_cap = (int)std::min<size_t>(m->newsCap, 0x7fffffff);
+    fp.frame_id = ++m->frameId;
     {
-        CHS_CUDA(cudaEventRecord(m->evt[3], st));
-        m->frameTimed = true;
+        // smallest odd stride >= 7919 that is coprime to the box size
+        long long stride = 7919;
+        auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
+        while (cand > 1 && gcd(stride, cand) != 1)
+            stride += 2;
+        fp.cand_stride = (int)(cand > 1 ? stride % cand : 1);
+        if (fp.cand_stride == 0)
+            fp.cand_stride = 1;
     }
-    CHS_CUDA(cudaGetLastError());
-    if ((rc = snapshot_counters(m, cand, dirtyBound)))
+
+    Counters *slotPtr = nullptr;
+    if ((rc = reserve_snapshot(m, fp.frame_id, cand, dirtyBound, &slotPtr)))
         return rc;
+    CHS_CUDA(frame_graph_launch(m->frameGraph, fp, m->dm, cand, slotPtr, m->profiling, m->evt, st));
+    if (m->profiling)
+        m->frameTimed = true;
     m->haveFrame = true;
     // the caller may reuse its host buffers as soon as we return (chisel_ros does: CR ChiselServer.cpp:285-295)
     if (copied)
@@ -618,9 +646,10 @@ int chs_create(const chs_config *cfg, chs_map **out)
     CHS_CUDA(cudaMalloc((void **)&m->dCtr, sizeof(Counters)));
     CHS_CUDA(cudaMemsetAsync(m->dCtr, 0, sizeof(Counters), m->stream));
     d.ctr = m->dCtr;
-    CHS_CUDA(cudaHostAlloc((void **)&m->hCtr, sizeof(Counters) * (chs_map::kRing + 1), cudaHostAllocDefault));
+    CHS_CUDA(cudaHostAlloc((void **)&m->hCtr, sizeof(Counters) * (chs_map::kRing + 1), cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hCtr, 0, sizeof(Counters) * (chs_map::kRing + 1));
     CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
+    m->frameGraph = frame_graph_create();
     for (int i = 0; i < 8; i++)
         CHS_CUDA(cudaEventCreate(&m->evt[i]));
     const long long initial = cfg->initial_chunks > 0 ? cfg->initial_chunks : 4096;
@@ -645,8 +674,8 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     for (uchar4 *p : m->colorSlabs)
         cudaFreeAsync(p, m->stream);
-    void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dHiz,
-                    m->dWork, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
+    void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dHiz,
+                    m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
                     m->dColors, m->dGrids};
     for (void *p : bufs)
         if (p)
@@ -656,10 +685,7 @@ int chs_destroy(chs_map *m)
     cudaFree(m->dm.color_slabs);
     cudaFree(m->dCtr);
     cudaFreeHost(m->hCtr);
-    for (InFlight &f : m->inflight)
-        cudaEventDestroy(f.ev);
-    for (cudaEvent_t e : m->eventPool)
-        cudaEventDestroy(e);
+    frame_graph_destroy(m->frameGraph);
     if (m->h2dDone)
         cudaEventDestroy(m->h2dDone);
     for (int i = 0; i < 8; i++)
@@ -753,10 +779,15 @@ int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
         return rc;
     const Counters &c = m->lastFrame;
     out->candidates = c.candidates;
-    out->processed_chunks = c.work_count;
-    out->n_upd = (int64_t)c.n_upd;
-    out->n_carve = (int64_t)c.n_carve;
-    out->n_col = (int64_t)c.n_col;
+    out->new_candidates = c.new_count;
+    out->brick_units = c.unit_count;
+    out->n_upd = out->n_carve = out->n_col = 0;
+    for (int k = 0; k < kCounterSlots; k++)
+    {
+        out->n_upd += (int64_t)c.n_upd[k];
+        out->n_carve += (int64_t)c.n_carve[k];
+        out->n_col += (int64_t)c.n_col[k];
+    }
     out->n_new = c.n_new;
     out->updated_chunks = c.updated_chunks;
     out->total_chunks = c.n_chunks;
@@ -778,7 +809,8 @@ int chs_get_timings(chs_map *m, chs_timings *out)
     {
         CHS_CUDA(cudaEventElapsedTime(&out->prepare_ms, m->evt[0], m->evt[1]));
         CHS_CUDA(cudaEventElapsedTime(&out->candidates_ms, m->evt[1], m->evt[2]));
-        CHS_CUDA(cudaEventElapsedTime(&out->integrate_ms, m->evt[2], m->evt[3]));
+        CHS_CUDA(cudaEventElapsedTime(&out->new_chunks_ms, m->evt[2], m->evt[7]));
+        CHS_CUDA(cudaEventElapsedTime(&out->integrate_ms, m->evt[7], m->evt[3]));
         CHS_CUDA(cudaEventElapsedTime(&out->frame_ms, m->evt[0], m->evt[3]));
     }
     if (m->meshTimed)

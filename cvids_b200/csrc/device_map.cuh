@@ -22,6 +22,7 @@ constexpr int kMaxSlabs = 1 << 13;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kIdBias = 1 << 20;                           // chunk IDs must lie in [-2^20, 2^20)
 constexpr int kHizLevels = 4;                              // tiles of 8, 16, 32, 64 pixels
+constexpr int kCounterSlots = 32;                          // per-frame voxel counters are spread over this many addresses
 
 enum : int
 {
@@ -62,16 +63,16 @@ struct Counters
     int n_dirty;
     int error_flags;
     // per frame (zeroed by frame_prepare)
-    int work_count;
+    int unit_count;                // brick units of existing chunks
+    int new_count;                 // new-chunk candidates
     int candidates;
     int n_new;
     int updated_chunks;
-    int pad;
-    unsigned long long n_upd, n_carve, n_col;
+    unsigned long long n_upd[kCounterSlots], n_carve[kCounterSlots], n_col[kCounterSlots];
     // per re-mesh
     unsigned long long mesh_verts, mesh_grids;
     int mesh_chunks;
-    int pad2;
+    int frame_id;                  // host ring slots only: id of the frame this snapshot was taken after (written last)
 };
 
 struct DeviceMap
@@ -82,6 +83,8 @@ struct DeviceMap
     float2 **dist_slabs;           // [kMaxSlabs] device pointers
     uchar4 **color_slabs;
     int *slot_ids;                 // [capacity*3] slot -> chunk ID
+    unsigned long long *brick_flags; // [capacity] bit b: 8^3 brick b may hold a voxel with weight > 0 && sdf < 1e-5 (carvable)
+    int *slot_epoch;               // [capacity] id of the last frame that updated the chunk (dirty marking runs once per chunk and frame)
     int capacity;                  // chunks the allocated slabs can hold
     unsigned long long *dirty_keys;
     unsigned dirty_mask;
@@ -188,13 +191,19 @@ struct FrameParams
     float weight;             // ConstantWeighter weight
     float depth_cutoff;       // 50 (depth path) / 100 (colour path)
     float sdf_carve_max;      // smallest float T with double(T) >= 1e-5: (double)sdf < 1e-5  <=>  sdf < T
+    int same_cam;             // colour pose + intrinsics bit-identical to the depth ones: reuse the projection
+    float wu_const;           // constant truncator: weight / (5 * trunc), formed on the host in binary32
     // candidate enumeration
     int lo[3], n[3];
     float planes[6][4];
     float2 *hiz[kHizLevels];  // {min lo, max hi} per tile
     int hizW[kHizLevels], hizH[kHizLevels];
-    int4 *work;
-    int work_cap;
+    int4 *units;              // brick units of existing chunks: {x, y, z, slot | brick << 24}
+    int units_cap;
+    int4 *news;               // new-chunk candidates: {x, y, z, -1}
+    int news_cap;
+    int cand_stride;          // multiplicative permutation of the candidate enumeration (coprime to the box size)
+    int frame_id;             // > 0, increases by one per integrated frame
 };
 
 } // namespace chs

@@ -2,13 +2,18 @@
 //
 //   frame_prepare_kernel     per-pixel truncation + {min near, max far} depth-range tiles ("Hi-Z") for culling
 //   chunk_candidates_kernel  enumerate the reference's candidate ID box, reproduce Frustum::Intersects, drop
-//                            chunks that provably cannot change, warp-ballot compact the rest into a work list
-//   integrate_kernel         projective SDF / weight / colour update, one CTA per work-list chunk
+//                            chunks / 8^3 bricks that provably cannot change, warp-ballot compact the rest into two
+//                            work lists (new-chunk candidates, brick units of existing chunks)
+//   integrate_new_chunks_kernel  exact band test of the new-chunk candidates; survivors are allocated and written once
+//   integrate_bricks_kernel      projective SDF / weight / colour update of existing chunks, a warp per half brick
 //
 // Exact-arithmetic rule: everything that decides a branch or produces stored state follows SURVEY.md
 // Appendix A operation by operation with __f*_rn intrinsics (never contracted into FMA; the file is also
 // built with -fmad=false). Culling code is free-form float math with explicit slack, and is conservative:
 // it may keep a chunk that turns out to be untouched, never drop one that would be touched.
+#include <algorithm>
+#include <cstddef>
+
 #include "device_map.cuh"
 #include "kernels.h"
 
@@ -40,19 +45,38 @@ __host__ __device__ inline float truncation_of(int kind, float param, float read
 }
 
 // ------------------------------------------------------------------------------------------------------
-// frame_prepare: one CTA per 64x64 pixel block.
+// frame_prepare: one CTA per 64x64 pixel block; writes the per-pixel truncation image (non-constant truncators) and
+// the four Hi-Z levels (tiles of 8, 16, 32, 64 pixels) holding {min over pixels of depth - band, max of depth + band}.
+__device__ __forceinline__ void hiz_accumulate(const FrameParams &fp, float d, float tr, float *lo, float *hi)
+{
+    // pixels that can never change a voxel: NaN, +-inf, beyond the cutoff (ProjectionIntegrator.h:74,134,141)
+    const bool valid = (d == d) && fabsf(d) <= 3.0e38f && !(d > fp.depth_cutoff) && (tr == tr);
+    if (valid)
+    {
+        const float band = tr + fp.diag;
+        // carving reaches every z < d - (trunc + carveDist); that is inside (.., d + band) unless carveDist is very negative
+        const float farExt = fp.carve ? fmaxf(band, -(tr + fp.carve_dist)) : band;
+        *lo = fminf(*lo, d - band);
+        *hi = fmaxf(*hi, d + farExt);
+    }
+}
+
 __global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, DeviceMap map)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < kCounterSlots)
     {
         Counters *c = map.ctr;
-        c->work_count = 0;
-        c->candidates = 0;
-        c->n_new = 0;
-        c->updated_chunks = 0;
-        c->n_upd = 0;
-        c->n_carve = 0;
-        c->n_col = 0;
+        if (threadIdx.x == 0)
+        {
+            c->unit_count = 0;
+            c->new_count = 0;
+            c->candidates = 0;
+            c->n_new = 0;
+            c->updated_chunks = 0;
+        }
+        c->n_upd[threadIdx.x] = 0;
+        c->n_carve[threadIdx.x] = 0;
+        c->n_col[threadIdx.x] = 0;
     }
     const int W = fp.cam.W, H = fp.cam.H;
     const int t = threadIdx.x;
@@ -60,37 +84,57 @@ __global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, Devi
     const int tx = blockIdx.x * 8 + (tile & 7), ty = blockIdx.y * 8 + (tile >> 3);
     float lo = INFINITY, hi = -INFINITY;
     const bool perPixel = fp.trunc_img != nullptr;
-    float *truncOut = (fp.trunc_kind == CHS_TRUNC_QUADRATIC || fp.trunc_kind == CHS_TRUNC_INVERSE) ? const_cast<float *>(fp.trunc_img) : nullptr;
-#pragma unroll
-    for (int r = 0; r < 2; r++)
+    const bool computeTrunc = fp.trunc_kind == CHS_TRUNC_QUADRATIC || fp.trunc_kind == CHS_TRUNC_INVERSE;
+    float *truncOut = computeTrunc ? const_cast<float *>(fp.trunc_img) : nullptr;
+    const bool vec = ((W & 3) == 0) && ((reinterpret_cast<size_t>(fp.depth) & 15) == 0) && !perPixel;
+    const int x0 = tx * 8;
+    if (vec && x0 + 8 <= W)
     {
-        const int y = ty * 8 + sub * 2 + r;
-        if (y >= H)
-            continue;
+        // constant truncator, aligned interior: four independent 128-bit loads per thread
+        float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int r = 0; r < 2; r++)
         {
-            const int x = tx * 8 + i;
-            if (x >= W)
+            const int y = ty * 8 + sub * 2 + r;
+            const bool in = y < H;
+            const float4 *row = reinterpret_cast<const float4 *>(fp.depth + (size_t)(in ? y : 0) * W + x0);
+            const float nanv = __int_as_float(0x7fc00000);
+            v[2 * r] = in ? __ldg(row) : make_float4(nanv, nanv, nanv, nanv);
+            v[2 * r + 1] = in ? __ldg(row + 1) : make_float4(nanv, nanv, nanv, nanv);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            hiz_accumulate(fp, v[k].x, fp.trunc_param, &lo, &hi);
+            hiz_accumulate(fp, v[k].y, fp.trunc_param, &lo, &hi);
+            hiz_accumulate(fp, v[k].z, fp.trunc_param, &lo, &hi);
+            hiz_accumulate(fp, v[k].w, fp.trunc_param, &lo, &hi);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+        {
+            const int y = ty * 8 + sub * 2 + r;
+            if (y >= H)
                 continue;
-            const float d = __ldg(fp.depth + (size_t)y * W + x);
-            float tr;
-            if (truncOut)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
             {
-                tr = truncation_of(fp.trunc_kind, fp.trunc_param, d);
-                truncOut[(size_t)y * W + x] = tr;
-            }
-            else
-                tr = perPixel ? __ldg(fp.trunc_img + (size_t)y * W + x) : fp.trunc_param;
-            // pixels that can never change a voxel: NaN, +-inf, beyond the cutoff (ProjectionIntegrator.h:74,134,141)
-            const bool valid = (d == d) && fabsf(d) <= 3.0e38f && !(d > fp.depth_cutoff) && (tr == tr);
-            if (valid)
-            {
-                const float band = tr + fp.diag;
-                // carving reaches every z < d - (trunc + carveDist); that is inside (.., d + band) unless carveDist is very negative
-                const float farExt = fp.carve ? fmaxf(band, -(tr + fp.carve_dist)) : band;
-                lo = fminf(lo, d - band);
-                hi = fmaxf(hi, d + farExt);
+                const int x = x0 + i;
+                if (x >= W)
+                    continue;
+                const float d = __ldg(fp.depth + (size_t)y * W + x);
+                float tr;
+                if (truncOut)
+                {
+                    tr = truncation_of(fp.trunc_kind, fp.trunc_param, d);
+                    truncOut[(size_t)y * W + x] = tr;
+                }
+                else
+                    tr = perPixel ? __ldg(fp.trunc_img + (size_t)y * W + x) : fp.trunc_param;
+                hiz_accumulate(fp, d, tr, &lo, &hi);
             }
         }
     }
@@ -154,14 +198,16 @@ __device__ __forceinline__ bool frustum_intersects_exact(const FrameParams &fp, 
     return false;
 }
 
-// Conservative depth-range test of one chunk against the Hi-Z tiles. Returns true if the chunk must be processed.
-__device__ bool chunk_may_change(const FrameParams &fp, const DeviceMap &map, int idx, int idy, int idz, bool exists)
+// Conservative depth-range classification of an axis-aligned box of voxel CENTRES (first centre at world position
+// (wx, wy, wz), `ext` metres along each axis) against the Hi-Z tiles:
+//   0  no voxel of the box can change this frame (off-image, behind the camera, no valid pixel, or behind every surface)
+//   1  the box lies entirely in free space in front of every surface: only carving of already-observed voxels can act
+//   2  some voxel may fall inside the truncation band
+// Free-form float math with explicit slack: may over-report, never under-report.
+__device__ int classify_box(const FrameParams &fp, float wx, float wy, float wz, float ext)
 {
     const CameraDev &c = fp.cam;
-    const float ext = (float)(map.cs - 1) * map.res;                   // span of voxel centres along one edge
-    const float ox = (float)(map.cs * idx) * map.res + map.half - c.t[0];
-    const float oy = (float)(map.cs * idy) * map.res + map.half - c.t[1];
-    const float oz = (float)(map.cs * idz) * map.res + map.half - c.t[2];
+    const float ox = wx - c.t[0], oy = wy - c.t[1], oz = wz - c.t[2];
     float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
     bool nearCross = false;
 #pragma unroll
@@ -189,7 +235,7 @@ __device__ bool chunk_may_change(const FrameParams &fp, const DeviceMap &map, in
     zmin -= slack;
     zmax += slack;
     if (zmax < 0.0f)
-        return false;                                                   // every centre behind the camera (ProjectionIntegrator.h:68)
+        return 0;                                                       // every centre behind the camera (ProjectionIntegrator.h:68)
     int x0, x1, y0, y1;
     if (nearCross)
     {
@@ -201,7 +247,7 @@ __device__ bool chunk_may_change(const FrameParams &fp, const DeviceMap &map, in
         const float fx0 = fmaxf(umin - 2.0f, 0.0f), fx1 = fminf(umax + 2.0f, c.Wf - 1.0f);
         const float fy0 = fmaxf(vmin - 2.0f, 0.0f), fy1 = fminf(vmax + 2.0f, c.Hf - 1.0f);
         if (!(fx0 <= fx1) || !(fy0 <= fy1))
-            return false;                                               // projects entirely off the image
+            return 0;                                                   // projects entirely off the image
         x0 = (int)fx0; x1 = (int)fx1; y0 = (int)fy0; y1 = (int)fy1;
     }
     // pick the finest level at which the rectangle spans at most 3 tiles per axis
@@ -214,90 +260,169 @@ __device__ bool chunk_may_change(const FrameParams &fp, const DeviceMap &map, in
     float lo = INFINITY, hi = -INFINITY;
     const float2 *tiles = fp.hiz[level];
     const int tw = fp.hizW[level];
-    for (int ty = y0 >> shift; ty <= (y1 >> shift); ty++)
-        for (int tx = x0 >> shift; tx <= (x1 >> shift); tx++)
+    const int tx0 = x0 >> shift, tx1 = x1 >> shift, ty0 = y0 >> shift, ty1 = y1 >> shift;
+    if (tx1 - tx0 <= 2 && ty1 - ty0 <= 2)
+    {
+        // common case: up to 3x3 tiles, all loads issued before the reduction
+        float2 v[9];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+            {
+                const int tx = min(tx0 + i, tx1), ty = min(ty0 + j, ty1);
+                v[j * 3 + i] = __ldg(tiles + ty * tw + tx);
+            }
+#pragma unroll
+        for (int k = 0; k < 9; k++)
         {
-            const float2 v = __ldg(tiles + ty * tw + tx);
-            lo = fminf(lo, v.x);
-            hi = fmaxf(hi, v.y);
+            lo = fminf(lo, v[k].x);
+            hi = fmaxf(hi, v[k].y);
         }
+    }
+    else
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++)
+            {
+                const float2 v = __ldg(tiles + ty * tw + tx);
+                lo = fminf(lo, v.x);
+                hi = fmaxf(hi, v.y);
+            }
     if (!(lo <= hi))
-        return false;                                                   // no valid depth pixel under the chunk
+        return 0;                                                       // no valid depth pixel under the box
     const float s2 = 1e-3f + 1e-5f * fmaxf(fabsf(lo), fabsf(hi));
     if (zmin > hi + s2)
-        return false;                                                   // entirely behind every surface it projects onto
-    if (zmax < lo - s2 && !(exists && fp.carve))
-        return false;                                                   // entirely in free space: only carving (of existing voxels) can act
-    return true;
+        return 0;                                                       // entirely behind every surface it projects onto
+    if (zmax < lo - s2)
+        return 1;                                                       // entirely in free space
+    return 2;
 }
 
-__global__ void __launch_bounds__(256) chunk_candidates_kernel(FrameParams fp, DeviceMap map)
+// One thread per ID of the candidate box (the reference's order -- x outer, y, z inner; ChunkManager.cpp:192-196 -- does
+// not affect the result, so IDs are enumerated by linear index). Survivors are split into two lists:
+//   news   non-existing chunks that may receive a band hit          -> integrate_new_chunks (CTA per chunk)
+//   units  8^3 bricks of existing chunks that may change            -> integrate_bricks (a warp per quarter brick)
+// Both lists are filled by warp-ballot compaction; the bricks of a kept chunk are classified by the lanes of the warp
+// in parallel.
+template <int CS>
+__global__ void __launch_bounds__(64) chunk_candidates_kernel(FrameParams fp, DeviceMap map)
 {
+    constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
     const int total = fp.n[0] * fp.n[1] * fp.n[2];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool candidate = false, keep = false;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    bool candidate = false, keepNew = false, keepOld = false;
     int x = 0, y = 0, z = 0, slot = -1;
-    if (i < total)
+    float bx = 0.0f, by = 0.0f, bz = 0.0f;
+    if (tid < total)
     {
-        // x outer, y, z inner -- the reference's order (ChunkManager.cpp:192-196); order does not affect the result
+        // surviving chunks are spatially clustered; a multiplicative permutation (stride coprime to total) spreads them
+        // over the warps so that the per-warp brick expansion below stays short
+        const int i = (int)(((long long)tid * fp.cand_stride) % total);
         const int nyz = fp.n[1] * fp.n[2];
         x = fp.lo[0] + i / nyz;
         const int r = i - (i / nyz) * nyz;
         y = fp.lo[1] + r / fp.n[2];
         z = fp.lo[2] + r % fp.n[2];
         // chunk box exactly as ChunkManager.cpp:199-201
-        const float ext = __fmul_rn((float)map.cs, map.res);
-        const float bx = __fmul_rn((float)(x * map.cs), map.res), by = __fmul_rn((float)(y * map.cs), map.res), bz = __fmul_rn((float)(z * map.cs), map.res);
+        const float ext = __fmul_rn((float)CS, map.res);
+        bx = __fmul_rn((float)(x * CS), map.res);
+        by = __fmul_rn((float)(y * CS), map.res);
+        bz = __fmul_rn((float)(z * CS), map.res);
         candidate = frustum_intersects_exact(fp, bx, by, bz, __fadd_rn(bx, ext), __fadd_rn(by, ext), __fadd_rn(bz, ext));
         if (candidate && map.world > 1)
             candidate = (owner_hash(x, y, z) % (unsigned)map.world) == (unsigned)map.rank;
         if (candidate)
         {
-            slot = hash_lookup(map, pack_id(x, y, z));
-            keep = chunk_may_change(fp, map, x, y, z, slot >= 0);
+            const int code = classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
+            // the hash table is only consulted for the few IDs the depth test could not reject
+            if (code == 2 || (code == 1 && fp.carve))
+            {
+                slot = hash_lookup(map, pack_id(x, y, z));
+                keepNew = slot < 0 && code == 2;
+                keepOld = slot >= 0;            // bricks decide below (free-space bricks need their carvable bit)
+            }
         }
     }
     const unsigned lane = threadIdx.x & 31;
     const unsigned candMask = __ballot_sync(0xffffffffu, candidate);
-    const unsigned keepMask = __ballot_sync(0xffffffffu, keep);
+    const unsigned newMask = __ballot_sync(0xffffffffu, keepNew);
+    unsigned oldMask = __ballot_sync(0xffffffffu, keepOld);
     int base = 0;
     if (lane == 0)
     {
         if (candMask)
             atomicAdd(&map.ctr->candidates, __popc(candMask));
-        if (keepMask)
-            base = atomicAdd(&map.ctr->work_count, __popc(keepMask));
+        if (newMask)
+            base = atomicAdd(&map.ctr->new_count, __popc(newMask));
     }
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep)
+    if (keepNew)
     {
-        const int pos = base + __popc(keepMask & ((1u << lane) - 1));
-        if (pos < fp.work_cap)
-            fp.work[pos] = make_int4(x, y, z, slot);
+        const int pos = base + __popc(newMask & ((1u << lane) - 1));
+        if (pos < fp.news_cap)
+            fp.news[pos] = make_int4(x, y, z, -1);
         else
             atomicOr(&map.ctr->error_flags, kErrWorkFull);
+    }
+    // expand the kept existing chunks into brick units: groups of GL lanes take one chunk each, lanes = bricks
+    constexpr int GL = NB >= 32 ? 32 : (NB < 8 ? 8 : NB);           // lanes per chunk (8 for 16^3 and 8^3 chunks, 32 for 32^3)
+    constexpr int GROUPS = 32 / GL;
+    const int group = (int)lane / GL, gl = (int)lane % GL;
+    while (oldMask)
+    {
+        // the group's chunk: the (group)-th set bit of oldMask, if any
+        unsigned mm = oldMask;
+        int src = -1;
+#pragma unroll
+        for (int k = 0; k < GROUPS; k++)
+        {
+            const int bit = mm ? __ffs(mm) - 1 : -1;
+            if (k == group)
+                src = bit;
+            if (mm)
+                mm &= mm - 1;
+        }
+        oldMask = mm;
+        const int srcLane = src < 0 ? 0 : src;
+        const int cxI = __shfl_sync(0xffffffffu, x, srcLane), cyI = __shfl_sync(0xffffffffu, y, srcLane), czI = __shfl_sync(0xffffffffu, z, srcLane);
+        const int cslot = __shfl_sync(0xffffffffu, slot, srcLane);
+        const float obx = __shfl_sync(0xffffffffu, bx, srcLane), oby = __shfl_sync(0xffffffffu, by, srcLane), obz = __shfl_sync(0xffffffffu, bz, srcLane);
+        const unsigned long long flags = src >= 0 ? map.brick_flags[cslot] : 0ull;
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += GL)
+        {
+            const int b = b0 + gl;
+            bool keepB = false;
+            if (src >= 0 && b < NB)
+            {
+                int code = 2;
+                if (NB > 1)
+                {
+                    const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
+                    code = classify_box(fp, obx + (float)(qx * 8) * map.res + map.half, oby + (float)(qy * 8) * map.res + map.half,
+                                        obz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
+                }
+                keepB = code == 2 || (code == 1 && fp.carve && ((flags >> b) & 1ull));
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, keepB);
+            int ubase = 0;
+            if (lane == 0 && bm)
+                ubase = atomicAdd(&map.ctr->unit_count, __popc(bm));
+            ubase = __shfl_sync(0xffffffffu, ubase, 0);
+            if (keepB)
+            {
+                const int pos = ubase + __popc(bm & ((1u << lane) - 1));
+                if (pos < fp.units_cap)
+                    fp.units[pos] = make_int4(cxI, cyI, czI, cslot | (b << 24));
+                else
+                    atomicOr(&map.ctr->error_flags, kErrWorkFull);
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// per-voxel evaluation
-
-struct VoxelEval
-{
-    int status;      // 0 nothing, 1 in band (integrate), 2 carve candidate
-    float sd;        // surfaceDist
-    float trunc;
-    float px, py, pz; // voxel centre, world
-};
-
-// pose.linear().transpose() * (p - t), each coefficient c0 + (c1 + c2)
-__device__ __forceinline__ void to_camera(const CameraDev &c, float px, float py, float pz, float *cx, float *cy, float *cz)
-{
-    const float d0 = __fsub_rn(px, c.t[0]), d1 = __fsub_rn(py, c.t[1]), d2 = __fsub_rn(pz, c.t[2]);
-    *cx = __fadd_rn(__fmul_rn(c.R[0], d0), __fadd_rn(__fmul_rn(c.R[3], d1), __fmul_rn(c.R[6], d2)));
-    *cy = __fadd_rn(__fmul_rn(c.R[1], d0), __fadd_rn(__fmul_rn(c.R[4], d1), __fmul_rn(c.R[7], d2)));
-    *cz = __fadd_rn(__fmul_rn(c.R[2], d0), __fadd_rn(__fmul_rn(c.R[5], d1), __fmul_rn(c.R[8], d2)));
-}
+// per-voxel arithmetic
 
 // PinholeCamera::ProjectPoint + IsPointOnImage (OC PinholeCamera.cpp:38-45, 61-64)
 __device__ __forceinline__ bool project_on_image(const CameraDev &c, float x, float y, float z, float *u, float *v)
@@ -308,34 +433,13 @@ __device__ __forceinline__ bool project_on_image(const CameraDev &c, float x, fl
     return *u >= 0.0f && *v >= 0.0f && *u < c.Wf && *v < c.Hf;
 }
 
-template <bool COLOR_PATH, bool PER_PIXEL>
-__device__ __forceinline__ VoxelEval eval_voxel(const FrameParams &fp, float px, float py, float pz)
+// pose.linear().transpose() * (p - t), each coefficient c0 + (c1 + c2)
+__device__ __forceinline__ void to_camera(const CameraDev &c, float px, float py, float pz, float *cx, float *cy, float *cz)
 {
-    VoxelEval e;
-    e.status = 0;
-    e.px = px; e.py = py; e.pz = pz;
-    float cx, cy, cz, u, v;
-    to_camera(fp.cam, px, py, pz, &cx, &cy, &cz);
-    if (!project_on_image(fp.cam, cx, cy, cz, &u, &v) || cz < 0.0f)
-        return e;
-    const int pix = (int)u + (int)v * fp.cam.W;
-    const float depth = __ldg(fp.depth + pix);
-    if (COLOR_PATH)
-    {
-        if (depth != depth || depth > 100.0f)                           // ProjectionIntegrator.h:134, :141
-            return e;
-    }
-    else if (depth > 50.0f)                                             // :74
-        return e;
-    const float trunc = PER_PIXEL ? __ldg(fp.trunc_img + pix) : fp.trunc_param;
-    const float sd = __fsub_rn(depth, cz);
-    e.sd = sd;
-    e.trunc = trunc;
-    if (fabsf(sd) < __fadd_rn(trunc, fp.diag))                          // :82 / :143
-        e.status = 1;
-    else if (fp.carve && sd > __fadd_rn(trunc, fp.carve_dist))          // :88 / :166
-        e.status = 2;
-    return e;
+    const float d0 = __fsub_rn(px, c.t[0]), d1 = __fsub_rn(py, c.t[1]), d2 = __fsub_rn(pz, c.t[2]);
+    *cx = __fadd_rn(__fmul_rn(c.R[0], d0), __fadd_rn(__fmul_rn(c.R[3], d1), __fmul_rn(c.R[6], d2)));
+    *cy = __fadd_rn(__fmul_rn(c.R[1], d0), __fadd_rn(__fmul_rn(c.R[4], d1), __fmul_rn(c.R[7], d2)));
+    *cz = __fadd_rn(__fmul_rn(c.R[2], d0), __fadd_rn(__fmul_rn(c.R[5], d1), __fmul_rn(c.R[8], d2)));
 }
 
 // DistVoxel::Integrate (OC DistVoxel.h:52-60)
@@ -345,27 +449,29 @@ __device__ __forceinline__ float2 dist_integrate(float2 v, float d, float wu)
     return make_float2(nd, __fadd_rn(v.y, wu));
 }
 
-// ColorVoxel::Integrate with weightUpdate = 1 (OC ColorVoxel.h:65-85); returns true if it wrote
-__device__ __forceinline__ bool color_integrate(uchar4 *cv, unsigned char r, unsigned char g, unsigned char b)
+// ColorVoxel::Integrate with weightUpdate = 1 (OC ColorVoxel.h:65-85) on a packed voxel (r | g << 8 | b << 16 | w << 24),
+// for w < 8 (the only weights ProjectionIntegrator.h:153 lets through). The reference evaluates, per channel,
+//     uint8( saturate( float(w * old + new) / float(w + 1) ) )
+// in binary32. N = w * old + new <= 2040 and D = w + 1 <= 8 are exact integers, a correctly rounded quotient of integers
+// that is not itself an integer stays at least 1/D - 2^-13 away from the next integer, and the cast truncates, so the
+// result is exactly floor(N / D): integer arithmetic, no rounding at all. floor(N / D) = (N * ceil(2^20 / D)) >> 20 for
+// N < 2048, D <= 8. tests/test_host_logic.py::test_color_integrate_integer_identity checks all 8 * 256 * 256 cases.
+__constant__ unsigned cRecip20[9] = {0u, 1048576u, 524288u, 349526u, 262144u, 209716u, 174763u, 149797u, 131072u};
+
+__device__ __forceinline__ unsigned color_integrate_packed(unsigned cv, unsigned r, unsigned g, unsigned b)
 {
-    const int w = cv->w;
-    if (w >= 255 - 1)
-        return false;
-    const float wf = (float)w, den = (float)(1 + w);
-    float fr = __fdiv_rn(__fadd_rn(__fmul_rn(wf, (float)cv->x), (float)(int)r), den);
-    float fg = __fdiv_rn(__fadd_rn(__fmul_rn(wf, (float)cv->y), (float)(int)g), den);
-    float fb = __fdiv_rn(__fadd_rn(__fmul_rn(wf, (float)cv->z), (float)(int)b), den);
-    fr = fminf(fmaxf(fr, 0.0f), 255.0f);
-    fg = fminf(fmaxf(fg, 0.0f), 255.0f);
-    fb = fminf(fmaxf(fb, 0.0f), 255.0f);
-    *cv = make_uchar4((unsigned char)fr, (unsigned char)fg, (unsigned char)fb, (unsigned char)(w + 1));
-    return true;
+    const unsigned w = cv >> 24;
+    const unsigned m = cRecip20[w + 1];
+    const unsigned nr = ((w * (cv & 0xFFu) + r) * m) >> 20;
+    const unsigned ng = ((w * ((cv >> 8) & 0xFFu) + g) * m) >> 20;
+    const unsigned nb = ((w * ((cv >> 16) & 0xFFu) + b) * m) >> 20;
+    return nr | (ng << 8) | (nb << 16) | ((w + 1) << 24);
 }
 
 // ColorImage::At (OC ColorImage.h:61-101)
-__device__ __forceinline__ void color_fetch(const FrameParams &fp, int row, int col, unsigned char *r, unsigned char *g, unsigned char *b)
+__device__ __forceinline__ void color_fetch(const FrameParams &fp, int pixel, unsigned *r, unsigned *g, unsigned *b)
 {
-    const uint8_t *p = fp.color + ((size_t)col + (size_t)row * fp.ccam.W) * fp.channels;
+    const uint8_t *p = fp.color + (size_t)pixel * fp.channels;          // Index(row, col, 0) = (col + row * width) * channels
     if (fp.channels >= 3)
     {
         *b = __ldg(p);
@@ -381,231 +487,556 @@ __device__ __forceinline__ void color_fetch(const FrameParams &fp, int row, int 
         *r = *g = *b = __ldg(p);
 }
 
-// Band hit on one voxel: colour first (ProjectionIntegrator.h:146-159), then distance (:161-162 / :84-85).
-template <bool COLOR_PATH>
-__device__ __forceinline__ void apply_band(const FrameParams &fp, const VoxelEval &e, float2 *dv, uchar4 *cv, bool hasColorVoxel, int *nCol)
+struct VoxelStats
 {
-    float wu = 1.0f;
-    if (COLOR_PATH)
+    int nUpd, nCarve, nCol;
+    bool updated, carvable;
+};
+
+// Per-lane terms of one 8x8x8 brick. Lane = (x = lane & 7, y sub-row = lane >> 3): the lane owns x and two y rows
+// (ly, ly + 4). The camera-space coordinates are assembled from per-axis products m0 (x), m1 (y), m2 (z):
+//   c_j = R(0,j)*d0 + (R(1,j)*d1 + R(2,j)*d2)   (Eigen order) -- bit-identical to the unhoisted form.
+struct BrickLane
+{
+    float px, pyv[2];
+    float m0[3], m1[2][3];
+    int vx, vy0, vz0;
+    float orgz;
+};
+
+__device__ __forceinline__ BrickLane brick_lane_setup(const FrameParams &fp, const DeviceMap &map, float orgx, float orgy, float orgz,
+                                                      int bx, int by, int bz, int lane)
+{
+    const CameraDev &c = fp.cam;
+    BrickLane L;
+    L.vx = bx * 8 + (lane & 7);
+    L.vy0 = by * 8 + (lane >> 3);
+    L.vz0 = bz * 8;
+    L.orgz = orgz;
+    // centre_k = float(k) * res + res/2 (ChunkManager.cpp:52,61); p = centre + origin (ProjectionIntegrator.h:64)
+    L.px = __fadd_rn(__fadd_rn(__fmul_rn((float)L.vx, map.res), map.half), orgx);
+    const float d0 = __fsub_rn(L.px, c.t[0]);
+    L.m0[0] = __fmul_rn(c.R[0], d0);
+    L.m0[1] = __fmul_rn(c.R[1], d0);
+    L.m0[2] = __fmul_rn(c.R[2], d0);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
     {
-        float cx, cy, cz, u, v;
-        to_camera(fp.ccam, e.px, e.py, e.pz, &cx, &cy, &cz);
-        if (hasColorVoxel && project_on_image(fp.ccam, cx, cy, cz, &u, &v) && cv->w < 8)
-        {
-            unsigned char r, g, b;
-            color_fetch(fp, (int)v, (int)u, &r, &g, &b);
-            if (color_integrate(cv, r, g, b))
-                (*nCol)++;
-        }
-        wu = __fdiv_rn(fp.weight, __fmul_rn(5.0f, e.trunc));            // ConstantWeighter.h:43-46
+        L.pyv[h] = __fadd_rn(__fadd_rn(__fmul_rn((float)(L.vy0 + 4 * h), map.res), map.half), orgy);
+        const float d1 = __fsub_rn(L.pyv[h], c.t[1]);
+        L.m1[h][0] = __fmul_rn(c.R[3], d1);
+        L.m1[h][1] = __fmul_rn(c.R[4], d1);
+        L.m1[h][2] = __fmul_rn(c.R[5], d1);
     }
-    *dv = dist_integrate(*dv, e.sd, wu);
+    return L;
 }
 
-// One CTA (256 threads) per work-list chunk. Thread t owns voxels t, t+256, ...: x is fixed per thread
-// (256 % CS == 0) and a warp reads/writes 32 consecutive voxels = 256 contiguous bytes of {sdf, weight}.
-template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-__global__ void __launch_bounds__(256) integrate_kernel(FrameParams fp, DeviceMap map)
+// One batch = the z pair (2q, 2q+1) of the brick x the lane's two y rows = four voxels per lane; the four depth gathers
+// and the four 8-byte state loads are issued together. Within a batch a warp touches four 64-byte row segments per z.
+//   MODE 0: existing chunk -- speculative loads of {sdf, weight} (and colour), stores only where a voxel changed
+//   MODE 1: fresh chunk    -- no loads; every voxel of the batch is written (initial or integrated value)
+//   MODE 2: test only      -- returns whether any of the lane's voxels falls inside the band (no traffic on the map)
+template <int CS, bool COLOR_PATH, bool PER_PIXEL, int MODE>
+__device__ __forceinline__ bool process_batch(const FrameParams &fp, const DeviceMap &map, const BrickLane &L, int q,
+                                              float2 *dist, unsigned *col, VoxelStats *st)
 {
-    constexpr int V = CS * CS * CS;
-    constexpr int ITER = V / 256;
-    __shared__ int sSlot;
-    __shared__ int sRed[3][8];
-    const int t = threadIdx.x;
-    const int nWork = min(map.ctr->work_count, fp.work_cap);
-    for (int w = blockIdx.x; w < nWork; w += gridDim.x)
-    {
-        const int4 item = fp.work[w];
-        int slot = item.w;
-        const bool isNew = slot < 0;
-        // origin_k = float(CS * ID_k) * res (Chunk.cpp:43); centre_k = float(k) * res + res/2 (ChunkManager.cpp:52,61)
-        const float orgx = __fmul_rn((float)(CS * item.x), map.res), orgy = __fmul_rn((float)(CS * item.y), map.res), orgz = __fmul_rn((float)(CS * item.z), map.res);
-        const int vx = t % CS;
-        const float px = __fadd_rn(__fadd_rn(__fmul_rn((float)vx, map.res), map.half), orgx);
-        int nUpd = 0, nCarve = 0, nCol = 0;
-        bool updated = false;
-
-        if (isNew)
-        {
-            // Pass 1: would ProjectionIntegrator::Integrate report an update? (carving cannot touch a fresh chunk: weight 0)
-            bool any = false;
-#pragma unroll 4
-            for (int it = 0; it < ITER; it++)
-            {
-                const int i = t + it * 256;
-                const int vy = (i / CS) % CS, vz = i / (CS * CS);
-                const float py = __fadd_rn(__fadd_rn(__fmul_rn((float)vy, map.res), map.half), orgy);
-                const float pz = __fadd_rn(__fadd_rn(__fmul_rn((float)vz, map.res), map.half), orgz);
-                any |= eval_voxel<COLOR_PATH, PER_PIXEL>(fp, px, py, pz).status == 1;
-            }
-            if (!__syncthreads_or(any))
-                continue;                                               // created-and-untouched => garbage collected (Chisel.h:102-110,170-173,202-207)
-            if (t == 0)
-            {
-                int s = atomicAdd(&map.ctr->n_chunks, 1);
-                if (s >= map.capacity)
-                {
-                    atomicOr(&map.ctr->error_flags, kErrPoolFull);
-                    atomicSub(&map.ctr->n_chunks, 1);
-                    s = -1;
-                }
-                else
-                {
-                    map.slot_ids[3 * s] = item.x;
-                    map.slot_ids[3 * s + 1] = item.y;
-                    map.slot_ids[3 * s + 2] = item.z;
-                    hash_insert_new(map, pack_id(item.x, item.y, item.z), s);
-                    atomicAdd(&map.ctr->n_new, 1);
-                }
-                sSlot = s;
-            }
-            __syncthreads();
-            slot = sSlot;
-            __syncthreads();
-            if (slot < 0)
-                continue;
-        }
-
-        float2 *dist = dist_ptr(map, slot);
-        uchar4 *col = map.use_color ? color_ptr(map, slot) : nullptr;
-#pragma unroll 4
-        for (int it = 0; it < ITER; it++)
-        {
-            const int i = t + it * 256;
-            const int vy = (i / CS) % CS, vz = i / (CS * CS);
-            const float py = __fadd_rn(__fadd_rn(__fmul_rn((float)vy, map.res), map.half), orgy);
-            const float pz = __fadd_rn(__fadd_rn(__fmul_rn((float)vz, map.res), map.half), orgz);
-            const VoxelEval e = eval_voxel<COLOR_PATH, PER_PIXEL>(fp, px, py, pz);
-            if (isNew)
-            {
-                // first write of the chunk: Chunk::Chunk initial state (DistVoxel.cpp:29-33, ColorVoxel.cpp) or the integrated value
-                float2 dv = make_float2(99999.0f, 0.0f);
-                uchar4 cv = make_uchar4(0, 0, 0, 0);
-                if (e.status == 1)
-                {
-                    apply_band<COLOR_PATH>(fp, e, &dv, &cv, col != nullptr, &nCol);
-                    nUpd++;
-                    updated = true;
-                }
-                dist[i] = dv;
-                if (col)
-                    col[i] = cv;
-            }
-            else if (e.status == 1)
-            {
-                float2 dv = dist[i];
-                uchar4 cv = make_uchar4(0, 0, 0, 0);
-                const int colBefore = nCol;
-                if (COLOR_PATH && col)
-                    cv = col[i];
-                apply_band<COLOR_PATH>(fp, e, &dv, &cv, col != nullptr, &nCol);
-                dist[i] = dv;
-                if (COLOR_PATH && nCol != colBefore)
-                    col[i] = cv;
-                nUpd++;
-                updated = true;
-            }
-            else if (e.status == 2)
-            {
-                float2 dv = dist[i];
-                if (dv.y > 0.0f && dv.x < fp.sdf_carve_max)             // weight > 0 && sdf < 1e-5 (:90 / :169)
-                {
-                    if (COLOR_PATH && !(dv.y < 5.0f))
-                        dv.y = __fsub_rn(dv.y, 1.0f);                   // :171-175
-                    else
-                        dv = make_float2(99999.0f, 0.0f);               // DistVoxel::Carve -> Reset
-                    dist[i] = dv;
-                    nCarve++;
-                    updated = true;
-                }
-            }
-        }
-
-        // block reduction of the counters and of the chunk's `updated` flag
-        const unsigned lane = t & 31, warp = t >> 5;
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            nUpd += __shfl_xor_sync(0xffffffffu, nUpd, o);
-            nCarve += __shfl_xor_sync(0xffffffffu, nCarve, o);
-            nCol += __shfl_xor_sync(0xffffffffu, nCol, o);
-        }
-        if (lane == 0)
-        {
-            sRed[0][warp] = nUpd;
-            sRed[1][warp] = nCarve;
-            sRed[2][warp] = nCol;
-        }
-        const bool anyUpdated = __syncthreads_or(updated);
-        if (t < 3)
-        {
-            int s = 0;
+    const CameraDev &c = fp.cam;
+    float pzv[2], m2[2][3];
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                s += sRed[t][k];
-            if (s)
-                atomicAdd(t == 0 ? &map.ctr->n_upd : (t == 1 ? &map.ctr->n_carve : &map.ctr->n_col), (unsigned long long)s);
-        }
-        if (anyUpdated)
+    for (int s = 0; s < 2; s++)
+    {
+        pzv[s] = __fadd_rn(__fadd_rn(__fmul_rn((float)(L.vz0 + 2 * q + s), map.res), map.half), L.orgz);
+        const float d2 = __fsub_rn(pzv[s], c.t[2]);
+        m2[s][0] = __fmul_rn(c.R[6], d2);
+        m2[s][1] = __fmul_rn(c.R[7], d2);
+        m2[s][2] = __fmul_rn(c.R[8], d2);
+    }
+    int pix[4], idx[4];
+    float cz[4], depth[4], trunc[4];
+    float2 dv[4];
+    unsigned cv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const int s = k >> 1, h = k & 1;
+        const float cx = __fadd_rn(L.m0[0], __fadd_rn(L.m1[h][0], m2[s][0]));
+        const float cy = __fadd_rn(L.m0[1], __fadd_rn(L.m1[h][1], m2[s][1]));
+        cz[k] = __fadd_rn(L.m0[2], __fadd_rn(L.m1[h][2], m2[s][2]));
+        // PinholeCamera::ProjectPoint + IsPointOnImage (PinholeCamera.cpp:38-45, 61-64); __frcp_rn is the correctly
+        // rounded reciprocal, i.e. exactly 1.0f / z
+        const float invZ = __frcp_rn(cz[k]);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, cx), invZ), c.cx);
+        const float v = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, cy), invZ), c.cy);
+        const bool on = u >= 0.0f && v >= 0.0f && u < c.Wf && v < c.Hf && !(cz[k] < 0.0f);      // ProjectionIntegrator.h:68 / :125
+        pix[k] = on ? (int)u + (int)v * c.W : -1;
+        idx[k] = ((L.vz0 + 2 * q + s) * CS + (L.vy0 + 4 * h)) * CS + L.vx;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        depth[k] = pix[k] >= 0 ? __ldg(fp.depth + pix[k]) : __int_as_float(0x7fc00000);
+        trunc[k] = PER_PIXEL ? (pix[k] >= 0 ? __ldg(fp.trunc_img + pix[k]) : 0.0f) : fp.trunc_param;
+        if (MODE == 0)
         {
-            // all 27 neighbour IDs become dirty, whether or not they exist (Chisel.h:89-101, 175-189)
-            if (t >= 32 && t < 32 + 27)
+            dv[k] = dist[idx[k]];
+            if (COLOR_PATH && col)
+                cv[k] = col[idx[k]];
+        }
+        else
+        {
+            dv[k] = make_float2(99999.0f, 0.0f);           // Chunk::Chunk initial state (DistVoxel.cpp:29-33)
+            cv[k] = 0u;
+        }
+    }
+    bool anyHit = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const float d = depth[k];
+        int status = 0;                                     // 1 band, 2 carve candidate
+        float sd = 0.0f;
+        // depth path: skip depth > 50 (:74); colour path: skip NaN (:134) and depth > 100 (:141). Off-image voxels have pix < 0.
+        const bool skip = (pix[k] < 0) || (COLOR_PATH ? (d != d || d > 100.0f) : (d > 50.0f));
+        if (!skip)
+        {
+            sd = __fsub_rn(d, cz[k]);
+            if (fabsf(sd) < __fadd_rn(trunc[k], fp.diag))                        // :82 / :143
+                status = 1;
+            else if (fp.carve && sd > __fadd_rn(trunc[k], fp.carve_dist))        // :88 / :166
+                status = 2;
+        }
+        if (MODE == 2)
+        {
+            anyHit |= status == 1;
+            continue;
+        }
+        bool wroteDist = false, wroteCol = false;
+        if (status == 1)
+        {
+            float wu = 1.0f;                                                      // the depth path ignores the weighter (Q7)
+            if (COLOR_PATH)
             {
-                const int k = t - 32;
-                dirty_insert(map, pack_id(item.x + k / 9 - 1, item.y + (k / 3) % 3 - 1, item.z + k % 3 - 1));
+                if (col)
+                {
+                    // colour first (:146-159)
+                    bool onC = true;
+                    int cpix = pix[k];
+                    if (!fp.same_cam)
+                    {
+                        const int s = k >> 1, h = k & 1;
+                        float ccx, ccy, ccz, cu, cvv;
+                        to_camera(fp.ccam, L.px, L.pyv[h], pzv[s], &ccx, &ccy, &ccz);
+                        onC = project_on_image(fp.ccam, ccx, ccy, ccz, &cu, &cvv);
+                        cpix = (int)cu + (int)cvv * fp.ccam.W;
+                    }
+                    if (onC && (cv[k] >> 24) < 8u)                                // ProjectionIntegrator.h:153
+                    {
+                        unsigned r, g, b;
+                        color_fetch(fp, cpix, &r, &g, &b);
+                        cv[k] = color_integrate_packed(cv[k], r, g, b);
+                        wroteCol = true;
+                    }
+                }
+                wu = PER_PIXEL ? __fdiv_rn(fp.weight, __fmul_rn(5.0f, trunc[k])) : fp.wu_const;   // ConstantWeighter.h:43-46
             }
-            if (t == 64)
-                atomicAdd(&map.ctr->updated_chunks, 1);
+            dv[k] = dist_integrate(dv[k], sd, wu);
+            wroteDist = true;
+            st->nUpd++;
+            st->nCol += wroteCol;
+        }
+        else if (MODE == 0 && status == 2)
+        {
+            if (dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max)                     // weight > 0 && sdf < 1e-5 (:90 / :169)
+            {
+                if (COLOR_PATH && !(dv[k].y < 5.0f))
+                    dv[k].y = __fsub_rn(dv[k].y, 1.0f);                           // :171-175
+                else
+                    dv[k] = make_float2(99999.0f, 0.0f);                          // DistVoxel::Carve -> Reset
+                wroteDist = true;
+                st->nCarve++;
+            }
+        }
+        if (wroteDist)
+        {
+            st->updated = true;
+            st->carvable |= dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max;
+        }
+        if (MODE == 1 || wroteDist)
+            dist[idx[k]] = dv[k];
+        if (col && (MODE == 1 || wroteCol))
+            col[idx[k]] = cv[k];
+    }
+    return anyHit;
+}
+
+// Chunk `slot` changed this frame: the FIRST warp to say so marks all 27 neighbour IDs dirty, whether or not they exist
+// (Chisel.h:89-101, 175-189), and counts the chunk. slot_epoch[slot] holds the id of the last frame that updated it.
+__device__ __forceinline__ void mark_chunk_updated(const FrameParams &fp, const DeviceMap &map, int slot, int x, int y, int z, int lane)
+{
+    int first = 0;
+    if (lane == 0)
+        first = atomicExch(&map.slot_epoch[slot], fp.frame_id) != fp.frame_id;
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first)
+    {
+        if (lane < 27)
+            dirty_insert(map, pack_id(x + lane / 9 - 1, y + (lane / 3) % 3 - 1, z + lane % 3 - 1));
+        if (lane == 31)
+            atomicAdd(&map.ctr->updated_chunks, 1);
+    }
+}
+
+// Block-level flush of the per-lane counters (one set of global atomics per CTA, spread over kCounterSlots addresses).
+__device__ __forceinline__ void flush_counters(const DeviceMap &map, const VoxelStats &st, int *sCnt)
+{
+    int a = st.nUpd, b = st.nCarve, c = st.nCol;
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (a) atomicAdd(&sCnt[0], a);
+        if (b) atomicAdd(&sCnt[1], b);
+        if (c) atomicAdd(&sCnt[2], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && sCnt[threadIdx.x])
+    {
+        unsigned long long *dst = threadIdx.x == 0 ? map.ctr->n_upd : (threadIdx.x == 1 ? map.ctr->n_carve : map.ctr->n_col);
+        atomicAdd(&dst[blockIdx.x % kCounterSlots], (unsigned long long)sCnt[threadIdx.x]);
+    }
+}
+
+// Existing chunks: one warp per half brick (8 x 8 x 4 voxels = two batches); no block-level synchronisation in the loop.
+// The grid is sized to what is resident at once and strides over the unit list, whose length only the device knows.
+template <int CS, bool COLOR_PATH, bool PER_PIXEL>
+__global__ void __launch_bounds__(256, 3) integrate_bricks_kernel(FrameParams fp, DeviceMap map)
+{
+    constexpr int BPA = CS / 8;
+    __shared__ int sCnt[3];
+    if (threadIdx.x < 3)
+        sCnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nTasks = min(map.ctr->unit_count, fp.units_cap) * 2;
+    VoxelStats st;
+    st.nUpd = st.nCarve = st.nCol = 0;
+    for (int g = blockIdx.x * 8 + (threadIdx.x >> 5); g < nTasks; g += gridDim.x * 8)
+    {
+        const int4 unit = fp.units[g >> 1];
+        const int slot = unit.w & 0xFFFFFF, b = unit.w >> 24;
+        // origin_k = float(CS * ID_k) * res (Chunk.cpp:43)
+        const float orgx = __fmul_rn((float)(CS * unit.x), map.res), orgy = __fmul_rn((float)(CS * unit.y), map.res), orgz = __fmul_rn((float)(CS * unit.z), map.res);
+        const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, b % BPA, (b / BPA) % BPA, b / (BPA * BPA), lane);
+        float2 *dist = dist_ptr(map, slot);
+        unsigned *col = map.use_color ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
+        st.updated = st.carvable = false;
+        process_batch<CS, COLOR_PATH, PER_PIXEL, 0>(fp, map, L, (g & 1) * 2, dist, col, &st);
+        process_batch<CS, COLOR_PATH, PER_PIXEL, 0>(fp, map, L, (g & 1) * 2 + 1, dist, col, &st);
+        if (__any_sync(0xffffffffu, st.carvable) && lane == 0)
+            atomicOr(&map.brick_flags[slot], 1ull << b);
+        if (__any_sync(0xffffffffu, st.updated))
+            mark_chunk_updated(fp, map, slot, unit.x, unit.y, unit.z, lane);
+    }
+    flush_counters(map, st, sCnt);
+}
+
+// New chunks: one CTA per candidate, a warp per brick (CS = 32: eight bricks per warp; CS = 8: warp 0 only). The chunk
+// is materialised only if the exact test finds a band hit: "created and untouched => garbage collected"
+// (Chisel.h:76-80,102-110 / :133-143,170-173,202-207) never allocates anything.
+template <int CS, bool COLOR_PATH, bool PER_PIXEL>
+__global__ void __launch_bounds__(256) integrate_new_chunks_kernel(FrameParams fp, DeviceMap map)
+{
+    constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
+    __shared__ int sCnt[3];
+    __shared__ int sSlotMem;
+    int *sSlot = &sSlotMem;
+    const int nBlocks = gridDim.x;
+    if (threadIdx.x < 3)
+        sCnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nWarps = blockDim.x >> 5;
+    const int nNew = min(map.ctr->new_count, fp.news_cap);
+    VoxelStats st;
+    st.nUpd = st.nCarve = st.nCol = 0;
+    for (int w = blockIdx.x; w < nNew; w += nBlocks)
+    {
+        const int4 item = fp.news[w];
+        const float orgx = __fmul_rn((float)(CS * item.x), map.res), orgy = __fmul_rn((float)(CS * item.y), map.res), orgz = __fmul_rn((float)(CS * item.z), map.res);
+        // Would ProjectionIntegrator::Integrate[Color] report an update? (carving cannot touch a fresh chunk: weight 0)
+        bool any = false;
+        for (int b = warp; b < NB && !any; b += nWarps)
+        {
+            const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
+            if (NB > 1 && classify_box(fp, orgx + (float)(bx * 8) * map.res + map.half, orgy + (float)(by * 8) * map.res + map.half,
+                                       orgz + (float)(bz * 8) * map.res + map.half, 7.0f * map.res) != 2)
+                continue;
+            const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, bx, by, bz, lane);
+            // all four batches in one basic block: the 16 depth gathers of the lane are in flight together
+            bool hit = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                hit |= process_batch<CS, COLOR_PATH, PER_PIXEL, 2>(fp, map, L, q, nullptr, nullptr, &st);
+            any = __any_sync(0xffffffffu, hit);
+        }
+        if (!__syncthreads_or(any))
+            continue;
+        if (t == 0)
+        {
+            int s = atomicAdd(&map.ctr->n_chunks, 1);
+            if (s >= map.capacity)
+            {
+                atomicOr(&map.ctr->error_flags, kErrPoolFull);
+                atomicSub(&map.ctr->n_chunks, 1);
+                s = -1;
+            }
+            else
+            {
+                map.slot_ids[3 * s] = item.x;
+                map.slot_ids[3 * s + 1] = item.y;
+                map.slot_ids[3 * s + 2] = item.z;
+                map.brick_flags[s] = 0ull;
+                map.slot_epoch[s] = 0;
+                hash_insert_new(map, pack_id(item.x, item.y, item.z), s);
+                atomicAdd(&map.ctr->n_new, 1);
+            }
+            *sSlot = s;
         }
         __syncthreads();
+        const int slot = *sSlot;
+        __syncthreads();
+        if (slot < 0)
+            continue;
+        float2 *dist = dist_ptr(map, slot);
+        unsigned *col = map.use_color ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
+        for (int b = warp; b < NB; b += nWarps)
+        {
+            const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, b % BPA, (b / BPA) % BPA, b / (BPA * BPA), lane);
+            st.updated = st.carvable = false;
+            for (int q = 0; q < 4; q++)
+                process_batch<CS, COLOR_PATH, PER_PIXEL, 1>(fp, map, L, q, dist, col, &st);
+            if (__any_sync(0xffffffffu, st.carvable) && lane == 0)
+                atomicOr(&map.brick_flags[slot], 1ull << b);
+        }
+        __syncthreads();                                                // brick_flags / slot_epoch initialisation vs. the marking below
+        if (warp == 0)
+            mark_chunk_updated(fp, map, slot, item.x, item.y, item.z, lane);
     }
+    flush_counters(map, st, sCnt);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // host launchers
 
-template <int CS>
-static void launch_integrate_cs(const FrameParams &fp, const DeviceMap &map, int grid, cudaStream_t st)
+template <typename K>
+static int resident_blocks(K kernel, int threads)
 {
-    const bool pp = fp.trunc_img != nullptr;
-    if (fp.color_path)
+    int dev = 0, sms = 148, perSm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0);
+    return sms * (perSm > 0 ? perSm : 1);
+}
+
+// Copies the counters to a slot of the pinned host ring when the frame's kernels are done. The host learns what a
+// frame did (chunk count for capacity planning, statistics) without a memcpy, an event or a synchronisation.
+__global__ void snapshot_kernel(DeviceMap map, Counters *hostSlot, int frameId)
+{
+    const int n = (int)(sizeof(Counters) / sizeof(int));
+    const int *src = reinterpret_cast<const int *>(map.ctr);
+    int *dst = reinterpret_cast<int *>(hostSlot);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (i != (int)(offsetof(Counters, frame_id) / sizeof(int)))
+            dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        *reinterpret_cast<volatile int *>(&hostSlot->frame_id) = frameId;
+        __threadfence_system();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The per-frame work as a CUDA graph:
+//     frame_prepare -> chunk_candidates -> { integrate_new_chunks || integrate_bricks } -> snapshot
+// built once per kernel variant; every frame only the kernel arguments and grid sizes are patched
+// (cudaGraphExecKernelNodeSetParams) and the graph is launched once. The profiling variant serialises the two integrate
+// kernels and brackets every kernel with event-record nodes.
+struct FrameGraphVariant
+{
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t nPrepare = nullptr, nCand = nullptr, nNew = nullptr, nBricks = nullptr, nSnap = nullptr;
+    void *fPrepare = nullptr, *fCand = nullptr, *fNew = nullptr, *fBricks = nullptr;
+    int newResident = 1, brickResident = 1;
+};
+
+struct FrameGraph
+{
+    FrameGraphVariant v[8];   // index = color_path | per_pixel << 1 | profiling << 2
+};
+
+template <int CS, bool COLOR_PATH, bool PER_PIXEL>
+static void variant_functions(FrameGraphVariant *g)
+{
+    g->fPrepare = (void *)frame_prepare_kernel;
+    g->fCand = (void *)chunk_candidates_kernel<CS>;
+    g->fNew = (void *)integrate_new_chunks_kernel<CS, COLOR_PATH, PER_PIXEL>;
+    g->fBricks = (void *)integrate_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>;
+    g->newResident = resident_blocks(integrate_new_chunks_kernel<CS, COLOR_PATH, PER_PIXEL>, 256);
+    g->brickResident = resident_blocks(integrate_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, 256);
+}
+
+template <int CS>
+static void variant_functions_cs(FrameGraphVariant *g, bool color, bool pp)
+{
+    if (color)
     {
         if (pp)
-            integrate_kernel<CS, true, true><<<grid, 256, 0, st>>>(fp, map);
+            variant_functions<CS, true, true>(g);
         else
-            integrate_kernel<CS, true, false><<<grid, 256, 0, st>>>(fp, map);
+            variant_functions<CS, true, false>(g);
     }
     else
     {
         if (pp)
-            integrate_kernel<CS, false, true><<<grid, 256, 0, st>>>(fp, map);
+            variant_functions<CS, false, true>(g);
         else
-            integrate_kernel<CS, false, false><<<grid, 256, 0, st>>>(fp, map);
+            variant_functions<CS, false, false>(g);
     }
 }
 
-void launch_frame_prepare(const FrameParams &fp, const DeviceMap &map, cudaStream_t st)
-{
-    dim3 grid((fp.cam.W + 63) / 64, (fp.cam.H + 63) / 64);
-    frame_prepare_kernel<<<grid, 256, 0, st>>>(fp, map);
-}
+FrameGraph *frame_graph_create() { return new FrameGraph(); }
 
-void launch_chunk_candidates(const FrameParams &fp, const DeviceMap &map, cudaStream_t st)
+void frame_graph_destroy(FrameGraph *fg)
 {
-    const int total = fp.n[0] * fp.n[1] * fp.n[2];
-    if (total <= 0)
+    if (!fg)
         return;
-    chunk_candidates_kernel<<<(total + 255) / 256, 256, 0, st>>>(fp, map);
+    for (FrameGraphVariant &g : fg->v)
+    {
+        if (g.exec)
+            cudaGraphExecDestroy(g.exec);
+        if (g.graph)
+            cudaGraphDestroy(g.graph);
+    }
+    delete fg;
 }
 
-void launch_integrate(const FrameParams &fp, const DeviceMap &map, int grid, cudaStream_t st)
+static cudaKernelNodeParams kernel_params(void *func, dim3 grid, dim3 block, void **args)
 {
-    switch (map.cs)
+    cudaKernelNodeParams p{};
+    p.func = func;
+    p.gridDim = grid;
+    p.blockDim = block;
+    p.sharedMemBytes = 0;
+    p.kernelParams = args;
+    p.extra = nullptr;
+    return p;
+}
+
+// events: [0] before prepare, [1] after prepare, [2] after candidates, [7] after new chunks, [3] after bricks (profiling only)
+cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const DeviceMap &mapIn, long long candidates, Counters *hostSlot,
+                               bool profiling, cudaEvent_t *evt, cudaStream_t st)
+{
+    FrameParams fp = fpIn;
+    DeviceMap map = mapIn;
+    int frameId = fp.frame_id;
+    const bool pp = fp.trunc_img != nullptr;
+    FrameGraphVariant &g = fg->v[(fp.color_path ? 1 : 0) | (pp ? 2 : 0) | (profiling ? 4 : 0)];
+    const int total = fp.n[0] * fp.n[1] * fp.n[2];
+    const long long nb = (long long)(map.cs / 8) * (map.cs / 8) * (map.cs / 8);
+    void *argsFrame[2] = {&fp, &map};
+    void *argsSnap[3] = {&map, &hostSlot, &frameId};
+    cudaError_t e;
+    const bool build = g.exec == nullptr;
+    if (build)
     {
-    case 8: launch_integrate_cs<8>(fp, map, grid, st); break;
-    case 16: launch_integrate_cs<16>(fp, map, grid, st); break;
-    case 32: launch_integrate_cs<32>(fp, map, grid, st); break;
-    default: break;
+        switch (map.cs)
+        {
+        case 8: variant_functions_cs<8>(&g, fp.color_path != 0, pp); break;
+        case 16: variant_functions_cs<16>(&g, fp.color_path != 0, pp); break;
+        default: variant_functions_cs<32>(&g, fp.color_path != 0, pp); break;
+        }
     }
+    const dim3 gPrepare((fp.cam.W + 63) / 64, (fp.cam.H + 63) / 64);
+    const dim3 gCand((unsigned)std::max(1, (total + 63) / 64));
+    const dim3 gNew((unsigned)std::max(1ll, std::min<long long>(candidates, g.newResident)));
+    const dim3 gBricks((unsigned)std::max(1ll, std::min<long long>((candidates * nb * 2 + 7) / 8, g.brickResident)));
+    cudaKernelNodeParams pPrepare = kernel_params(g.fPrepare, gPrepare, dim3(256), argsFrame);
+    cudaKernelNodeParams pCand = kernel_params(g.fCand, gCand, dim3(64), argsFrame);
+    cudaKernelNodeParams pNew = kernel_params(g.fNew, gNew, dim3(256), argsFrame);
+    cudaKernelNodeParams pBricks = kernel_params(g.fBricks, gBricks, dim3(256), argsFrame);
+    cudaKernelNodeParams pSnap = kernel_params((void *)snapshot_kernel, dim3(1), dim3(128), argsSnap);
+    if (build)
+    {
+        if ((e = cudaGraphCreate(&g.graph, 0)) != cudaSuccess)
+            return e;
+        cudaGraphNode_t prev = nullptr, ev;
+        auto addEvent = [&](cudaEvent_t event) -> cudaError_t {
+            cudaError_t r = cudaGraphAddEventRecordNode(&ev, g.graph, prev ? &prev : nullptr, prev ? 1 : 0, event);
+            prev = ev;
+            return r;
+        };
+        if (profiling && (e = addEvent(evt[0])) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphAddKernelNode(&g.nPrepare, g.graph, prev ? &prev : nullptr, prev ? 1 : 0, &pPrepare)) != cudaSuccess)
+            return e;
+        prev = g.nPrepare;
+        if (profiling && (e = addEvent(evt[1])) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphAddKernelNode(&g.nCand, g.graph, &prev, 1, &pCand)) != cudaSuccess)
+            return e;
+        prev = g.nCand;
+        if (profiling)
+        {
+            // serial: candidates -> e2 -> new -> e7 -> bricks -> e3 -> snapshot
+            if ((e = addEvent(evt[2])) != cudaSuccess)
+                return e;
+            if ((e = cudaGraphAddKernelNode(&g.nNew, g.graph, &prev, 1, &pNew)) != cudaSuccess)
+                return e;
+            prev = g.nNew;
+            if ((e = addEvent(evt[7])) != cudaSuccess)
+                return e;
+            if ((e = cudaGraphAddKernelNode(&g.nBricks, g.graph, &prev, 1, &pBricks)) != cudaSuccess)
+                return e;
+            prev = g.nBricks;
+            if ((e = addEvent(evt[3])) != cudaSuccess)
+                return e;
+            if ((e = cudaGraphAddKernelNode(&g.nSnap, g.graph, &prev, 1, &pSnap)) != cudaSuccess)
+                return e;
+        }
+        else
+        {
+            // the two integrate kernels touch disjoint chunks: parallel branches
+            if ((e = cudaGraphAddKernelNode(&g.nNew, g.graph, &prev, 1, &pNew)) != cudaSuccess)
+                return e;
+            if ((e = cudaGraphAddKernelNode(&g.nBricks, g.graph, &prev, 1, &pBricks)) != cudaSuccess)
+                return e;
+            cudaGraphNode_t deps[2] = {g.nNew, g.nBricks};
+            if ((e = cudaGraphAddKernelNode(&g.nSnap, g.graph, deps, 2, &pSnap)) != cudaSuccess)
+                return e;
+        }
+        if ((e = cudaGraphInstantiate(&g.exec, g.graph, 0)) != cudaSuccess)
+            return e;
+    }
+    else
+    {
+        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nPrepare, &pPrepare)) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nCand, &pCand)) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nNew, &pNew)) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nBricks, &pBricks)) != cudaSuccess)
+            return e;
+        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nSnap, &pSnap)) != cudaSuccess)
+            return e;
+    }
+    return cudaGraphLaunch(g.exec, st);
 }
 
 float host_truncation(int kind, float param, float depth) { return truncation_of(kind, param, depth); }

@@ -9,9 +9,12 @@
 namespace chs
 {
 
-void launch_frame_prepare(const FrameParams &fp, const DeviceMap &map, cudaStream_t st);
-void launch_chunk_candidates(const FrameParams &fp, const DeviceMap &map, cudaStream_t st);
-void launch_integrate(const FrameParams &fp, const DeviceMap &map, int grid, cudaStream_t st);
+struct FrameGraph;
+FrameGraph *frame_graph_create();
+void frame_graph_destroy(FrameGraph *fg);
+// Enqueue one frame (prepare -> candidates -> {new chunks || bricks} -> counter snapshot into hostSlot) as one graph launch.
+cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fp, const DeviceMap &map, long long candidates, Counters *hostSlot,
+                               bool profiling, cudaEvent_t *evt, cudaStream_t st);
 float host_truncation(int kind, float param, float depth);
 
 // table maintenance (capi.cu)

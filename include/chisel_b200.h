@@ -85,7 +85,8 @@ typedef struct
 typedef struct
 {
     int64_t candidates;          /* chunk IDs the reference would iterate (box passing Frustum::Intersects), owned by this rank */
-    int64_t processed_chunks;    /* candidates that survived the conservative depth-range cull */
+    int64_t new_candidates;      /* non-existing candidates that survived the conservative depth-range cull (tested exactly) */
+    int64_t brick_units;         /* 8^3 bricks of existing chunks that survived the cull (each visited once) */
     int64_t n_upd;               /* voxels on which DistVoxel::Integrate ran */
     int64_t n_carve;             /* voxels reset or decremented by carving */
     int64_t n_col;               /* voxels whose colour was written */
@@ -108,7 +109,7 @@ typedef struct
  * (recorded only while profiling is enabled; chs_get_timings synchronises). Milliseconds. */
 typedef struct
 {
-    float prepare_ms, candidates_ms, integrate_ms, frame_ms;
+    float prepare_ms, candidates_ms, new_chunks_ms, integrate_ms, frame_ms;   /* integrate_ms: the brick kernel (existing chunks) */
     float mesh_count_ms, mesh_emit_ms, mesh_ms;
 } chs_timings;
 

@@ -92,3 +92,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dp, f)).read()
                 assert not bad.search(text), os.path.join(dp, f)
+
+
+def test_color_integrate_integer_identity():
+    """The CUDA kernel evaluates ColorVoxel::Integrate (ColorVoxel.h:65-85) in integer arithmetic. Exhaustive proof that
+    (N * ceil(2^20 / D)) >> 20 equals the reference's uint8(saturate(float(w*old + new) / float(w + 1))) in binary32 for
+    every colour weight the integrator lets through (w < 8, ProjectionIntegrator.h:153) and every old / new byte."""
+    recip = np.array([0, 1048576, 524288, 349526, 262144, 209716, 174763, 149797, 131072], np.uint64)
+    for d in range(1, 9):
+        assert recip[d] == -(-(1 << 20) // d)
+    old = np.arange(256, dtype=np.float32)[:, None]
+    new = np.arange(256, dtype=np.float32)[None, :]
+    for w in range(8):
+        wf = np.float32(w)
+        ref = np.clip((wf * old + new) / np.float32(w + 1), np.float32(0), np.float32(255)).astype(np.uint8)
+        n = (w * np.arange(256, dtype=np.uint64)[:, None] + np.arange(256, dtype=np.uint64)[None, :])
+        got = ((n * recip[w + 1]) >> np.uint64(20)).astype(np.uint8)
+        assert np.array_equal(ref, got), w
