@@ -69,7 +69,7 @@ EXPORTS = (
     "chs_last_error_string", "chs_abi_version", "chs_create", "chs_destroy", "chs_reset", "chs_synchronize",
     "chs_set_stream", "chs_set_profiling", "chs_integrate_depth", "chs_integrate_depth_color", "chs_get_frame_stats",
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
-    "chs_chunk_ids", "chs_download_chunk", "chs_download_all", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
+    "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner",
 )
 
@@ -103,6 +103,7 @@ def load_library(build_if_missing: bool = True):
     lib.chs_download_meshes.argtypes = [vp] + [vp] * 7
     lib.chs_num_chunks.argtypes = [vp, C.POINTER(i64)]
     lib.chs_chunk_ids.argtypes = [vp, vp, i64]
+    lib.chs_has_chunk.argtypes = [vp, vp, C.POINTER(i32)]
     lib.chs_download_chunk.argtypes = [vp, vp, vp, vp, vp]
     lib.chs_download_all.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.chs_num_dirty.argtypes = [vp, C.POINTER(i64)]
@@ -193,13 +194,10 @@ class ChunkManager:
         return out
 
     def has_chunk(self, cid) -> bool:
-        try:
-            self.get_chunk(cid, want_color=False)
-            return True
-        except ChiselError as e:
-            if e.code == CHS_ERR_NOT_FOUND:
-                return False
-            raise
+        found = C.c_int()
+        cid = np.ascontiguousarray(cid, np.int32)
+        _check(self._o._lib.chs_has_chunk(self._o._h, _ptr(cid), C.byref(found)))
+        return bool(found.value)
 
     def get_chunk(self, cid, want_color=True):
         V = self._o.chunk ** 3

@@ -847,6 +847,22 @@ int chs_chunk_ids(chs_map *m, int32_t *ids, int64_t cap)
     return CHS_OK;
 }
 
+int chs_has_chunk(chs_map *m, const int32_t id[3], int *found)
+{
+    if (!m || !id || !found)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    *found = 0;
+    if (id[0] < -kIdBias || id[0] >= kIdBias || id[1] < -kIdBias || id[1] >= kIdBias || id[2] < -kIdBias || id[2] >= kIdBias)
+        return CHS_OK;
+    *found = m->hostIndex.find(pack_id(id[0], id[1], id[2])) != m->hostIndex.end() ? 1 : 0;
+    return CHS_OK;
+}
+
 static int download_slot(chs_map *m, int slot, float *sdf, float *weight, uint8_t *rgbw)
 {
     const int V = m->dm.V;

@@ -1,0 +1,161 @@
+// open_chisel/Chisel.h -- drop-in facade of chisel::Chisel (OC/include/open_chisel/Chisel.h:37-229, OC/src/Chisel.cpp) over
+// libchisel_b200. Source compatible with the calls chisel_ros makes (CR/src/ChiselServer.cpp:189-200, 495-525, 346, 554,
+// 721, 729-737): swap the include path, link -lchisel_b200, nothing else changes.
+//
+// Semantics kept: UpdateMeshes re-meshes on every 10th call only (Chisel.cpp:50-59; counter per instance instead of
+// process-global, quirk Q4); every new-and-untouched chunk is garbage collected (the deterministic reading of quirk Q2).
+// Not kept: the reference's printf chatter and its per-frame PrintMemoryStatistics scan (Chisel.h:62,109-111).
+#ifndef CHISEL_B200_CHISEL_H_
+#define CHISEL_B200_CHISEL_H_
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+#include <chisel_b200.h>
+#include <open_chisel/ChunkManager.h>
+#include <open_chisel/ProjectionIntegrator.h>
+#include <open_chisel/camera/ColorImage.h>
+#include <open_chisel/camera/DepthImage.h>
+#include <open_chisel/camera/PinholeCamera.h>
+#include <open_chisel/geometry/Frustum.h>
+#include <open_chisel/geometry/Geometry.h>
+#include <open_chisel/io/PLY.h>
+#include <open_chisel/pointcloud/PointCloud.h>
+
+namespace chisel
+{
+class Chisel
+{
+  public:
+    Chisel() : updateCalls(0), dirtyVersion(-1) {}
+    Chisel(const Eigen::Vector3i &chunkSize, float voxelResolution, bool useColor) : chunkManager(chunkSize, voxelResolution, useColor), updateCalls(0), dirtyVersion(-1) {}
+    // multi-GPU / explicit-stream variant (not in the reference): this instance keeps the chunk IDs it owns
+    Chisel(const Eigen::Vector3i &chunkSize, float voxelResolution, bool useColor, int device, int rank, int world, void *stream = nullptr)
+        : chunkManager(chunkSize, voxelResolution, useColor, device, rank, world, stream), updateCalls(0), dirtyVersion(-1)
+    {
+    }
+    virtual ~Chisel() {}
+
+    const ChunkManager &GetChunkManager() const { return chunkManager; }
+    ChunkManager &GetMutableChunkManager() { return chunkManager; }
+    void SetChunkManager(const ChunkManager &manager) { chunkManager = manager; }
+
+    template <class DataType>
+    void IntegrateDepthScan(const ProjectionIntegrator &integrator, const std::shared_ptr<const DepthImage<DataType>> &depthImage, const Transform &extrinsic,
+                            const PinholeCamera &camera)
+    {
+        const chs_integrator integ = integrator.ToC(*depthImage, &truncScratch);
+        const chs_camera cam = camera.ToC();
+        float pose[12];
+        b200::PoseToArray(extrinsic, pose);
+        b200::Check(chs_integrate_depth(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam), "chs_integrate_depth");
+        chunkManager.Touch();
+    }
+
+    template <class DataType, class ColorType>
+    void IntegrateDepthScanColor(const ProjectionIntegrator &integrator, const std::shared_ptr<const DepthImage<DataType>> &depthImage, const Transform &depthExtrinsic,
+                                 const PinholeCamera &depthCamera, const std::shared_ptr<const ColorImage<ColorType>> &colorImage, const Transform &colorExtrinsic,
+                                 const PinholeCamera &colorCamera)
+    {
+        static_assert(sizeof(ColorType) == 1, "8-bit colour images only (the reference instantiates <float, uint8_t>, CR ChiselServer.h:50-51)");
+        const chs_integrator integ = integrator.ToC(*depthImage, &truncScratch);
+        const chs_camera cam = depthCamera.ToC(), ccam = colorCamera.ToC();
+        float pose[12], cpose[12];
+        b200::PoseToArray(depthExtrinsic, pose);
+        b200::PoseToArray(colorExtrinsic, cpose);
+        b200::Check(chs_integrate_depth_color(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam,
+                                              reinterpret_cast<const uint8_t *>(colorImage->GetData()), static_cast<int>(colorImage->GetNumChannels()), cpose, &ccam),
+                    "chs_integrate_depth_color");
+        chunkManager.Touch();
+    }
+
+    // The point-cloud fusion mode (Chisel.cpp:107-157) is outside the hot path this library accelerates.
+    void IntegratePointCloud(const ProjectionIntegrator &, const PointCloud &, const Transform &, float, float)
+    {
+        std::fprintf(stderr, "chisel_b200: IntegratePointCloud is not implemented (fusion_mode=DepthImage is the supported mode)\n");
+    }
+
+    void GarbageCollect(const ChunkIDList &) {}     // untouched new chunks are never materialised on the device
+
+    // Chisel.cpp:50-59: re-mesh the dirty set on calls 1, 11, 21, ...; dirty IDs accumulate in between.
+    void UpdateMeshes()
+    {
+        if (updateCalls++ % 10 == 0)
+        {
+            chunkManager.RecomputeDirtyMeshes();
+            meshesToUpdate.clear();
+            dirtyVersion = -1;
+        }
+    }
+
+    bool SaveAllMeshesToPLY(const std::string &filename)
+    {
+        // Chisel.cpp:69-105: concatenate every chunk mesh, indices 0..n-1
+        MeshPtr full = std::make_shared<Mesh>();
+        size_t v = 0;
+        for (const std::pair<const ChunkID, MeshPtr> &it : chunkManager.GetAllMeshes())
+        {
+            for (const Vec3 &vert : it.second->vertices)
+            {
+                full->vertices.push_back(vert);
+                full->indices.push_back(v++);
+            }
+            for (const Vec3 &c : it.second->colors)
+                full->colors.push_back(c);
+            for (const Vec3 &n : it.second->normals)
+                full->normals.push_back(n);
+        }
+        return SaveMeshPLYASCII(filename, full);
+    }
+
+    void Reset()
+    {
+        chunkManager.Reset();
+        meshesToUpdate.clear();
+        dirtyVersion = -1;
+    }
+
+    // Host mirror of the device dirty set (Chisel.h:221-224), refreshed when a frame was integrated since the last call.
+    const ChunkSet &GetMeshesToUpdate() const
+    {
+        int64_t n = 0;
+        b200::Check(chs_num_dirty(chunkManager.Handle(), &n), "chs_num_dirty");
+        if (dirtyVersion != n || n == 0)
+        {
+            meshesToUpdate.clear();
+            std::vector<int32_t> ids(3 * n);
+            if (n)
+                b200::Check(chs_dirty_ids(chunkManager.Handle(), ids.data(), n), "chs_dirty_ids");
+            for (int64_t i = 0; i < n; i++)
+                meshesToUpdate[ChunkID(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2])] = true;
+            dirtyVersion = n;                        // the set only grows between re-meshes, so its size identifies it
+        }
+        return meshesToUpdate;
+    }
+
+  protected:
+    template <class DataType>
+    const float *DepthAsFloat(const DepthImage<DataType> &img)
+    {
+        return ConvertDepth(img.GetData(), static_cast<size_t>(img.GetWidth()) * img.GetHeight());
+    }
+    const float *ConvertDepth(const float *p, size_t) { return p; }
+    template <class DataType>
+    const float *ConvertDepth(const DataType *p, size_t n)
+    {
+        depthScratch.resize(n);
+        for (size_t i = 0; i < n; i++)
+            depthScratch[i] = static_cast<float>(p[i]);     // DepthImage::DepthAt (DepthImage.h:66-70)
+        return depthScratch.data();
+    }
+
+    ChunkManager chunkManager;
+    mutable ChunkSet meshesToUpdate;
+    int updateCalls;
+    mutable int64_t dirtyVersion;
+    std::vector<float> truncScratch, depthScratch;
+};
+typedef std::shared_ptr<Chisel> ChiselPtr;
+typedef std::shared_ptr<const Chisel> ChiselConstPtr;
+} // namespace chisel
+#endif

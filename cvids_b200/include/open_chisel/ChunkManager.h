@@ -1,0 +1,220 @@
+// open_chisel/ChunkManager.h -- facade over the device-resident map (C ABI: chisel_b200.h).
+//
+// The reference's ChunkManager IS the map (an unordered_map of heap chunks, OC/include/open_chisel/ChunkManager.h:58-223).
+// Here the map lives in HBM; this class owns the chs_map handle and serves the reference's read API from host mirrors
+// that are refreshed lazily, off the timed path: GetChunks() / GetChunk() download voxels on demand, GetAllMeshes() is
+// the MeshMap that Chisel::UpdateMeshes maintains with the reference's publication rule (ChunkManager.cpp:101-127).
+#ifndef CHISEL_B200_CHUNKMANAGER_H_
+#define CHISEL_B200_CHUNKMANAGER_H_
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <chisel_b200.h>
+#include <open_chisel/Chunk.h>
+#include <open_chisel/geometry/Geometry.h>
+#include <open_chisel/mesh/Mesh.h>
+
+namespace chisel
+{
+// Teschner's three-prime spatial hash, as in the reference (ChunkManager.h:40-51)
+struct ChunkHasher
+{
+    static constexpr size_t p1 = 73856093;
+    static constexpr size_t p2 = 19349663;
+    static constexpr size_t p3 = 8349279;
+    std::size_t operator()(const ChunkID &key) const { return (key(0) * p1 ^ key(1) * p2 ^ key(2) * p3); }
+};
+typedef std::unordered_map<ChunkID, ChunkPtr, ChunkHasher> ChunkMap;
+typedef std::unordered_map<ChunkID, bool, ChunkHasher> ChunkSet;
+typedef std::unordered_map<ChunkID, MeshPtr, ChunkHasher> MeshMap;
+
+namespace b200
+{
+inline void Check(int rc, const char *what)
+{
+    if (rc != CHS_OK)
+        throw std::runtime_error(std::string(what) + ": " + chs_last_error_string());
+}
+} // namespace b200
+
+class ChunkManager
+{
+  public:
+    ChunkManager() : chunkSize(16, 16, 16), voxelResolutionMeters(0.03f), useColor(false), version(0), chunksVersion(-1) {}   // Q15: useColor initialised
+    ChunkManager(const Eigen::Vector3i &size, float res, bool color, int device = -1, int rank = 0, int world = 1, void *stream = nullptr)
+        : chunkSize(size), voxelResolutionMeters(res), useColor(color), version(0), chunksVersion(-1)
+    {
+        if (size(0) != size(1) || size(0) != size(2))
+            throw std::invalid_argument("chisel_b200: cubic chunks only (Chunk::GetVoxelID is only correct for them, quirk Q12)");
+        chs_config cfg;
+        cfg.chunk_size = size(0);
+        cfg.resolution = res;
+        cfg.use_color = color ? 1 : 0;
+        cfg.device = device;
+        cfg.rank = rank;
+        cfg.world = world;
+        cfg.initial_chunks = 0;
+        cfg.stream = stream;
+        chs_map *h = nullptr;
+        b200::Check(chs_create(&cfg, &h), "chs_create");
+        handle.reset(h, [](chs_map *p) { chs_destroy(p); });
+        CacheCentroids();
+    }
+
+    chs_map *Handle() const { return handle.get(); }
+    void Touch() { version++; }                                  // the device map changed: host mirrors are stale
+
+    const Eigen::Vector3i &GetChunkSize() const { return chunkSize; }
+    float GetResolution() const { return voxelResolutionMeters; }
+    bool GetUseColor() const { return useColor; }
+    const Vec3List &GetCentroids() const { return centroids; }
+
+    bool HasChunk(const ChunkID &id) const
+    {
+        int found = 0;
+        const int32_t cid[3] = {id(0), id(1), id(2)};
+        b200::Check(chs_has_chunk(handle.get(), cid, &found), "chs_has_chunk");
+        return found != 0;
+    }
+    bool HasChunk(int x, int y, int z) const { return HasChunk(ChunkID(x, y, z)); }
+
+    // unordered_map::at semantics: throws std::out_of_range for a missing chunk (ChunkManager.h:84-87)
+    ChunkPtr GetChunk(const ChunkID &id) const
+    {
+        ChunkPtr c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor);
+        const size_t V = c->GetTotalNumVoxels();
+        std::vector<float> sdf(V), w(V);
+        std::vector<uint8_t> rgbw(useColor ? 4 * V : 0);
+        const int32_t cid[3] = {id(0), id(1), id(2)};
+        const int rc = chs_download_chunk(handle.get(), cid, sdf.data(), w.data(), useColor ? rgbw.data() : nullptr);
+        if (rc == CHS_ERR_NOT_FOUND)
+            throw std::out_of_range("ChunkManager::GetChunk: no such chunk");
+        b200::Check(rc, "chs_download_chunk");
+        Fill(c.get(), sdf.data(), w.data(), useColor ? rgbw.data() : nullptr);
+        return c;
+    }
+    ChunkPtr GetChunk(int x, int y, int z) const { return GetChunk(ChunkID(x, y, z)); }
+    ChunkID GetIDAt(const Vec3 &pos) const
+    {
+        // ChunkManager.h:136-145 with per-instance factors (identical to the reference's first instance, quirk Q1)
+        const float rx = 1.0f / (chunkSize(0) * voxelResolutionMeters), ry = 1.0f / (chunkSize(1) * voxelResolutionMeters), rz = 1.0f / (chunkSize(2) * voxelResolutionMeters);
+        return ChunkID(static_cast<int>(std::floor(pos(0) * rx)), static_cast<int>(std::floor(pos(1) * ry)), static_cast<int>(std::floor(pos(2) * rz)));
+    }
+
+    // Whole-map host mirror (one bulk transfer), refreshed only if the device map changed since the last call.
+    const ChunkMap &GetChunks() const
+    {
+        if (chunksVersion != version)
+        {
+            chunks.clear();
+            int64_t n = 0;
+            b200::Check(chs_num_chunks(handle.get(), &n), "chs_num_chunks");
+            const size_t V = static_cast<size_t>(chunkSize(0)) * chunkSize(1) * chunkSize(2);
+            std::vector<int32_t> ids(3 * n);
+            std::vector<float> sdf(n * V), w(n * V);
+            std::vector<uint8_t> rgbw(useColor ? n * V * 4 : 0);
+            if (n)
+                b200::Check(chs_download_all(handle.get(), n, ids.data(), sdf.data(), w.data(), useColor ? rgbw.data() : nullptr), "chs_download_all");
+            for (int64_t i = 0; i < n; i++)
+            {
+                const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+                ChunkPtr c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor);
+                Fill(c.get(), sdf.data() + i * V, w.data() + i * V, useColor ? rgbw.data() + i * V * 4 : nullptr);
+                chunks[id] = c;
+            }
+            chunksVersion = version;
+        }
+        return chunks;
+    }
+
+    const MeshMap &GetAllMeshes() const { return allMeshes; }
+    MeshMap &GetAllMutableMeshes() { return allMeshes; }
+    const MeshPtr &GetMesh(const ChunkID &id) const { return allMeshes.at(id); }
+    bool HasMesh(const ChunkID &id) const { return allMeshes.find(id) != allMeshes.end(); }
+
+    // ChunkManager::RecomputeMeshes (ChunkManager.cpp:130-169): the set that is re-meshed is the DEVICE dirty set, which
+    // is what Chisel passes (meshesToUpdate); it is cleared afterwards like Chisel.cpp:57. New meshes are published only
+    // if they have occupied cells; meshes that already exist are replaced even if they became empty (quirk Q10).
+    void RecomputeMeshes(const ChunkSet & /*dirty: the device holds the authoritative set*/) { RecomputeDirtyMeshes(); }
+    void RecomputeDirtyMeshes()
+    {
+        b200::Check(chs_update_meshes(handle.get()), "chs_update_meshes");
+        chs_mesh_counts mc;
+        b200::Check(chs_mesh_counts_last(handle.get(), &mc), "chs_mesh_counts_last");
+        std::vector<int32_t> ids(3 * mc.n_chunks);
+        std::vector<int64_t> voff(mc.n_chunks + 1), goff(mc.n_chunks + 1);
+        std::vector<float> v(3 * mc.n_vertices), nr(3 * mc.n_vertices), col(mc.has_colors ? 3 * mc.n_vertices : 0), g(3 * mc.n_grids);
+        b200::Check(chs_download_meshes(handle.get(), ids.data(), voff.data(), goff.data(), v.data(), nr.data(), mc.has_colors ? col.data() : nullptr, g.data()),
+                    "chs_download_meshes");
+        for (int64_t i = 0; i < mc.n_chunks; i++)
+        {
+            const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+            const bool had = HasMesh(id);
+            if (!had && goff[i + 1] == goff[i])
+                continue;
+            MeshPtr m = had ? allMeshes[id] : std::make_shared<Mesh>();
+            m->Clear();
+            for (int64_t k = voff[i]; k < voff[i + 1]; k++)
+            {
+                m->vertices.push_back(Vec3(v[3 * k], v[3 * k + 1], v[3 * k + 2]));
+                m->normals.push_back(Vec3(nr[3 * k], nr[3 * k + 1], nr[3 * k + 2]));
+                if (mc.has_colors)
+                    m->colors.push_back(Vec3(col[3 * k], col[3 * k + 1], col[3 * k + 2]));
+                m->indices.push_back(static_cast<VertIndex>(k - voff[i]));          // MarchingCubes.h:91-93
+            }
+            for (int64_t k = goff[i]; k < goff[i + 1]; k++)
+                m->grids.push_back(Vec3(g[3 * k], g[3 * k + 1], g[3 * k + 2]));
+            allMeshes[id] = m;
+        }
+    }
+
+    void Reset()
+    {
+        b200::Check(chs_reset(handle.get()), "chs_reset");
+        allMeshes.clear();
+        chunks.clear();
+        Touch();
+    }
+
+    // ChunkManager::CacheCentroids (ChunkManager.cpp:50-65)
+    void CacheCentroids()
+    {
+        const Vec3 half = Vec3(voxelResolutionMeters, voxelResolutionMeters, voxelResolutionMeters) * 0.5f;
+        centroids.resize(static_cast<size_t>(chunkSize(0)) * chunkSize(1) * chunkSize(2));
+        size_t i = 0;
+        for (int z = 0; z < chunkSize(2); z++)
+            for (int y = 0; y < chunkSize(1); y++)
+                for (int x = 0; x < chunkSize(0); x++)
+                    centroids[i++] = Vec3(x, y, z) * voxelResolutionMeters + half;
+    }
+
+  protected:
+    void Fill(Chunk *c, const float *sdf, const float *w, const uint8_t *rgbw) const
+    {
+        std::vector<DistVoxel> &dv = c->GetMutableVoxels();
+        for (size_t i = 0; i < dv.size(); i++)
+            dv[i] = DistVoxel(sdf[i], w[i]);
+        if (rgbw)
+        {
+            std::vector<ColorVoxel> &cv = c->GetMutableColorVoxels();
+            for (size_t i = 0; i < cv.size(); i++)
+                cv[i] = ColorVoxel(rgbw[4 * i], rgbw[4 * i + 1], rgbw[4 * i + 2], rgbw[4 * i + 3]);
+        }
+    }
+
+    std::shared_ptr<chs_map> handle;
+    Eigen::Vector3i chunkSize;
+    float voxelResolutionMeters;
+    bool useColor;
+    Vec3List centroids;
+    MeshMap allMeshes;
+    long version;
+    mutable ChunkMap chunks;
+    mutable long chunksVersion;
+};
+typedef std::shared_ptr<ChunkManager> ChunkManagerPtr;
+typedef std::shared_ptr<const ChunkManager> ChunkManagerConstPtr;
+} // namespace chisel
+#endif

@@ -145,6 +145,7 @@ int chs_download_meshes(chs_map *map, int32_t *ids, int64_t *vert_offsets, int64
 
 int chs_num_chunks(chs_map *map, int64_t *n);                  /* synchronises */
 int chs_chunk_ids(chs_map *map, int32_t *ids, int64_t cap);    /* pool order */
+int chs_has_chunk(chs_map *map, const int32_t id[3], int *found); /* ChunkManager::HasChunk */
 /* sdf, weight [V]; rgbw [4V] (r, g, b, colour weight) or NULL. CHS_ERR_NOT_FOUND if the chunk is absent. */
 int chs_download_chunk(chs_map *map, const int32_t id[3], float *sdf, float *weight, uint8_t *rgbw);
 /* Whole map in one transfer, pool order: ids [3n], sdf/weight [n*V], rgbw [n*4V] or NULL. */

@@ -1,0 +1,91 @@
+"""The drop-in C++ facade (cvids_b200/include/open_chisel) driven by a chisel_ros-style client.
+
+CPU suite: the client compiles and links against the facade; in the build container the SAME source also compiles against
+the reference's own headers and sources, and that binary's dump equals the C oracle's (so the client and the oracle agree
+on what the reference does through its public API).
+GPU suite: the facade binary runs on the device and its dump equals the oracle's on the same stream, bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cvids_b200 import scenes
+from tests import common, facade_util
+from tests.common import Setup
+
+HAVE_REF = os.path.isdir(facade_util.REF)
+CASES = {
+    # depth-only path: serial in the reference, hence deterministic
+    "depth": dict(setup=Setup(16, 0.05, False), color=False, n=12),
+    # colour path with the truncator chisel_ros instantiates; the reference's threaded path is run pinned to one core (quirk Q2)
+    "color_inverse": dict(setup=Setup(8, 0.1, True, trunc_kind=common.TRUNC_INVERSE, trunc_param=2.0, carve_dist=0.0), color=True, n=11),
+}
+
+
+def _stream(tmp_path, case):
+    c = CASES[case]
+    path = str(tmp_path / (case + ".stream"))
+    frames = facade_util.write_stream(path, c["setup"], common.SMALL_CAM,
+                                      common.orbit_stream(common.SMALL_CAM, c["n"], total=30, color=c["color"], seed=3),
+                                      3 if c["color"] else 0)
+    return path, frames
+
+
+def _oracle_expectation(case, frames):
+    """What the reference does for this client: integrate every frame, UpdateMeshes after each; the gate re-meshes on
+    calls 1, 11, 21, ... (Chisel.cpp:50-59)."""
+    c = CASES[case]
+    drv = common.Driver(c["setup"], "oracle")
+    for i, (depth, col, pose) in enumerate(frames):
+        drv.integrate(depth, pose, common.SMALL_CAM.as_array(), col)
+        if i % 10 == 0:
+            drv.remesh()
+    return drv
+
+
+def _compare(dump, drv, with_colors):
+    common.assert_state_equal(dump["state"], drv.state())
+    assert np.array_equal(dump["dirty"], drv.dirty())
+    common.assert_meshes_equal(dump["meshes"], drv.meshes(), with_colors=with_colors)
+    ids = dump["state"][0]
+    res, cs = drv.setup.resolution, drv.setup.chunk
+    assert np.allclose(dump["centers"], (ids.astype(np.float32) + 0.5) * np.float32(cs * res), atol=1e-5)
+
+
+def test_facade_client_compiles_and_links():
+    exe = facade_util.build_facade_client()
+    assert os.path.exists(exe)
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libchisel_b200.so" in out
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_same_client_against_the_reference(tmp_path, case):
+    exe = facade_util.build_reference_client()
+    stream, frames = _stream(tmp_path, case)
+    dump = str(tmp_path / "ref.dump")
+    subprocess.run(["taskset", "-c", "0", exe, stream, dump], check=True, stdout=subprocess.DEVNULL)
+    d = facade_util.read_dump(dump)
+    _compare(d, _oracle_expectation(case, frames), CASES[case]["color"])
+    assert d["remeshes"] == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_facade_client_on_device(tmp_path, case):
+    exe = facade_util.build_facade_client()
+    stream, frames = _stream(tmp_path, case)
+    dump = str(tmp_path / "b200.dump")
+    subprocess.run([exe, stream, dump], check=True)
+    d = facade_util.read_dump(dump)
+    drv = _oracle_expectation(case, frames)
+    _compare(d, drv, CASES[case]["color"])
+    assert d["remeshes"] == 2
+    from oracle.pyoracle import OracleChisel
+    lines = OracleChisel(16, 0.05, False).frustum(frames[-1][2], common.SMALL_CAM.as_array())[1]
+    assert np.array_equal(d["lines"].view(np.uint32), lines.view(np.uint32))
+    ply = open(dump + ".ply").read().split("\n")
+    nverts = sum(len(m["vertices"]) for m in d["meshes"].values())
+    assert ply[0] == "ply" and ("element vertex %d" % nverts) in ply[2]
