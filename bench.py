@@ -169,7 +169,7 @@ def run_reference(args):
 def run_cuda(args):
     import torch
     import torch.distributed as dist
-    from cvids_b200 import capi
+    from cvids_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,19 +203,17 @@ def run_cuda(args):
         poses = pt.cpu().numpy()
 
     nfr = warm + steps
-    d_depth = torch.empty((nfr, H, W), dtype=torch.float32, device=dev)
-    d_color = torch.empty((nfr, H, W, channels), dtype=torch.uint8, device=dev)
-    h_depth = h_color = None
+    # one contiguous byte buffer per frame [depth f32 | colour u8] so that a frame is ONE NCCL broadcast (sharding.py)
+    fbytes = sharding.frame_nbytes(W, H, channels)
+    dbytes = 4 * W * H
+    d_frames = torch.empty((nfr, fbytes), dtype=torch.uint8, device=dev)
+    h_frames = None
     if rank == 0:
-        h_depth = torch.empty((nfr, H, W), dtype=torch.float32).pin_memory()
-        h_color = torch.empty((nfr, H, W, channels), dtype=torch.uint8).pin_memory()
+        h_frames = torch.empty((nfr, fbytes), dtype=torch.uint8).pin_memory()
         for i, fr in enumerate(frames):
-            h_depth[i].copy_(torch.from_numpy(fr[0]))
-            h_color[i].copy_(torch.from_numpy(fr[1]))
-        d_depth.copy_(h_depth)
-        d_color.copy_(h_color)
-    recv_depth = torch.empty((H, W), dtype=torch.float32, device=dev)
-    recv_color = torch.empty((H, W, channels), dtype=torch.uint8, device=dev)
+            h_frames[i].copy_(torch.from_numpy(sharding.pack_frame(fr[0], fr[1])))
+        d_frames.copy_(h_frames)
+    recv = torch.empty(fbytes, dtype=torch.uint8, device=dev)
     # L2 flush between timed steps: write a 256 MiB buffer, then read another one, so that L2 ends up full of CLEAN
     # foreign lines (a write-only flush leaves ~126 MB of dirty lines whose write-back would be charged to the step)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
@@ -238,14 +236,11 @@ def run_cuda(args):
 
     def step_device(m, i):
         """inputs resident in HBM (rank 0) -> [NCCL broadcast] -> integrate"""
+        src = d_frames[i] if rank == 0 else recv
         if world > 1:
-            src_d = d_depth[i] if rank == 0 else recv_depth
-            src_c = d_color[i] if rank == 0 else recv_color
-            dist.broadcast(src_d, 0)
-            dist.broadcast(src_c, 0)
-        else:
-            src_d, src_c = d_depth[i], d_color[i]
-        m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(src_d.data_ptr(), src_c.data_ptr()), channels=channels)
+            sharding.broadcast_frame(src, 0)
+        p = src.data_ptr()
+        m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(p, p + dbytes), channels=channels)
 
     # ---------------- leg A: device-resident inputs, CUDA events per step, L2 flushed between steps -------------
     m = new_map()
@@ -305,6 +300,21 @@ def run_cuda(args):
             t_new += tm["new_chunks_ms"] / 1000.0
             per_frame.append((st["n_upd"], st["brick_units"], st["candidates"], tm["integrate_ms"], st["updated_chunks"], st["n_new"], st["new_candidates"]))
     total_chunks = m.frame_stats()["total_chunks"]
+    # meshing: one re-mesh of everything the run left dirty (Chisel::UpdateMeshes without its every-10th gate), cold L2
+    n_dirty = len(m.get_meshes_to_update())
+    flush_l2(0)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    m.recompute_meshes()
+    t_mesh_wall = time.perf_counter() - t0
+    mt = m.timings()
+    mc = m.last_mesh_counts()
+    V_halo = (CFG.chunk + 1) ** 3
+    b_mc = mc["n_chunks"] * V_halo * 12 + mc["n_vertices"] * 36 + mc["n_grids"] * 12        # B_mc of SURVEY 8(d), colour map
+    mesh_info = {"dirty_ids": n_dirty, "remeshed_chunks": mc["n_chunks"], "triangles": mc["n_vertices"] // 3, "grids": mc["n_grids"],
+                 "device_ms": mt["mesh_ms"], "count_ms": mt["mesh_count_ms"], "emit_ms": mt["mesh_emit_ms"],
+                 "wall_ms_incl_download_and_host_merge": 1000.0 * t_mesh_wall,
+                 "algorithmic_bytes": b_mc, "achieved_gbs": b_mc / (mt["mesh_ms"] * 1e-3) / 1e9 if mt["mesh_ms"] > 0 else None}
     m.close()
 
     # ---------------- leg B: end to end through the C ABI with pinned HOST frames + D2H counters ----------------
@@ -313,14 +323,13 @@ def run_cuda(args):
     def step_host(i):
         if world > 1:
             if rank == 0:
-                recv_depth.copy_(h_depth[i], non_blocking=True)
-                recv_color.copy_(h_color[i], non_blocking=True)
-            dist.broadcast(recv_depth, 0)
-            dist.broadcast(recv_color, 0)
-            m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(recv_depth.data_ptr(), recv_color.data_ptr()), channels=channels)
+                recv.copy_(h_frames[i], non_blocking=True)
+            sharding.broadcast_frame(recv, 0)
+            p = recv.data_ptr()
+            m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(p, p + dbytes), channels=channels)
         else:
-            lib_d = h_depth[i].numpy()
-            lib_c = h_color[i].numpy()
+            hb = h_frames[i].numpy()
+            lib_d, lib_c = sharding.unpack_frame(hb, W, H, channels)
             m.integrate_depth_scan_color(integ, lib_d, poses[i], camv, lib_c)
         return m.frame_stats()["n_upd"]
 
@@ -375,6 +384,7 @@ def run_cuda(args):
                          "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps,
                          "new_chunks_ms_per_launch": 1000.0 * t_new / steps},
             "wall_s_timed_region": wall_a,
+            "mesh": mesh_info,
         }
         if world == 1 and not args.no_cpu:
             n_cpu = min(steps, args.cpu_frames)

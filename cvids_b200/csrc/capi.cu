@@ -103,6 +103,8 @@ struct chs_map
     // frame staging
     float *dDepth = nullptr, *dTrunc = nullptr;
     uint8_t *dColor = nullptr;
+    unsigned *dColorPacked = nullptr;
+    size_t colorPackedCap = 0;
     float2 *dHiz = nullptr;
     int4 *dUnits = nullptr, *dNews = nullptr;
     size_t depthCap = 0, truncCap = 0, colorCap = 0, hizCap = 0, unitsCap = 0, newsCap = 0;
@@ -110,13 +112,14 @@ struct chs_map
     cudaEvent_t h2dDone = nullptr;
     // counters
     Counters *dCtr = nullptr;
-    Counters *hCtr = nullptr;           // pinned ring
+    Counters *hCtr = nullptr;           // pinned: staging for direct reads of the device counters
+    HostSnapshot *hSnap = nullptr;      // pinned, device-mapped ring written by the last CTA of every frame
     static constexpr int kRing = 16;
     int ringNext = 0;
     std::deque<InFlight> inflight;
     FrameGraph *frameGraph = nullptr;
     long long knownChunks = 0, knownDirty = 0;
-    Counters lastFrame{};
+    HostSnapshot lastFrame{};
     bool haveFrame = false;
     // profiling
     bool profiling = false;
@@ -300,15 +303,15 @@ static int poll_inflight(chs_map *m, bool block)
     while (!m->inflight.empty())
     {
         InFlight &f = m->inflight.front();
-        const volatile Counters *c = &m->hCtr[f.slot];
-        if (c->frame_id != f.frameId)
+        const volatile HostSnapshot *c = &m->hSnap[f.slot];
+        if (c->id0 != f.frameId || c->id1 != f.frameId || c->id2 != f.frameId || c->id3 != f.frameId)
         {
             if (block)
                 return fail(CHS_ERR_CUDA, "counter snapshot missing after synchronisation");
             break;
         }
         std::atomic_thread_fence(std::memory_order_acquire);
-        m->lastFrame = m->hCtr[f.slot];
+        m->lastFrame = m->hSnap[f.slot];
         m->knownChunks = m->lastFrame.n_chunks;
         m->knownDirty = m->lastFrame.n_dirty;
         m->inflight.pop_front();
@@ -317,7 +320,7 @@ static int poll_inflight(chs_map *m, bool block)
 }
 
 // Reserve a ring slot for the frame about to be launched.
-static int reserve_snapshot(chs_map *m, int frameId, long long newBound, long long dirtyBound, Counters **slotOut)
+static int reserve_snapshot(chs_map *m, int frameId, long long newBound, long long dirtyBound, HostSnapshot **slotOut)
 {
     if ((int)m->inflight.size() >= chs_map::kRing)
     {
@@ -333,9 +336,9 @@ static int reserve_snapshot(chs_map *m, int frameId, long long newBound, long lo
     m->ringNext = (m->ringNext + 1) % chs_map::kRing;
     f.newBound = newBound;
     f.dirtyBound = dirtyBound;
-    m->hCtr[f.slot].frame_id = -1;
+    m->hSnap[f.slot].id0 = m->hSnap[f.slot].id1 = m->hSnap[f.slot].id2 = m->hSnap[f.slot].id3 = -1;
     m->inflight.push_back(f);
-    *slotOut = &m->hCtr[f.slot];
+    *slotOut = &m->hSnap[f.slot];
     return CHS_OK;
 }
 
@@ -469,6 +472,9 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
         }
         else
             fp.color = color;
+        if ((rc = grow_buffer(&m->dColorPacked, &m->colorPackedCap, (size_t)ccam->width * ccam->height, st)))
+            return rc;
+        fp.color_packed = m->dColorPacked;
     }
     if (copied)
         CHS_CUDA(cudaEventRecord(m->h2dDone, st));
@@ -535,10 +541,12 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
             fp.cand_stride = 1;
     }
 
-    Counters *slotPtr = nullptr;
+    HostSnapshot *slotPtr = nullptr;
     if ((rc = reserve_snapshot(m, fp.frame_id, cand, dirtyBound, &slotPtr)))
         return rc;
-    CHS_CUDA(frame_graph_launch(m->frameGraph, fp, m->dm, cand, slotPtr, m->profiling, m->evt, st));
+    // size the new-chunk kernel's grid from what recent frames needed (the kernel strides, so any size is correct)
+    const long long newHint = m->haveFrame ? std::max<long long>(64, 2ll * m->lastFrame.new_count) : cand;
+    CHS_CUDA(frame_graph_launch(m->frameGraph, fp, m->dm, cand, newHint, slotPtr, m->profiling, m->evt, st));
     if (m->profiling)
         m->frameTimed = true;
     m->haveFrame = true;
@@ -648,6 +656,8 @@ int chs_create(const chs_config *cfg, chs_map **out)
     d.ctr = m->dCtr;
     CHS_CUDA(cudaHostAlloc((void **)&m->hCtr, sizeof(Counters) * (chs_map::kRing + 1), cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hCtr, 0, sizeof(Counters) * (chs_map::kRing + 1));
+    CHS_CUDA(cudaHostAlloc((void **)&m->hSnap, sizeof(HostSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
+    std::memset(m->hSnap, 0, sizeof(HostSnapshot) * chs_map::kRing);
     CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
     m->frameGraph = frame_graph_create();
     for (int i = 0; i < 8; i++)
@@ -674,7 +684,7 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     for (uchar4 *p : m->colorSlabs)
         cudaFreeAsync(p, m->stream);
-    void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dHiz,
+    void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dColorPacked, m->dHiz,
                     m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
                     m->dColors, m->dGrids};
     for (void *p : bufs)
@@ -685,6 +695,7 @@ int chs_destroy(chs_map *m)
     cudaFree(m->dm.color_slabs);
     cudaFree(m->dCtr);
     cudaFreeHost(m->hCtr);
+    cudaFreeHost(m->hSnap);
     frame_graph_destroy(m->frameGraph);
     if (m->h2dDone)
         cudaEventDestroy(m->h2dDone);
@@ -777,17 +788,13 @@ int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
     int rc = poll_inflight(m, true);
     if (rc)
         return rc;
-    const Counters &c = m->lastFrame;
+    const HostSnapshot &c = m->lastFrame;
     out->candidates = c.candidates;
     out->new_candidates = c.new_count;
     out->brick_units = c.unit_count;
-    out->n_upd = out->n_carve = out->n_col = 0;
-    for (int k = 0; k < kCounterSlots; k++)
-    {
-        out->n_upd += (int64_t)c.n_upd[k];
-        out->n_carve += (int64_t)c.n_carve[k];
-        out->n_col += (int64_t)c.n_col[k];
-    }
+    out->n_upd = (int64_t)(((unsigned long long)(unsigned)c.n_upd_hi << 32) | (unsigned)c.n_upd_lo);
+    out->n_carve = c.n_carve;
+    out->n_col = c.n_col;
     out->n_new = c.n_new;
     out->updated_chunks = c.updated_chunks;
     out->total_chunks = c.n_chunks;

@@ -68,11 +68,24 @@ struct Counters
     int candidates;
     int n_new;
     int updated_chunks;
+    int tickets;                   // CTAs of the two integrate kernels that have finished (the last one takes the snapshot)
+    int pad;
     unsigned long long n_upd[kCounterSlots], n_carve[kCounterSlots], n_col[kCounterSlots];
     // per re-mesh
     unsigned long long mesh_verts, mesh_grids;
     int mesh_chunks;
-    int frame_id;                  // host ring slots only: id of the frame this snapshot was taken after (written last)
+    int pad2;
+};
+
+// What the host needs to know about a finished frame; written into a pinned ring slot by the last CTA of the frame as
+// four 16-byte lines, EACH carrying the frame id in its first word: a slot is valid for frame f when all four ids equal f,
+// so no system-scope fence or flag ordering is needed (a 16-byte aligned store is one transaction on the bus).
+struct HostSnapshot
+{
+    int id0, n_chunks, n_dirty, error_flags;
+    int id1, unit_count, new_count, candidates;
+    int id2, n_new, updated_chunks, n_carve;
+    int id3, n_col, n_upd_lo, n_upd_hi;
 };
 
 struct DeviceMap
@@ -180,7 +193,8 @@ struct FrameParams
     CameraDev ccam;           // colour camera + pose
     const float *depth;       // W*H
     const float *trunc_img;   // W*H or nullptr (constant truncator)
-    const uint8_t *color;     // cW*cH*channels
+    const uint8_t *color;     // cW*cH*channels, as the caller handed it over
+    unsigned *color_packed;   // cW*cH packed r | g << 8 | b << 16, written by frame_prepare (ColorImage::At, OC ColorImage.h:61-101)
     int channels;
     int color_path;           // 0: Integrate (ProjectionIntegrator.h:51-99), 1: IntegrateColor (:101-183)
     int trunc_kind;
@@ -204,6 +218,8 @@ struct FrameParams
     int news_cap;
     int cand_stride;          // multiplicative permutation of the candidate enumeration (coprime to the box size)
     int frame_id;             // > 0, increases by one per integrated frame
+    int total_ctas;           // CTAs of integrate_new_chunks + integrate_bricks of this frame
+    HostSnapshot *host_slot;  // pinned, device-mapped
 };
 
 } // namespace chs

@@ -73,10 +73,56 @@ __global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, Devi
             c->candidates = 0;
             c->n_new = 0;
             c->updated_chunks = 0;
+            c->tickets = 0;
         }
         c->n_upd[threadIdx.x] = 0;
         c->n_carve[threadIdx.x] = 0;
         c->n_col[threadIdx.x] = 0;
+    }
+    if (fp.color_path)
+    {
+        // ColorImage::At (OC ColorImage.h:61-101) once per pixel instead of once per voxel: mono replicates, 3/4 channels are
+        // B,G,R(,A); stored as r | g << 8 | b << 16 so that the integrate kernel fetches a colour with one 32-bit load
+        const int n = fp.ccam.W * fp.ccam.H, ch = fp.channels;
+        const int nThreads = gridDim.x * gridDim.y * blockDim.x;
+        const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        int done = 0;
+        if (ch == 3 && (reinterpret_cast<size_t>(fp.color) & 3) == 0 && (reinterpret_cast<size_t>(fp.color_packed) & 15) == 0)
+        {
+            // BGR fast path: four pixels = three aligned 32-bit words in, one 128-bit word out
+            const unsigned *p32 = reinterpret_cast<const unsigned *>(fp.color);
+            const int n4 = n >> 2;
+            for (int i = gtid; i < n4; i += nThreads)
+            {
+                const unsigned a = __ldg(p32 + 3 * i), b = __ldg(p32 + 3 * i + 1), c = __ldg(p32 + 3 * i + 2);
+                uint4 o;
+                o.x = ((a >> 16) & 0xFFu) | (a & 0xFF00u) | ((a & 0xFFu) << 16);                         // B0 G0 R0
+                o.y = ((b >> 8) & 0xFFu) | ((b & 0xFFu) << 8) | ((a >> 24) << 16);                       // B1 | G1 R1
+                o.z = (c & 0xFFu) | ((b >> 24) << 8) | (((b >> 16) & 0xFFu) << 16);                      // B2 G2 | R2
+                o.w = (c >> 24) | (((c >> 16) & 0xFFu) << 8) | (((c >> 8) & 0xFFu) << 16);               // B3 G3 R3
+                reinterpret_cast<uint4 *>(fp.color_packed)[i] = o;
+            }
+            done = n4 << 2;
+        }
+        for (int i = done + gtid; i < n; i += nThreads)
+        {
+            const uint8_t *p = fp.color + (size_t)i * ch;
+            unsigned r, g, b;
+            if (ch >= 3)
+            {
+                b = __ldg(p);
+                g = __ldg(p + 1);
+                r = __ldg(p + 2);
+            }
+            else if (ch == 2)
+            {
+                r = __ldg(p);
+                g = b = __ldg(p + 1);
+            }
+            else
+                r = g = b = __ldg(p);
+            fp.color_packed[i] = r | (g << 8) | (b << 16);
+        }
     }
     const int W = fp.cam.W, H = fp.cam.H;
     const int t = threadIdx.x;
@@ -298,26 +344,33 @@ __device__ int classify_box(const FrameParams &fp, float wx, float wy, float wz,
     return 2;
 }
 
-// One thread per ID of the candidate box (the reference's order -- x outer, y, z inner; ChunkManager.cpp:192-196 -- does
-// not affect the result, so IDs are enumerated by linear index). Survivors are split into two lists:
-//   news   non-existing chunks that may receive a band hit          -> integrate_new_chunks (CTA per chunk)
-//   units  8^3 bricks of existing chunks that may change            -> integrate_bricks (a warp per quarter brick)
-// Both lists are filled by warp-ballot compaction; the bricks of a kept chunk are classified by the lanes of the warp
-// in parallel.
+// One lane per (candidate chunk, 8^3 brick): groups of GL lanes share a chunk ID of the candidate box (the reference's
+// order -- x outer, y, z inner; ChunkManager.cpp:192-196 -- does not affect the result, so IDs are enumerated by linear
+// index). Every brick is classified against the Hi-Z tiles directly; the hash table is consulted (by the group leader)
+// only for chunks with a brick the depth test could not reject. Survivors go, by warp-ballot compaction, to
+//   news   non-existing chunks with a brick that may receive a band hit   -> integrate_new_chunks_kernel (CTA per chunk)
+//   units  bricks of existing chunks that may change                       -> integrate_bricks_kernel (warp per half brick)
 template <int CS>
-__global__ void __launch_bounds__(64) chunk_candidates_kernel(FrameParams fp, DeviceMap map)
+__global__ void __launch_bounds__(256) chunk_candidates_kernel(FrameParams fp, DeviceMap map)
 {
     constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
+    constexpr int GL = NB >= 32 ? 32 : NB;                          // lanes per chunk: 1 (8^3), 8 (16^3), 32 (32^3)
+    constexpr int BPL = NB / GL;                                     // bricks per lane: 2 for 32^3 chunks, else 1
     const int total = fp.n[0] * fp.n[1] * fp.n[2];
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    bool candidate = false, keepNew = false, keepOld = false;
-    int x = 0, y = 0, z = 0, slot = -1;
-    float bx = 0.0f, by = 0.0f, bz = 0.0f;
-    if (tid < total)
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(tid / GL);
+    const int gl = (int)(tid % GL);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned groupMask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~(unsigned)(GL - 1)));
+    const bool leader = gl == 0;
+    bool candidate = false;
+    int x = 0, y = 0, z = 0;
+    int code[BPL];
+#pragma unroll
+    for (int k = 0; k < BPL; k++)
+        code[k] = 0;
+    if (i < total)
     {
-        // surviving chunks are spatially clustered; a multiplicative permutation (stride coprime to total) spreads them
-        // over the warps so that the per-warp brick expansion below stays short
-        const int i = (int)(((long long)tid * fp.cand_stride) % total);
         const int nyz = fp.n[1] * fp.n[2];
         x = fp.lo[0] + i / nyz;
         const int r = i - (i / nyz) * nyz;
@@ -325,28 +378,48 @@ __global__ void __launch_bounds__(64) chunk_candidates_kernel(FrameParams fp, De
         z = fp.lo[2] + r % fp.n[2];
         // chunk box exactly as ChunkManager.cpp:199-201
         const float ext = __fmul_rn((float)CS, map.res);
-        bx = __fmul_rn((float)(x * CS), map.res);
-        by = __fmul_rn((float)(y * CS), map.res);
-        bz = __fmul_rn((float)(z * CS), map.res);
+        const float bx = __fmul_rn((float)(x * CS), map.res), by = __fmul_rn((float)(y * CS), map.res), bz = __fmul_rn((float)(z * CS), map.res);
         candidate = frustum_intersects_exact(fp, bx, by, bz, __fadd_rn(bx, ext), __fadd_rn(by, ext), __fadd_rn(bz, ext));
         if (candidate && map.world > 1)
             candidate = (owner_hash(x, y, z) % (unsigned)map.world) == (unsigned)map.rank;
         if (candidate)
         {
-            const int code = classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
-            // the hash table is only consulted for the few IDs the depth test could not reject
-            if (code == 2 || (code == 1 && fp.carve))
+#pragma unroll
+            for (int k = 0; k < BPL; k++)
             {
-                slot = hash_lookup(map, pack_id(x, y, z));
-                keepNew = slot < 0 && code == 2;
-                keepOld = slot >= 0;            // bricks decide below (free-space bricks need their carvable bit)
+                const int b = gl + k * GL;
+                const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
+                code[k] = classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
+                                       bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
             }
         }
     }
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned candMask = __ballot_sync(0xffffffffu, candidate);
+    bool has2 = false, has1 = false;
+#pragma unroll
+    for (int k = 0; k < BPL; k++)
+    {
+        has2 |= code[k] == 2;
+        has1 |= code[k] == 1;
+    }
+    const unsigned m2 = __ballot_sync(0xffffffffu, has2) & groupMask;
+    const unsigned m1 = __ballot_sync(0xffffffffu, has1) & groupMask;
+    const bool chunkBand = m2 != 0u, chunkFree = m1 != 0u;
+    // group leader: one hash lookup per undecided chunk, one flag word per existing one
+    int slot = -1;
+    unsigned long long flags = 0ull;
+    if (leader && (chunkBand || (chunkFree && fp.carve)))
+    {
+        slot = hash_lookup(map, pack_id(x, y, z));
+        if (slot >= 0 && chunkFree && fp.carve)
+            flags = map.brick_flags[slot];
+    }
+    const int leaderLane = (int)(lane & ~(unsigned)(GL - 1));
+    slot = __shfl_sync(0xffffffffu, slot, leaderLane);
+    flags = __shfl_sync(0xffffffffu, flags, leaderLane);
+
+    const bool keepNew = leader && slot < 0 && chunkBand;
+    const unsigned candMask = __ballot_sync(0xffffffffu, candidate && leader);
     const unsigned newMask = __ballot_sync(0xffffffffu, keepNew);
-    unsigned oldMask = __ballot_sync(0xffffffffu, keepOld);
     int base = 0;
     if (lane == 0)
     {
@@ -364,59 +437,23 @@ __global__ void __launch_bounds__(64) chunk_candidates_kernel(FrameParams fp, De
         else
             atomicOr(&map.ctr->error_flags, kErrWorkFull);
     }
-    // expand the kept existing chunks into brick units: groups of GL lanes take one chunk each, lanes = bricks
-    constexpr int GL = NB >= 32 ? 32 : (NB < 8 ? 8 : NB);           // lanes per chunk (8 for 16^3 and 8^3 chunks, 32 for 32^3)
-    constexpr int GROUPS = 32 / GL;
-    const int group = (int)lane / GL, gl = (int)lane % GL;
-    while (oldMask)
+#pragma unroll
+    for (int k = 0; k < BPL; k++)
     {
-        // the group's chunk: the (group)-th set bit of oldMask, if any
-        unsigned mm = oldMask;
-        int src = -1;
-#pragma unroll
-        for (int k = 0; k < GROUPS; k++)
+        const int b = gl + k * GL;
+        const bool keepB = slot >= 0 && (code[k] == 2 || (code[k] == 1 && fp.carve && ((flags >> b) & 1ull)));
+        const unsigned bm = __ballot_sync(0xffffffffu, keepB);
+        int ubase = 0;
+        if (lane == 0 && bm)
+            ubase = atomicAdd(&map.ctr->unit_count, __popc(bm));
+        ubase = __shfl_sync(0xffffffffu, ubase, 0);
+        if (keepB)
         {
-            const int bit = mm ? __ffs(mm) - 1 : -1;
-            if (k == group)
-                src = bit;
-            if (mm)
-                mm &= mm - 1;
-        }
-        oldMask = mm;
-        const int srcLane = src < 0 ? 0 : src;
-        const int cxI = __shfl_sync(0xffffffffu, x, srcLane), cyI = __shfl_sync(0xffffffffu, y, srcLane), czI = __shfl_sync(0xffffffffu, z, srcLane);
-        const int cslot = __shfl_sync(0xffffffffu, slot, srcLane);
-        const float obx = __shfl_sync(0xffffffffu, bx, srcLane), oby = __shfl_sync(0xffffffffu, by, srcLane), obz = __shfl_sync(0xffffffffu, bz, srcLane);
-        const unsigned long long flags = src >= 0 ? map.brick_flags[cslot] : 0ull;
-#pragma unroll
-        for (int b0 = 0; b0 < NB; b0 += GL)
-        {
-            const int b = b0 + gl;
-            bool keepB = false;
-            if (src >= 0 && b < NB)
-            {
-                int code = 2;
-                if (NB > 1)
-                {
-                    const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
-                    code = classify_box(fp, obx + (float)(qx * 8) * map.res + map.half, oby + (float)(qy * 8) * map.res + map.half,
-                                        obz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
-                }
-                keepB = code == 2 || (code == 1 && fp.carve && ((flags >> b) & 1ull));
-            }
-            const unsigned bm = __ballot_sync(0xffffffffu, keepB);
-            int ubase = 0;
-            if (lane == 0 && bm)
-                ubase = atomicAdd(&map.ctr->unit_count, __popc(bm));
-            ubase = __shfl_sync(0xffffffffu, ubase, 0);
-            if (keepB)
-            {
-                const int pos = ubase + __popc(bm & ((1u << lane) - 1));
-                if (pos < fp.units_cap)
-                    fp.units[pos] = make_int4(cxI, cyI, czI, cslot | (b << 24));
-                else
-                    atomicOr(&map.ctr->error_flags, kErrWorkFull);
-            }
+            const int pos = ubase + __popc(bm & ((1u << lane) - 1));
+            if (pos < fp.units_cap)
+                fp.units[pos] = make_int4(x, y, z, slot | (b << 24));
+            else
+                atomicOr(&map.ctr->error_flags, kErrWorkFull);
         }
     }
 }
@@ -458,33 +495,14 @@ __device__ __forceinline__ float2 dist_integrate(float2 v, float d, float wu)
 // N < 2048, D <= 8. tests/test_host_logic.py::test_color_integrate_integer_identity checks all 8 * 256 * 256 cases.
 __constant__ unsigned cRecip20[9] = {0u, 1048576u, 524288u, 349526u, 262144u, 209716u, 174763u, 149797u, 131072u};
 
-__device__ __forceinline__ unsigned color_integrate_packed(unsigned cv, unsigned r, unsigned g, unsigned b)
+__device__ __forceinline__ unsigned color_integrate_packed(unsigned cv, unsigned rgb)
 {
     const unsigned w = cv >> 24;
     const unsigned m = cRecip20[w + 1];
-    const unsigned nr = ((w * (cv & 0xFFu) + r) * m) >> 20;
-    const unsigned ng = ((w * ((cv >> 8) & 0xFFu) + g) * m) >> 20;
-    const unsigned nb = ((w * ((cv >> 16) & 0xFFu) + b) * m) >> 20;
+    const unsigned nr = ((w * (cv & 0xFFu) + (rgb & 0xFFu)) * m) >> 20;
+    const unsigned ng = ((w * ((cv >> 8) & 0xFFu) + ((rgb >> 8) & 0xFFu)) * m) >> 20;
+    const unsigned nb = ((w * ((cv >> 16) & 0xFFu) + ((rgb >> 16) & 0xFFu)) * m) >> 20;
     return nr | (ng << 8) | (nb << 16) | ((w + 1) << 24);
-}
-
-// ColorImage::At (OC ColorImage.h:61-101)
-__device__ __forceinline__ void color_fetch(const FrameParams &fp, int pixel, unsigned *r, unsigned *g, unsigned *b)
-{
-    const uint8_t *p = fp.color + (size_t)pixel * fp.channels;          // Index(row, col, 0) = (col + row * width) * channels
-    if (fp.channels >= 3)
-    {
-        *b = __ldg(p);
-        *g = __ldg(p + 1);
-        *r = __ldg(p + 2);
-    }
-    else if (fp.channels == 2)
-    {
-        *r = __ldg(p);
-        *g = *b = __ldg(p + 1);
-    }
-    else
-        *r = *g = *b = __ldg(p);
 }
 
 struct VoxelStats
@@ -554,7 +572,8 @@ __device__ __forceinline__ bool process_batch(const FrameParams &fp, const Devic
     int pix[4], idx[4];
     float cz[4], depth[4], trunc[4];
     float2 dv[4];
-    unsigned cv[4];
+    unsigned cv[4], cpx[4];
+    const bool specColor = COLOR_PATH && MODE != 2 && fp.same_cam && col != nullptr;
 #pragma unroll
     for (int k = 0; k < 4; k++)
     {
@@ -575,6 +594,7 @@ __device__ __forceinline__ bool process_batch(const FrameParams &fp, const Devic
     for (int k = 0; k < 4; k++)
     {
         depth[k] = pix[k] >= 0 ? __ldg(fp.depth + pix[k]) : __int_as_float(0x7fc00000);
+        cpx[k] = (specColor && pix[k] >= 0) ? __ldg(fp.color_packed + pix[k]) : 0u;   // same pixel as the depth when the cameras coincide
         trunc[k] = PER_PIXEL ? (pix[k] >= 0 ? __ldg(fp.trunc_img + pix[k]) : 0.0f) : fp.trunc_param;
         if (MODE == 0)
         {
@@ -631,9 +651,8 @@ __device__ __forceinline__ bool process_batch(const FrameParams &fp, const Devic
                     }
                     if (onC && (cv[k] >> 24) < 8u)                                // ProjectionIntegrator.h:153
                     {
-                        unsigned r, g, b;
-                        color_fetch(fp, cpix, &r, &g, &b);
-                        cv[k] = color_integrate_packed(cv[k], r, g, b);
+                        const unsigned rgb = fp.same_cam ? cpx[k] : __ldg(fp.color_packed + cpix);
+                        cv[k] = color_integrate_packed(cv[k], rgb);
                         wroteCol = true;
                     }
                 }
@@ -686,8 +705,10 @@ __device__ __forceinline__ void mark_chunk_updated(const FrameParams &fp, const 
     }
 }
 
-// Block-level flush of the per-lane counters (one set of global atomics per CTA, spread over kCounterSlots addresses).
-__device__ __forceinline__ void flush_counters(const DeviceMap &map, const VoxelStats &st, int *sCnt)
+// Block-level flush of the per-lane counters (one set of global atomics per CTA, spread over kCounterSlots addresses),
+// then a ticket: the LAST CTA of the frame's two integrate kernels copies what the host needs into the pinned ring slot
+// (no snapshot kernel, no memcpy, no event: the host polls frame_id).
+__device__ __forceinline__ void flush_counters(const FrameParams &fp, const DeviceMap &map, const VoxelStats &st, int *sCnt)
 {
     int a = st.nUpd, b = st.nCarve, c = st.nCol;
     for (int o = 16; o > 0; o >>= 1)
@@ -707,6 +728,39 @@ __device__ __forceinline__ void flush_counters(const DeviceMap &map, const Voxel
     {
         unsigned long long *dst = threadIdx.x == 0 ? map.ctr->n_upd : (threadIdx.x == 1 ? map.ctr->n_carve : map.ctr->n_col);
         atomicAdd(&dst[blockIdx.x % kCounterSlots], (unsigned long long)sCnt[threadIdx.x]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        int last = 0;
+        if (threadIdx.x == 0)
+        {
+            __threadfence();
+            last = atomicAdd(&map.ctr->tickets, 1) == fp.total_ctas - 1;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last)
+        {
+            __threadfence();
+            const volatile Counters *ctr = map.ctr;
+            static_assert(kCounterSlots == 32, "one lane per counter slot");
+            long long u = (long long)ctr->n_upd[threadIdx.x], v = (long long)ctr->n_carve[threadIdx.x], w = (long long)ctr->n_col[threadIdx.x];
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                u += __shfl_xor_sync(0xffffffffu, u, o);
+                v += __shfl_xor_sync(0xffffffffu, v, o);
+                w += __shfl_xor_sync(0xffffffffu, w, o);
+            }
+            if (threadIdx.x == 0)
+            {
+                int4 *h = reinterpret_cast<int4 *>(fp.host_slot);
+                const int id = fp.frame_id;
+                h[0] = make_int4(id, ctr->n_chunks, ctr->n_dirty, ctr->error_flags);
+                h[1] = make_int4(id, ctr->unit_count, ctr->new_count, ctr->candidates);
+                h[2] = make_int4(id, ctr->n_new, ctr->updated_chunks, (int)v);
+                h[3] = make_int4(id, (int)w, (int)(u & 0xffffffffll), (int)(u >> 32));
+            }
+        }
     }
 }
 
@@ -741,7 +795,7 @@ __global__ void __launch_bounds__(256, 3) integrate_bricks_kernel(FrameParams fp
         if (__any_sync(0xffffffffu, st.updated))
             mark_chunk_updated(fp, map, slot, unit.x, unit.y, unit.z, lane);
     }
-    flush_counters(map, st, sCnt);
+    flush_counters(fp, map, st, sCnt);
 }
 
 // New chunks: one CTA per candidate, a warp per brick (CS = 32: eight bricks per warp; CS = 8: warp 0 only). The chunk
@@ -784,6 +838,15 @@ __global__ void __launch_bounds__(256) integrate_new_chunks_kernel(FrameParams f
         }
         if (!__syncthreads_or(any))
             continue;
+        // The chunk survives, hence it is updated: mark its 27-neighbourhood dirty (Chisel.h:89-101, 175-189) on warp 1
+        // while thread 0 allocates -- the two chains of global atomics overlap.
+        if (warp == (nWarps > 1 ? 1 : 0))
+        {
+            if (lane < 27)
+                dirty_insert(map, pack_id(item.x + lane / 9 - 1, item.y + (lane / 3) % 3 - 1, item.z + lane % 3 - 1));
+            if (lane == 31)
+                atomicAdd(&map.ctr->updated_chunks, 1);
+        }
         if (t == 0)
         {
             int s = atomicAdd(&map.ctr->n_chunks, 1);
@@ -799,7 +862,7 @@ __global__ void __launch_bounds__(256) integrate_new_chunks_kernel(FrameParams f
                 map.slot_ids[3 * s + 1] = item.y;
                 map.slot_ids[3 * s + 2] = item.z;
                 map.brick_flags[s] = 0ull;
-                map.slot_epoch[s] = 0;
+                map.slot_epoch[s] = fp.frame_id;
                 hash_insert_new(map, pack_id(item.x, item.y, item.z), s);
                 atomicAdd(&map.ctr->n_new, 1);
             }
@@ -807,25 +870,27 @@ __global__ void __launch_bounds__(256) integrate_new_chunks_kernel(FrameParams f
         }
         __syncthreads();
         const int slot = *sSlot;
-        __syncthreads();
         if (slot < 0)
+        {
+            __syncthreads();
             continue;
+        }
         float2 *dist = dist_ptr(map, slot);
         unsigned *col = map.use_color ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
         for (int b = warp; b < NB; b += nWarps)
         {
             const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, b % BPA, (b / BPA) % BPA, b / (BPA * BPA), lane);
             st.updated = st.carvable = false;
+#pragma unroll 1
             for (int q = 0; q < 4; q++)
                 process_batch<CS, COLOR_PATH, PER_PIXEL, 1>(fp, map, L, q, dist, col, &st);
+            // brick_flags[slot] was zeroed by thread 0 before the barrier above
             if (__any_sync(0xffffffffu, st.carvable) && lane == 0)
                 atomicOr(&map.brick_flags[slot], 1ull << b);
         }
-        __syncthreads();                                                // brick_flags / slot_epoch initialisation vs. the marking below
-        if (warp == 0)
-            mark_chunk_updated(fp, map, slot, item.x, item.y, item.z, lane);
+        __syncthreads();                                                // sSlot is reused by the next item
     }
-    flush_counters(map, st, sCnt);
+    flush_counters(fp, map, st, sCnt);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -841,28 +906,9 @@ static int resident_blocks(K kernel, int threads)
     return sms * (perSm > 0 ? perSm : 1);
 }
 
-// Copies the counters to a slot of the pinned host ring when the frame's kernels are done. The host learns what a
-// frame did (chunk count for capacity planning, statistics) without a memcpy, an event or a synchronisation.
-__global__ void snapshot_kernel(DeviceMap map, Counters *hostSlot, int frameId)
-{
-    const int n = (int)(sizeof(Counters) / sizeof(int));
-    const int *src = reinterpret_cast<const int *>(map.ctr);
-    int *dst = reinterpret_cast<int *>(hostSlot);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (i != (int)(offsetof(Counters, frame_id) / sizeof(int)))
-            dst[i] = src[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        *reinterpret_cast<volatile int *>(&hostSlot->frame_id) = frameId;
-        __threadfence_system();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // The per-frame work as a CUDA graph:
-//     frame_prepare -> chunk_candidates -> { integrate_new_chunks || integrate_bricks } -> snapshot
+//     frame_prepare -> chunk_candidates -> { integrate_new_chunks || integrate_bricks }   (the last CTA snapshots the counters)
 // built once per kernel variant; every frame only the kernel arguments and grid sizes are patched
 // (cudaGraphExecKernelNodeSetParams) and the graph is launched once. The profiling variant serialises the two integrate
 // kernels and brackets every kernel with event-record nodes.
@@ -870,7 +916,7 @@ struct FrameGraphVariant
 {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t nPrepare = nullptr, nCand = nullptr, nNew = nullptr, nBricks = nullptr, nSnap = nullptr;
+    cudaGraphNode_t nPrepare = nullptr, nCand = nullptr, nNew = nullptr, nBricks = nullptr;
     void *fPrepare = nullptr, *fCand = nullptr, *fNew = nullptr, *fBricks = nullptr;
     int newResident = 1, brickResident = 1;
 };
@@ -939,18 +985,17 @@ static cudaKernelNodeParams kernel_params(void *func, dim3 grid, dim3 block, voi
 }
 
 // events: [0] before prepare, [1] after prepare, [2] after candidates, [7] after new chunks, [3] after bricks (profiling only)
-cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const DeviceMap &mapIn, long long candidates, Counters *hostSlot,
+cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const DeviceMap &mapIn, long long candidates, long long newHint, HostSnapshot *hostSlot,
                                bool profiling, cudaEvent_t *evt, cudaStream_t st)
 {
     FrameParams fp = fpIn;
     DeviceMap map = mapIn;
-    int frameId = fp.frame_id;
+    fp.host_slot = hostSlot;
     const bool pp = fp.trunc_img != nullptr;
     FrameGraphVariant &g = fg->v[(fp.color_path ? 1 : 0) | (pp ? 2 : 0) | (profiling ? 4 : 0)];
     const int total = fp.n[0] * fp.n[1] * fp.n[2];
     const long long nb = (long long)(map.cs / 8) * (map.cs / 8) * (map.cs / 8);
     void *argsFrame[2] = {&fp, &map};
-    void *argsSnap[3] = {&map, &hostSlot, &frameId};
     cudaError_t e;
     const bool build = g.exec == nullptr;
     if (build)
@@ -963,14 +1008,15 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
         }
     }
     const dim3 gPrepare((fp.cam.W + 63) / 64, (fp.cam.H + 63) / 64);
-    const dim3 gCand((unsigned)std::max(1, (total + 63) / 64));
-    const dim3 gNew((unsigned)std::max(1ll, std::min<long long>(candidates, g.newResident)));
+    const long long candLanes = (long long)total * std::min<long long>(nb, 32);
+    const dim3 gCand((unsigned)std::max(1ll, (candLanes + 255) / 256));
+    const dim3 gNew((unsigned)std::max(1ll, std::min<long long>(std::min<long long>(candidates, newHint), g.newResident)));
     const dim3 gBricks((unsigned)std::max(1ll, std::min<long long>((candidates * nb * 2 + 7) / 8, g.brickResident)));
+    fp.total_ctas = (int)(gNew.x + gBricks.x);
     cudaKernelNodeParams pPrepare = kernel_params(g.fPrepare, gPrepare, dim3(256), argsFrame);
-    cudaKernelNodeParams pCand = kernel_params(g.fCand, gCand, dim3(64), argsFrame);
+    cudaKernelNodeParams pCand = kernel_params(g.fCand, gCand, dim3(256), argsFrame);
     cudaKernelNodeParams pNew = kernel_params(g.fNew, gNew, dim3(256), argsFrame);
     cudaKernelNodeParams pBricks = kernel_params(g.fBricks, gBricks, dim3(256), argsFrame);
-    cudaKernelNodeParams pSnap = kernel_params((void *)snapshot_kernel, dim3(1), dim3(128), argsSnap);
     if (build)
     {
         if ((e = cudaGraphCreate(&g.graph, 0)) != cudaSuccess)
@@ -1006,8 +1052,6 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
             prev = g.nBricks;
             if ((e = addEvent(evt[3])) != cudaSuccess)
                 return e;
-            if ((e = cudaGraphAddKernelNode(&g.nSnap, g.graph, &prev, 1, &pSnap)) != cudaSuccess)
-                return e;
         }
         else
         {
@@ -1015,9 +1059,6 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
             if ((e = cudaGraphAddKernelNode(&g.nNew, g.graph, &prev, 1, &pNew)) != cudaSuccess)
                 return e;
             if ((e = cudaGraphAddKernelNode(&g.nBricks, g.graph, &prev, 1, &pBricks)) != cudaSuccess)
-                return e;
-            cudaGraphNode_t deps[2] = {g.nNew, g.nBricks};
-            if ((e = cudaGraphAddKernelNode(&g.nSnap, g.graph, deps, 2, &pSnap)) != cudaSuccess)
                 return e;
         }
         if ((e = cudaGraphInstantiate(&g.exec, g.graph, 0)) != cudaSuccess)
@@ -1032,8 +1073,6 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
         if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nNew, &pNew)) != cudaSuccess)
             return e;
         if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nBricks, &pBricks)) != cudaSuccess)
-            return e;
-        if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nSnap, &pSnap)) != cudaSuccess)
             return e;
     }
     return cudaGraphLaunch(g.exec, st);

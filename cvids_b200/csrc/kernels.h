@@ -12,8 +12,9 @@ namespace chs
 struct FrameGraph;
 FrameGraph *frame_graph_create();
 void frame_graph_destroy(FrameGraph *fg);
+// newHint: expected number of new-chunk candidates (sizes that kernel's grid; any value is correct).
 // Enqueue one frame (prepare -> candidates -> {new chunks || bricks} -> counter snapshot into hostSlot) as one graph launch.
-cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fp, const DeviceMap &map, long long candidates, Counters *hostSlot,
+cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fp, const DeviceMap &map, long long candidates, long long newHint, HostSnapshot *hostSlot,
                                bool profiling, cudaEvent_t *evt, cudaStream_t st);
 float host_truncation(int kind, float param, float depth);
 
