@@ -69,7 +69,7 @@ EXPORTS = (
     "chs_last_error_string", "chs_abi_version", "chs_create", "chs_destroy", "chs_reset", "chs_synchronize",
     "chs_set_stream", "chs_set_profiling", "chs_integrate_depth", "chs_integrate_depth_color", "chs_get_frame_stats",
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
-    "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
+    "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner",
 )
 
@@ -106,6 +106,9 @@ def load_library(build_if_missing: bool = True):
     lib.chs_has_chunk.argtypes = [vp, vp, C.POINTER(i32)]
     lib.chs_download_chunk.argtypes = [vp, vp, vp, vp, vp]
     lib.chs_download_all.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.chs_export_chunks.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.chs_import_chunks.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.chs_set_dirty.argtypes = [vp, i64, vp]
     lib.chs_num_dirty.argtypes = [vp, C.POINTER(i64)]
     lib.chs_dirty_ids.argtypes = [vp, vp, i64]
     lib.chs_frustum.argtypes = [vp, C.POINTER(chs_camera), vp, vp, vp]
@@ -358,6 +361,31 @@ class Chisel:
                 colors=(col[a:b].copy() if col is not None else np.zeros((0, 3), np.float32)),
                 grids=g[goff[i]:goff[i + 1]].copy())
         return out
+
+    # ---- chunk export / import / explicit dirty set (ghost chunks for sharded meshing, checkpoints) ----
+    def export_chunks(self, ids):
+        """(found [n] bool, sdf [n,V], weight [n,V], rgbw [n,V,4]) for the listed IDs; rows of absent chunks are zero."""
+        ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1, 3))
+        n, V = len(ids), self.chunk ** 3
+        found = np.zeros(n, np.uint8)
+        sdf = np.zeros((n, V), np.float32)
+        w = np.zeros((n, V), np.float32)
+        rgbw = np.zeros((n, V, 4), np.uint8)
+        if n:
+            _check(self._lib.chs_export_chunks(self._h, n, _ptr(ids), _ptr(found), _ptr(sdf), _ptr(w), _ptr(rgbw) if self.use_color else None))
+        return found.astype(bool), sdf, w, rgbw
+
+    def import_chunks(self, ids, sdf, weight, rgbw=None):
+        ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1, 3))
+        if len(ids):
+            sdf = np.ascontiguousarray(sdf, np.float32)
+            weight = np.ascontiguousarray(weight, np.float32)
+            c = np.ascontiguousarray(rgbw, np.uint8) if (rgbw is not None and self.use_color) else None
+            _check(self._lib.chs_import_chunks(self._h, len(ids), _ptr(ids), _ptr(sdf), _ptr(weight), _ptr(c)))
+
+    def set_dirty(self, ids):
+        ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1, 3))
+        _check(self._lib.chs_set_dirty(self._h, len(ids), _ptr(ids) if len(ids) else None))
 
     # ---- helpers mirroring the oracle front-ends (tests swap implementations) ----
     def state(self):

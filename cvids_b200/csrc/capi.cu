@@ -947,6 +947,164 @@ int chs_download_all(chs_map *m, int64_t cap, int32_t *ids, float *sdf, float *w
     return CHS_OK;
 }
 
+// ---- chunk export / import / explicit dirty set: the primitives behind sharded meshing (ghost chunks) and map checkpoints ----
+
+__global__ void import_insert_kernel(DeviceMap map, const int *ids, int firstSlot, int n)
+{
+    // append n new chunks (IDs known to be absent) at slots firstSlot .. firstSlot + n - 1
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int s = firstSlot + i;
+        map.slot_ids[3 * s] = ids[3 * i];
+        map.slot_ids[3 * s + 1] = ids[3 * i + 1];
+        map.slot_ids[3 * s + 2] = ids[3 * i + 2];
+        map.brick_flags[s] = ~0ull;              // unknown history: assume every brick may hold a carvable voxel (conservative)
+        map.slot_epoch[s] = 0;
+        hash_insert_new(map, pack_id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]), s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        map.ctr->n_chunks = firstSlot + n;
+}
+
+__global__ void set_dirty_kernel(DeviceMap map, const int *ids, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dirty_insert(map, pack_id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]));
+}
+
+static bool id_in_range(const int32_t *id)
+{
+    return id[0] >= -kIdBias && id[0] < kIdBias && id[1] >= -kIdBias && id[1] < kIdBias && id[2] >= -kIdBias && id[2] < kIdBias;
+}
+
+// Voxels of the listed chunks (host buffers, n*V each; rgbw n*4V or NULL). found[i] = 0 for IDs this map does not hold
+// (their output rows are left untouched).
+int chs_export_chunks(chs_map *m, int64_t n, const int32_t *ids, uint8_t *found, float *sdf, float *weight, uint8_t *rgbw)
+{
+    if (!m || !ids || !found)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    const int V = m->dm.V;
+    std::vector<float2> tmp((size_t)V);
+    for (int64_t i = 0; i < n; i++)
+    {
+        found[i] = 0;
+        if (!id_in_range(ids + 3 * i))
+            continue;
+        auto it = m->hostIndex.find(pack_id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]));
+        if (it == m->hostIndex.end())
+            continue;
+        found[i] = 1;
+        if ((rc = download_slot(m, it->second, sdf ? sdf + (size_t)i * V : nullptr, weight ? weight + (size_t)i * V : nullptr,
+                                rgbw ? rgbw + (size_t)i * V * 4 : nullptr)))
+            return rc;
+    }
+    return CHS_OK;
+}
+
+// Insert or overwrite chunks from host buffers (n*V each; rgbw may be NULL). Existing chunks keep their slot.
+int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sdf, const float *weight, const uint8_t *rgbw)
+{
+    if (!m || !ids || !sdf || !weight)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    if ((rc = refresh_host_ids(m, m->knownChunks)))
+        return rc;
+    const int V = m->dm.V;
+    std::vector<int> slots((size_t)n);
+    std::vector<int32_t> newIds;
+    long long next = m->knownChunks;
+    for (int64_t i = 0; i < n; i++)
+    {
+        if (!id_in_range(ids + 3 * i))
+            return fail(CHS_ERR_INVALID, "chunk IDs outside [-2^20, 2^20)");
+        const unsigned long long key = pack_id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+        auto it = m->hostIndex.find(key);
+        if (it != m->hostIndex.end())
+            slots[(size_t)i] = it->second;
+        else
+        {
+            slots[(size_t)i] = (int)next;
+            m->hostIndex[key] = (int)next++;
+            for (int k = 0; k < 3; k++)
+            {
+                newIds.push_back(ids[3 * i + k]);
+                m->hostIds.push_back(ids[3 * i + k]);
+            }
+        }
+    }
+    const long long nNew = next - m->knownChunks;
+    if ((rc = ensure_pool(m, next + 1)) || (rc = ensure_hash(m, next + 1)))
+        return rc;
+    cudaStream_t st = m->stream;
+    std::vector<float2> tmp((size_t)V);
+    for (int64_t i = 0; i < n; i++)
+    {
+        const int slot = slots[(size_t)i];
+        for (int v = 0; v < V; v++)
+            tmp[(size_t)v] = make_float2(sdf[(size_t)i * V + v], weight[(size_t)i * V + v]);
+        float2 *dst = m->distSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
+        CHS_CUDA(cudaMemcpyAsync(dst, tmp.data(), sizeof(float2) * V, cudaMemcpyHostToDevice, st));
+        if (m->cfg.use_color)
+        {
+            uchar4 *cd = m->colorSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
+            if (rgbw)
+                CHS_CUDA(cudaMemcpyAsync(cd, rgbw + (size_t)i * V * 4, 4 * (size_t)V, cudaMemcpyHostToDevice, st));
+            else
+                CHS_CUDA(cudaMemsetAsync(cd, 0, 4 * (size_t)V, st));
+        }
+        CHS_CUDA(cudaStreamSynchronize(st));             // tmp is reused
+    }
+    if (nNew > 0)
+    {
+        int *dIds = nullptr;
+        CHS_CUDA(cudaMallocAsync((void **)&dIds, sizeof(int) * 3 * (size_t)nNew, st));
+        CHS_CUDA(cudaMemcpyAsync(dIds, newIds.data(), sizeof(int) * 3 * (size_t)nNew, cudaMemcpyHostToDevice, st));
+        import_insert_kernel<<<(int)std::min<long long>((nNew + 255) / 256, 148), 256, 0, st>>>(m->dm, dIds, (int)m->knownChunks, (int)nNew);
+        CHS_CUDA(cudaGetLastError());
+        CHS_CUDA(cudaFreeAsync(dIds, st));
+        CHS_CUDA(cudaStreamSynchronize(st));
+        m->knownChunks = next;
+    }
+    return CHS_OK;
+}
+
+// Replace the dirty set by the given IDs (Chisel::meshesToUpdate assigned from outside).
+int chs_set_dirty(chs_map *m, int64_t n, const int32_t *ids)
+{
+    if (!m || (n > 0 && !ids))
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    for (int64_t i = 0; i < n; i++)
+        if (!id_in_range(ids + 3 * i))
+            return fail(CHS_ERR_INVALID, "chunk IDs outside [-2^20, 2^20)");
+    cudaStream_t st = m->stream;
+    if ((rc = ensure_dirty(m, n + 16)))
+        return rc;
+    launch_fill_u64(m->dm.dirty_keys, m->dirtySize, kEmptyKey, st);
+    CHS_CUDA(cudaMemsetAsync(&m->dCtr->n_dirty, 0, sizeof(int), st));
+    if (n > 0)
+    {
+        int *dIds = nullptr;
+        CHS_CUDA(cudaMallocAsync((void **)&dIds, sizeof(int) * 3 * (size_t)n, st));
+        CHS_CUDA(cudaMemcpyAsync(dIds, ids, sizeof(int) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+        set_dirty_kernel<<<(int)std::min<long long>((n + 255) / 256, 148), 256, 0, st>>>(m->dm, dIds, (int)n);
+        CHS_CUDA(cudaGetLastError());
+        CHS_CUDA(cudaFreeAsync(dIds, st));
+    }
+    CHS_CUDA(cudaStreamSynchronize(st));
+    m->knownDirty = n;
+    return CHS_OK;
+}
+
 int chs_num_dirty(chs_map *m, int64_t *n)
 {
     if (!m || !n)

@@ -75,3 +75,76 @@ def gather_to_root(obj, dst: int = 0):
     out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
     dist.gather_object(obj, out, dst=dst)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sharded meshing: marching cubes reads the +x/+y/+z neighbour chunks and the gradient normals read
+# +-1 voxel, i.e. chunks owned by other ranks. Each re-mesh therefore runs in three phases:
+#   1. all-gather the per-rank dirty ID lists -> the global dirty set D (a rank marks the 27-neighbourhood of ITS updated
+#      chunks, whoever owns those IDs);
+#   2. every rank exports the chunks it owns inside the 27-neighbourhood of D; the exports are all-gathered, and each
+#      rank imports them into a scratch "ghost" map (a plain 1-rank map, reset per re-mesh);
+#   3. every rank meshes the dirty IDs IT owns on its ghost map; meshes are gathered on the root.
+# The result is the single-GPU mesh bit for bit, with one documented exception: the reference's colour lookup samples
+# voxel INDICES as if they were metres (quirk Q9); if the map happens to hold chunks at those aliased positions outside
+# the exchanged neighbourhood, their colours are not seen by the ghost map.
+
+def neighbourhood27(ids: np.ndarray) -> np.ndarray:
+    ids = np.asarray(ids, np.int32).reshape(-1, 3)
+    if not len(ids):
+        return ids
+    off = np.array([(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)], np.int32)
+    return np.unique((ids[:, None, :] + off[None, :, :]).reshape(-1, 3), axis=0)
+
+
+def phase1_dirty(shard) -> np.ndarray:
+    return shard.get_meshes_to_update()
+
+
+def phase2_export(shard, dirty_all: np.ndarray):
+    """This rank's contribution: (ids, sdf, weight, rgbw) of the chunks it holds in the 27-neighbourhood of D."""
+    need = neighbourhood27(dirty_all)
+    found, sdf, w, rgbw = shard.export_chunks(need)
+    return need[found], sdf[found], w[found], rgbw[found]
+
+
+def phase3_mesh(ghost, contributions, dirty_all: np.ndarray, rank: int, world: int) -> dict:
+    """Mesh the dirty IDs `rank` owns on the ghost map; returns {id: mesh} for every re-meshed chunk (incl. empty ones)."""
+    ghost.reset()
+    for ids, sdf, w, rgbw in contributions:
+        ghost.import_chunks(ids, sdf, w, rgbw)
+    mine = dirty_all[owners(dirty_all, world) == rank] if len(dirty_all) else dirty_all
+    ghost.set_dirty(mine)
+    ghost._lib.chs_update_meshes(ghost._h)
+    return ghost.download_last_meshes()
+
+
+def merge_remeshed(all_meshes: dict, remeshed: dict) -> None:
+    """The reference's publication rule (ChunkManager.cpp:101-127, quirk Q10) on the root's MeshMap."""
+    for cid, mesh in remeshed.items():
+        if cid in all_meshes or len(mesh["grids"]) > 0:
+            all_meshes[cid] = mesh
+
+
+def sharded_remesh(shard, ghost, rank: int, world: int, all_meshes: dict | None = None, root: int = 0):
+    """One distributed re-mesh over torch.distributed (any backend; payloads travel as pickled NumPy arrays). Returns the
+    root's MeshMap (None elsewhere)."""
+    import torch.distributed as dist
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    dirty_all = merge_dirty(all_gather(phase1_dirty(shard)))
+    contributions = all_gather(phase2_export(shard, dirty_all))
+    remeshed = phase3_mesh(ghost, contributions, dirty_all, rank, world)
+    shard.set_dirty(np.zeros((0, 3), np.int32))                      # meshesToUpdate.clear() (Chisel.cpp:57)
+    gathered = gather_to_root(remeshed, root)
+    if rank != root:
+        return None
+    if all_meshes is None:
+        all_meshes = {}
+    for part in gathered:
+        merge_remeshed(all_meshes, part)
+    return all_meshes

@@ -150,6 +150,12 @@ int chs_has_chunk(chs_map *map, const int32_t id[3], int *found); /* ChunkManage
 int chs_download_chunk(chs_map *map, const int32_t id[3], float *sdf, float *weight, uint8_t *rgbw);
 /* Whole map in one transfer, pool order: ids [3n], sdf/weight [n*V], rgbw [n*4V] or NULL. */
 int chs_download_all(chs_map *map, int64_t cap_chunks, int32_t *ids, float *sdf, float *weight, uint8_t *rgbw);
+/* Chunk export / import and explicit dirty set: the primitives behind sharded meshing (ghost copies of neighbour chunks
+ * owned by other ranks) and map checkpoint / resume (the reference's GetAllChunks wire format, CR Serialization.h:31-84, is
+ * broken). Host buffers: sdf, weight [n*V]; rgbw [n*4V] or NULL. */
+int chs_export_chunks(chs_map *map, int64_t n, const int32_t *ids, uint8_t *found, float *sdf, float *weight, uint8_t *rgbw);
+int chs_import_chunks(chs_map *map, int64_t n, const int32_t *ids, const float *sdf, const float *weight, const uint8_t *rgbw);
+int chs_set_dirty(chs_map *map, int64_t n, const int32_t *ids);
 int chs_num_dirty(chs_map *map, int64_t *n);                   /* synchronises */
 int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
 

@@ -222,6 +222,54 @@ def test_sharded_union_equals_single_map():
     assert np.array_equal(dirty, single.dirty())
 
 
+def test_export_import_roundtrip_and_checkpoint():
+    """chs_export_chunks / chs_import_chunks / chs_set_dirty: a map rebuilt from its exported chunks is the same map (the
+    checkpoint / resume path the reference lacks), and it meshes identically."""
+    setup = Setup(16, 0.05, True)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    for depth, col, pose in common.orbit_stream(common.SMALL_CAM, 4, total=30, color=True, seed=5):
+        a.integrate(depth, pose, common.SMALL_CAM.as_array(), col)
+    ids, sdf, w, rgbw = a.state()
+    found, s2, w2, c2 = a.m.export_chunks(np.concatenate([ids, [[999, 999, 999]]]))
+    assert found[:-1].all() and not found[-1]
+    assert np.array_equal(s2[:-1].view(np.uint32), sdf.view(np.uint32)) and np.array_equal(c2[:-1], rgbw)
+    b.m.import_chunks(ids[::-1], sdf[::-1], w[::-1], rgbw[::-1])
+    common.assert_state_equal(b.state(), a.state())
+    b.m.import_chunks(ids[:3], sdf[:3], w[:3], rgbw[:3])                 # overwrite keeps slots
+    common.assert_state_equal(b.state(), a.state())
+    b.m.set_dirty(a.dirty())
+    assert np.array_equal(b.dirty(), a.dirty())
+    a.remesh(); b.remesh()
+    common.assert_meshes_equal(a.meshes(), b.meshes())
+    assert len(b.dirty()) == 0
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_sharded_meshing_equals_single_map(color):
+    """Row (e), meshing: N virtual ranks on one device, ghost-chunk exchange of the dirty neighbourhood (sharding.py);
+    the gathered meshes must equal the 1-rank meshes index for index, across two re-mesh rounds."""
+    from cvids_b200 import sharding
+    setup = Setup(16, 0.05, color)
+    world = 3
+    single = common.Driver(setup, "cuda")
+    shards = [common.Driver(setup, "cuda", rank=r, world=world) for r in range(world)]
+    ghosts = [common.Driver(setup, "cuda") for _ in range(world)]
+    root_meshes = {}
+    frames = list(common.orbit_stream(common.SMALL_CAM, 8, total=30, color=color, seed=6))
+    for i, (depth, col, pose) in enumerate(frames):
+        for d in [single] + shards:
+            d.integrate(depth, pose, common.SMALL_CAM.as_array(), col)
+        if i in (3, 7):
+            single.remesh()
+            dirty_all = sharding.merge_dirty([sharding.phase1_dirty(s.m) for s in shards])
+            contributions = [sharding.phase2_export(s.m, dirty_all) for s in shards]
+            for r in range(world):
+                sharding.merge_remeshed(root_meshes, sharding.phase3_mesh(ghosts[r].m, contributions, dirty_all, r, world))
+                shards[r].m.set_dirty(np.zeros((0, 3), np.int32))
+            common.assert_meshes_equal(root_meshes, single.meshes(), "round at frame %d" % i)
+    assert sum(len(m["vertices"]) for m in root_meshes.values()) > 3000
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 at full size (752x480, 2 cm, colour): size-independent properties instead of the oracle.
     (1) with ConstantWeighter(1) and trunc 4 voxels the update weight is 1/(5*0.08f) ~ 2.5, so every weight is a
