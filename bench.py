@@ -174,6 +174,8 @@ def run_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback")
     torch.cuda.set_device(local)
