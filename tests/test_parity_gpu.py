@@ -270,6 +270,79 @@ def test_sharded_meshing_equals_single_map(color):
     assert sum(len(m["vertices"]) for m in root_meshes.values()) > 3000
 
 
+def test_multi_agent_interleaved_config3_shape():
+    """BASELINE config 3 shape, reduced: four agents' trajectories (phase offsets pi/2) fused into ONE shared map in the
+    canonical round-robin order; running averages are order dependent, so the order is part of the contract."""
+    setup = Setup(16, 0.05, False)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    cam = common.SMALL_CAM
+    for f in range(4):
+        for agent in range(4):
+            pose = scenes.orbit_pose(f, 24, agent * np.pi / 2)
+            depth, _ = scenes.render(scenes.ROOM, cam, pose)
+            a.integrate(depth, pose, cam.as_array())
+            b.integrate(depth, pose, cam.as_array())
+    common.assert_state_equal(a.state(), b.state())
+    a.remesh(); b.remesh()
+    common.assert_meshes_equal(a.meshes(), b.meshes())
+    # the agent-major order visits the same voxels the same number of times: same chunk set, same weights
+    c = common.Driver(setup, "cuda")
+    for agent in range(4):
+        for f in range(4):
+            pose = scenes.orbit_pose(f, 24, agent * np.pi / 2)
+            depth, _ = scenes.render(scenes.ROOM, cam, pose)
+            c.integrate(depth, pose, cam.as_array())
+    sa, sc = a.state(), c.state()
+    assert np.array_equal(sa[0], sc[0]) and np.array_equal(sa[2], sc[2])
+    assert np.allclose(sa[1], sc[1], atol=1e-5)
+
+
+def test_hall_1cm_config4_shape_parity():
+    """BASELINE config 4 voxel size (1 cm) on the pillar hall, small camera: parity against the oracle incl. meshes."""
+    setup = Setup(16, 0.01, False)
+    hall = scenes.hall(seed=3, size=(20.0, 20.0, 4.0), spacing=4.0)
+    cam = scenes.Camera(131.25, 131.25, 79.5, 59.5, 160, 120, near=0.05, far=3.0)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    for f in range(2):
+        pose = scenes.yaw_pose(0.3 + 0.05 * f, (0.9 + 0.02 * f, 0.4, 0.1))
+        depth, _ = scenes.render(hall, cam, pose)
+        a.integrate(depth, pose, cam.as_array())
+        b.integrate(depth, pose, cam.as_array())
+        ca, cb = a.counters(), b.counters()
+        assert ca["candidates"] == cb["candidates"] and ca["n_upd"] == cb["n_upd"] and ca["n_new"] == cb["n_new"]
+    common.assert_state_equal(a.state(), b.state())
+    a.remesh(); b.remesh()
+    common.assert_meshes_equal(a.meshes(), b.meshes())
+
+
+def test_hall_1cm_full_size_meshing_properties():
+    """Config 4 at full frame size (640x480, 1 cm): properties instead of the oracle. Re-meshing the same dirty set twice is
+    idempotent; every mesh vertex lies within one voxel diagonal of an observed voxel; triangle count is substantial."""
+    setup = Setup(16, 0.01, False)
+    hall = scenes.hall(seed=3, size=(20.0, 20.0, 4.0), spacing=4.0)
+    cam = scenes.Camera(525.0, 525.0, 319.5, 239.5, 640, 480, near=0.05, far=3.0)
+    a = common.Driver(setup, "cuda")
+    for f in range(3):
+        pose = scenes.yaw_pose(0.3 + 0.05 * f, (0.9 + 0.02 * f, 0.4, 0.1))
+        depth, _ = scenes.render(hall, cam, pose)
+        a.integrate(depth, pose, cam.as_array())
+        assert a.counters()["error_flags"] == 0
+    dirty = a.dirty()
+    a.remesh()
+    m1 = {k: {f: v.copy() for f, v in m.items()} for k, m in a.meshes().items()}
+    a.m.set_dirty(dirty)
+    a.remesh()
+    common.assert_meshes_equal(a.meshes(), m1, "re-mesh idempotence")
+    tris = sum(len(m["vertices"]) for m in m1.values()) // 3
+    assert tris > 50000, tris
+    ids = np.asarray(sorted(m1), np.int32)
+    v = np.concatenate([m["vertices"] for m in m1.values()])
+    cid = np.floor(v / np.float32(0.16)).astype(np.int32)
+    known = set(map(tuple, a.state()[0]))
+    frac_in_known = np.mean([tuple(c) in known for c in cid[::997]])
+    assert frac_in_known > 0.99
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 at full size (752x480, 2 cm, colour): size-independent properties instead of the oracle.
     (1) with ConstantWeighter(1) and trunc 4 voxels the update weight is 1/(5*0.08f) ~ 2.5, so every weight is a
