@@ -13,6 +13,7 @@
 // it may keep a chunk that turns out to be untouched, never drop one that would be touched.
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 
 #include "device_map.cuh"
 #include "kernels.h"
@@ -61,28 +62,12 @@ __device__ __forceinline__ void hiz_accumulate(const FrameParams &fp, float d, f
     }
 }
 
-__global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, DeviceMap map)
+// ColorImage::At (OC ColorImage.h:61-101) once per pixel instead of once per voxel: mono replicates, 3/4 channels are
+// B,G,R(,A); stored as r | g << 8 | b << 16 so that the integrate kernels fetch a colour with one 32-bit load. Runs as a
+// graph branch parallel to frame_prepare -> chunk_candidates (only the integrate kernels consume its output).
+__global__ void __launch_bounds__(256) color_pack_kernel(FrameParams fp)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < kCounterSlots)
     {
-        Counters *c = map.ctr;
-        if (threadIdx.x == 0)
-        {
-            c->unit_count = 0;
-            c->new_count = 0;
-            c->candidates = 0;
-            c->n_new = 0;
-            c->updated_chunks = 0;
-            c->tickets = 0;
-        }
-        c->n_upd[threadIdx.x] = 0;
-        c->n_carve[threadIdx.x] = 0;
-        c->n_col[threadIdx.x] = 0;
-    }
-    if (fp.color_path)
-    {
-        // ColorImage::At (OC ColorImage.h:61-101) once per pixel instead of once per voxel: mono replicates, 3/4 channels are
-        // B,G,R(,A); stored as r | g << 8 | b << 16 so that the integrate kernel fetches a colour with one 32-bit load
         const int n = fp.ccam.W * fp.ccam.H, ch = fp.channels;
         const int nThreads = gridDim.x * gridDim.y * blockDim.x;
         const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -123,6 +108,26 @@ __global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, Devi
                 r = g = b = __ldg(p);
             fp.color_packed[i] = r | (g << 8) | (b << 16);
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) frame_prepare_kernel(FrameParams fp, DeviceMap map)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < kCounterSlots)
+    {
+        Counters *c = map.ctr;
+        if (threadIdx.x == 0)
+        {
+            c->unit_count = 0;
+            c->new_count = 0;
+            c->candidates = 0;
+            c->n_new = 0;
+            c->updated_chunks = 0;
+            c->tickets = 0;
+        }
+        c->n_upd[threadIdx.x] = 0;
+        c->n_carve[threadIdx.x] = 0;
+        c->n_col[threadIdx.x] = 0;
     }
     const int W = fp.cam.W, H = fp.cam.H;
     const int t = threadIdx.x;
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(256) chunk_candidates_kernel(FrameParams fp, D
     const bool leader = gl == 0;
     bool candidate = false;
     int x = 0, y = 0, z = 0;
+    float bx = 0.0f, by = 0.0f, bz = 0.0f;
     int code[BPL];
 #pragma unroll
     for (int k = 0; k < BPL; k++)
@@ -378,20 +384,25 @@ __global__ void __launch_bounds__(256) chunk_candidates_kernel(FrameParams fp, D
         z = fp.lo[2] + r % fp.n[2];
         // chunk box exactly as ChunkManager.cpp:199-201
         const float ext = __fmul_rn((float)CS, map.res);
-        const float bx = __fmul_rn((float)(x * CS), map.res), by = __fmul_rn((float)(y * CS), map.res), bz = __fmul_rn((float)(z * CS), map.res);
+        bx = __fmul_rn((float)(x * CS), map.res);
+        by = __fmul_rn((float)(y * CS), map.res);
+        bz = __fmul_rn((float)(z * CS), map.res);
         candidate = frustum_intersects_exact(fp, bx, by, bz, __fadd_rn(bx, ext), __fadd_rn(by, ext), __fadd_rn(bz, ext));
         if (candidate && map.world > 1)
             candidate = (owner_hash(x, y, z) % (unsigned)map.world) == (unsigned)map.rank;
-        if (candidate)
-        {
+    }
+    // one lane per brick: a single classification stage keeps the dependent-latency chain short (a chunk-level pre-test
+    // saved instructions but added a dependent stage and measured slower)
+    if (candidate)
+    {
 #pragma unroll
-            for (int k = 0; k < BPL; k++)
-            {
-                const int b = gl + k * GL;
-                const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
-                code[k] = classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
-                                       bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
-            }
+        for (int k = 0; k < BPL; k++)
+        {
+            const int b = gl + k * GL;
+            const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
+            code[k] = (NB == 1) ? classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res)
+                                : classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
+                                               bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
         }
     }
     bool has2 = false, has1 = false;
@@ -916,7 +927,7 @@ struct FrameGraphVariant
 {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t nPrepare = nullptr, nCand = nullptr, nNew = nullptr, nBricks = nullptr;
+    cudaGraphNode_t nPrepare = nullptr, nCand = nullptr, nNew = nullptr, nBricks = nullptr, nPack = nullptr;
     void *fPrepare = nullptr, *fCand = nullptr, *fNew = nullptr, *fBricks = nullptr;
     int newResident = 1, brickResident = 1;
 };
@@ -996,6 +1007,7 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
     const int total = fp.n[0] * fp.n[1] * fp.n[2];
     const long long nb = (long long)(map.cs / 8) * (map.cs / 8) * (map.cs / 8);
     void *argsFrame[2] = {&fp, &map};
+    void *argsPack[1] = {&fp};
     cudaError_t e;
     const bool build = g.exec == nullptr;
     if (build)
@@ -1013,6 +1025,8 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
     const dim3 gNew((unsigned)std::max(1ll, std::min<long long>(std::min<long long>(candidates, newHint), g.newResident)));
     const dim3 gBricks((unsigned)std::max(1ll, std::min<long long>((candidates * nb * 2 + 7) / 8, g.brickResident)));
     fp.total_ctas = (int)(gNew.x + gBricks.x);
+    const int packPixels = fp.color_path ? fp.ccam.W * fp.ccam.H : 0;
+    cudaKernelNodeParams pPack = kernel_params((void *)color_pack_kernel, dim3((unsigned)std::max(1, std::min(148 * 4, (packPixels / 4 + 255) / 256))), dim3(256), argsPack);
     cudaKernelNodeParams pPrepare = kernel_params(g.fPrepare, gPrepare, dim3(256), argsFrame);
     cudaKernelNodeParams pCand = kernel_params(g.fCand, gCand, dim3(256), argsFrame);
     cudaKernelNodeParams pNew = kernel_params(g.fNew, gNew, dim3(256), argsFrame);
@@ -1027,12 +1041,24 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
             prev = ev;
             return r;
         };
+        // production: colour packing runs beside the candidates kernel (both wait for prepare; only the integrate kernels
+        // consume it). As a second ROOT node it measured 15 us slower per frame, hence not there.
+        const bool packBeside = fp.color_path && !profiling;
+        if (fp.color_path && !packBeside)
+        {
+            // profiling variant: first in the serial chain
+            if ((e = cudaGraphAddKernelNode(&g.nPack, g.graph, nullptr, 0, &pPack)) != cudaSuccess)
+                return e;
+            prev = g.nPack;
+        }
         if (profiling && (e = addEvent(evt[0])) != cudaSuccess)
             return e;
         if ((e = cudaGraphAddKernelNode(&g.nPrepare, g.graph, prev ? &prev : nullptr, prev ? 1 : 0, &pPrepare)) != cudaSuccess)
             return e;
         prev = g.nPrepare;
         if (profiling && (e = addEvent(evt[1])) != cudaSuccess)
+            return e;
+        if (packBeside && (e = cudaGraphAddKernelNode(&g.nPack, g.graph, &prev, 1, &pPack)) != cudaSuccess)
             return e;
         if ((e = cudaGraphAddKernelNode(&g.nCand, g.graph, &prev, 1, &pCand)) != cudaSuccess)
             return e;
@@ -1055,10 +1081,12 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
         }
         else
         {
-            // the two integrate kernels touch disjoint chunks: parallel branches
-            if ((e = cudaGraphAddKernelNode(&g.nNew, g.graph, &prev, 1, &pNew)) != cudaSuccess)
+            // the two integrate kernels touch disjoint chunks: parallel branches (both wait for the packed colour image)
+            cudaGraphNode_t deps[2] = {prev, g.nPack};
+            const size_t nDeps = packBeside ? 2 : 1;
+            if ((e = cudaGraphAddKernelNode(&g.nNew, g.graph, deps, nDeps, &pNew)) != cudaSuccess)
                 return e;
-            if ((e = cudaGraphAddKernelNode(&g.nBricks, g.graph, &prev, 1, &pBricks)) != cudaSuccess)
+            if ((e = cudaGraphAddKernelNode(&g.nBricks, g.graph, deps, nDeps, &pBricks)) != cudaSuccess)
                 return e;
         }
         if ((e = cudaGraphInstantiate(&g.exec, g.graph, 0)) != cudaSuccess)
@@ -1066,6 +1094,8 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fpIn, const De
     }
     else
     {
+        if (g.nPack && (e = cudaGraphExecKernelNodeSetParams(g.exec, g.nPack, &pPack)) != cudaSuccess)
+            return e;
         if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nPrepare, &pPrepare)) != cudaSuccess)
             return e;
         if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nCand, &pCand)) != cudaSuccess)

@@ -76,10 +76,12 @@ __device__ __forceinline__ void cell_of_rank(int k, int *x, int *y, int *z)
     }
 }
 
-// Halo tile: (CS+1)^3 SDF values; NaN marks a corner that makes the cell unmeshable (weight <= 0.5 or the
-// neighbour chunk is missing: ChunkManager.cpp:274-278, 311-314, 336-367).
+// Halo tiles: (CS+1)^3 raw SDF values of the chunk and its +x/+y/+z neighbours plus one class byte per voxel. The weight is
+// only ever compared with two thresholds, so the tile keeps the two outcomes instead of the value (5 bytes per halo voxel;
+// 33^3 voxels of a 32^3 chunk fit the 227 KB of one CTA): bit 0 = meshable corner, !(weight <= 0.5) (ChunkManager.cpp:274-278,
+// 311-314, 336-367); bit 1 = observed for the gradient taps, weight > 1e-12 (:476-499). 0 = the chunk does not exist.
 template <int CS>
-__device__ void load_halo(const DeviceMap &map, int slot, float *tile, int *nbrSlots)
+__device__ void load_halo(const DeviceMap &map, int slot, float wMin, float *tileS, unsigned char *tileW, int *nbrSlots)
 {
     constexpr int H = CS + 1;
     const int t = threadIdx.x;
@@ -92,15 +94,17 @@ __device__ void load_halo(const DeviceMap &map, int slot, float *tile, int *nbrS
         const int x = i % H, y = (i / H) % H, z = i / (H * H);
         const int n = (x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0);
         const int s = nbrSlots[n];
-        float v = __int_as_float(0x7fc00000);
+        float sdf = 0.0f;
+        unsigned char cls = 0;
         if (s >= 0)
         {
             const int vx = x == CS ? 0 : x, vy = y == CS ? 0 : y, vz = z == CS ? 0 : z;
             const float2 d = dist_ptr(map, s)[(vz * CS + vy) * CS + vx];
-            if (!(d.y <= 0.5f))
-                v = d.x;
+            sdf = d.x;
+            cls = (unsigned char)((!(d.y <= 0.5f) ? 1 : 0) | ((d.y > wMin) ? 2 : 0));
         }
-        tile[i] = v;
+        tileS[i] = sdf;
+        tileW[i] = cls;
     }
     __syncthreads();
 }
@@ -112,7 +116,7 @@ __device__ __forceinline__ int corner_dz(int i) { return (0xF0 >> i) & 1; }
 
 // returns the cube configuration, or -1 if any corner is unobserved
 template <int CS>
-__device__ __forceinline__ int cell_config(const float *tile, int x, int y, int z, float *sdf)
+__device__ __forceinline__ int cell_config(const float *tileS, const unsigned char *tileW, int x, int y, int z, float *sdf)
 {
     constexpr int H = CS + 1;
     int cfg = 0;
@@ -120,9 +124,10 @@ __device__ __forceinline__ int cell_config(const float *tile, int x, int y, int 
 #pragma unroll
     for (int i = 0; i < 8; i++)
     {
-        const float v = tile[((z + corner_dz(i)) * H + (y + corner_dy(i))) * H + (x + corner_dx(i))];
+        const int ti = ((z + corner_dz(i)) * H + (y + corner_dy(i))) * H + (x + corner_dx(i));
+        const float v = tileS[ti];
         sdf[i] = v;
-        ok &= (v == v);
+        ok &= (tileW[ti] & 1) != 0;
         cfg |= (v < 0.0f) ? (1 << i) : 0;                   // MarchingCubes::CalculateVertexConfiguration (MarchingCubes.h:106-116)
     }
     return ok ? cfg : -1;
@@ -134,18 +139,20 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(MeshParams mp, DeviceMa
     extern __shared__ float tile[];
     __shared__ int nbr[8];
     __shared__ int red[2][8];
-    constexpr int V = CS * CS * CS, CPT = V / 256;
+    constexpr int V = CS * CS * CS, CPT = V / 256, H3 = (CS + 1) * (CS + 1) * (CS + 1);
+    float *tileS = tile;
+    unsigned char *tileW = reinterpret_cast<unsigned char *>(tile + H3);
     const int n = map.ctr->mesh_chunks;
     for (int c = blockIdx.x; c < n; c += gridDim.x)
     {
-        load_halo<CS>(map, mp.mesh_slots[c], tile, nbr);
+        load_halo<CS>(map, mp.mesh_slots[c], mp.w_observed_min, tileS, tileW, nbr);
         int tris = 0, grids = 0;
         for (int j = 0; j < CPT; j++)
         {
             int x, y, z;
             float sdf[8];
             cell_of_rank<CS>(threadIdx.x * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
             if (cfg >= 0)
             {
                 const int nt = cTriCount[cfg];
@@ -247,66 +254,100 @@ struct P3
     float x, y, z;
 };
 
-// ChunkManager::GetIDAt (OC ChunkManager.h:136-145): floor(pos * 1/(chunkSize*res)) per axis
-__device__ __forceinline__ int lookup_chunk_at(const DeviceMap &map, float rfChunk, P3 pos)
+// Lookup context of one thread: the chunk being meshed, its +neighbour slots and halo tiles (shared memory), and a
+// one-entry cache of the last hash lookup. Position -> (chunk, voxel) arithmetic is the reference's, bit for bit; only the
+// memory the voxel is fetched from differs (shared-memory tile when the voxel lies inside it, else the pool).
+template <int CS>
+struct LookupCtx
 {
-    const float fx = floorf(__fmul_rn(pos.x, rfChunk)), fy = floorf(__fmul_rn(pos.y, rfChunk)), fz = floorf(__fmul_rn(pos.z, rfChunk));
+    int ox, oy, oz;               // ID of the chunk being meshed
+    const int *nbr;               // [8] slots of chunks (ox+dx, oy+dy, oz+dz), -1 if missing
+    const float *tileS;
+    const unsigned char *tileW;
+    float rfChunk, rfVoxel, wMin;
+    unsigned long long cKey;
+    int cSlot;
+};
+
+// ChunkManager::GetIDAt (OC ChunkManager.h:136-145): floor(pos * 1/(chunkSize*res)) per axis; then the chunk's slot
+template <int CS>
+__device__ __forceinline__ int lookup_chunk_at(const DeviceMap &map, LookupCtx<CS> &c, P3 pos, int *ix, int *iy, int *iz)
+{
+    const float fx = floorf(__fmul_rn(pos.x, c.rfChunk)), fy = floorf(__fmul_rn(pos.y, c.rfChunk)), fz = floorf(__fmul_rn(pos.z, c.rfChunk));
     // outside the packable range (or NaN) there is no chunk
     if (!(fabsf(fx) < (float)(kIdBias - 1)) || !(fabsf(fy) < (float)(kIdBias - 1)) || !(fabsf(fz) < (float)(kIdBias - 1)))
         return -1;
-    return hash_lookup(map, pack_id((int)fx, (int)fy, (int)fz));
+    *ix = (int)fx;
+    *iy = (int)fy;
+    *iz = (int)fz;
+    const int dx = *ix - c.ox, dy = *iy - c.oy, dz = *iz - c.oz;
+    if ((unsigned)dx < 2u && (unsigned)dy < 2u && (unsigned)dz < 2u)
+        return c.nbr[dx | (dy << 1) | (dz << 2)];
+    const unsigned long long key = pack_id(*ix, *iy, *iz);
+    if (key != c.cKey)
+    {
+        c.cKey = key;
+        c.cSlot = hash_lookup(map, key);
+    }
+    return c.cSlot;
 }
 
-// Chunk::GetVoxelID(const Vec3&) (OC Chunk.cpp:72-86): floor(rel * (1/res)), then (z*N + y)*N + x
-__device__ __forceinline__ int voxel_id_of_rel(const DeviceMap &map, float rfVoxel, P3 rel)
+// Chunk origin from its ID: float(CS * ID_k) * res (Chunk.cpp:43)
+template <int CS>
+__device__ __forceinline__ P3 origin_of(const DeviceMap &map, int ix, int iy, int iz)
 {
-    const int x = (int)floorf(__fmul_rn(rel.x, rfVoxel)), y = (int)floorf(__fmul_rn(rel.y, rfVoxel)), z = (int)floorf(__fmul_rn(rel.z, rfVoxel));
-    return (z * map.cs + y) * map.cs + x;
-}
-
-__device__ __forceinline__ P3 chunk_origin(const DeviceMap &map, int slot)
-{
-    P3 o;
-    o.x = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot]), map.res);
-    o.y = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot + 1]), map.res);
-    o.z = __fmul_rn((float)(map.cs * map.slot_ids[3 * slot + 2]), map.res);
+    P3 o = {__fmul_rn((float)(CS * ix), map.res), __fmul_rn((float)(CS * iy), map.res), __fmul_rn((float)(CS * iz), map.res)};
     return o;
 }
 
-// ChunkManager::GetSDF (ChunkManager.cpp:476-499)
-__device__ __forceinline__ bool get_sdf(const DeviceMap &map, float rfChunk, float rfVoxel, float wMin, P3 pos, float *out)
+// ChunkManager::GetSDF (ChunkManager.cpp:476-499); Chunk::GetVoxelID(const Vec3&) (Chunk.cpp:72-86): floor(rel * (1/res))
+template <int CS, bool TILED>
+__device__ __forceinline__ bool get_sdf(const DeviceMap &map, LookupCtx<CS> &c, P3 pos, float *out)
 {
-    const int slot = lookup_chunk_at(map, rfChunk, pos);
+    int ix, iy, iz;
+    const int slot = lookup_chunk_at<CS>(map, c, pos, &ix, &iy, &iz);
     if (slot < 0)
         return false;
-    const P3 o = chunk_origin(map, slot);
-    P3 rel = {__fsub_rn(pos.x, o.x), __fsub_rn(pos.y, o.y), __fsub_rn(pos.z, o.z)};
-    const int id = voxel_id_of_rel(map, rfVoxel, rel);
-    if (id < 0 || id >= map.V)
+    const P3 o = origin_of<CS>(map, ix, iy, iz);
+    const int vx = (int)floorf(__fmul_rn(__fsub_rn(pos.x, o.x), c.rfVoxel)), vy = (int)floorf(__fmul_rn(__fsub_rn(pos.y, o.y), c.rfVoxel)),
+              vz = (int)floorf(__fmul_rn(__fsub_rn(pos.z, o.z), c.rfVoxel));
+    const int id = (vz * CS + vy) * CS + vx;
+    if (id < 0 || id >= CS * CS * CS)
         return false;
+    const int tx = (ix - c.ox) * CS + vx, ty = (iy - c.oy) * CS + vy, tz = (iz - c.oz) * CS + vz;
+    if (TILED && (unsigned)vx < (unsigned)CS && (unsigned)vy < (unsigned)CS && (unsigned)vz < (unsigned)CS && (unsigned)tx <= (unsigned)CS &&
+        (unsigned)ty <= (unsigned)CS && (unsigned)tz <= (unsigned)CS)
+    {
+        const int ti = (tz * (CS + 1) + ty) * (CS + 1) + tx;
+        if (!(c.tileW[ti] & 2))                             // weight > 1e-12
+            return false;
+        *out = c.tileS[ti];
+        return true;
+    }
     const float2 d = dist_ptr(map, slot)[id];
-    if (!(d.y > wMin))                                      // weight > 1e-12
+    if (!(d.y > c.wMin))                                    // weight > 1e-12
         return false;
     *out = d.x;
     return true;
 }
 
 // ChunkManager::GetSDFAndGradient + ComputeNormalsFromGradients (ChunkManager.cpp:449-474, 609-626)
-__device__ bool gradient_normal(const DeviceMap &map, float rfChunk, float rfVoxel, float wMin, P3 v, P3 *n)
+template <int CS, bool TILED>
+__device__ bool gradient_normal(const DeviceMap &map, LookupCtx<CS> &c, P3 v, P3 *n)
 {
     const float r = map.res, h = __fdiv_rn(r, 2.0f);
     P3 p = {__fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.x, r)), r), h), __fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.y, r)), r), h),
             __fadd_rn(__fmul_rn(floorf(__fdiv_rn(v.z, r)), r), h)};
-    float c, xp, yp, zp, xm, ym, zm;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, p, &c))
+    float ctr, xp, yp, zp, xm, ym, zm;
+    if (!get_sdf<CS, TILED>(map, c, p, &ctr))
         return false;
     // posf +/- Vector3f(res, 0, 0): the untouched components add 0.0f (identity for non-zero values)
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, r), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, 0.0f)}, &xp)) return false;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, r), __fadd_rn(p.z, 0.0f)}, &yp)) return false;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, r)}, &zp)) return false;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, r), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, 0.0f)}, &xm)) return false;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, r), __fsub_rn(p.z, 0.0f)}, &ym)) return false;
-    if (!get_sdf(map, rfChunk, rfVoxel, wMin, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, r)}, &zm)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fadd_rn(p.x, r), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, 0.0f)}, &xp)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, r), __fadd_rn(p.z, 0.0f)}, &yp)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fadd_rn(p.x, 0.0f), __fadd_rn(p.y, 0.0f), __fadd_rn(p.z, r)}, &zp)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fsub_rn(p.x, r), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, 0.0f)}, &xm)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, r), __fsub_rn(p.z, 0.0f)}, &ym)) return false;
+    if (!get_sdf<CS, TILED>(map, c, P3{__fsub_rn(p.x, 0.0f), __fsub_rn(p.y, 0.0f), __fsub_rn(p.z, r)}, &zm)) return false;
     // Eigen::Vector3f(double, double, double): differences in double, narrowed once
     float gx = (float)((double)xp - (double)xm), gy = (float)((double)yp - (double)ym), gz = (float)((double)zp - (double)zm);
     float z2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
@@ -328,15 +369,18 @@ __device__ bool gradient_normal(const DeviceMap &map, float rfChunk, float rfVox
 }
 
 // ChunkManager::GetColorVoxel (ChunkManager.cpp:588-607)
-__device__ __forceinline__ bool get_color_voxel(const DeviceMap &map, float rfChunk, float rfVoxel, P3 pos, uchar4 *out)
+template <int CS>
+__device__ __forceinline__ bool get_color_voxel(const DeviceMap &map, LookupCtx<CS> &c, P3 pos, uchar4 *out)
 {
-    const int slot = lookup_chunk_at(map, rfChunk, pos);
+    int ix, iy, iz;
+    const int slot = lookup_chunk_at<CS>(map, c, pos, &ix, &iy, &iz);
     if (slot < 0)
         return false;
-    const P3 o = chunk_origin(map, slot);
-    P3 rel = {__fsub_rn(pos.x, o.x), __fsub_rn(pos.y, o.y), __fsub_rn(pos.z, o.z)};
-    const int id = voxel_id_of_rel(map, rfVoxel, rel);
-    if (id < 0 || id >= map.V)
+    const P3 o = origin_of<CS>(map, ix, iy, iz);
+    const int vx = (int)floorf(__fmul_rn(__fsub_rn(pos.x, o.x), c.rfVoxel)), vy = (int)floorf(__fmul_rn(__fsub_rn(pos.y, o.y), c.rfVoxel)),
+              vz = (int)floorf(__fmul_rn(__fsub_rn(pos.z, o.z), c.rfVoxel));
+    const int id = (vz * CS + vy) * CS + vx;
+    if (id < 0 || id >= CS * CS * CS)
         return false;
     *out = color_ptr(map, slot)[id];
     return true;
@@ -358,7 +402,8 @@ __device__ __forceinline__ float lerp_channel(float a000, float a100, float a010
 
 // ChunkManager::InterpolateColor (ChunkManager.cpp:501-573), bug-compatible (quirk Q9: the eight lookups pass voxel
 // INDICES where GetColorVoxel expects metres), with the Chunk::GetColorAt fallback (Chunk.cpp:118-136).
-__device__ P3 interpolate_color(const DeviceMap &map, float rfChunk, float rfVoxel, P3 p)
+template <int CS>
+__device__ P3 interpolate_color(const DeviceMap &map, LookupCtx<CS> &c, P3 p)
 {
     const float r = map.res;
     const float fx0 = floorf(__fdiv_rn(p.x, r)), fy0 = floorf(__fdiv_rn(p.y, r)), fz0 = floorf(__fdiv_rn(p.z, r));
@@ -366,30 +411,31 @@ __device__ P3 interpolate_color(const DeviceMap &map, float rfChunk, float rfVox
     const float x0 = (float)(int)fx0, y0 = (float)(int)fy0, z0 = (float)(int)fz0;
     const float x1 = (float)((int)fx0 + 1), y1 = (float)((int)fy0 + 1), z1 = (float)((int)fz0 + 1);
     uchar4 v000, v001, v011, v111, v110, v100, v010, v101;
-    bool all = get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y0, z0}, &v000);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y0, z1}, &v001);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y1, z1}, &v011);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y1, z1}, &v111);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y1, z0}, &v110);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y0, z0}, &v100);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x0, y1, z0}, &v010);
-    all = all && get_color_voxel(map, rfChunk, rfVoxel, P3{x1, y0, z1}, &v101);
+    bool all = get_color_voxel<CS>(map, c, P3{x0, y0, z0}, &v000);
+    all = all && get_color_voxel<CS>(map, c, P3{x0, y0, z1}, &v001);
+    all = all && get_color_voxel<CS>(map, c, P3{x0, y1, z1}, &v011);
+    all = all && get_color_voxel<CS>(map, c, P3{x1, y1, z1}, &v111);
+    all = all && get_color_voxel<CS>(map, c, P3{x1, y1, z0}, &v110);
+    all = all && get_color_voxel<CS>(map, c, P3{x1, y0, z0}, &v100);
+    all = all && get_color_voxel<CS>(map, c, P3{x0, y1, z0}, &v010);
+    all = all && get_color_voxel<CS>(map, c, P3{x1, y0, z1}, &v101);
     if (!all)
     {
-        const int slot = lookup_chunk_at(map, rfChunk, p);
+        int ix, iy, iz;
+        const int slot = lookup_chunk_at<CS>(map, c, p, &ix, &iy, &iz);
         P3 zero = {0.0f, 0.0f, 0.0f};
         if (slot < 0)
             return zero;
-        const P3 o = chunk_origin(map, slot);
-        const float ext = __fmul_rn((float)map.cs, r);
+        const P3 o = origin_of<CS>(map, ix, iy, iz);
+        const float ext = __fmul_rn((float)CS, r);
         const P3 mx = {__fadd_rn(o.x, ext), __fadd_rn(o.y, ext), __fadd_rn(o.z, ext)};
         if (!(p.x >= o.x && p.y >= o.y && p.z >= o.z && p.x <= mx.x && p.y <= mx.y && p.z <= mx.z))
             return zero;
         const int cx = (int)__fdiv_rn(__fsub_rn(p.x, o.x), r), cy = (int)__fdiv_rn(__fsub_rn(p.y, o.y), r), cz = (int)__fdiv_rn(__fsub_rn(p.z, o.z), r);
-        if (!(cx >= 0 && cx < map.cs && cy >= 0 && cy < map.cs && cz >= 0 && cz < map.cs))
+        if (!(cx >= 0 && cx < CS && cy >= 0 && cy < CS && cz >= 0 && cz < CS))
             return zero;
-        const uchar4 c = color_ptr(map, slot)[(cz * map.cs + cy) * map.cs + cx];
-        P3 out = {__fdiv_rn((float)c.x, 255.0f), __fdiv_rn((float)c.y, 255.0f), __fdiv_rn((float)c.z, 255.0f)};
+        const uchar4 cv = color_ptr(map, slot)[(cz * CS + cy) * CS + cx];
+        P3 out = {__fdiv_rn((float)cv.x, 255.0f), __fdiv_rn((float)cv.y, 255.0f), __fdiv_rn((float)cv.z, 255.0f)};
         return out;
     }
     const float xd = __fdiv_rn(__fsub_rn(p.x, x0), 1.0f), yd = __fdiv_rn(__fsub_rn(p.y, y0), 1.0f), zd = __fdiv_rn(__fsub_rn(p.z, z0), 1.0f);
@@ -419,21 +465,21 @@ __device__ __forceinline__ P3 interpolate_vertex(P3 a, P3 b, float s1, float s2)
     return o;
 }
 
-template <int CS>
+template <int CS, bool TILED>
 __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap map)
 {
     extern __shared__ float tile[];
     __shared__ int nbr[8];
     __shared__ int warpTot[2][8];
-    constexpr int V = CS * CS * CS, CPT = V / 256;
+    constexpr int V = CS * CS * CS, CPT = V / 256, H3 = (CS + 1) * (CS + 1) * (CS + 1);
+    float *tileS = tile;
+    unsigned char *tileW = reinterpret_cast<unsigned char *>(tile + H3);
     const int n = map.ctr->mesh_chunks;
-    const float rfChunk = __fdiv_rn(1.0f, __fmul_rn((float)CS, map.res));
-    const float rfVoxel = __fdiv_rn(1.0f, map.res);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int c = blockIdx.x; c < n; c += gridDim.x)
     {
         const int slot = mp.mesh_slots[c];
-        load_halo<CS>(map, slot, tile, nbr);
+        load_halo<CS>(map, slot, mp.w_observed_min, tileS, tileW, nbr);
         // pass 1: this thread's triangle / grid totals over its CPT consecutive cells
         int tris = 0, grids = 0;
         for (int j = 0; j < CPT; j++)
@@ -441,7 +487,7 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
             int x, y, z;
             float sdf[8];
             cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
             if (cfg >= 0)
             {
                 const int nt = cTriCount[cfg];
@@ -472,16 +518,18 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
             baseT += warpTot[0][w];
             baseG += warpTot[1][w];
         }
-        long long vOut = mp.vert_offsets[c] + 3ll * baseT;
+        const long long vBase = mp.vert_offsets[c], vEnd = mp.vert_offsets[c + 1];
+        long long vOut = vBase + 3ll * baseT;
         long long gOut = mp.grid_offsets[c] + baseG;
-        const P3 org = chunk_origin(map, slot);
-        // pass 2: emit
+        const int idx = map.slot_ids[3 * slot], idy = map.slot_ids[3 * slot + 1], idz = map.slot_ids[3 * slot + 2];
+        const P3 org = {__fmul_rn((float)(CS * idx), map.res), __fmul_rn((float)(CS * idy), map.res), __fmul_rn((float)(CS * idz), map.res)};
+        // pass 2: positions and flat normals, in the reference's emission order
         for (int j = 0; j < CPT; j++)
         {
             int x, y, z;
             float sdf[8];
             cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tile, x, y, z, sdf);
+            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
             if (cfg < 0)
                 continue;
             const int nt = cTriCount[cfg];
@@ -533,24 +581,46 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
                 {
                     if (vOut < mp.cap_vertices)
                     {
-                        P3 nn = nf;
-                        gradient_normal(map, rfChunk, rfVoxel, mp.w_observed_min, p[k], &nn);   // overwrites the flat normal when all 7 taps exist
                         mp.vertices[3 * vOut] = p[k].x;
                         mp.vertices[3 * vOut + 1] = p[k].y;
                         mp.vertices[3 * vOut + 2] = p[k].z;
-                        mp.normals[3 * vOut] = nn.x;
-                        mp.normals[3 * vOut + 1] = nn.y;
-                        mp.normals[3 * vOut + 2] = nn.z;
-                        if (mp.colors)
-                        {
-                            const P3 col = interpolate_color(map, rfChunk, rfVoxel, p[k]);
-                            mp.colors[3 * vOut] = col.x;
-                            mp.colors[3 * vOut + 1] = col.y;
-                            mp.colors[3 * vOut + 2] = col.z;
-                        }
+                        mp.normals[3 * vOut] = nf.x;
+                        mp.normals[3 * vOut + 1] = nf.y;
+                        mp.normals[3 * vOut + 2] = nf.z;
                     }
                     vOut++;
                 }
+            }
+        }
+        __syncthreads();
+        // pass 3, vertex-parallel (balanced, coalesced): gradient normals overwrite the flat ones where all seven taps
+        // exist (ChunkManager.cpp:609-626); colours (ChunkManager.cpp:628-639)
+        LookupCtx<CS> ctx;
+        ctx.ox = idx; ctx.oy = idy; ctx.oz = idz;
+        ctx.nbr = nbr;
+        ctx.tileS = tileS; ctx.tileW = tileW;
+        ctx.rfChunk = __fdiv_rn(1.0f, __fmul_rn((float)CS, map.res));
+        ctx.rfVoxel = __fdiv_rn(1.0f, map.res);
+        ctx.wMin = mp.w_observed_min;
+        ctx.cKey = kEmptyKey;
+        ctx.cSlot = -1;
+        const long long vLimit = vEnd < mp.cap_vertices ? vEnd : mp.cap_vertices;
+        for (long long v = vBase + t; v < vLimit; v += 256)
+        {
+            const P3 p = {mp.vertices[3 * v], mp.vertices[3 * v + 1], mp.vertices[3 * v + 2]};
+            P3 nn;
+            if (gradient_normal<CS, TILED>(map, ctx, p, &nn))
+            {
+                mp.normals[3 * v] = nn.x;
+                mp.normals[3 * v + 1] = nn.y;
+                mp.normals[3 * v + 2] = nn.z;
+            }
+            if (mp.colors)
+            {
+                const P3 col = interpolate_color<CS>(map, ctx, p);
+                mp.colors[3 * v] = col.x;
+                mp.colors[3 * v + 1] = col.y;
+                mp.colors[3 * v + 2] = col.z;
             }
         }
         __syncthreads();
@@ -568,12 +638,12 @@ void launch_mesh_select(const MeshParams &mp, const DeviceMap &map, cudaStream_t
 template <int CS>
 static void mesh_launch_cs(const MeshParams &mp, const DeviceMap &map, int grid, cudaStream_t st, bool emit)
 {
-    const size_t smem = sizeof(float) * (CS + 1) * (CS + 1) * (CS + 1);
+    const size_t smem = (sizeof(float) + 1) * (CS + 1) * (CS + 1) * (CS + 1) + 16;   // SDF tile + class-byte tile
     if (emit)
     {
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute(mesh_emit_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mesh_emit_kernel<CS><<<grid, 256, smem, st>>>(mp, map);
+            cudaFuncSetAttribute(mesh_emit_kernel<CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mesh_emit_kernel<CS, true><<<grid, 256, smem, st>>>(mp, map);
     }
     else
     {
