@@ -56,6 +56,11 @@ class chs_frame_stats(C.Structure):
                                          "updated_chunks", "total_chunks", "dirty_chunks", "error_flags")]
 
 
+class chs_frame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("color", C.c_void_p), ("trunc_per_pixel", C.c_void_p),
+                ("pose", C.c_float * 12), ("color_pose", C.c_float * 12)]
+
+
 class chs_mesh_counts(C.Structure):
     _fields_ = [("n_chunks", C.c_int64), ("n_vertices", C.c_int64), ("n_grids", C.c_int64), ("has_colors", C.c_int)]
 
@@ -67,7 +72,8 @@ class chs_timings(C.Structure):
 
 EXPORTS = (
     "chs_last_error_string", "chs_abi_version", "chs_create", "chs_destroy", "chs_reset", "chs_synchronize",
-    "chs_set_stream", "chs_set_profiling", "chs_integrate_depth", "chs_integrate_depth_color", "chs_get_frame_stats",
+    "chs_set_stream", "chs_set_profiling", "chs_integrate_depth", "chs_integrate_depth_color", "chs_integrate_batch",
+    "chs_get_batch_stats", "chs_get_frame_stats",
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner",
@@ -97,6 +103,9 @@ def load_library(build_if_missing: bool = True):
     lib.chs_integrate_depth.argtypes = [vp, C.POINTER(chs_integrator), vp, i32, vp, C.POINTER(chs_camera)]
     lib.chs_integrate_depth_color.argtypes = [vp, C.POINTER(chs_integrator), vp, i32, vp, C.POINTER(chs_camera),
                                               vp, i32, vp, C.POINTER(chs_camera)]
+    lib.chs_integrate_batch.argtypes = [vp, C.POINTER(chs_integrator), i32, C.POINTER(chs_frame), i32, C.POINTER(chs_camera), i32,
+                                        C.POINTER(chs_camera)]
+    lib.chs_get_batch_stats.argtypes = [vp, C.POINTER(chs_frame_stats), i32, C.POINTER(i32)]
     lib.chs_get_frame_stats.argtypes = [vp, C.POINTER(chs_frame_stats)]
     lib.chs_get_timings.argtypes = [vp, C.POINTER(chs_timings)]
     lib.chs_mesh_counts_last.argtypes = [vp, C.POINTER(chs_mesh_counts)]
@@ -286,6 +295,50 @@ class Chisel:
             integ = integrator.as_struct(device_ptrs[2] if len(device_ptrs) > 2 else None)
             _check(self._lib.chs_integrate_depth_color(self._h, C.byref(integ), device_ptrs[0], MEM_DEVICE, _ptr(p),
                                                        C.byref(cam), device_ptrs[1], channels, _ptr(cp), C.byref(ccam)))
+
+    def integrate_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
+                        device_ptrs=None, channels=None, truncs=None):
+        """n consecutive frames in one call (chs_integrate_batch): the same result as n calls of integrate_depth_scan[_color]
+        in order. depths/colors: lists of host arrays, or with device_ptrs=[(depth_ptr, color_ptr|None, trunc_ptr|None), ...]
+        device memory. colors=None (and no colour device pointers): the depth path."""
+        cam = make_camera(cam)
+        n = len(poses)
+        use_color = (colors is not None) or (device_ptrs is not None and len(device_ptrs) and device_ptrs[0][1] is not None)
+        ccam = (cam if color_cam is None else make_camera(color_cam)) if use_color else None
+        arr = (chs_frame * max(n, 1))()
+        keep = []
+        for i in range(n):
+            p = _pose(poses[i])
+            cp = p if (color_poses is None or color_poses[i] is None) else _pose(color_poses[i])
+            arr[i].pose[:] = p.tolist()
+            arr[i].color_pose[:] = cp.tolist()
+            if device_ptrs is None:
+                d = np.ascontiguousarray(depths[i], np.float32)
+                keep.append(d)
+                arr[i].depth = d.ctypes.data
+                if use_color:
+                    c = np.ascontiguousarray(colors[i], np.uint8)
+                    keep.append(c)
+                    arr[i].color = c.ctypes.data
+                    channels = c.shape[2] if c.ndim == 3 else 1
+                if truncs is not None:
+                    t = np.ascontiguousarray(truncs[i], np.float32)
+                    keep.append(t)
+                    arr[i].trunc_per_pixel = t.ctypes.data
+            else:
+                arr[i].depth = device_ptrs[i][0]
+                arr[i].color = device_ptrs[i][1]
+                arr[i].trunc_per_pixel = device_ptrs[i][2] if len(device_ptrs[i]) > 2 else None
+        integ = integrator.as_struct(device_ptr=0) if integrator.trunc_kind == TRUNC_PER_PIXEL else integrator.as_struct()
+        _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, MEM_HOST if device_ptrs is None else MEM_DEVICE,
+                                             C.byref(cam), int(channels or 0), C.byref(ccam) if ccam is not None else None))
+
+    def batch_stats(self) -> list:
+        n = C.c_int()
+        _check(self._lib.chs_get_batch_stats(self._h, None, 0, C.byref(n)))
+        arr = (chs_frame_stats * max(n.value, 1))()
+        _check(self._lib.chs_get_batch_stats(self._h, arr, n.value, C.byref(n)))
+        return [{k: getattr(arr[i], k) for k, _ in chs_frame_stats._fields_} for i in range(n.value)]
 
     def frame_stats(self) -> dict:
         s = chs_frame_stats()

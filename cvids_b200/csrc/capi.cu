@@ -84,6 +84,8 @@ struct InFlight
     long long newBound;     // upper bound of chunks this frame may add
     long long dirtyBound;   // upper bound of dirty IDs this frame may add
     int slot;               // index into the pinned counter ring
+    bool batch = false;     // a fused multi-frame batch: frameId is the batch id, slot indexes the batch snapshot ring
+    int batchIndex = -1;    // single frame that belongs to a chs_integrate_batch call run frame by frame: its index in that call
 };
 
 } // namespace chs
@@ -121,6 +123,18 @@ struct chs_map
     long long knownChunks = 0, knownDirty = 0;
     HostSnapshot lastFrame{};
     bool haveFrame = false;
+    // fused multi-frame path (integrate_batch.cu)
+    FrameParams *dBatchFrames = nullptr;
+    BatchCounters *dBctr = nullptr;
+    HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
+    unsigned long long *dSlotBatch = nullptr;  // [capacity]
+    float *bDepth = nullptr, *bTrunc = nullptr;
+    uint8_t *bColor = nullptr;
+    unsigned *bColorPacked = nullptr;
+    float2 *bHiz = nullptr;
+    size_t bDepthCap = 0, bTruncCap = 0, bColorCap = 0, bColorPackedCap = 0, bHizCap = 0;
+    int batchId = 0, batchRingNext = 0;
+    std::vector<chs_frame_stats> batchStats;   // per-frame counters of the last chs_integrate_batch call
     // profiling
     bool profiling = false;
     cudaEvent_t evt[8] = {};
@@ -234,6 +248,17 @@ static int ensure_pool(chs_map *m, long long chunks)
         CHS_CUDA(cudaFreeAsync(m->dm.slot_epoch, m->stream));
     }
     m->dm.slot_epoch = (int *)epoch;
+    void *sb = nullptr;
+    rc = alloc_async(&sb, sizeof(unsigned long long) * (size_t)newCap, m->stream);
+    if (rc)
+        return rc;
+    CHS_CUDA(cudaMemsetAsync(sb, 0, sizeof(unsigned long long) * (size_t)newCap, m->stream));
+    if (m->dSlotBatch)
+    {
+        CHS_CUDA(cudaMemcpyAsync(sb, m->dSlotBatch, sizeof(unsigned long long) * (size_t)m->dm.capacity, cudaMemcpyDeviceToDevice, m->stream));
+        CHS_CUDA(cudaFreeAsync(m->dSlotBatch, m->stream));
+    }
+    m->dSlotBatch = (unsigned long long *)sb;
     m->dm.capacity = (int)newCap;
     return CHS_OK;
 }
@@ -294,6 +319,60 @@ static int ensure_dirty(chs_map *m, long long ids)
     return CHS_OK;
 }
 
+static chs_frame_stats stats_of(const HostSnapshot &c)
+{
+    chs_frame_stats o{};
+    o.candidates = c.candidates;
+    o.new_candidates = c.new_count;
+    o.brick_units = c.unit_count;
+    o.n_upd = (int64_t)(((unsigned long long)(unsigned)c.n_upd_hi << 32) | (unsigned)c.n_upd_lo);
+    o.n_carve = c.n_carve;
+    o.n_col = c.n_col;
+    o.n_new = c.n_new;
+    o.updated_chunks = c.updated_chunks;
+    o.total_chunks = c.n_chunks;
+    o.dirty_chunks = c.n_dirty;
+    o.error_flags = c.error_flags;
+    return o;
+}
+
+// A fused batch has finished: per-frame counters of its K frames; the map totals are those after the last frame.
+static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base)
+{
+    m->knownChunks = b.n_chunks;
+    m->knownDirty = b.n_dirty;
+    const int K = std::min(std::max(b.K, 0), kMaxBatch);
+    if (base < 0)
+        base = 0;
+    if ((int)m->batchStats.size() < base + K)
+        m->batchStats.resize((size_t)(base + K));
+    for (int f = 0; f < K; f++)
+    {
+        chs_frame_stats &o = m->batchStats[base + f];
+        o.candidates = b.candidates[f];
+        o.new_candidates = b.new_count;          // per batch: the work lists are shared by the K frames
+        o.brick_units = b.unit_count;
+        o.n_upd = b.n_upd[f];
+        o.n_carve = b.n_carve[f];
+        o.n_col = b.n_col[f];
+        o.n_new = b.n_new[f];
+        o.updated_chunks = b.updated_chunks[f];
+        o.total_chunks = b.n_chunks;
+        o.dirty_chunks = b.n_dirty;
+        o.error_flags = b.error_flags;
+    }
+    if (K > 0)
+    {
+        // chs_get_frame_stats after a batch reports its last frame
+        const chs_frame_stats &o = m->batchStats[base + K - 1];
+        HostSnapshot &c = m->lastFrame;
+        c.n_chunks = b.n_chunks; c.n_dirty = b.n_dirty; c.error_flags = b.error_flags;
+        c.unit_count = b.unit_count; c.new_count = b.new_count; c.candidates = (int)o.candidates;
+        c.n_new = (int)o.n_new; c.updated_chunks = (int)o.updated_chunks; c.n_carve = (int)o.n_carve;
+        c.n_col = (int)o.n_col; c.n_upd_lo = (int)(o.n_upd & 0xffffffffll); c.n_upd_hi = (int)(o.n_upd >> 32);
+    }
+}
+
 // Retire completed counter snapshots (the frame graph's last node writes them into the pinned ring); `block` waits
 // for all of them.
 static int poll_inflight(chs_map *m, bool block)
@@ -303,6 +382,20 @@ static int poll_inflight(chs_map *m, bool block)
     while (!m->inflight.empty())
     {
         InFlight &f = m->inflight.front();
+        if (f.batch)
+        {
+            const volatile HostBatchSnapshot *b = &m->hBatchSnap[f.slot];
+            if (b->head != f.frameId || b->tail != f.frameId)
+            {
+                if (block)
+                    return fail(CHS_ERR_CUDA, "batch counter snapshot missing after synchronisation");
+                break;
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            retire_batch(m, m->hBatchSnap[f.slot], f.batchIndex);
+            m->inflight.pop_front();
+            continue;
+        }
         const volatile HostSnapshot *c = &m->hSnap[f.slot];
         if (c->id0 != f.frameId || c->id1 != f.frameId || c->id2 != f.frameId || c->id3 != f.frameId)
         {
@@ -314,6 +407,8 @@ static int poll_inflight(chs_map *m, bool block)
         m->lastFrame = m->hSnap[f.slot];
         m->knownChunks = m->lastFrame.n_chunks;
         m->knownDirty = m->lastFrame.n_dirty;
+        if (f.batchIndex >= 0 && f.batchIndex < (int)m->batchStats.size())
+            m->batchStats[f.batchIndex] = stats_of(m->lastFrame);
         m->inflight.pop_front();
     }
     return CHS_OK;
@@ -363,37 +458,39 @@ static void fill_camera(CameraDev *c, const float pose[12], const chs_camera &ca
     c->Wf = (float)cam.width; c->Hf = (float)cam.height;
 }
 
-static int integrate_common(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12],
-                            const chs_camera *cam, const uint8_t *color, int channels, const float cpose[12],
-                            const chs_camera *ccam, bool colorPath)
+struct FramePlan
 {
-    if (!m || !integ || !depth || !pose || !cam)
-        return fail(CHS_ERR_INVALID, "null argument");
+    FrustumGeom fg;
+    CandidateBox box;
+    long long cand;         // IDs in the candidate box (ChunkManager.cpp:187-196)
+    long long dirtyBound;   // IDs in the box grown by one chunk per side: what the frame can mark dirty
+};
+
+// Host part of Chisel.h:64-68 / :119-123: frustum and candidate ID box, exact.
+static int plan_frame(chs_map *m, const float pose[12], const chs_camera *cam, FramePlan *pl)
+{
     if (cam->width <= 0 || cam->height <= 0 || !finite12(pose))
         return fail(CHS_ERR_INVALID, "bad camera size or non-finite pose (quirk Q14: rejected at the boundary)");
-    if (colorPath && (!color || !cpose || !ccam || channels < 1 || channels > 4 || !finite12(cpose) || ccam->width <= 0 || ccam->height <= 0))
-        return fail(CHS_ERR_INVALID, "bad colour arguments");
-    if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !integ->trunc_per_pixel)
-        return fail(CHS_ERR_INVALID, "CHS_TRUNC_PER_PIXEL without trunc_per_pixel");
-    CHS_CUDA(cudaSetDevice(m->device));
-    cudaStream_t st = m->stream;
-
-    FrustumGeom fg;
-    build_frustum(pose, *cam, &fg);
-    CandidateBox box;
-    if (!candidate_box(fg, m->cfg.chunk_size, m->cfg.resolution, &box))
+    build_frustum(pose, *cam, &pl->fg);
+    if (!candidate_box(pl->fg, m->cfg.chunk_size, m->cfg.resolution, &pl->box))
         return fail(CHS_ERR_INVALID, "frustum is not finite or lies outside the packable chunk-ID range");
     for (int k = 0; k < 3; k++)
-        if (box.lo[k] - 1 < -kIdBias || box.hi[k] + 1 >= kIdBias)
+        if (pl->box.lo[k] - 1 < -kIdBias || pl->box.hi[k] + 1 >= kIdBias)
             return fail(CHS_ERR_INVALID, "chunk IDs outside [-2^20, 2^20)");
-    const long long cand = box.count();
-    if (cand > (1ll << 26))
+    pl->cand = pl->box.count();
+    if (pl->cand > (1ll << 26))
         return fail(CHS_ERR_CAPACITY, "candidate box larger than 2^26 chunks");
-    long long dirtyBound = 1;
+    pl->dirtyBound = 1;
     for (int k = 0; k < 3; k++)
-        dirtyBound *= (long long)(box.hi[k] - box.lo[k] + 3);
+        pl->dirtyBound *= (long long)(pl->box.hi[k] - pl->box.lo[k] + 3);
+    return CHS_OK;
+}
 
-    // capacity: known counts + bounds of frames whose counters have not come back yet + this frame
+// Capacity: known counts + bounds of launches whose counters have not come back yet + this launch (`cand` new chunks,
+// `dirtyBound` dirty IDs at most); work lists for `cand` chunks.
+static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound)
+{
+    cudaStream_t st = m->stream;
     int rc = poll_inflight(m, false);
     if (rc)
         return rc;
@@ -408,27 +505,104 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
         // tighten the bound before growing: wait for outstanding counters
         if ((rc = poll_inflight(m, true)))
             return rc;
-        chunkUb = m->knownChunks + cand;
-        dirtyUb = m->knownDirty + dirtyBound;
-        // head-room for several frames in flight: the bound per frame is the candidate count
+        // head-room for several launches in flight: the bound per launch is the candidate count
         const long long wantChunks = m->knownChunks + 4 * cand + m->knownChunks / 4;
         const long long wantDirty = m->knownDirty + 4 * dirtyBound + m->knownDirty / 4;
         if ((rc = ensure_pool(m, wantChunks)) || (rc = ensure_hash(m, wantChunks)) || (rc = ensure_dirty(m, wantDirty)))
             return rc;
     }
-    {
-        const int bpa = m->cfg.chunk_size / 8;
-        if ((rc = grow_buffer(&m->dUnits, &m->unitsCap, (size_t)cand * bpa * bpa * bpa, st)) || (rc = grow_buffer(&m->dNews, &m->newsCap, (size_t)cand, st)))
-            return rc;
-    }
+    const int bpa = m->cfg.chunk_size / 8;
+    if ((rc = grow_buffer(&m->dUnits, &m->unitsCap, (size_t)cand * bpa * bpa * bpa, st)) || (rc = grow_buffer(&m->dNews, &m->newsCap, (size_t)cand, st)))
+        return rc;
+    return CHS_OK;
+}
 
-    const size_t npx = (size_t)cam->width * cam->height;
-    FrameParams fp{};
+static size_t hiz_tiles(const chs_camera *cam)
+{
+    size_t total = 0;
+    for (int l = 0; l < kHizLevels; l++)
+    {
+        const int tile = 8 << l;
+        total += (size_t)((cam->width + tile - 1) / tile) * ((cam->height + tile - 1) / tile);
+    }
+    return total;
+}
+
+// Everything of FrameParams except the image pointers, the work lists and the ids.
+static void fill_frame_params(chs_map *m, const chs_integrator *integ, const float pose[12], const chs_camera *cam, const float cpose[12],
+                              const chs_camera *ccam, bool colorPath, int channels, const FramePlan &pl, float2 *hizBase, FrameParams *out)
+{
+    FrameParams &fp = *out;
     fill_camera(&fp.cam, pose, *cam);
     if (colorPath)
         fill_camera(&fp.ccam, cpose, *ccam);
     else
         fp.ccam = fp.cam;
+    fp.channels = channels;
+    fp.color_path = colorPath ? 1 : 0;
+    fp.trunc_kind = integ->trunc_kind;
+    fp.trunc_param = integ->trunc_param;
+    // ProjectionIntegrator.h:59 / :108 -- double expression, narrowed once
+    fp.diag = (float)(2.0 * std::sqrt((double)3.0f) * (double)m->cfg.resolution);
+    fp.carve_dist = integ->carving_dist;
+    fp.carve = integ->carving_enabled ? 1 : 0;
+    fp.weight = integ->weight;
+    fp.depth_cutoff = colorPath ? 100.0f : 50.0f;
+    fp.same_cam = (colorPath && std::memcmp(&fp.cam, &fp.ccam, sizeof(CameraDev)) == 0) ? 1 : 0;
+    fp.wu_const = integ->weight / (5 * integ->trunc_param);            // ConstantWeighter.h:43-46 (binary32, used for the constant truncator)
+    {
+        float T = (float)1e-5;
+        if ((double)T < 1e-5)
+            T = std::nextafterf(T, INFINITY);
+        fp.sdf_carve_max = T;
+    }
+    for (int k = 0; k < 3; k++)
+    {
+        fp.lo[k] = pl.box.lo[k];
+        fp.n[k] = pl.box.hi[k] - pl.box.lo[k] + 1;
+    }
+    for (int p = 0; p < 6; p++)
+    {
+        for (int k = 0; k < 3; k++)
+            fp.planes[p][k] = pl.fg.plane[p].n[k];
+        fp.planes[p][3] = pl.fg.plane[p].d;
+    }
+    size_t off = 0;
+    for (int l = 0; l < kHizLevels; l++)
+    {
+        const int tile = 8 << l;
+        fp.hizW[l] = (cam->width + tile - 1) / tile;
+        fp.hizH[l] = (cam->height + tile - 1) / tile;
+        fp.hiz[l] = hizBase + off;
+        off += (size_t)fp.hizW[l] * fp.hizH[l];
+    }
+}
+
+static int integrate_common(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12],
+                            const chs_camera *cam, const uint8_t *color, int channels, const float cpose[12],
+                            const chs_camera *ccam, bool colorPath, int batchIndex = -1)
+{
+    if (!m || !integ || !depth || !pose || !cam)
+        return fail(CHS_ERR_INVALID, "null argument");
+    if (colorPath && (!color || !cpose || !ccam || channels < 1 || channels > 4 || !finite12(cpose) || ccam->width <= 0 || ccam->height <= 0))
+        return fail(CHS_ERR_INVALID, "bad colour arguments");
+    if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !integ->trunc_per_pixel)
+        return fail(CHS_ERR_INVALID, "CHS_TRUNC_PER_PIXEL without trunc_per_pixel");
+    CHS_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    FramePlan pl;
+    int rc = plan_frame(m, pose, cam, &pl);
+    if (rc)
+        return rc;
+    const long long cand = pl.cand, dirtyBound = pl.dirtyBound;
+    if ((rc = ensure_capacity(m, cand, dirtyBound)))
+        return rc;
+
+    const size_t npx = (size_t)cam->width * cam->height;
+    if ((rc = grow_buffer(&m->dHiz, &m->hizCap, hiz_tiles(cam), st)))
+        return rc;
+    FrameParams fp{};
+    fill_frame_params(m, integ, pose, cam, cpose, ccam, colorPath, channels, pl, m->dHiz, &fp);
     // inputs
     bool copied = false;
     if (mem == CHS_MEM_HOST)
@@ -478,53 +652,6 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
     }
     if (copied)
         CHS_CUDA(cudaEventRecord(m->h2dDone, st));
-    fp.channels = channels;
-    fp.color_path = colorPath ? 1 : 0;
-    fp.trunc_kind = integ->trunc_kind;
-    fp.trunc_param = integ->trunc_param;
-    // ProjectionIntegrator.h:59 / :108 -- double expression, narrowed once
-    fp.diag = (float)(2.0 * std::sqrt((double)3.0f) * (double)m->cfg.resolution);
-    fp.carve_dist = integ->carving_dist;
-    fp.carve = integ->carving_enabled ? 1 : 0;
-    fp.weight = integ->weight;
-    fp.depth_cutoff = colorPath ? 100.0f : 50.0f;
-    fp.same_cam = (colorPath && std::memcmp(&fp.cam, &fp.ccam, sizeof(CameraDev)) == 0) ? 1 : 0;
-    fp.wu_const = integ->weight / (5 * integ->trunc_param);            // ConstantWeighter.h:43-46 (binary32, used for the constant truncator)
-    {
-        float T = (float)1e-5;
-        if ((double)T < 1e-5)
-            T = std::nextafterf(T, INFINITY);
-        fp.sdf_carve_max = T;
-    }
-    for (int k = 0; k < 3; k++)
-    {
-        fp.lo[k] = box.lo[k];
-        fp.n[k] = box.hi[k] - box.lo[k] + 1;
-    }
-    for (int p = 0; p < 6; p++)
-    {
-        for (int k = 0; k < 3; k++)
-            fp.planes[p][k] = fg.plane[p].n[k];
-        fp.planes[p][3] = fg.plane[p].d;
-    }
-    size_t hizTotal = 0;
-    for (int l = 0; l < kHizLevels; l++)
-    {
-        const int tile = 8 << l;
-        fp.hizW[l] = (cam->width + tile - 1) / tile;
-        fp.hizH[l] = (cam->height + tile - 1) / tile;
-        hizTotal += (size_t)fp.hizW[l] * fp.hizH[l];
-    }
-    if ((rc = grow_buffer(&m->dHiz, &m->hizCap, hizTotal, st)))
-        return rc;
-    {
-        size_t off = 0;
-        for (int l = 0; l < kHizLevels; l++)
-        {
-            fp.hiz[l] = m->dHiz + off;
-            off += (size_t)fp.hizW[l] * fp.hizH[l];
-        }
-    }
     fp.units = m->dUnits;
     fp.units_cap = (int)std::min<size_t>(m->unitsCap, 0x1fffffff);
     fp.news = m->dNews;
@@ -544,6 +671,7 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
     HostSnapshot *slotPtr = nullptr;
     if ((rc = reserve_snapshot(m, fp.frame_id, cand, dirtyBound, &slotPtr)))
         return rc;
+    m->inflight.back().batchIndex = batchIndex;
     // size the new-chunk kernel's grid from what recent frames needed (the kernel strides, so any size is correct)
     const long long newHint = m->haveFrame ? std::max<long long>(64, 2ll * m->lastFrame.new_count) : cand;
     CHS_CUDA(frame_graph_launch(m->frameGraph, fp, m->dm, cand, newHint, slotPtr, m->profiling, m->evt, st));
@@ -551,6 +679,151 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
         m->frameTimed = true;
     m->haveFrame = true;
     // the caller may reuse its host buffers as soon as we return (chisel_ros does: CR ChiselServer.cpp:285-295)
+    if (copied)
+        CHS_CUDA(cudaEventSynchronize(m->h2dDone));
+    return CHS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// chs_integrate_batch: n consecutive frames of one sensor stream (same image size, intrinsics and integrator). Sub-batches of
+// up to kMaxBatch frames go through the fused kernels (integrate_batch.cu); the map afterwards is bit-identical to n calls of
+// chs_integrate_depth[_color] in order. Frames whose colour camera differs from the depth camera are integrated one by one.
+static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K, const chs_frame *frames, int mem, const chs_camera *cam,
+                                 int channels, const chs_camera *ccam, bool colorPath, int statsBase)
+{
+    cudaStream_t st = m->stream;
+    int rc;
+    FramePlan pl[kMaxBatch];
+    int ulo[3], uhi[3];
+    for (int f = 0; f < K; f++)
+    {
+        if ((rc = plan_frame(m, frames[f].pose, cam, &pl[f])))
+            return rc;
+        for (int k = 0; k < 3; k++)
+        {
+            ulo[k] = f == 0 ? pl[f].box.lo[k] : std::min(ulo[k], pl[f].box.lo[k]);
+            uhi[k] = f == 0 ? pl[f].box.hi[k] : std::max(uhi[k], pl[f].box.hi[k]);
+        }
+    }
+    long long unionCand = 1, dirtyBound = 1;
+    for (int k = 0; k < 3; k++)
+    {
+        unionCand *= (long long)(uhi[k] - ulo[k] + 1);
+        dirtyBound *= (long long)(uhi[k] - ulo[k] + 3);
+    }
+    if (unionCand > (1ll << 26))
+        return CHS_ERR_NOT_FOUND;                                   // frames too far apart to share a box: the caller falls back to single frames
+    if ((rc = ensure_capacity(m, unionCand, dirtyBound)))
+        return rc;
+
+    const size_t npx = (size_t)cam->width * cam->height;
+    const size_t cpx = colorPath ? (size_t)ccam->width * ccam->height : 0;
+    const size_t tiles = hiz_tiles(cam);
+    const bool computeTrunc = integ->trunc_kind == CHS_TRUNC_QUADRATIC || integ->trunc_kind == CHS_TRUNC_INVERSE;
+    const bool perPixel = integ->trunc_kind != CHS_TRUNC_CONSTANT;
+    if ((rc = grow_buffer(&m->bHiz, &m->bHizCap, tiles * kMaxBatch, st)))
+        return rc;
+    if (mem == CHS_MEM_HOST && (rc = grow_buffer(&m->bDepth, &m->bDepthCap, npx * kMaxBatch, st)))
+        return rc;
+    if ((computeTrunc || (perPixel && mem == CHS_MEM_HOST)) && (rc = grow_buffer(&m->bTrunc, &m->bTruncCap, npx * kMaxBatch, st)))
+        return rc;
+    if (colorPath)
+    {
+        if (mem == CHS_MEM_HOST && (rc = grow_buffer(&m->bColor, &m->bColorCap, cpx * channels * kMaxBatch, st)))
+            return rc;
+        if ((rc = grow_buffer(&m->bColorPacked, &m->bColorPackedCap, cpx * kMaxBatch, st)))
+            return rc;
+    }
+    FrameParams fps[kMaxBatch];
+    std::memset(fps, 0, sizeof(fps));
+    bool copied = false;
+    for (int f = 0; f < K; f++)
+    {
+        FrameParams &fp = fps[f];
+        fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], m->bHiz + tiles * f, &fp);
+        if (mem == CHS_MEM_HOST)
+        {
+            CHS_CUDA(cudaMemcpyAsync(m->bDepth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, st));
+            fp.depth = m->bDepth + npx * f;
+            copied = true;
+        }
+        else
+            fp.depth = frames[f].depth;
+        fp.trunc_img = nullptr;
+        if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL)
+        {
+            if (mem == CHS_MEM_HOST)
+            {
+                CHS_CUDA(cudaMemcpyAsync(m->bTrunc + npx * f, frames[f].trunc_per_pixel, npx * sizeof(float), cudaMemcpyHostToDevice, st));
+                fp.trunc_img = m->bTrunc + npx * f;
+            }
+            else
+                fp.trunc_img = frames[f].trunc_per_pixel;
+        }
+        else if (computeTrunc)
+            fp.trunc_img = m->bTrunc + npx * f;                     // written by batch_prepare
+        if (colorPath)
+        {
+            if (mem == CHS_MEM_HOST)
+            {
+                CHS_CUDA(cudaMemcpyAsync(m->bColor + cpx * channels * f, frames[f].color, cpx * channels, cudaMemcpyHostToDevice, st));
+                fp.color = m->bColor + cpx * channels * f;
+            }
+            else
+                fp.color = frames[f].color;
+            fp.color_packed = m->bColorPacked + cpx * f;
+        }
+        fp.frame_id = ++m->frameId;
+    }
+    if (copied)
+        CHS_CUDA(cudaEventRecord(m->h2dDone, st));
+    // the frame table: pageable source, staged by the driver before the call returns
+    CHS_CUDA(cudaMemcpyAsync(m->dBatchFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, st));
+
+    // reserve a slot of the batch snapshot ring
+    if ((int)m->inflight.size() >= chs_map::kRing && (rc = poll_inflight(m, true)))
+        return rc;
+    InFlight inf;
+    inf.frameId = ++m->batchId;
+    inf.slot = m->batchRingNext;
+    m->batchRingNext = (m->batchRingNext + 1) % chs_map::kRing;
+    inf.newBound = unionCand;
+    inf.dirtyBound = dirtyBound;
+    inf.batch = true;
+    inf.batchIndex = statsBase;
+    m->hBatchSnap[inf.slot].head = m->hBatchSnap[inf.slot].tail = -1;
+    m->inflight.push_back(inf);
+
+    BatchParams bp{};
+    bp.frames = m->dBatchFrames;
+    bp.K = K;
+    for (int k = 0; k < 3; k++)
+    {
+        bp.lo[k] = ulo[k];
+        bp.n[k] = uhi[k] - ulo[k] + 1;
+    }
+    bp.units = m->dUnits;
+    bp.units_cap = (int)std::min<size_t>(m->unitsCap, 0x1fffffff);
+    bp.news = m->dNews;
+    bp.news_cap = (int)std::min<size_t>(m->newsCap, 0x7fffffff);
+    bp.batch_id = inf.frameId;
+    bp.bctr = m->dBctr;
+    bp.host_slot = &m->hBatchSnap[inf.slot];
+    bp.slot_batch = m->dSlotBatch;
+    BatchLaunchInfo info{};
+    info.W = cam->width;
+    info.H = cam->height;
+    info.cW = colorPath ? ccam->width : 0;
+    info.cH = colorPath ? ccam->height : 0;
+    info.unionCandidates = unionCand;
+    info.newHint = m->haveFrame ? std::max<long long>(64, 2ll * m->lastFrame.new_count * K) : unionCand;
+    info.colorPath = colorPath;
+    info.perPixel = perPixel;
+    info.profiling = m->profiling;
+    CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, st));
+    if (m->profiling)
+        m->frameTimed = true;
+    m->haveFrame = true;
     if (copied)
         CHS_CUDA(cudaEventSynchronize(m->h2dDone));
     return CHS_OK;
@@ -658,6 +931,11 @@ int chs_create(const chs_config *cfg, chs_map **out)
     std::memset(m->hCtr, 0, sizeof(Counters) * (chs_map::kRing + 1));
     CHS_CUDA(cudaHostAlloc((void **)&m->hSnap, sizeof(HostSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hSnap, 0, sizeof(HostSnapshot) * chs_map::kRing);
+    CHS_CUDA(cudaMalloc((void **)&m->dBatchFrames, sizeof(FrameParams) * kMaxBatch));
+    CHS_CUDA(cudaMalloc((void **)&m->dBctr, sizeof(BatchCounters)));
+    CHS_CUDA(cudaMemsetAsync(m->dBctr, 0, sizeof(BatchCounters), m->stream));
+    CHS_CUDA(cudaHostAlloc((void **)&m->hBatchSnap, sizeof(HostBatchSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
+    std::memset(m->hBatchSnap, 0, sizeof(HostBatchSnapshot) * chs_map::kRing);
     CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
     m->frameGraph = frame_graph_create();
     for (int i = 0; i < 8; i++)
@@ -686,7 +964,7 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dColorPacked, m->dHiz,
                     m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
-                    m->dColors, m->dGrids};
+                    m->dColors, m->dGrids, m->dSlotBatch, m->bDepth, m->bTrunc, m->bColor, m->bColorPacked, m->bHiz};
     for (void *p : bufs)
         if (p)
             cudaFreeAsync(p, m->stream);
@@ -694,6 +972,9 @@ int chs_destroy(chs_map *m)
     cudaFree(m->dm.dist_slabs);
     cudaFree(m->dm.color_slabs);
     cudaFree(m->dCtr);
+    cudaFree(m->dBatchFrames);
+    cudaFree(m->dBctr);
+    cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
     frame_graph_destroy(m->frameGraph);
@@ -780,6 +1061,75 @@ int chs_integrate_depth_color(chs_map *m, const chs_integrator *integ, const flo
     return integrate_common(m, integ, depth, mem, pose, cam, color, channels, cpose, ccam, true);
 }
 
+int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const chs_frame *frames, int mem, const chs_camera *cam, int channels,
+                        const chs_camera *ccam)
+{
+    if (!m || !integ || !frames || !cam || n < 0)
+        return fail(CHS_ERR_INVALID, "null argument");
+    const bool colorPath = ccam != nullptr;
+    if (colorPath && (channels < 1 || channels > 4 || ccam->width <= 0 || ccam->height <= 0))
+        return fail(CHS_ERR_INVALID, "bad colour arguments");
+    bool fusable = true;
+    for (int f = 0; f < n; f++)
+    {
+        if (!frames[f].depth || (colorPath && !frames[f].color) || (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !frames[f].trunc_per_pixel))
+            return fail(CHS_ERR_INVALID, "frame without depth / colour / truncation image");
+        if (!finite12(frames[f].pose) || (colorPath && !finite12(frames[f].color_pose)))
+            return fail(CHS_ERR_INVALID, "non-finite pose (quirk Q14: rejected at the boundary)");
+        // the fused kernels reuse the depth projection for the colour lookup
+        if (colorPath && (std::memcmp(frames[f].pose, frames[f].color_pose, sizeof(float) * 12) != 0 || std::memcmp(cam, ccam, 4 * sizeof(float) + 2 * sizeof(int)) != 0))
+            fusable = false;
+    }
+    CHS_CUDA(cudaSetDevice(m->device));
+    int rc = poll_inflight(m, true);                        // batchStats is about to be rewritten
+    if (rc)
+        return rc;
+    m->batchStats.assign((size_t)n, chs_frame_stats{});
+    int f = 0;
+    while (f < n)
+    {
+        const int K = std::min(n - f, (int)kMaxBatch);
+        rc = CHS_ERR_NOT_FOUND;
+        if (fusable && K >= 2)
+            rc = integrate_batch_fused(m, integ, K, frames + f, mem, cam, channels, ccam, colorPath, f);
+        if (rc == CHS_ERR_NOT_FOUND)
+        {
+            // frame by frame (single frame, separate colour camera, or frames too far apart to share a candidate box)
+            for (int j = f; j < f + K; j++)
+            {
+                chs_integrator one = *integ;
+                one.trunc_per_pixel = frames[j].trunc_per_pixel;
+                if ((rc = integrate_common(m, &one, frames[j].depth, mem, frames[j].pose, cam, frames[j].color, channels, frames[j].color_pose, ccam, colorPath, j)))
+                    return rc;
+            }
+        }
+        else if (rc)
+            return rc;
+        f += K;
+    }
+    return CHS_OK;
+}
+
+int chs_get_batch_stats(chs_map *m, chs_frame_stats *out, int cap, int *n)
+{
+    if (!m || !n)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    int rc = poll_inflight(m, true);
+    if (rc)
+        return rc;
+    *n = (int)m->batchStats.size();
+    int flags = 0;
+    for (int i = 0; i < *n && i < cap && out; i++)
+    {
+        out[i] = m->batchStats[i];
+        flags |= (int)out[i].error_flags;
+    }
+    if (flags)
+        return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(flags));
+    return CHS_OK;
+}
+
 int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
 {
     if (!m || !out)
@@ -789,17 +1139,7 @@ int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
     if (rc)
         return rc;
     const HostSnapshot &c = m->lastFrame;
-    out->candidates = c.candidates;
-    out->new_candidates = c.new_count;
-    out->brick_units = c.unit_count;
-    out->n_upd = (int64_t)(((unsigned long long)(unsigned)c.n_upd_hi << 32) | (unsigned)c.n_upd_lo);
-    out->n_carve = c.n_carve;
-    out->n_col = c.n_col;
-    out->n_new = c.n_new;
-    out->updated_chunks = c.updated_chunks;
-    out->total_chunks = c.n_chunks;
-    out->dirty_chunks = c.n_dirty;
-    out->error_flags = c.error_flags;
+    *out = stats_of(c);
     if (c.error_flags)
         return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(c.error_flags));
     return CHS_OK;

@@ -18,6 +18,55 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fp, const Devi
                                bool profiling, cudaEvent_t *evt, cudaStream_t st);
 float host_truncation(int kind, float param, float depth);
 
+// ---- fused multi-frame integration (integrate_batch.cu) ----
+// K <= kMaxBatch consecutive frames in one pass: every voxel of the map is independent of every other voxel, so applying
+// frames f0 < f1 < ... to a voxel while its state sits in registers gives the same bits as K separate passes.
+constexpr int kMaxBatch = 16;
+
+struct BatchCounters
+{
+    int unit_count, new_count, tickets, pad;
+    int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch], pad2[kMaxBatch];
+    unsigned long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
+};
+
+// Written into a pinned slot by the last CTA of a batch: head, payload, system fence, tail. Valid for batch b when
+// head == tail == b.
+struct HostBatchSnapshot
+{
+    int head, n_chunks, n_dirty, error_flags;
+    int unit_count, new_count, K, pad;
+    int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch];
+    long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
+    int tail, pad3[3];
+};
+
+struct BatchParams
+{
+    const FrameParams *frames;      // device array [K]; each entry is complete, exactly as the single-frame path would fill it
+    int K;
+    int lo[3], n[3];                // union of the K candidate ID boxes
+    int4 *units;                    // bricks of existing chunks: {id key low, id key high, slot | brick << 24, frame mask}
+    int units_cap;
+    int4 *news;                     // chunks that do not exist yet: {x, y, z, candidate-frame mask | band-frame mask << 16}
+    int news_cap;
+    int batch_id;                   // > 0, increases by one per batch
+    int total_ctas;                 // CTAs of the brick kernel (the last one takes the snapshot)
+    BatchCounters *bctr;
+    HostBatchSnapshot *host_slot;   // pinned, device-mapped
+    unsigned long long *slot_batch; // [capacity] (batch id << 32) | mask of the batch's frames that updated the chunk
+};
+
+struct BatchLaunchInfo
+{
+    int W, H, cW, cH;               // depth / colour image size (identical for all frames of a batch)
+    long long unionCandidates;      // chunk IDs in the union box
+    long long newHint;
+    bool colorPath, perPixel, profiling;
+};
+// events (profiling): [0] start, [1] after prepare, [2] after candidates, [7] after new chunks, [3] after bricks
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st);
+
 // table maintenance (capi.cu)
 void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st);
 void launch_rebuild_hash(const DeviceMap &map, int nChunks, cudaStream_t st);

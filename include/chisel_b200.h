@@ -11,6 +11,7 @@
  *   chs_reset                chisel::Chisel::Reset                                   OC/src/Chisel.cpp:44-48, CR/src/ChiselServer.cpp:200
  *   chs_integrate_depth      chisel::Chisel::IntegrateDepthScan<float>               OC/include/open_chisel/Chisel.h:59-112, CR/src/ChiselServer.cpp:501
  *   chs_integrate_depth_color chisel::Chisel::IntegrateDepthScanColor<float,uint8_t> OC/include/open_chisel/Chisel.h:114-213, CR/src/ChiselServer.cpp:497
+ *   chs_integrate_batch      n consecutive calls of the two entries above (the caller queues frames; OC Chisel.h:59-213)
  *   chs_update_meshes        ChunkManager::RecomputeMeshes(meshesToUpdate) + clear    OC/src/ChunkManager.cpp:130-169, OC/src/Chisel.cpp:55-57
  *                            (the every-10th-call gate of Chisel::UpdateMeshes, Chisel.cpp:50-59, lives in the facade)
  *   chs_num_dirty/_dirty_ids chisel::Chisel::GetMeshesToUpdate                       OC/include/open_chisel/Chisel.h:221-224, CR/src/ChiselServer.cpp:346,554
@@ -131,6 +132,23 @@ int chs_integrate_depth(chs_map *map, const chs_integrator *integ, const float *
 int chs_integrate_depth_color(chs_map *map, const chs_integrator *integ, const float *depth, int mem,
                               const float pose[12], const chs_camera *cam, const uint8_t *color, int channels,
                               const float color_pose[12], const chs_camera *color_cam);
+/* One frame of a batch. Pointers live in the memory space named by `mem` of the call. */
+typedef struct
+{
+    const float *depth;            /* width*height float metres */
+    const uint8_t *color;          /* colour path only: color_cam.width*height*channels */
+    const float *trunc_per_pixel;  /* CHS_TRUNC_PER_PIXEL only */
+    float pose[12];
+    float color_pose[12];          /* colour path only */
+} chs_frame;
+/* n consecutive frames of one stream (same image size, intrinsics and integrator) in one call: n calls of
+ * Chisel::IntegrateDepthScan (color_cam == NULL) or IntegrateDepthScanColor, in order, with bit-identical results. Groups of
+ * up to 16 frames run through the fused multi-frame kernels (every touched voxel is read and written once per group; see
+ * DESIGN.md section 5); frames whose colour camera differs from the depth camera are integrated one by one. */
+int chs_integrate_batch(chs_map *map, const chs_integrator *integ, int n_frames, const chs_frame *frames, int mem,
+                        const chs_camera *cam, int channels, const chs_camera *color_cam);
+/* per-frame counters of the last chs_integrate_batch call; *n = its frame count. Synchronises. */
+int chs_get_batch_stats(chs_map *map, chs_frame_stats *out, int cap, int *n);
 int chs_get_frame_stats(chs_map *map, chs_frame_stats *out);   /* synchronises */
 int chs_get_timings(chs_map *map, chs_timings *out);           /* synchronises */
 

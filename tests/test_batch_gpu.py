@@ -1,0 +1,165 @@
+"""GPU suite for the fused multi-frame path (chs_integrate_batch, cvids_b200/csrc/integrate_batch.cu): K frames in one pass
+must leave the map, the dirty set, the meshes and the per-frame counters bit-identical to K single-frame integrations -- checked
+against the CPU oracle (which integrates frame by frame, like the reference) and against the single-frame CUDA path."""
+import numpy as np
+import pytest
+
+from cvids_b200 import scenes
+from tests import common
+from tests.common import Setup
+
+pytestmark = pytest.mark.gpu
+
+COUNTERS = ("candidates", "n_upd", "n_carve", "n_col", "n_new", "updated_chunks")
+
+
+def _run_batched(setup, frames, cam, batch, remesh=True, truncs=False, **cuda_kw):
+    """Feed `frames` to the CUDA map in groups of `batch` (chs_integrate_batch) and frame by frame to the oracle."""
+    a, b = common.Driver(setup, "cuda", **cuda_kw), common.Driver(setup, "oracle")
+    camv = cam.as_array()
+    frames = list(frames)
+    i = 0
+    while i < len(frames):
+        grp = frames[i:i + batch]
+        color = grp[0][1] is not None
+        a.m.integrate_batch(a.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp] if color else None)
+        want = []
+        for depth, col, pose in grp:
+            b.integrate(depth, pose, camv, col)
+            want.append(b.counters())
+        got = a.m.batch_stats()
+        assert len(got) == len(grp)
+        for j, (g, w) in enumerate(zip(got, want)):
+            for k in COUNTERS:
+                assert g[k] == w[k], "frame %d counter %s: cuda batch %d oracle %d" % (i + j, k, g[k], w[k])
+        assert np.array_equal(a.dirty(), b.dirty()), "dirty sets differ after the batch ending at frame %d" % (i + len(grp) - 1)
+        if remesh:
+            a.remesh()
+            b.remesh()
+        i += len(grp)
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
+    if remesh:
+        common.assert_meshes_equal(a.meshes(), b.meshes())
+    return a, b
+
+
+@pytest.mark.parametrize("batch", [2, 5, 16])
+def test_batch_color_room_2cm(batch):
+    _run_batched(Setup(16, 0.02, True), common.orbit_stream(common.SMALL_CAM, 10, total=30, color=True, nan_frac=0.03, seed=7, noise=0.004),
+                 common.SMALL_CAM, batch)
+
+
+def test_batch_depth_path_5cm():
+    _run_batched(Setup(16, 0.05, False), common.orbit_stream(common.MID_CAM, 12, total=30, seed=3), common.MID_CAM, 6)
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_batch_carving(color):
+    """The obstacle appears and disappears INSIDE one batch: band updates and carving of the same voxels in one pass."""
+    _run_batched(Setup(16, 0.05, color, weight=2.0), common.carve_stream(common.SMALL_CAM, color=color), common.SMALL_CAM, 10)
+    _run_batched(Setup(16, 0.05, color, weight=2.0), common.carve_stream(common.SMALL_CAM, color=color), common.SMALL_CAM, 3)
+
+
+def test_batch_carving_disabled():
+    _run_batched(Setup(16, 0.05, False, carve=False), common.carve_stream(common.SMALL_CAM), common.SMALL_CAM, 5)
+
+
+@pytest.mark.parametrize("kind,param", [(common.TRUNC_INVERSE, 2.0), (common.TRUNC_QUADRATIC, 4.0)])
+def test_batch_truncators(kind, param):
+    _run_batched(Setup(16, 0.05, True, trunc_kind=kind, trunc_param=param, carve_dist=0.0),
+                 common.orbit_stream(common.SMALL_CAM, 6, total=30, color=True, seed=2), common.SMALL_CAM, 3)
+
+
+@pytest.mark.parametrize("chunk,res", [(8, 0.1), (8, 0.04), (32, 0.03)])
+def test_batch_chunk_sizes(chunk, res):
+    _run_batched(Setup(chunk, res, True), common.orbit_stream(common.SMALL_CAM, 6, total=30, color=True, seed=4), common.SMALL_CAM, 3)
+
+
+def test_batch_multi_agent_interleave():
+    """Frames of four agents with different poses, interleaved round-robin (config 3 shape), eight per batch."""
+    def frames():
+        for f in range(4):
+            for agent in range(4):
+                pose = scenes.orbit_pose(f, 30, phase=agent * np.pi / 2)
+                depth, col = scenes.render(scenes.ROOM, common.SMALL_CAM, pose, color=True, seed=100 * agent + f)
+                yield depth, col, pose
+    _run_batched(Setup(16, 0.05, True), frames(), common.SMALL_CAM, 8)
+
+
+def test_batch_equals_single_frame_cuda_and_mixed_calls():
+    """Batch calls, single-frame calls and a batch of one may be mixed freely on one map."""
+    setup = Setup(16, 0.04, True)
+    frames = list(common.orbit_stream(common.SMALL_CAM, 9, total=30, color=True, nan_frac=0.02, seed=11))
+    camv = common.SMALL_CAM.as_array()
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    for depth, col, pose in frames:
+        a.integrate(depth, pose, camv, col)
+    grp = frames[:4]
+    b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+    b.integrate(*[frames[4][k] for k in (0, 2)], camv, frames[4][1])
+    grp = frames[5:6]
+    b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+    assert len(b.m.batch_stats()) == 1
+    grp = frames[6:]
+    b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
+    a.remesh()
+    b.remesh()
+    common.assert_meshes_equal(a.meshes(), b.meshes())
+
+
+def test_batch_separate_color_camera_runs_frame_by_frame():
+    setup = Setup(16, 0.05, True)
+    cam, ccam = common.SMALL_CAM, scenes.Camera(140.0, 139.0, 80.0, 60.0, 160, 120)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    depths, cols, poses, cposes = [], [], [], []
+    for f in range(3):
+        pose = scenes.orbit_pose(f, 30)
+        cpose = scenes.orbit_pose(f, 30, phase=0.02)
+        depth, _ = scenes.render(scenes.ROOM, cam, pose)
+        _, col = scenes.render(scenes.ROOM, ccam, cpose, color=True)
+        depths.append(depth); cols.append(col); poses.append(pose); cposes.append(cpose)
+        b.integrate(depth, pose, cam.as_array(), col, cpose, ccam.as_array())
+    a.m.integrate_batch(a.integ, depths, poses, cam.as_array(), cols, cposes, ccam.as_array())
+    assert len(a.m.batch_stats()) == 3
+    common.assert_state_equal(a.state(), b.state())
+
+
+def test_batch_larger_than_sixteen_and_device_memory():
+    import torch
+    setup = Setup(16, 0.05, True)
+    cam = common.SMALL_CAM
+    frames = list(common.orbit_stream(cam, 20, total=40, color=True, seed=5))
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    for depth, col, pose in frames:
+        a.integrate(depth, pose, cam.as_array(), col)
+    dd = [torch.from_numpy(f[0]).cuda() for f in frames]
+    dc = [torch.from_numpy(f[1]).cuda() for f in frames]
+    torch.cuda.synchronize()
+    b.m.integrate_batch(b.integ, None, [f[2] for f in frames], cam.as_array(), device_ptrs=[(d.data_ptr(), c.data_ptr()) for d, c in zip(dd, dc)],
+                        channels=3)
+    st = b.m.batch_stats()
+    assert len(st) == 20 and all(s["n_upd"] > 0 for s in st)
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
+
+
+def test_batch_sharded_union_equals_single_map():
+    """Ownership filter in the fused candidates kernel: the union of three shards equals the unsharded map."""
+    setup = Setup(16, 0.05, True)
+    cam = common.SMALL_CAM
+    frames = list(common.orbit_stream(cam, 6, total=30, color=True, seed=9))
+    whole = common.Driver(setup, "cuda")
+    whole.m.integrate_batch(whole.integ, [f[0] for f in frames], [f[2] for f in frames], cam.as_array(), [f[1] for f in frames])
+    ids_w, sdf_w, w_w, c_w = whole.state()
+    parts = []
+    for r in range(3):
+        d = common.Driver(setup, "cuda", rank=r, world=3)
+        d.m.integrate_batch(d.integ, [f[0] for f in frames], [f[2] for f in frames], cam.as_array(), [f[1] for f in frames])
+        parts.append(d.state())
+    ids = np.concatenate([p[0] for p in parts])
+    order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+    merged = tuple(np.concatenate([p[k] for p in parts])[order] for k in range(4))
+    common.assert_state_equal(merged, (ids_w, sdf_w, w_w, c_w))
