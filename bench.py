@@ -42,7 +42,7 @@ METRIC = "tsdf_voxel_updates_per_s"
 UNIT = "GVox/s"
 CFG = scenes.CONFIG2
 WORKLOAD = "configs[1]: single-agent EuRoC-shape 752x480 depth+colour stream, analytic room, 2 cm voxels, 16^3 chunks, " \
-           "trunc 4 voxels, IntegrateDepthScanColor; step = 1 frame"
+           "trunc 4 voxels, IntegrateDepthScanColor; step = %d consecutive frame(s) in one chs_integrate_batch call"
 
 
 def frames_for(lo: int, hi: int):
@@ -145,19 +145,25 @@ def cpu_arm(frames, warm, steps, budget_s):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores, same workload and step (B consecutive
+    frames, integrated one by one -- the reference has no batch entry). Bounded by --cpu-budget seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    warm, steps = args.warmup, args.steps
-    frames = frames_for(0, warm + steps)
+    B = max(1, min(args.batch, 16))
+    warm, steps = args.warmup * B, args.steps * B
+    n_unique = min(warm + steps, CFG.n_frames)
+    frames = frames_for(0, n_unique)
+    frames = [frames[i % n_unique] for i in range(warm + steps)]
     r = cpu_arm(frames, warm, steps, budget_s=args.cpu_budget)
+    steps_done = r["steps_done"] / B
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_done"],
-        "warmup": warm, "ms_per_step": 1000.0 * r["seconds"] / max(r["steps_done"], 1), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_s": r["fps"],
-        "config": {"workload": WORKLOAD, "threads": "16 std::threads hard-coded by the reference (Chisel.h:150)" if r["kind"] == "reference" else "1 (C port)"},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / max(steps_done, 1e-9), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_step": B, "frames_per_s": r["fps"],
+        "config": {"workload": WORKLOAD % B, "threads": "16 std::threads hard-coded by the reference (Chisel.h:150)" if r["kind"] == "reference" else "1 (C port)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
-                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames" % (r["steps_done"], warm)},
+                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames, %.1f s" % (r["steps_done"], warm, r["seconds"])},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -187,15 +193,17 @@ def run_cuda(args):
     assert stream.cuda_stream != 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    warm, steps = args.warmup, args.steps
+    warm, steps, B = args.warmup, args.steps, max(1, min(args.batch, 16))
     cam = CFG.cam
     camv = cam.as_array()
     channels = 3
     H, W = cam.height, cam.width
+    nfr = (warm + steps) * B                       # frames of the stream used by the batched legs
+    n_unique = min(nfr, CFG.n_frames)              # the 200-frame orbit wraps around after that
 
     # rank 0 owns the stream; other ranks receive frames by NCCL broadcast
-    frames = frames_for(0, warm + steps) if rank == 0 else None
-    poses = np.zeros((warm + steps, 12), np.float32)
+    frames = frames_for(0, n_unique) if rank == 0 else None
+    poses = np.zeros((n_unique, 12), np.float32)
     if rank == 0:
         for i, fr in enumerate(frames):
             poses[i] = fr[2].reshape(12)
@@ -204,18 +212,18 @@ def run_cuda(args):
         dist.broadcast(pt, 0)
         poses = pt.cpu().numpy()
 
-    nfr = warm + steps
-    # one contiguous byte buffer per frame [depth f32 | colour u8] so that a frame is ONE NCCL broadcast (sharding.py)
+    # one contiguous byte buffer per frame [depth f32 | colour u8] so that a frame (or a batch of consecutive frames) is ONE
+    # NCCL broadcast (sharding.py)
     fbytes = sharding.frame_nbytes(W, H, channels)
     dbytes = 4 * W * H
-    d_frames = torch.empty((nfr, fbytes), dtype=torch.uint8, device=dev)
+    d_frames = torch.empty((n_unique, fbytes), dtype=torch.uint8, device=dev)
     h_frames = None
     if rank == 0:
-        h_frames = torch.empty((nfr, fbytes), dtype=torch.uint8).pin_memory()
+        h_frames = torch.empty((n_unique, fbytes), dtype=torch.uint8).pin_memory()
         for i, fr in enumerate(frames):
             h_frames[i].copy_(torch.from_numpy(sharding.pack_frame(fr[0], fr[1])))
         d_frames.copy_(h_frames)
-    recv = torch.empty(fbytes, dtype=torch.uint8, device=dev)
+    recv = torch.empty((B, fbytes), dtype=torch.uint8, device=dev)
     # L2 flush between timed steps: write a 256 MiB buffer, then read another one, so that L2 ends up full of CLEAN
     # foreign lines (a write-only flush leaves ~126 MB of dirty lines whose write-back would be charged to the step)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
@@ -236,104 +244,149 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_device(m, i):
-        """inputs resident in HBM (rank 0) -> [NCCL broadcast] -> integrate"""
-        src = d_frames[i] if rank == 0 else recv
+    def frame_ids(step, b=B):
+        return [(step * b + j) % n_unique for j in range(b)]
+
+    def step_device(m, step, b=B):
+        """One step = b consecutive frames, inputs resident in HBM (rank 0) -> [NCCL broadcast] -> fused integration."""
+        ids = frame_ids(step, b)
         if world > 1:
+            # consecutive frames are contiguous in d_frames (unless the orbit wraps inside the batch)
+            contiguous = ids[-1] - ids[0] == b - 1
+            if rank == 0:
+                src = d_frames[ids[0]:ids[0] + b] if contiguous else d_frames[ids]
+                if not contiguous:
+                    recv[:b].copy_(src)
+                    src = recv[:b]
+            else:
+                src = recv[:b]
             sharding.broadcast_frame(src, 0)
-        p = src.data_ptr()
-        m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(p, p + dbytes), channels=channels)
+            base = src.data_ptr()
+            ptrs = [(base + j * fbytes, base + j * fbytes + dbytes) for j in range(b)]
+        else:
+            base = d_frames.data_ptr()
+            ptrs = [(base + i * fbytes, base + i * fbytes + dbytes) for i in ids]
+        if b == 1:
+            m.integrate_depth_scan_color(integ, None, poses[ids[0]], camv, None, device_ptrs=ptrs[0], channels=channels)
+        else:
+            m.integrate_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
+
+    def timed_leg(b, n_warm, n_steps, do_flush):
+        """CUDA events around every step on the stream the kernels run on; returns (device seconds, wall seconds, clocks)."""
+        m = new_map()
+        for i in range(n_warm):
+            step_device(m, i, b)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        if do_flush:
+            for k in range(n_steps):
+                flush_l2(k)
+                ev[k][0].record(stream)
+                step_device(m, n_warm + k, b)
+                ev[k][1].record(stream)
+        else:
+            ev[0][0].record(stream)
+            for k in range(n_steps):
+                step_device(m, n_warm + k, b)
+            ev[0][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clk = sampler.stop()
+        t = sum(a.elapsed_time(c) for a, c in (ev if do_flush else ev[:1])) / 1000.0
+        m.close()
+        return t, wall, clk
 
     # ---------------- leg A: device-resident inputs, CUDA events per step, L2 flushed between steps -------------
-    m = new_map()
-    for i in range(warm):
-        step_device(m, i)
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(steps):
-        flush_l2(k)
-        ev[k][0].record(stream)
-        step_device(m, warm + k)
-        ev[k][1].record(stream)
-    barrier()
-    wall_a = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1000.0
-    m.close()
-
+    t_dev, wall_a, clocks = timed_leg(B, warm, steps, True)
     # ---------------- leg A': same, no flush (the map working set stays in L2 as it does in a live stream) -------
-    m = new_map()
-    for i in range(warm):
-        step_device(m, i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(steps):
-        step_device(m, warm + k)
-    e1.record(stream)
-    barrier()
-    t_warm = e0.elapsed_time(e1) / 1000.0
-    m.close()
+    t_warm, _, _ = timed_leg(B, warm, steps, False)
+    # ---------------- leg S: one frame per call (chs_integrate_depth_color, the reference's call granularity) ----
+    s_steps, s_warm = min(60, n_unique - 10), 10
+    t_single, _, _ = timed_leg(1, s_warm, s_steps, True) if B > 1 else (t_dev, 0, 0)
 
-    # ---------------- leg C: per-frame counters and integrate-kernel time (profiling events inside the library) --
+    # ---------------- leg C: per-frame counters and kernel times (profiling events inside the library) ----------
     m = new_map()
     m.set_profiling(True)
-    upd_local = 0
+    upd_local = upd_single = 0
     bytes_alg = 0
     t_integrate = t_prepare = t_cand = t_new = 0.0
-    per_frame = []
+    per_step = []
     for i in range(warm + steps):
         if i >= warm:
             flush_l2(i)
         step_device(m, i)
+        sts = m.batch_stats() if B > 1 else [m.frame_stats()]
+        if i * B < s_warm + s_steps:
+            upd_single += sum(st["n_upd"] for j, st in enumerate(sts) if s_warm <= i * B + j < s_warm + s_steps)
         if i >= warm:
-            st = m.frame_stats()
             tm = m.timings()
-            upd_local += st["n_upd"]
-            b = algorithmic_bytes(st, cam, channels, True)
-            bytes_alg += b
+            upd_local += sum(st["n_upd"] for st in sts)
+            bytes_alg += sum(algorithmic_bytes(st, cam, channels, True) for st in sts)
             t_integrate += tm["integrate_ms"] / 1000.0
             t_prepare += tm["prepare_ms"] / 1000.0
             t_cand += tm["candidates_ms"] / 1000.0
             t_new += tm["new_chunks_ms"] / 1000.0
-            per_frame.append((st["n_upd"], st["brick_units"], st["candidates"], tm["integrate_ms"], st["updated_chunks"], st["n_new"], st["new_candidates"]))
+            per_step.append((sum(st["n_upd"] for st in sts), sts[-1]["brick_units"], sum(st["candidates"] for st in sts), tm["integrate_ms"],
+                             sum(st["updated_chunks"] for st in sts), sum(st["n_new"] for st in sts), sts[-1]["new_candidates"]))
     total_chunks = m.frame_stats()["total_chunks"]
-    # meshing: one re-mesh of everything the run left dirty (Chisel::UpdateMeshes without its every-10th gate), cold L2
-    n_dirty = len(m.get_meshes_to_update())
+    # meshing: re-mesh of everything the run left dirty (Chisel::UpdateMeshes without its every-10th gate): once cold (first
+    # launch, cold L2), then the same dirty set again twice (steady state; the dirty set is restored with chs_set_dirty)
+    dirty = m.get_meshes_to_update()
+    n_dirty = len(dirty)
     flush_l2(0)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     m.recompute_meshes()
     t_mesh_wall = time.perf_counter() - t0
-    mt = m.timings()
+    mt_cold = m.timings()
+    mt = mt_cold
+    for _ in range(2):
+        m.set_dirty(dirty)
+        flush_l2(1)
+        _check_ok = m._lib.chs_update_meshes(m._h)
+        assert _check_ok == 0
+        mt = m.timings()
     mc = m.last_mesh_counts()
     V_halo = (CFG.chunk + 1) ** 3
     b_mc = mc["n_chunks"] * V_halo * 12 + mc["n_vertices"] * 36 + mc["n_grids"] * 12        # B_mc of SURVEY 8(d), colour map
     mesh_info = {"dirty_ids": n_dirty, "remeshed_chunks": mc["n_chunks"], "triangles": mc["n_vertices"] // 3, "grids": mc["n_grids"],
                  "device_ms": mt["mesh_ms"], "count_ms": mt["mesh_count_ms"], "emit_ms": mt["mesh_emit_ms"],
-                 "wall_ms_incl_download_and_host_merge": 1000.0 * t_mesh_wall,
+                 "first_call_device_ms": mt_cold["mesh_ms"],
+                 "wall_ms_first_call_incl_download_and_host_merge": 1000.0 * t_mesh_wall,
                  "algorithmic_bytes": b_mc, "achieved_gbs": b_mc / (mt["mesh_ms"] * 1e-3) / 1e9 if mt["mesh_ms"] > 0 else None}
     m.close()
 
     # ---------------- leg B: end to end through the C ABI with pinned HOST frames + D2H counters ----------------
     m = new_map()
 
-    def step_host(i):
+    def step_host(step):
+        ids = frame_ids(step)
         if world > 1:
             if rank == 0:
-                recv.copy_(h_frames[i], non_blocking=True)
-            sharding.broadcast_frame(recv, 0)
-            p = recv.data_ptr()
-            m.integrate_depth_scan_color(integ, None, poses[i], camv, None, device_ptrs=(p, p + dbytes), channels=channels)
+                for j, i in enumerate(ids):
+                    recv[j].copy_(h_frames[i], non_blocking=True)
+            sharding.broadcast_frame(recv[:B], 0)
+            base = recv.data_ptr()
+            ptrs = [(base + j * fbytes, base + j * fbytes + dbytes) for j in range(B)]
+            if B == 1:
+                m.integrate_depth_scan_color(integ, None, poses[ids[0]], camv, None, device_ptrs=ptrs[0], channels=channels)
+            else:
+                m.integrate_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
         else:
-            hb = h_frames[i].numpy()
-            lib_d, lib_c = sharding.unpack_frame(hb, W, H, channels)
-            m.integrate_depth_scan_color(integ, lib_d, poses[i], camv, lib_c)
-        return m.frame_stats()["n_upd"]
+            ds, cs = [], []
+            for i in ids:
+                lib_d, lib_c = sharding.unpack_frame(h_frames[i].numpy(), W, H, channels)
+                ds.append(lib_d)
+                cs.append(lib_c)
+            if B == 1:
+                m.integrate_depth_scan_color(integ, ds[0], poses[ids[0]], camv, cs[0])
+            else:
+                m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs)
+        return sum(st["n_upd"] for st in m.batch_stats()) if B > 1 else m.frame_stats()["n_upd"]
 
     for i in range(warm):
         step_host(i)
@@ -347,49 +400,58 @@ def run_cuda(args):
     m.close()
 
     # ---------------- reduce over ranks -------------------------------------------------------------------------
-    vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate, t_warm], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(upd_local), float(upd_e2e), float(bytes_alg), float(total_chunks)], dtype=torch.float64, device=dev)
+    vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate, t_warm, t_single], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(upd_local), float(upd_e2e), float(bytes_alg), float(total_chunks), float(upd_single)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_dev, t_e2e, wall_a, t_int_max, t_warm = vals.tolist()
-    upd_total, upd_e2e_total, bytes_total, chunks_total = sums.tolist()
+    t_dev, t_e2e, wall_a, t_int_max, t_warm, t_single = vals.tolist()
+    upd_total, upd_e2e_total, bytes_total, chunks_total, upd_single_total = sums.tolist()
 
     if rank == 0:
         peak, peak_src = peaks()
-        # roofline of the dominant kernel on THIS rank (rank 0): algorithmic bytes it processed / its event time
-        achieved = bytes_alg / t_integrate / 1e9 if t_integrate > 0 else 0.0
-        h2d = 4 * W * H + channels * W * H
+        # roofline of the integrate kernels on THIS rank (rank 0): algorithmic bytes they processed / their event time
+        t_kernels = t_integrate + t_new
+        achieved = bytes_alg / t_kernels / 1e9 if t_kernels > 0 else 0.0
+        h2d = (4 * W * H + channels * W * H) * B
+        kname = "batch_bricks_kernel<16,color> + batch_new_chunks_kernel<16,color>" if B > 1 else "integrate_bricks_kernel<16,color> + integrate_new_chunks_kernel<16,color>"
         line = {
             "metric": METRIC, "value": upd_total / t_dev / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": 1000.0 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "frames_per_s": steps / t_dev,
-            "l2_warm": {"value": upd_total / t_warm / 1e9, "unit": UNIT, "frames_per_s": steps / t_warm, "ms_per_step": 1000.0 * t_warm / steps,
+            "frames_per_step": B, "frames_per_s": steps * B / t_dev,
+            "l2_warm": {"value": upd_total / t_warm / 1e9, "unit": UNIT, "frames_per_s": steps * B / t_warm, "ms_per_step": 1000.0 * t_warm / steps,
                         "note": "same steps back to back without the L2 flush; includes host launch gaps"},
-            "config": {"workload": WORKLOAD, "parallelism": "chunk-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "1 GPU",
+            "single_frame_calls": {"value": upd_single_total / t_single / 1e9 if t_single > 0 else None, "unit": UNIT,
+                                   "frames_per_s": s_steps / t_single if t_single > 0 else None, "ms_per_frame": 1000.0 * t_single / max(s_steps, 1),
+                                   "note": "one frame per call (chs_integrate_depth_color, the reference's call granularity), frames %d..%d, L2 flushed" % (s_warm, s_warm + s_steps - 1)},
+            "config": {"workload": WORKLOAD % B, "parallelism": "chunk-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "1 GPU",
                        "l2": "256 MiB write + 256 MiB read between steps, excluded from the step time" if flush is not None else
                              "no flush: frame stream (%d MB) > L2, map working set stays in L2" % ((h2d * nfr) >> 20),
                        "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
-                       "rank0_per_step": {"candidate_chunks": float(np.mean([p[2] for p in per_frame])),
-                                          "brick_units": float(np.mean([p[1] for p in per_frame])),
-                                          "new_chunk_candidates": float(np.mean([p[6] for p in per_frame])),
-                                          "updated_chunks": float(np.mean([p[4] for p in per_frame])),
-                                          "new_chunks": float(np.mean([p[5] for p in per_frame]))}},
-            "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88, "timing": "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
-            "gpu_launches": 4 * steps,
+                       "rank0_per_step": {"candidate_chunks": float(np.mean([p[2] for p in per_step])),
+                                          "brick_units": float(np.mean([p[1] for p in per_step])),
+                                          "new_chunk_candidates": float(np.mean([p[6] for p in per_step])),
+                                          "updated_chunks": float(np.mean([p[4] for p in per_step])),
+                                          "new_chunks": float(np.mean([p[5] for p in per_step]))}},
+            "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * B / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * B,
+                    "timing": "wall clock around chs_integrate_batch(host frames) + chs_get_batch_stats" if B > 1 else
+                              "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
+            "gpu_launches": (5 if B > 1 else 5) * steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "integrate_bricks_kernel<16,color>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                         "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_integrate / steps,
+                         "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_kernels / steps,
+                         "bricks_ms_per_launch": 1000.0 * t_integrate / steps, "new_chunks_ms_per_launch": 1000.0 * t_new / steps,
                          "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps,
-                         "new_chunks_ms_per_launch": 1000.0 * t_new / steps},
+                         "note": "algorithmic bytes = B_int of SURVEY 8(d) summed over the step's frames; with %d frames fused the voxel state "
+                                 "moves through HBM once per step, so DRAM traffic is BELOW the algorithmic bytes" % B},
             "wall_s_timed_region": wall_a,
             "mesh": mesh_info,
         }
         if world == 1 and not args.no_cpu:
-            n_cpu = min(steps, args.cpu_frames)
+            n_cpu = min(steps * B, args.cpu_frames)
             r = cpu_arm(frames, 0, n_cpu, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
                                     "frames_per_s": r["fps"],
@@ -402,8 +464,9 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=10, help="frames per step (chs_integrate_batch); 1 = one frame per call")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -56,6 +56,38 @@ void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cuda
     fill_u64_kernel<<<grid, 256, 0, st>>>(p, n, v);
 }
 
+__global__ void fill_i32_kernel(int *p, size_t n, int v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+static void launch_fill_i32(int *p, size_t n, int v, cudaStream_t st)
+{
+    if (n == 0)
+        return;
+    fill_i32_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(p, n, v);
+}
+
+// Pool invariant: every slot at or above n_chunks holds the state Chunk::Chunk produces -- {sdf 99999, weight 0} and colour 0
+// (OC Chunk.cpp:33-48, DistVoxel.cpp:29-33, ColorVoxel.cpp) -- so that the fused kernels create a chunk without writing it.
+__global__ void fill_pool_kernel(DeviceMap map, int firstSlot, int nSlots)
+{
+    const size_t n = (size_t)nSlots * map.V;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const int slot = firstSlot + (int)(i / map.V);
+        const int v = (int)(i % map.V);
+        dist_ptr(map, slot)[v] = make_float2(99999.0f, 0.0f);
+        if (map.use_color)
+            color_ptr(map, slot)[v] = make_uchar4(0, 0, 0, 0);
+    }
+}
+static void launch_fill_pool(const DeviceMap &map, int firstSlot, int nSlots, cudaStream_t st)
+{
+    if (nSlots > 0)
+        fill_pool_kernel<<<148 * 8, 256, 0, st>>>(map, firstSlot, nSlots);
+}
+
 // Re-insert every pool slot into a freshly emptied (larger) table.
 __global__ void rebuild_hash_kernel(DeviceMap map)
 {
@@ -126,6 +158,7 @@ struct chs_map
     // fused multi-frame path (integrate_batch.cu)
     FrameParams *dBatchFrames = nullptr;
     BatchCounters *dBctr = nullptr;
+    int *dHizTickets = nullptr;                // [kMaxBatch + 1] self-resetting block counters of frame_prepare
     HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
     unsigned long long *dSlotBatch = nullptr;  // [capacity]
     float *bDepth = nullptr, *bTrunc = nullptr;
@@ -259,7 +292,10 @@ static int ensure_pool(chs_map *m, long long chunks)
         CHS_CUDA(cudaFreeAsync(m->dSlotBatch, m->stream));
     }
     m->dSlotBatch = (unsigned long long *)sb;
+    const int oldCap = m->dm.capacity;
     m->dm.capacity = (int)newCap;
+    launch_fill_pool(m->dm, oldCap, (int)newCap - oldCap, m->stream);
+    CHS_CUDA(cudaGetLastError());
     return CHS_OK;
 }
 
@@ -285,6 +321,7 @@ static int ensure_hash(chs_map *m, long long chunks)
     m->dm.mask = (unsigned)(need - 1);
     m->hashSize = need;
     launch_fill_u64(m->dm.keys, need, kEmptyKey, m->stream);
+    launch_fill_i32(m->dm.vals, need, -1, m->stream);               // empty entries hold -1: "claimed, value not published yet"
     launch_rebuild_hash(m->dm, 0, m->stream);
     CHS_CUDA(cudaGetLastError());
     return CHS_OK;
@@ -568,6 +605,7 @@ static void fill_frame_params(chs_map *m, const chs_integrator *integ, const flo
         fp.planes[p][3] = pl.fg.plane[p].d;
     }
     size_t off = 0;
+    fp.hiz_levels = kHizLevels;
     for (int l = 0; l < kHizLevels; l++)
     {
         const int tile = 8 << l;
@@ -575,7 +613,10 @@ static void fill_frame_params(chs_map *m, const chs_integrator *integ, const flo
         fp.hizH[l] = (cam->height + tile - 1) / tile;
         fp.hiz[l] = hizBase + off;
         off += (size_t)fp.hizW[l] * fp.hizH[l];
+        if (l >= 3 && fp.hizW[l] <= 3 && fp.hizH[l] <= 3 && fp.hiz_levels == kHizLevels)
+            fp.hiz_levels = l + 1;
     }
+    fp.hiz_blocks = fp.hizW[3] * fp.hizH[3];
 }
 
 static int integrate_common(chs_map *m, const chs_integrator *integ, const float *depth, int mem, const float pose[12],
@@ -603,6 +644,7 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
         return rc;
     FrameParams fp{};
     fill_frame_params(m, integ, pose, cam, cpose, ccam, colorPath, channels, pl, m->dHiz, &fp);
+    fp.hiz_ticket = m->dHizTickets + kMaxBatch;
     // inputs
     bool copied = false;
     if (mem == CHS_MEM_HOST)
@@ -741,6 +783,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     {
         FrameParams &fp = fps[f];
         fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], m->bHiz + tiles * f, &fp);
+        fp.hiz_ticket = m->dHizTickets + f;
         if (mem == CHS_MEM_HOST)
         {
             CHS_CUDA(cudaMemcpyAsync(m->bDepth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -804,8 +847,16 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     bp.units = m->dUnits;
     bp.units_cap = (int)std::min<size_t>(m->unitsCap, 0x1fffffff);
-    bp.news = m->dNews;
-    bp.news_cap = (int)std::min<size_t>(m->newsCap, 0x7fffffff);
+    {
+        // smallest odd stride >= 7919 that is coprime to the box size
+        long long stride = 7919;
+        auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
+        while (unionCand > 1 && gcd(stride, unionCand) != 1)
+            stride += 2;
+        bp.cand_stride = (int)(unionCand > 1 ? stride % unionCand : 1);
+        if (bp.cand_stride == 0)
+            bp.cand_stride = 1;
+    }
     bp.batch_id = inf.frameId;
     bp.bctr = m->dBctr;
     bp.host_slot = &m->hBatchSnap[inf.slot];
@@ -932,6 +983,8 @@ int chs_create(const chs_config *cfg, chs_map **out)
     CHS_CUDA(cudaHostAlloc((void **)&m->hSnap, sizeof(HostSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hSnap, 0, sizeof(HostSnapshot) * chs_map::kRing);
     CHS_CUDA(cudaMalloc((void **)&m->dBatchFrames, sizeof(FrameParams) * kMaxBatch));
+    CHS_CUDA(cudaMalloc((void **)&m->dHizTickets, sizeof(int) * (kMaxBatch + 1)));
+    CHS_CUDA(cudaMemsetAsync(m->dHizTickets, 0, sizeof(int) * (kMaxBatch + 1), m->stream));
     CHS_CUDA(cudaMalloc((void **)&m->dBctr, sizeof(BatchCounters)));
     CHS_CUDA(cudaMemsetAsync(m->dBctr, 0, sizeof(BatchCounters), m->stream));
     CHS_CUDA(cudaHostAlloc((void **)&m->hBatchSnap, sizeof(HostBatchSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
@@ -974,6 +1027,7 @@ int chs_destroy(chs_map *m)
     cudaFree(m->dCtr);
     cudaFree(m->dBatchFrames);
     cudaFree(m->dBctr);
+    cudaFree(m->dHizTickets);
     cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
@@ -998,7 +1052,11 @@ int chs_reset(chs_map *m)
     int rc = poll_inflight(m, true);
     if (rc)
         return rc;
+    if ((rc = sync_counts(m)))
+        return rc;
+    launch_fill_pool(m->dm, 0, (int)std::min<long long>(m->knownChunks, m->dm.capacity), m->stream);   // restore the pool invariant
     launch_fill_u64(m->dm.keys, m->hashSize, kEmptyKey, m->stream);
+    launch_fill_i32(m->dm.vals, m->hashSize, -1, m->stream);
     launch_fill_u64(m->dm.dirty_keys, m->dirtySize, kEmptyKey, m->stream);
     CHS_CUDA(cudaMemsetAsync(m->dCtr, 0, sizeof(Counters), m->stream));
     CHS_CUDA(cudaStreamSynchronize(m->stream));

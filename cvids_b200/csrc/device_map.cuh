@@ -21,7 +21,7 @@ constexpr int kSlabChunks = 1 << kSlabChunksLog2;          // 1024 chunks per sl
 constexpr int kMaxSlabs = 1 << 13;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kIdBias = 1 << 20;                           // chunk IDs must lie in [-2^20, 2^20)
-constexpr int kHizLevels = 4;                              // tiles of 8, 16, 32, 64 pixels
+constexpr int kHizLevels = 8;                              // tiles of 8, 16, 32, 64 pixels (per 64x64 block) and 128 .. 1024 pixels (built by the last block)
 constexpr int kCounterSlots = 32;                          // per-frame voxel counters are spread over this many addresses
 
 enum : int
@@ -212,6 +212,9 @@ struct FrameParams
     float planes[6][4];
     float2 *hiz[kHizLevels];  // {min lo, max hi} per tile
     int hizW[kHizLevels], hizH[kHizLevels];
+    int hiz_levels;           // levels in use: the coarsest one has at most 3x3 tiles (or is level kHizLevels - 1)
+    int hiz_blocks;           // 64x64 pixel blocks of the image = CTAs that build levels 0..3
+    int *hiz_ticket;          // counts finished blocks of this frame; the last one builds levels 4.. and resets it
     int4 *units;              // brick units of existing chunks: {x, y, z, slot | brick << 24}
     int units_cap;
     int4 *news;               // new-chunk candidates: {x, y, z, -1}

@@ -14,15 +14,15 @@
 // four dependent kernels a frame needs. Fusing K frames amortises the launches and the dependent-latency chains K-fold,
 // reads and writes each touched voxel once instead of K times, and gives every warp K frames of independent work.
 //
-//   batch_prepare_kernel      grid.z = frame: Hi-Z tiles (+ per-pixel truncation) of every frame; zeroes the batch counters
-//   batch_color_pack_kernel   grid.y = frame: packed colour images
+//   batch_prepare_kernel      grid.y = frame: Hi-Z tiles (+ per-pixel truncation) and the packed colour image of every frame
 //   batch_candidates_kernel   thread per (chunk of the UNION candidate box, 8^3 brick): exact Frustum::Intersects and the
 //                             conservative depth-range class per frame -> per-brick frame masks; warp-ballot compaction
-//   batch_new_chunks_kernel   CTA per chunk that does not exist yet: frames in order, exact band test until the first hit,
-//                             allocation, then ordinary integration of the remaining frames
-//   batch_bricks_kernel       warp per half brick of an existing chunk: state of 8 voxels per lane in registers, loop over the
-//                             brick's frame mask, one store per changed voxel at the end
+//   batch_bricks_kernel       warp per half brick: state of 8 voxels per lane in registers, straight-line update per frame of the
+//                             brick's frame mask, one store per changed voxel at the end; tasks from an atomic queue. Bricks of
+//                             chunks that do not exist yet start from the initial state in registers and create the chunk
+//                             (hash insert + pool bump, no voxel traffic: free pool slots are kept initialised) on the first hit
 #include <algorithm>
+#include <cstddef>
 
 #include "device_map.cuh"
 #include "integrate_device.cuh"
@@ -32,6 +32,7 @@ namespace chs
 {
 
 static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams is copied word-wise into shared memory");
+constexpr int kVirtualSlot = 0xFFFFFF;      // unit of a chunk that does not exist yet
 
 // All frames of the batch into shared memory: afterwards `sF[f]` is read with warp-uniform shared loads.
 __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &bp)
@@ -44,29 +45,33 @@ __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp)
+// grid = (tiles + pack blocks, K): the first `tiles` CTAs of a frame build its Hi-Z levels, the others pack its colour image
+__global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, DeviceMap map, int tilesX, int tiles)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    if (blockIdx.x == 0 && blockIdx.y == 0)
     {
         int *c = reinterpret_cast<int *>(bp.bctr);
         for (int i = threadIdx.x; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
-            c[i] = 0;
+            c[i] = i == (int)(offsetof(BatchCounters, chunks_at_start) / 4) ? map.ctr->n_chunks : 0;
     }
-    frame_prepare_tile(bp.frames[blockIdx.z], blockIdx.x, blockIdx.y);
-}
-
-__global__ void __launch_bounds__(256) batch_color_pack_kernel(BatchParams bp)
-{
-    color_pack_body(bp.frames[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    const FrameParams &fp = bp.frames[blockIdx.y];
+    if ((int)blockIdx.x < tiles)
+        frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
+    else
+        color_pack_body(fp, (blockIdx.x - tiles) * blockDim.x + threadIdx.x, (gridDim.x - tiles) * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// One lane per (chunk of the union box, 8^3 brick). Per frame: is the chunk inside that frame's candidate ID box and does it
-// pass Frustum::Intersects (ChunkManager.cpp:182-212, exact)? If so, classify the brick against the frame's Hi-Z tiles.
-//   bandM  frames in which some voxel of the brick may fall inside the truncation band
-//   freeM  frames in which the brick lies in free space (only carving of observed voxels can act)
-// A free-space frame is kept when the brick can hold a carvable voxel: the brick's flag is set already, or an earlier band
-// frame of this batch may create one (conservative: any band frame of the batch).
+// A group of GL lanes per chunk of the union box (GL = bricks per chunk, at most 32), two stages:
+//   1. chunk level, lanes spread over FRAMES: is the chunk inside frame f's candidate ID box and does it pass
+//      Frustum::Intersects (ChunkManager.cpp:182-212, exact)? If so, classify the whole chunk against the frame's Hi-Z tiles.
+//      Most (chunk, frame) pairs end here: behind the surface, off the image, or in free space with nothing to carve.
+//   2. brick level, lanes spread over BRICKS: classify the lane's brick for the frames that survived stage 1.
+//        bandM  frames in which some voxel of the brick may fall inside the truncation band
+//        freeM  frames in which the brick lies in free space (only carving of observed voxels can act)
+//      A free-space frame is kept when the brick can hold a carvable voxel: its flag is set already, or a band frame of
+//      this batch may create one (conservative: any band frame of the batch).
+// Chunk indices go through a multiplicative permutation so that the few surviving chunks spread over all CTAs.
 template <int CS>
 __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, DeviceMap map)
 {
@@ -78,31 +83,32 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     const int K = bp.K;
     const int total = bp.n[0] * bp.n[1] * bp.n[2];
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = (int)(tid / GL);
+    const int slotIdx = (int)(tid / GL);
     const int gl = (int)(tid % GL);
     const unsigned lane = threadIdx.x & 31;
     const bool leader = gl == 0;
     const bool carve = sF[0].carve != 0;
     int x = 0, y = 0, z = 0;
-    unsigned candM = 0u, bandM[BPL], freeM[BPL];
-#pragma unroll
-    for (int k = 0; k < BPL; k++)
-        bandM[k] = freeM[k] = 0u;
-    if (i < total)
+    float bx = 0.0f, by = 0.0f, bz = 0.0f;
+    unsigned candM = 0u, chunkBand = 0u, chunkFree = 0u;
+    const bool inBox = slotIdx < total;
+    if (inBox)
     {
+        const int i = (int)(((long long)slotIdx * bp.cand_stride) % total);
         const int nyz = bp.n[1] * bp.n[2];
         x = bp.lo[0] + i / nyz;
         const int r = i - (i / nyz) * nyz;
         y = bp.lo[1] + r / bp.n[2];
         z = bp.lo[2] + r % bp.n[2];
         const bool mine = map.world <= 1 || (owner_hash(x, y, z) % (unsigned)map.world) == (unsigned)map.rank;
+        // chunk box exactly as ChunkManager.cpp:199-201
+        const float ext = __fmul_rn((float)CS, map.res);
+        bx = __fmul_rn((float)(x * CS), map.res);
+        by = __fmul_rn((float)(y * CS), map.res);
+        bz = __fmul_rn((float)(z * CS), map.res);
+        const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
         if (mine)
-        {
-            // chunk box exactly as ChunkManager.cpp:199-201
-            const float ext = __fmul_rn((float)CS, map.res);
-            const float bx = __fmul_rn((float)(x * CS), map.res), by = __fmul_rn((float)(y * CS), map.res), bz = __fmul_rn((float)(z * CS), map.res);
-            const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
-            for (int f = 0; f < K; f++)
+            for (int f = gl; f < K; f += GL)
             {
                 const FrameParams &fp = sF[f];
                 if ((unsigned)(x - fp.lo[0]) >= (unsigned)fp.n[0] || (unsigned)(y - fp.lo[1]) >= (unsigned)fp.n[1] || (unsigned)(z - fp.lo[2]) >= (unsigned)fp.n[2])
@@ -110,33 +116,56 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
                 if (!frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
                     continue;
                 candM |= 1u << f;
-#pragma unroll
-                for (int k = 0; k < BPL; k++)
-                {
-                    const int b = gl + k * GL;
-                    const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
-                    const int code = (NB == 1) ? classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res)
-                                               : classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
-                                                              bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
-                    bandM[k] |= (code == 2 ? 1u : 0u) << f;
-                    freeM[k] |= (code == 1 ? 1u : 0u) << f;
-                }
+                const int code = classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
+                chunkBand |= (code == 2 ? 1u : 0u) << f;
+                chunkFree |= (code == 1 ? 1u : 0u) << f;
             }
-        }
-    }
-    // chunk-level unions over the group's lanes (groups are aligned sub-warps of GL lanes)
-    unsigned chunkBand = 0u, chunkFree = 0u;
-#pragma unroll
-    for (int k = 0; k < BPL; k++)
-    {
-        chunkBand |= bandM[k];
-        chunkFree |= freeM[k];
     }
 #pragma unroll
     for (int o = 1; o < GL; o <<= 1)
     {
+        candM |= __shfl_xor_sync(0xffffffffu, candM, o);
         chunkBand |= __shfl_xor_sync(0xffffffffu, chunkBand, o);
         chunkFree |= __shfl_xor_sync(0xffffffffu, chunkFree, o);
+    }
+    // stage 2: the lane's brick(s) in the surviving frames
+    unsigned bandM[BPL], freeM[BPL];
+#pragma unroll
+    for (int k = 0; k < BPL; k++)
+        bandM[k] = freeM[k] = 0u;
+    if (NB == 1)
+    {
+        bandM[0] = chunkBand;
+        freeM[0] = chunkFree;
+    }
+    else
+    {
+        unsigned todo = chunkBand | (carve ? chunkFree : 0u);
+        while (todo)
+        {
+            const int f = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const FrameParams &fp = sF[f];
+#pragma unroll
+            for (int k = 0; k < BPL; k++)
+            {
+                const int b = gl + k * GL;
+                const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
+                const int code = classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
+                                              bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
+                bandM[k] |= (code == 2 ? 1u : 0u) << f;
+                freeM[k] |= (code == 1 ? 1u : 0u) << f;
+            }
+        }
+        // the chunk-level band mask that decides creation is the union of the brick-level ones (tighter than stage 1)
+        unsigned u = 0u;
+#pragma unroll
+        for (int k = 0; k < BPL; k++)
+            u |= bandM[k];
+#pragma unroll
+        for (int o = 1; o < GL; o <<= 1)
+            u |= __shfl_xor_sync(0xffffffffu, u, o);
+        chunkBand = u;
     }
     int slot = -1;
     unsigned long long flags = 0ull;
@@ -161,29 +190,24 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     if ((int)lane < K && myCount)
         atomicAdd(&bp.bctr->candidates[lane], myCount);
 
-    const bool keepNew = leader && slot < 0 && chunkBand;
-    const unsigned newMask = __ballot_sync(0xffffffffu, keepNew);
-    int base = 0;
+    // chunks that do not exist yet (slot < 0) become VIRTUAL units: batch_bricks_kernel creates the chunk if a frame hits
+    const bool exists = slot >= 0;
+    const bool virt = !exists && chunkBand != 0u;
+    const unsigned newMask = __ballot_sync(0xffffffffu, leader && virt);
     if (lane == 0 && newMask)
-        base = atomicAdd(&bp.bctr->new_count, __popc(newMask));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keepNew)
-    {
-        const int pos = base + __popc(newMask & ((1u << lane) - 1));
-        if (pos < bp.news_cap)
-            bp.news[pos] = make_int4(x, y, z, (int)(candM | (chunkBand << 16)));
-        else
-            atomicOr(&map.ctr->error_flags, kErrWorkFull);
-    }
+        atomicAdd(&bp.bctr->new_count, __popc(newMask));
     const unsigned long long key = pack_id(x, y, z);
 #pragma unroll
     for (int k = 0; k < BPL; k++)
     {
         const int b = gl + k * GL;
-        unsigned m = 0u;
-        if (slot >= 0)
-            m = bandM[k] | ((carve && (((flags >> b) & 1ull) || bandM[k])) ? freeM[k] : 0u);
-        const bool keepB = m != 0u;
+        // free-space frames can only carve: the brick must hold an observed voxel -- its flag says so, or an EARLIER band frame
+        // of this batch may create one (batch_bricks_kernel checks the actual register state before it spends a frame on it)
+        const unsigned afterBand = bandM[k] ? ~((bandM[k] & (0u - bandM[k])) | ((bandM[k] & (0u - bandM[k])) - 1u)) : 0u;
+        unsigned fm = carve ? freeM[k] : 0u;
+        if (!(exists && ((flags >> b) & 1ull)))
+            fm &= afterBand;
+        const bool keepB = (exists && (bandM[k] | fm) != 0u) || (virt && bandM[k] != 0u);
         const unsigned bm = __ballot_sync(0xffffffffu, keepB);
         int ubase = 0;
         if (lane == 0 && bm)
@@ -193,7 +217,8 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
         {
             const int pos = ubase + __popc(bm & ((1u << lane) - 1));
             if (pos < bp.units_cap)
-                bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), slot | (b << 24), (int)m);
+                bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
+                                          (int)(bandM[k] | (fm << 16)));
             else
                 atomicOr(&map.ctr->error_flags, kErrWorkFull);
         }
@@ -259,6 +284,25 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
     const volatile Counters *g = map.ctr;
     volatile HostBatchSnapshot *h = bp.host_slot;
     const int t = threadIdx.x;
+    // chunks created by this batch occupy the slots [chunks_at_start, n_chunks); a chunk is born in the first frame that
+    // updated it (the lowest bit of its frame mask)
+    {
+        __shared__ int sNew[kMaxBatch];
+        if (t < kMaxBatch)
+            sNew[t] = 0;
+        __syncthreads();
+        const int n0 = c->chunks_at_start, n1 = min(g->n_chunks, map.capacity);
+        for (int s = n0 + t; s < n1; s += blockDim.x)
+        {
+            const unsigned m = (unsigned)(*reinterpret_cast<volatile unsigned long long *>(&bp.slot_batch[s]) & 0xFFFFull);
+            if (m)
+                atomicAdd(&sNew[__ffs(m) - 1], 1);
+        }
+        __syncthreads();
+        if (t < kMaxBatch)
+            bp.bctr->n_new[t] = sNew[t];
+        __syncthreads();
+    }
     if (t == 0)
     {
         h->head = bp.batch_id;
@@ -287,15 +331,21 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
 // ------------------------------------------------------------------------------------------------------
 // One frame applied to the lane's eight voxels of a half brick (z slices 4*half .. 4*half+3, y rows ly and ly+4), state in
 // registers. Same arithmetic as process_batch<MODE 0> (ProjectionIntegrator.h:51-183); colour and depth cameras coincide.
-template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-__device__ __forceinline__ void frame_on_half_brick(const FrameParams &fp, const DeviceMap &map, const BrickLane &L, int half, bool hasCol,
+//
+// FAST = true: straight-line code. The reciprocal of the projection and the quotient of DistVoxel::Integrate use the
+// range-check-free correctly rounded forms (integrate_device.cuh), every update is computed for all eight voxels and selected
+// by predicate, so the eight dependency chains interleave. The caller's warp votes guarantee the operand ranges; if a vote
+// fails, nothing has been modified yet and the frame is redone with FAST = false (__frcp_rn / __fdiv_rn, branches).
+// Returns false (FAST only) when an operand is out of range.
+template <int CS, bool COLOR_PATH, bool PER_PIXEL, bool FAST>
+__device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const DeviceMap &map, const BrickLane &L, int half, bool hasCol,
                                                     float2 (&dv)[8], unsigned (&cv)[8], unsigned &wroteD, unsigned &wroteC,
                                                     int &nUpd, int &nCarve, int &nCol, bool &carvable)
 {
     const CameraDev &c = fp.cam;
     int pix[8];
-    float cz[8], depth[8], trunc[8];
-    unsigned cpx[8];
+    float cz[8];
+    bool ok = true;
 #pragma unroll
     for (int s = 0; s < 4; s++)
     {
@@ -309,20 +359,96 @@ __device__ __forceinline__ void frame_on_half_brick(const FrameParams &fp, const
             const float cx = __fadd_rn(L.m0[0], __fadd_rn(L.m1[h][0], m20));
             const float cy = __fadd_rn(L.m0[1], __fadd_rn(L.m1[h][1], m21));
             cz[k] = __fadd_rn(L.m0[2], __fadd_rn(L.m1[h][2], m22));
-            const float invZ = __frcp_rn(cz[k]);                                           // == 1.0f / z, correctly rounded
+            if (FAST)
+                ok &= rcp_in_range(cz[k]);
+            const float invZ = FAST ? rcp_rn_inrange(cz[k]) : __frcp_rn(cz[k]);                // == 1.0f / z, correctly rounded
             const float u = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, cx), invZ), c.cx);
             const float v = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, cy), invZ), c.cy);
             const bool on = u >= 0.0f && v >= 0.0f && u < c.Wf && v < c.Hf && !(cz[k] < 0.0f);
             pix[k] = on ? (int)u + (int)v * c.W : -1;
         }
     }
+    if (FAST && !__all_sync(0xffffffffu, ok))
+        return false;
+    float depth[8], trunc[8];
+    unsigned cpx[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
     {
         depth[k] = pix[k] >= 0 ? __ldg(fp.depth + pix[k]) : __int_as_float(0x7fc00000);
-        cpx[k] = (COLOR_PATH && hasCol && pix[k] >= 0) ? __ldg(fp.color_packed + pix[k]) : 0u;
+        // the colour of a voxel is frozen once its colour weight reaches 8 (:153): no fetch for those
+        cpx[k] = (COLOR_PATH && hasCol && pix[k] >= 0 && (cv[k] >> 24) < 8u) ? __ldg(fp.color_packed + pix[k]) : 0u;
         trunc[k] = PER_PIXEL ? (pix[k] >= 0 ? __ldg(fp.trunc_img + pix[k]) : 0.0f) : fp.trunc_param;
     }
+    if constexpr (FAST)
+    {
+        // predicates and the operands of the division for all eight voxels
+        unsigned band = 0u, crv = 0u;
+        float sd[8], num[8], den[8], wu[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const float d = depth[k];
+            const bool skip = (pix[k] < 0) || (COLOR_PATH ? (d != d || d > 100.0f) : (d > 50.0f));
+            sd[k] = __fsub_rn(d, cz[k]);
+            const bool inBand = !skip && fabsf(sd[k]) < __fadd_rn(trunc[k], fp.diag);                       // :82 / :143
+            const bool canCarve = !skip && !inBand && fp.carve && sd[k] > __fadd_rn(trunc[k], fp.carve_dist)  // :88 / :166
+                                  && dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max;                           // :90 / :169
+            band |= (inBand ? 1u : 0u) << k;
+            crv |= (canCarve ? 1u : 0u) << k;
+            wu[k] = COLOR_PATH ? (PER_PIXEL ? fp.weight : fp.wu_const) : 1.0f;
+            if (COLOR_PATH && PER_PIXEL)
+            {
+                const float t5 = __fmul_rn(5.0f, trunc[k]);                                                  // ConstantWeighter.h:43-46
+                ok &= !inBand || div_in_range(fp.weight, t5);
+                wu[k] = div_rn_inrange(fp.weight, inBand ? t5 : 1.0f);
+            }
+            num[k] = inBand ? __fadd_rn(__fmul_rn(dv[k].y, dv[k].x), __fmul_rn(wu[k], sd[k])) : 0.0f;      // DistVoxel.h:52-60
+            den[k] = inBand ? __fadd_rn(wu[k], dv[k].y) : 1.0f;
+            ok &= div_in_range(num[k], den[k]);
+        }
+        if (!__all_sync(0xffffffffu, ok))
+            return false;
+        if (!__any_sync(0xffffffffu, (band | crv) != 0u))
+            return true;
+        unsigned colM = 0u;
+        if (COLOR_PATH && hasCol)
+        {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                colM |= ((((band >> k) & 1u) && (cv[k] >> 24) < 8u) ? 1u : 0u) << k;                         // :153
+        }
+        const bool anyCol = COLOR_PATH && __any_sync(0xffffffffu, colM != 0u);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const bool inBand = (band >> k) & 1u, canCarve = (crv >> k) & 1u;
+            const float q = div_rn_inrange(num[k], den[k]);
+            const float2 upd = make_float2(q, __fadd_rn(dv[k].y, wu[k]));
+            const float2 carved = (COLOR_PATH && !(dv[k].y < 5.0f)) ? make_float2(dv[k].x, __fsub_rn(dv[k].y, 1.0f))   // :171-175
+                                                                      : make_float2(99999.0f, 0.0f);                    // DistVoxel::Carve -> Reset
+            if (COLOR_PATH && anyCol)
+            {
+                const bool colOk = (colM >> k) & 1u;
+                const unsigned w = min(cv[k] >> 24, 7u);
+                const unsigned mrec = cRecip20[w + 1];
+                const unsigned nr = ((w * (cv[k] & 0xFFu) + (cpx[k] & 0xFFu)) * mrec) >> 20;
+                const unsigned ng = ((w * ((cv[k] >> 8) & 0xFFu) + ((cpx[k] >> 8) & 0xFFu)) * mrec) >> 20;
+                const unsigned nb = ((w * ((cv[k] >> 16) & 0xFFu) + ((cpx[k] >> 16) & 0xFFu)) * mrec) >> 20;
+                cv[k] = colOk ? (nr | (ng << 8) | (nb << 16) | ((w + 1) << 24)) : cv[k];
+                wroteC |= (colOk ? 1u : 0u) << k;
+                nCol += colOk;
+            }
+            dv[k].x = inBand ? upd.x : (canCarve ? carved.x : dv[k].x);
+            dv[k].y = inBand ? upd.y : (canCarve ? carved.y : dv[k].y);
+            carvable |= (inBand || canCarve) && dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max;
+        }
+        wroteD |= band | crv;
+        nUpd += __popc(band);
+        nCarve += __popc(crv);
+        return true;
+    }
+    if constexpr (!FAST)
 #pragma unroll
     for (int k = 0; k < 8; k++)
     {
@@ -363,9 +489,61 @@ __device__ __forceinline__ void frame_on_half_brick(const FrameParams &fp, const
             }
         }
     }
+    return true;
 }
 
-// Existing chunks: a warp per half brick, persistent grid striding over the unit list.
+// Pool slot of chunk `key`, creating the chunk if it does not exist (lane 0 of a warp whose half brick of a VIRTUAL unit was
+// hit). Several warps of one new chunk race: the one whose CAS claims the hash entry bumps the pool, fills the side arrays and
+// publishes the slot; the others wait for the value (vals of empty entries hold -1). No voxel is written here: pool slots at
+// and above n_chunks always hold the initial state {99999, 0} / colour 0 (capi.cu keeps that invariant), which is exactly
+// what Chunk::Chunk produces (Chunk.cpp:33-48, DistVoxel.cpp:29-33).
+__device__ __forceinline__ int get_or_create_chunk(const BatchParams &bp, const DeviceMap &map, unsigned long long key, int x, int y, int z)
+{
+    unsigned i = (unsigned)mix64(key) & map.mask;
+    while (true)
+    {
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&map.keys[i]);
+        if (k == kEmptyKey)
+        {
+            k = atomicCAS(&map.keys[i], kEmptyKey, key);
+            if (k == kEmptyKey)
+            {
+                int s = atomicAdd(&map.ctr->n_chunks, 1);
+                if (s >= map.capacity)
+                {
+                    atomicOr(&map.ctr->error_flags, kErrPoolFull);
+                    atomicSub(&map.ctr->n_chunks, 1);
+                    s = 0;                                          // reported through error_flags; keep the kernel well defined
+                }
+                else
+                {
+                    map.slot_ids[3 * s] = x;
+                    map.slot_ids[3 * s + 1] = y;
+                    map.slot_ids[3 * s + 2] = z;
+                    map.brick_flags[s] = 0ull;
+                    map.slot_epoch[s] = 0;
+                    bp.slot_batch[s] = 0ull;
+                }
+                __threadfence();
+                *reinterpret_cast<volatile int *>(&map.vals[i]) = s;
+                return s;
+            }
+        }
+        if (k == key)
+        {
+            int s;
+            while ((s = *reinterpret_cast<volatile int *>(&map.vals[i])) < 0)
+                __nanosleep(20);
+            __threadfence();
+            return s;
+        }
+        i = (i + 1) & map.mask;
+    }
+}
+
+// A warp per half brick; tasks are handed out by an atomic counter because their cost (1 .. K frames) varies. Units of
+// chunks that do not exist yet start from the initial state; the chunk is created when (and only if) a frame hits
+// ("created and untouched => garbage collected", Chisel.h:76-80,102-110 / :133-143,170-173,202-207, never allocates anything).
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, DeviceMap map)
 {
@@ -377,27 +555,50 @@ __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, De
     const int lane = threadIdx.x & 31;
     const int nTasks = min(bp.bctr->unit_count, bp.units_cap) * 2;
     const bool hasCol = COLOR_PATH && map.use_color;
-    for (int g = blockIdx.x * 8 + (threadIdx.x >> 5); g < nTasks; g += gridDim.x * 8)
+    const float carveMax = sF[0].sdf_carve_max;
+    while (true)
     {
+        int g = 0;
+        if (lane == 0)
+            g = atomicAdd(&bp.bctr->next_task, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= nTasks)
+            break;
         const int4 unit = bp.units[g >> 1];
         const int half = g & 1;
         int x, y, z;
-        unpack_id(((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x, &x, &y, &z);
-        const int slot = unit.z & 0xFFFFFF, b = unit.z >> 24;
-        unsigned mask = (unsigned)unit.w;
+        const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
+        unpack_id(key, &x, &y, &z);
+        int slot = unit.z & 0xFFFFFF;
+        const int b = unit.z >> 24;
+        const bool virt = slot == kVirtualSlot;
+        const unsigned bandM = (unsigned)unit.w & 0xFFFFu;
+        unsigned mask = bandM | ((unsigned)unit.w >> 16);
         const float orgx = __fmul_rn((float)(CS * x), map.res), orgy = __fmul_rn((float)(CS * y), map.res), orgz = __fmul_rn((float)(CS * z), map.res);
         const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
-        float2 *dist = dist_ptr(map, slot);
-        unsigned *col = hasCol ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
         const int idx0 = ((bz * 8 + 4 * half) * CS + (by * 8 + (lane >> 3))) * CS + bx * 8 + (lane & 7);
         float2 dv[8];
         unsigned cv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
+        if (!virt)
         {
-            const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
-            dv[k] = dist[idx];
-            cv[k] = hasCol ? col[idx] : 0u;
+            const float2 *dist = dist_ptr(map, slot);
+            const unsigned *col = hasCol ? reinterpret_cast<const unsigned *>(color_ptr(map, slot)) : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
+                dv[k] = dist[idx];
+                cv[k] = hasCol ? col[idx] : 0u;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                dv[k] = make_float2(99999.0f, 0.0f);                // Chunk::Chunk initial state (DistVoxel.cpp:29-33)
+                cv[k] = 0u;
+            }
         }
         unsigned wroteD = 0u, wroteC = 0u, updMask = 0u;
         bool carvable = false;
@@ -406,186 +607,80 @@ __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, De
             const int f = __ffs(mask) - 1;
             mask &= mask - 1;
             const FrameParams &fp = sF[f];
+            if (!((bandM >> f) & 1u))
+            {
+                // free-space frame: it can only carve, and only voxels with weight > 0 && sdf < 1e-5 (:90 / :169)
+                bool c = false;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    c |= dv[k].y > 0.0f && dv[k].x < carveMax;
+                if (!__any_sync(0xffffffffu, c))
+                    continue;
+            }
             const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, bx, by, bz, lane);
             int nUpd = 0, nCarve = 0, nCol = 0;
-            const unsigned before = wroteD;
             unsigned wd = 0u;
-            frame_on_half_brick<CS, COLOR_PATH, PER_PIXEL>(fp, map, L, half, hasCol, dv, cv, wd, wroteC, nUpd, nCarve, nCol, carvable);
-            wroteD = before | wd;
-            batch_count_frame(&sB, f, nUpd, nCarve, nCol, lane);
+            if (!frame_on_half_brick<CS, COLOR_PATH, PER_PIXEL, true>(fp, map, L, half, hasCol, dv, cv, wd, wroteC, nUpd, nCarve, nCol, carvable))
+                frame_on_half_brick<CS, COLOR_PATH, PER_PIXEL, false>(fp, map, L, half, hasCol, dv, cv, wd, wroteC, nUpd, nCarve, nCol, carvable);
+            wroteD |= wd;
             if (__any_sync(0xffffffffu, wd != 0u))
+            {
+                batch_count_frame(&sB, f, nUpd, nCarve, nCol, lane);
                 updMask |= 1u << f;
+            }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
+        if (!updMask)
+            continue;                                               // nothing changed: no store, no chunk, no dirty mark
+        if (virt)
         {
-            const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
-            if ((wroteD >> k) & 1u)
-                dist[idx] = dv[k];
-            if (hasCol && ((wroteC >> k) & 1u))
-                col[idx] = cv[k];
+            if (lane == 0)
+                slot = get_or_create_chunk(bp, map, key, x, y, z);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        }
+        {
+            float2 *dist = dist_ptr(map, slot);
+            unsigned *col = hasCol ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
+                if ((wroteD >> k) & 1u)
+                    dist[idx] = dv[k];
+                if (hasCol && ((wroteC >> k) & 1u))
+                    col[idx] = cv[k];
+            }
         }
         if (__any_sync(0xffffffffu, carvable) && lane == 0)
             atomicOr(&map.brick_flags[slot], 1ull << b);
-        if (updMask)
+        // (batch id << 32) | frames of this batch that updated the chunk: the first warp of the batch marks the 27 neighbour IDs
+        // dirty (Chisel.h:89-101, 175-189); every newly set frame bit counts the chunk once for that frame
+        unsigned newBits = 0u;
+        int first = 0;
+        if (lane == 0)
         {
-            // (batch id << 32) | frames of this batch that updated the chunk: the first warp of the batch marks the 27 neighbour IDs
-            // dirty (Chisel.h:89-101, 175-189); every newly set frame bit counts the chunk once for that frame
-            unsigned newBits = 0u;
-            int first = 0;
-            if (lane == 0)
+            const unsigned long long tag = (unsigned long long)(unsigned)bp.batch_id << 32;
+            unsigned long long old = bp.slot_batch[slot], assumed, cur;
+            do
             {
-                const unsigned long long tag = (unsigned long long)(unsigned)bp.batch_id << 32;
-                unsigned long long old = bp.slot_batch[slot], assumed, cur;
-                do
-                {
-                    assumed = old;
-                    cur = ((assumed >> 32) == (unsigned long long)(unsigned)bp.batch_id) ? assumed : tag;
-                    const unsigned long long nw = cur | updMask;
-                    if (nw == assumed)
-                        break;
-                    old = atomicCAS(&bp.slot_batch[slot], assumed, nw);
-                } while (old != assumed);
-                first = (assumed >> 32) != (unsigned long long)(unsigned)bp.batch_id;
-                newBits = updMask & ~(unsigned)(cur & 0xffffffffull);
-            }
-            first = __shfl_sync(0xffffffffu, first, 0);
-            newBits = __shfl_sync(0xffffffffu, newBits, 0);
-            if (first && lane < 27)
-                dirty_insert(map, pack_id(x + lane / 9 - 1, y + (lane / 3) % 3 - 1, z + lane % 3 - 1));
-            if (lane < kMaxBatch && ((newBits >> lane) & 1u))
-                atomicAdd(&sB.chunks[lane], 1);
+                assumed = old;
+                cur = ((assumed >> 32) == (unsigned long long)(unsigned)bp.batch_id) ? assumed : tag;
+                const unsigned long long nw = cur | updMask;
+                if (nw == assumed)
+                    break;
+                old = atomicCAS(&bp.slot_batch[slot], assumed, nw);
+            } while (old != assumed);
+            first = (assumed >> 32) != (unsigned long long)(unsigned)bp.batch_id;
+            newBits = updMask & ~(unsigned)(cur & 0xffffffffull);
         }
+        first = __shfl_sync(0xffffffffu, first, 0);
+        newBits = __shfl_sync(0xffffffffu, newBits, 0);
+        if (first && lane < 27)
+            dirty_insert(map, pack_id(x + lane / 9 - 1, y + (lane / 3) % 3 - 1, z + lane % 3 - 1));
+        if (lane < kMaxBatch && ((newBits >> lane) & 1u))
+            atomicAdd(&sB.chunks[lane], 1);
     }
     batch_flush(bp, &sB);
     batch_snapshot(bp, map);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Chunks that do not exist at the start of the batch: one CTA per chunk, a warp per brick. Frames in order: until the chunk
-// exists only frames with a possible band hit are tested (exactly); the first hit allocates it ("created and untouched =>
-// garbage collected", Chisel.h:76-80,102-110 / :133-143,170-173,202-207, never allocates anything) and writes every voxel once;
-// for the remaining frames it is an ordinary chunk (state goes through global memory: the same lane owns the same voxels).
-template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-__global__ void __launch_bounds__(256) batch_new_chunks_kernel(BatchParams bp, DeviceMap map)
-{
-    constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
-    __shared__ FrameParams sF[kMaxBatch];
-    __shared__ BatchShared sB;
-    __shared__ int sSlot;
-    batch_shared_zero(&sB);
-    load_frames(sF, bp);
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nWarps = blockDim.x >> 5;
-    const int nNew = min(bp.bctr->new_count, bp.news_cap);
-    const int K = bp.K;
-    for (int w = blockIdx.x; w < nNew; w += gridDim.x)
-    {
-        const int4 item = bp.news[w];
-        const unsigned candM = (unsigned)item.w & 0xFFFFu, bandM = (unsigned)item.w >> 16;
-        const float orgx = __fmul_rn((float)(CS * item.x), map.res), orgy = __fmul_rn((float)(CS * item.y), map.res), orgz = __fmul_rn((float)(CS * item.z), map.res);
-        int slot = -1;
-        float2 *dist = nullptr;
-        unsigned *col = nullptr;
-        for (int f = 0; f < K; f++)
-        {
-            if (!((candM >> f) & 1u))
-                continue;
-            const FrameParams &fp = sF[f];
-            VoxelStats st;
-            st.nUpd = st.nCarve = st.nCol = 0;
-            st.updated = st.carvable = false;
-            if (slot < 0)
-            {
-                if (!((bandM >> f) & 1u))
-                    continue;
-                bool any = false;
-                for (int b = warp; b < NB && !any; b += nWarps)
-                {
-                    const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
-                    if (NB > 1 && classify_box(fp, orgx + (float)(bx * 8) * map.res + map.half, orgy + (float)(by * 8) * map.res + map.half,
-                                               orgz + (float)(bz * 8) * map.res + map.half, 7.0f * map.res) != 2)
-                        continue;
-                    const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, bx, by, bz, lane);
-                    bool hit = false;
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        hit |= process_batch<CS, COLOR_PATH, PER_PIXEL, 2>(fp, map, L, q, nullptr, nullptr, &st);
-                    any = __any_sync(0xffffffffu, hit);
-                }
-                if (!__syncthreads_or(any))
-                    continue;
-                if (warp == (nWarps > 1 ? 1 : 0) && lane < 27)
-                    dirty_insert(map, pack_id(item.x + lane / 9 - 1, item.y + (lane / 3) % 3 - 1, item.z + lane % 3 - 1));
-                if (t == 0)
-                {
-                    int s = atomicAdd(&map.ctr->n_chunks, 1);
-                    if (s >= map.capacity)
-                    {
-                        atomicOr(&map.ctr->error_flags, kErrPoolFull);
-                        atomicSub(&map.ctr->n_chunks, 1);
-                        s = -1;
-                    }
-                    else
-                    {
-                        map.slot_ids[3 * s] = item.x;
-                        map.slot_ids[3 * s + 1] = item.y;
-                        map.slot_ids[3 * s + 2] = item.z;
-                        map.brick_flags[s] = 0ull;
-                        map.slot_epoch[s] = 0;
-                        bp.slot_batch[s] = ((unsigned long long)(unsigned)bp.batch_id << 32) | 0xFFFFull;
-                        hash_insert_new(map, pack_id(item.x, item.y, item.z), s);
-                        sB.fresh[f] += 1;
-                        sB.chunks[f] += 1;
-                    }
-                    sSlot = s;
-                }
-                __syncthreads();
-                slot = sSlot;
-                __syncthreads();
-                if (slot < 0)
-                    break;                                              // pool full: reported through error_flags
-                dist = dist_ptr(map, slot);
-                col = map.use_color ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
-                for (int b = warp; b < NB; b += nWarps)
-                {
-                    const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, b % BPA, (b / BPA) % BPA, b / (BPA * BPA), lane);
-                    st.carvable = false;
-#pragma unroll 1
-                    for (int q = 0; q < 4; q++)
-                        process_batch<CS, COLOR_PATH, PER_PIXEL, 1>(fp, map, L, q, dist, col, &st);
-                    if (__any_sync(0xffffffffu, st.carvable) && lane == 0)
-                        atomicOr(&map.brick_flags[slot], 1ull << b);
-                }
-                batch_count_frame(&sB, f, st.nUpd, st.nCarve, st.nCol, lane);
-            }
-            else
-            {
-                bool updated = false;
-                for (int b = warp; b < NB; b += nWarps)
-                {
-                    const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
-                    const int code = (NB == 1) ? classify_box(fp, orgx + map.half, orgy + map.half, orgz + map.half, (float)(CS - 1) * map.res)
-                                               : classify_box(fp, orgx + (float)(bx * 8) * map.res + map.half, orgy + (float)(by * 8) * map.res + map.half,
-                                                              orgz + (float)(bz * 8) * map.res + map.half, 7.0f * map.res);
-                    if (code == 0 || (code == 1 && !fp.carve))
-                        continue;
-                    const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, bx, by, bz, lane);
-                    st.updated = st.carvable = false;
-#pragma unroll 1
-                    for (int q = 0; q < 4; q++)
-                        process_batch<CS, COLOR_PATH, PER_PIXEL, 0>(fp, map, L, q, dist, col, &st);
-                    if (__any_sync(0xffffffffu, st.carvable) && lane == 0)
-                        atomicOr(&map.brick_flags[slot], 1ull << b);
-                    updated |= __any_sync(0xffffffffu, st.updated);
-                }
-                batch_count_frame(&sB, f, st.nUpd, st.nCarve, st.nCol, lane);
-                if (__syncthreads_or(updated) && t == 0)
-                    sB.chunks[f] += 1;
-            }
-        }
-        __syncthreads();
-    }
-    batch_flush(bp, &sB);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -604,34 +699,24 @@ static int batch_resident(Kern kernel, int threads)
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st)
 {
-    static int residentNew = 0, residentBricks = 0;
-    if (!residentNew)
-    {
-        residentNew = batch_resident(batch_new_chunks_kernel<CS, COLOR_PATH, PER_PIXEL>, 256);
+    static int residentBricks = 0;
+    if (!residentBricks)
         residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, 256);
-    }
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
     const long long lanes = info.unionCandidates * std::min<long long>(NB, 32);
     const unsigned gCand = (unsigned)std::max(1ll, (lanes + 255) / 256);
-    const unsigned gNew = (unsigned)std::max(1ll, std::min<long long>(std::min<long long>(info.unionCandidates, info.newHint), residentNew));
     const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * 2 + 7) / 8, residentBricks));
     bp.total_ctas = (int)gBricks;
     cudaError_t e;
     if (info.profiling && (e = cudaEventRecord(evt[0], st)) != cudaSuccess)
         return e;
-    batch_prepare_kernel<<<dim3((info.W + 63) / 64, (info.H + 63) / 64, bp.K), 256, 0, st>>>(bp);
-    if (info.colorPath)
-    {
-        const int px = info.cW * info.cH;
-        batch_color_pack_kernel<<<dim3((unsigned)std::max(1, std::min(148 * 2, (px / 4 + 255) / 256)), bp.K), 256, 0, st>>>(bp);
-    }
+    const int tilesX = (info.W + 63) / 64, tiles = tilesX * ((info.H + 63) / 64);
+    const int packBlocks = info.colorPath ? std::max(1, std::min(148, (info.cW * info.cH / 4 + 255) / 256)) : 0;
+    batch_prepare_kernel<<<dim3(tiles + packBlocks, bp.K), 256, 0, st>>>(bp, map, tilesX, tiles);
     if (info.profiling && (e = cudaEventRecord(evt[1], st)) != cudaSuccess)
         return e;
     batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
-    if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
-        return e;
-    batch_new_chunks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gNew, 256, 0, st>>>(bp, map);
-    if (info.profiling && (e = cudaEventRecord(evt[7], st)) != cudaSuccess)
+    if (info.profiling && ((e = cudaEventRecord(evt[2], st)) != cudaSuccess || (e = cudaEventRecord(evt[7], st)) != cudaSuccess))
         return e;
     batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, 256, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)

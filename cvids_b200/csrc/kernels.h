@@ -25,7 +25,8 @@ constexpr int kMaxBatch = 16;
 
 struct BatchCounters
 {
-    int unit_count, new_count, tickets, pad;
+    int unit_count, new_count, tickets, next_task;
+    int chunks_at_start, pad[3];
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch], pad2[kMaxBatch];
     unsigned long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
 };
@@ -46,10 +47,10 @@ struct BatchParams
     const FrameParams *frames;      // device array [K]; each entry is complete, exactly as the single-frame path would fill it
     int K;
     int lo[3], n[3];                // union of the K candidate ID boxes
-    int4 *units;                    // bricks of existing chunks: {id key low, id key high, slot | brick << 24, frame mask}
+    int4 *units;                    // bricks: {id key low, id key high, slot | brick << 24, band frames | free-space frames << 16};
+                                    // slot 0xFFFFFF: the chunk does not exist yet
     int units_cap;
-    int4 *news;                     // chunks that do not exist yet: {x, y, z, candidate-frame mask | band-frame mask << 16}
-    int news_cap;
+    int cand_stride;                // multiplicative permutation of the union box enumeration (coprime to its size)
     int batch_id;                   // > 0, increases by one per batch
     int total_ctas;                 // CTAs of the brick kernel (the last one takes the snapshot)
     BatchCounters *bctr;
