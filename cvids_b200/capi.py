@@ -73,10 +73,10 @@ class chs_timings(C.Structure):
 EXPORTS = (
     "chs_last_error_string", "chs_abi_version", "chs_create", "chs_destroy", "chs_reset", "chs_synchronize",
     "chs_set_stream", "chs_set_profiling", "chs_integrate_depth", "chs_integrate_depth_color", "chs_integrate_batch",
-    "chs_get_batch_stats", "chs_get_frame_stats",
+    "chs_get_batch_stats", "chs_last_batch_ticket", "chs_wait_batch", "chs_get_frame_stats",
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
-    "chs_candidate_ids", "chs_truncation", "chs_owner",
+    "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic",
 )
 
 _lib = None
@@ -87,12 +87,13 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    path = os.environ.get("CHS_LIB_PATH") or LIB_PATH       # CHS_LIB_PATH: A/B runs of differently tuned builds (tools/)
+    if build_if_missing and path == LIB_PATH:
         from . import build as _build
         _build.build()
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(path):
         raise ChiselError(CHS_ERR_CUDA, "libchisel_b200.so is missing and could not be built")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_float)
     lib.chs_last_error_string.restype = C.c_char_p
     lib.chs_create.argtypes = [C.POINTER(chs_config), C.POINTER(vp)]
@@ -106,6 +107,8 @@ def load_library(build_if_missing: bool = True):
     lib.chs_integrate_batch.argtypes = [vp, C.POINTER(chs_integrator), i32, C.POINTER(chs_frame), i32, C.POINTER(chs_camera), i32,
                                         C.POINTER(chs_camera)]
     lib.chs_get_batch_stats.argtypes = [vp, C.POINTER(chs_frame_stats), i32, C.POINTER(i32)]
+    lib.chs_last_batch_ticket.argtypes = [vp, C.POINTER(i64)]
+    lib.chs_wait_batch.argtypes = [vp, i64, C.POINTER(chs_frame_stats), i32, C.POINTER(i32)]
     lib.chs_get_frame_stats.argtypes = [vp, C.POINTER(chs_frame_stats)]
     lib.chs_get_timings.argtypes = [vp, C.POINTER(chs_timings)]
     lib.chs_mesh_counts_last.argtypes = [vp, C.POINTER(chs_mesh_counts)]
@@ -122,6 +125,7 @@ def load_library(build_if_missing: bool = True):
     lib.chs_dirty_ids.argtypes = [vp, vp, i64]
     lib.chs_frustum.argtypes = [vp, C.POINTER(chs_camera), vp, vp, vp]
     lib.chs_candidate_ids.argtypes = [i32, C.c_float, vp, C.POINTER(chs_camera), vp, i64, C.POINTER(i64)]
+    lib.chs_selftest_arithmetic.argtypes = [i64, C.POINTER(i64 * 4)]
     lib.chs_truncation.restype = C.c_float
     lib.chs_truncation.argtypes = [i32, C.c_float, C.c_float]
     lib.chs_owner.restype = C.c_uint32
@@ -333,6 +337,21 @@ class Chisel:
         _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, MEM_HOST if device_ptrs is None else MEM_DEVICE,
                                              C.byref(cam), int(channels or 0), C.byref(ccam) if ccam is not None else None))
 
+    def last_batch_ticket(self) -> int:
+        t = C.c_int64()
+        _check(self._lib.chs_last_batch_ticket(self._h, C.byref(t)))
+        return t.value
+
+    def wait_batch(self, ticket: int) -> list:
+        """Counters of ONE integrate_batch call; calls issued after it stay in flight."""
+        arr = (chs_frame_stats * 16)()
+        n = C.c_int()
+        _check(self._lib.chs_wait_batch(self._h, ticket, arr, 16, C.byref(n)))
+        if n.value > 16:
+            arr = (chs_frame_stats * n.value)()
+            _check(self._lib.chs_wait_batch(self._h, ticket, arr, n.value, C.byref(n)))
+        return [{k: getattr(arr[i], k) for k, _ in chs_frame_stats._fields_} for i in range(n.value)]
+
     def batch_stats(self) -> list:
         n = C.c_int()
         _check(self._lib.chs_get_batch_stats(self._h, None, 0, C.byref(n)))
@@ -472,6 +491,12 @@ def candidate_ids(chunk, resolution, pose, cam) -> np.ndarray:
     out = np.zeros((n.value, 3), np.int32)
     _check(lib.chs_candidate_ids(chunk, resolution, _ptr(p), C.byref(cam), _ptr(out), n.value, C.byref(n)))
     return out
+
+
+def selftest_arithmetic(div_pairs: int = 1 << 30) -> dict:
+    out = (C.c_int64 * 4)()
+    _check(load_library().chs_selftest_arithmetic(div_pairs, C.byref(out)))
+    return dict(rcp_mismatches=out[0], rcp_tested=out[1], div_mismatches=out[2], div_tested=out[3])
 
 
 def truncation(kind, param, depth) -> float:

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <immintrin.h>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -117,7 +118,8 @@ struct InFlight
     long long dirtyBound;   // upper bound of dirty IDs this frame may add
     int slot;               // index into the pinned counter ring
     bool batch = false;     // a fused multi-frame batch: frameId is the batch id, slot indexes the batch snapshot ring
-    int batchIndex = -1;    // single frame that belongs to a chs_integrate_batch call run frame by frame: its index in that call
+    int batchIndex = -1;    // index of this launch's first frame within its chs_integrate_batch call (-1: not part of one)
+    int callId = 0;         // the chs_integrate_batch call it belongs to
 };
 
 } // namespace chs
@@ -156,18 +158,33 @@ struct chs_map
     HostSnapshot lastFrame{};
     bool haveFrame = false;
     // fused multi-frame path (integrate_batch.cu)
-    FrameParams *dBatchFrames = nullptr;
-    BatchCounters *dBctr = nullptr;
-    int *dHizTickets = nullptr;                // [kMaxBatch + 1] self-resetting block counters of frame_prepare
+    // Two staging sets, used alternately: while the kernels of batch i read set i & 1 on the map's stream, the H2D copies and
+    // the prepare kernel of batch i + 1 fill the other set on the copy stream.
+    struct BatchSet
+    {
+        FrameParams *dFrames = nullptr;
+        BatchCounters *dBctr = nullptr;
+        float *depth = nullptr, *trunc = nullptr;
+        uint8_t *color = nullptr;
+        unsigned *packed = nullptr;
+        float2 *hiz = nullptr;
+        size_t depthCap = 0, truncCap = 0, colorCap = 0, packedCap = 0, hizCap = 0;
+        cudaEvent_t copied = nullptr, prepared = nullptr, released = nullptr;
+        bool used = false;
+    } bset[2];
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t callEvent = nullptr;
+    int *dHizTickets = nullptr;                // [2 * kMaxBatch + 1] self-resetting block counters of frame_prepare
     HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
     unsigned long long *dSlotBatch = nullptr;  // [capacity]
-    float *bDepth = nullptr, *bTrunc = nullptr;
-    uint8_t *bColor = nullptr;
-    unsigned *bColorPacked = nullptr;
-    float2 *bHiz = nullptr;
-    size_t bDepthCap = 0, bTruncCap = 0, bColorCap = 0, bColorPackedCap = 0, bHizCap = 0;
     int batchId = 0, batchRingNext = 0;
-    std::vector<chs_frame_stats> batchStats;   // per-frame counters of the last chs_integrate_batch call
+    // per-frame counters of the most recent chs_integrate_batch calls (a call is identified by its ticket)
+    struct CallStats
+    {
+        int id = 0, pending = 0;
+        std::vector<chs_frame_stats> st;
+    } callStats[4];
+    int callId = 0;
     // profiling
     bool profiling = false;
     cudaEvent_t evt[8] = {};
@@ -374,18 +391,24 @@ static chs_frame_stats stats_of(const HostSnapshot &c)
 }
 
 // A fused batch has finished: per-frame counters of its K frames; the map totals are those after the last frame.
-static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base)
+static chs_map::CallStats *call_stats(chs_map *m, int callId)
+{
+    chs_map::CallStats &c = m->callStats[callId & 3];
+    return (callId > 0 && c.id == callId) ? &c : nullptr;
+}
+
+static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base, int callId)
 {
     m->knownChunks = b.n_chunks;
     m->knownDirty = b.n_dirty;
     const int K = std::min(std::max(b.K, 0), kMaxBatch);
     if (base < 0)
         base = 0;
-    if ((int)m->batchStats.size() < base + K)
-        m->batchStats.resize((size_t)(base + K));
+    chs_map::CallStats *cs = call_stats(m, callId);
+    std::vector<chs_frame_stats> local((size_t)K);
     for (int f = 0; f < K; f++)
     {
-        chs_frame_stats &o = m->batchStats[base + f];
+        chs_frame_stats &o = local[f];
         o.candidates = b.candidates[f];
         o.new_candidates = b.new_count;          // per batch: the work lists are shared by the K frames
         o.brick_units = b.unit_count;
@@ -401,12 +424,18 @@ static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base)
     if (K > 0)
     {
         // chs_get_frame_stats after a batch reports its last frame
-        const chs_frame_stats &o = m->batchStats[base + K - 1];
+        const chs_frame_stats &o = local[K - 1];
         HostSnapshot &c = m->lastFrame;
         c.n_chunks = b.n_chunks; c.n_dirty = b.n_dirty; c.error_flags = b.error_flags;
         c.unit_count = b.unit_count; c.new_count = b.new_count; c.candidates = (int)o.candidates;
         c.n_new = (int)o.n_new; c.updated_chunks = (int)o.updated_chunks; c.n_carve = (int)o.n_carve;
         c.n_col = (int)o.n_col; c.n_upd_lo = (int)(o.n_upd & 0xffffffffll); c.n_upd_hi = (int)(o.n_upd >> 32);
+    }
+    if (cs)
+    {
+        for (int f = 0; f < K && base + f < (int)cs->st.size(); f++)
+            cs->st[base + f] = local[f];
+        cs->pending -= K;
     }
 }
 
@@ -429,7 +458,7 @@ static int poll_inflight(chs_map *m, bool block)
                 break;
             }
             std::atomic_thread_fence(std::memory_order_acquire);
-            retire_batch(m, m->hBatchSnap[f.slot], f.batchIndex);
+            retire_batch(m, m->hBatchSnap[f.slot], f.batchIndex, f.callId);
             m->inflight.pop_front();
             continue;
         }
@@ -444,8 +473,12 @@ static int poll_inflight(chs_map *m, bool block)
         m->lastFrame = m->hSnap[f.slot];
         m->knownChunks = m->lastFrame.n_chunks;
         m->knownDirty = m->lastFrame.n_dirty;
-        if (f.batchIndex >= 0 && f.batchIndex < (int)m->batchStats.size())
-            m->batchStats[f.batchIndex] = stats_of(m->lastFrame);
+        if (chs_map::CallStats *cs = call_stats(m, f.callId))
+            if (f.batchIndex >= 0 && f.batchIndex < (int)cs->st.size())
+            {
+                cs->st[f.batchIndex] = stats_of(m->lastFrame);
+                cs->pending -= 1;
+            }
         m->inflight.pop_front();
     }
     return CHS_OK;
@@ -644,7 +677,7 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
         return rc;
     FrameParams fp{};
     fill_frame_params(m, integ, pose, cam, cpose, ccam, colorPath, channels, pl, m->dHiz, &fp);
-    fp.hiz_ticket = m->dHizTickets + kMaxBatch;
+    fp.hiz_ticket = m->dHizTickets + 2 * kMaxBatch;
     // inputs
     bool copied = false;
     if (mem == CHS_MEM_HOST)
@@ -714,6 +747,7 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
     if ((rc = reserve_snapshot(m, fp.frame_id, cand, dirtyBound, &slotPtr)))
         return rc;
     m->inflight.back().batchIndex = batchIndex;
+    m->inflight.back().callId = batchIndex >= 0 ? m->callId : 0;
     // size the new-chunk kernel's grid from what recent frames needed (the kernel strides, so any size is correct)
     const long long newHint = m->haveFrame ? std::max<long long>(64, 2ll * m->lastFrame.new_count) : cand;
     CHS_CUDA(frame_graph_launch(m->frameGraph, fp, m->dm, cand, newHint, slotPtr, m->profiling, m->evt, st));
@@ -763,65 +797,87 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     const size_t tiles = hiz_tiles(cam);
     const bool computeTrunc = integ->trunc_kind == CHS_TRUNC_QUADRATIC || integ->trunc_kind == CHS_TRUNC_INVERSE;
     const bool perPixel = integ->trunc_kind != CHS_TRUNC_CONSTANT;
-    if ((rc = grow_buffer(&m->bHiz, &m->bHizCap, tiles * kMaxBatch, st)))
+    const bool hostMem = mem == CHS_MEM_HOST;
+    const int setIdx = (m->batchId + 1) & 1;
+    chs_map::BatchSet &bs = m->bset[setIdx];
+    cudaStream_t cs = m->copyStream;
+    // the set is free once the kernels of the batch that used it last (two batches ago) are done
+    if (bs.used)
+        CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
+    {
+        const bool grow = tiles * kMaxBatch > bs.hizCap || (hostMem && npx * kMaxBatch > bs.depthCap) ||
+                          ((computeTrunc || (perPixel && hostMem)) && npx * kMaxBatch > bs.truncCap) ||
+                          (colorPath && ((hostMem && cpx * channels * kMaxBatch > bs.colorCap) || cpx * kMaxBatch > bs.packedCap));
+        if (grow)
+        {
+            // rare (first batch, or a larger image): nothing may still be reading the old buffers
+            CHS_CUDA(cudaStreamSynchronize(st));
+            CHS_CUDA(cudaStreamSynchronize(cs));
+        }
+    }
+    if ((rc = grow_buffer(&bs.hiz, &bs.hizCap, tiles * kMaxBatch, cs)))
         return rc;
-    if (mem == CHS_MEM_HOST && (rc = grow_buffer(&m->bDepth, &m->bDepthCap, npx * kMaxBatch, st)))
+    if (hostMem && (rc = grow_buffer(&bs.depth, &bs.depthCap, npx * kMaxBatch, cs)))
         return rc;
-    if ((computeTrunc || (perPixel && mem == CHS_MEM_HOST)) && (rc = grow_buffer(&m->bTrunc, &m->bTruncCap, npx * kMaxBatch, st)))
+    if ((computeTrunc || (perPixel && hostMem)) && (rc = grow_buffer(&bs.trunc, &bs.truncCap, npx * kMaxBatch, cs)))
         return rc;
     if (colorPath)
     {
-        if (mem == CHS_MEM_HOST && (rc = grow_buffer(&m->bColor, &m->bColorCap, cpx * channels * kMaxBatch, st)))
+        if (hostMem && (rc = grow_buffer(&bs.color, &bs.colorCap, cpx * channels * kMaxBatch, cs)))
             return rc;
-        if ((rc = grow_buffer(&m->bColorPacked, &m->bColorPackedCap, cpx * kMaxBatch, st)))
+        if ((rc = grow_buffer(&bs.packed, &bs.packedCap, cpx * kMaxBatch, cs)))
             return rc;
+    }
+    if (mem == CHS_MEM_DEVICE)
+    {
+        // device inputs are ordered by the map's stream (the caller produced them there): prepare must not run ahead of them
+        CHS_CUDA(cudaEventRecord(m->callEvent, st));
+        CHS_CUDA(cudaStreamWaitEvent(cs, m->callEvent, 0));
     }
     FrameParams fps[kMaxBatch];
     std::memset(fps, 0, sizeof(fps));
-    bool copied = false;
     for (int f = 0; f < K; f++)
     {
         FrameParams &fp = fps[f];
-        fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], m->bHiz + tiles * f, &fp);
-        fp.hiz_ticket = m->dHizTickets + f;
-        if (mem == CHS_MEM_HOST)
+        fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], bs.hiz + tiles * f, &fp);
+        fp.hiz_ticket = m->dHizTickets + setIdx * kMaxBatch + f;
+        if (hostMem)
         {
-            CHS_CUDA(cudaMemcpyAsync(m->bDepth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, st));
-            fp.depth = m->bDepth + npx * f;
-            copied = true;
+            CHS_CUDA(cudaMemcpyAsync(bs.depth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, cs));
+            fp.depth = bs.depth + npx * f;
         }
         else
             fp.depth = frames[f].depth;
         fp.trunc_img = nullptr;
         if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL)
         {
-            if (mem == CHS_MEM_HOST)
+            if (hostMem)
             {
-                CHS_CUDA(cudaMemcpyAsync(m->bTrunc + npx * f, frames[f].trunc_per_pixel, npx * sizeof(float), cudaMemcpyHostToDevice, st));
-                fp.trunc_img = m->bTrunc + npx * f;
+                CHS_CUDA(cudaMemcpyAsync(bs.trunc + npx * f, frames[f].trunc_per_pixel, npx * sizeof(float), cudaMemcpyHostToDevice, cs));
+                fp.trunc_img = bs.trunc + npx * f;
             }
             else
                 fp.trunc_img = frames[f].trunc_per_pixel;
         }
         else if (computeTrunc)
-            fp.trunc_img = m->bTrunc + npx * f;                     // written by batch_prepare
+            fp.trunc_img = bs.trunc + npx * f;                      // written by batch_prepare
         if (colorPath)
         {
-            if (mem == CHS_MEM_HOST)
+            if (hostMem)
             {
-                CHS_CUDA(cudaMemcpyAsync(m->bColor + cpx * channels * f, frames[f].color, cpx * channels, cudaMemcpyHostToDevice, st));
-                fp.color = m->bColor + cpx * channels * f;
+                CHS_CUDA(cudaMemcpyAsync(bs.color + cpx * channels * f, frames[f].color, cpx * channels, cudaMemcpyHostToDevice, cs));
+                fp.color = bs.color + cpx * channels * f;
             }
             else
                 fp.color = frames[f].color;
-            fp.color_packed = m->bColorPacked + cpx * f;
+            fp.color_packed = bs.packed + cpx * f;
         }
         fp.frame_id = ++m->frameId;
     }
-    if (copied)
-        CHS_CUDA(cudaEventRecord(m->h2dDone, st));
+    if (hostMem)
+        CHS_CUDA(cudaEventRecord(bs.copied, cs));
     // the frame table: pageable source, staged by the driver before the call returns
-    CHS_CUDA(cudaMemcpyAsync(m->dBatchFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, st));
+    CHS_CUDA(cudaMemcpyAsync(bs.dFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
 
     // reserve a slot of the batch snapshot ring
     if ((int)m->inflight.size() >= chs_map::kRing && (rc = poll_inflight(m, true)))
@@ -834,11 +890,12 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     inf.dirtyBound = dirtyBound;
     inf.batch = true;
     inf.batchIndex = statsBase;
+    inf.callId = m->callId;
     m->hBatchSnap[inf.slot].head = m->hBatchSnap[inf.slot].tail = -1;
     m->inflight.push_back(inf);
 
     BatchParams bp{};
-    bp.frames = m->dBatchFrames;
+    bp.frames = bs.dFrames;
     bp.K = K;
     for (int k = 0; k < 3; k++)
     {
@@ -858,7 +915,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             bp.cand_stride = 1;
     }
     bp.batch_id = inf.frameId;
-    bp.bctr = m->dBctr;
+    bp.bctr = bs.dBctr;
     bp.host_slot = &m->hBatchSnap[inf.slot];
     bp.slot_batch = m->dSlotBatch;
     BatchLaunchInfo info{};
@@ -871,12 +928,15 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     info.colorPath = colorPath;
     info.perPixel = perPixel;
     info.profiling = m->profiling;
-    CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, st));
+    CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st));
+    CHS_CUDA(cudaEventRecord(bs.released, st));
+    bs.used = true;
     if (m->profiling)
         m->frameTimed = true;
     m->haveFrame = true;
-    if (copied)
-        CHS_CUDA(cudaEventSynchronize(m->h2dDone));
+    // the caller may reuse its host buffers as soon as we return
+    if (hostMem)
+        CHS_CUDA(cudaEventSynchronize(bs.copied));
     return CHS_OK;
 }
 
@@ -982,11 +1042,19 @@ int chs_create(const chs_config *cfg, chs_map **out)
     std::memset(m->hCtr, 0, sizeof(Counters) * (chs_map::kRing + 1));
     CHS_CUDA(cudaHostAlloc((void **)&m->hSnap, sizeof(HostSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hSnap, 0, sizeof(HostSnapshot) * chs_map::kRing);
-    CHS_CUDA(cudaMalloc((void **)&m->dBatchFrames, sizeof(FrameParams) * kMaxBatch));
-    CHS_CUDA(cudaMalloc((void **)&m->dHizTickets, sizeof(int) * (kMaxBatch + 1)));
-    CHS_CUDA(cudaMemsetAsync(m->dHizTickets, 0, sizeof(int) * (kMaxBatch + 1), m->stream));
-    CHS_CUDA(cudaMalloc((void **)&m->dBctr, sizeof(BatchCounters)));
-    CHS_CUDA(cudaMemsetAsync(m->dBctr, 0, sizeof(BatchCounters), m->stream));
+    CHS_CUDA(cudaMalloc((void **)&m->dHizTickets, sizeof(int) * (2 * kMaxBatch + 1)));
+    CHS_CUDA(cudaMemsetAsync(m->dHizTickets, 0, sizeof(int) * (2 * kMaxBatch + 1), m->stream));
+    CHS_CUDA(cudaStreamCreateWithFlags(&m->copyStream, cudaStreamNonBlocking));
+    CHS_CUDA(cudaEventCreateWithFlags(&m->callEvent, cudaEventDisableTiming));
+    for (chs_map::BatchSet &bs : m->bset)
+    {
+        CHS_CUDA(cudaMalloc((void **)&bs.dFrames, sizeof(FrameParams) * kMaxBatch));
+        CHS_CUDA(cudaMalloc((void **)&bs.dBctr, sizeof(BatchCounters)));
+        CHS_CUDA(cudaMemsetAsync(bs.dBctr, 0, sizeof(BatchCounters), m->stream));
+        CHS_CUDA(cudaEventCreateWithFlags(&bs.copied, cudaEventDisableTiming));
+        CHS_CUDA(cudaEventCreateWithFlags(&bs.prepared, cudaEventDisableTiming));
+        CHS_CUDA(cudaEventCreateWithFlags(&bs.released, cudaEventDisableTiming));
+    }
     CHS_CUDA(cudaHostAlloc((void **)&m->hBatchSnap, sizeof(HostBatchSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hBatchSnap, 0, sizeof(HostBatchSnapshot) * chs_map::kRing);
     CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
@@ -1010,6 +1078,8 @@ int chs_destroy(chs_map *m)
     if (!m)
         return CHS_OK;
     cudaSetDevice(m->device);
+    if (m->copyStream)
+        cudaStreamSynchronize(m->copyStream);
     cudaStreamSynchronize(m->stream);
     for (float2 *p : m->distSlabs)
         cudaFreeAsync(p, m->stream);
@@ -1017,7 +1087,8 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dColorPacked, m->dHiz,
                     m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
-                    m->dColors, m->dGrids, m->dSlotBatch, m->bDepth, m->bTrunc, m->bColor, m->bColorPacked, m->bHiz};
+                    m->dColors, m->dGrids, m->dSlotBatch, m->bset[0].depth, m->bset[0].trunc, m->bset[0].color, m->bset[0].packed, m->bset[0].hiz,
+                    m->bset[1].depth, m->bset[1].trunc, m->bset[1].color, m->bset[1].packed, m->bset[1].hiz};
     for (void *p : bufs)
         if (p)
             cudaFreeAsync(p, m->stream);
@@ -1025,9 +1096,19 @@ int chs_destroy(chs_map *m)
     cudaFree(m->dm.dist_slabs);
     cudaFree(m->dm.color_slabs);
     cudaFree(m->dCtr);
-    cudaFree(m->dBatchFrames);
-    cudaFree(m->dBctr);
+    for (chs_map::BatchSet &bs : m->bset)
+    {
+        cudaFree(bs.dFrames);
+        cudaFree(bs.dBctr);
+        if (bs.copied) cudaEventDestroy(bs.copied);
+        if (bs.prepared) cudaEventDestroy(bs.prepared);
+        if (bs.released) cudaEventDestroy(bs.released);
+    }
     cudaFree(m->dHizTickets);
+    if (m->callEvent)
+        cudaEventDestroy(m->callEvent);
+    if (m->copyStream)
+        cudaStreamDestroy(m->copyStream);
     cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
@@ -1139,10 +1220,15 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
             fusable = false;
     }
     CHS_CUDA(cudaSetDevice(m->device));
-    int rc = poll_inflight(m, true);                        // batchStats is about to be rewritten
+    int rc = poll_inflight(m, false);
     if (rc)
         return rc;
-    m->batchStats.assign((size_t)n, chs_frame_stats{});
+    {
+        chs_map::CallStats &c = m->callStats[++m->callId & 3];
+        c.id = m->callId;
+        c.pending = n;
+        c.st.assign((size_t)n, chs_frame_stats{});
+    }
     int f = 0;
     while (f < n)
     {
@@ -1168,6 +1254,26 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
     return CHS_OK;
 }
 
+static int copy_call_stats(chs_map *m, int callId, chs_frame_stats *out, int cap, int *n)
+{
+    chs_map::CallStats *cs = call_stats(m, callId);
+    if (!cs)
+    {
+        *n = 0;
+        return callId == 0 ? CHS_OK : fail(CHS_ERR_NOT_FOUND, "the counters of that chs_integrate_batch call are no longer kept (only the last 4 calls are)");
+    }
+    *n = (int)cs->st.size();
+    int flags = 0;
+    for (int i = 0; i < *n && i < cap && out; i++)
+    {
+        out[i] = cs->st[i];
+        flags |= (int)out[i].error_flags;
+    }
+    if (flags)
+        return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(flags));
+    return CHS_OK;
+}
+
 int chs_get_batch_stats(chs_map *m, chs_frame_stats *out, int cap, int *n)
 {
     if (!m || !n)
@@ -1176,16 +1282,44 @@ int chs_get_batch_stats(chs_map *m, chs_frame_stats *out, int cap, int *n)
     int rc = poll_inflight(m, true);
     if (rc)
         return rc;
-    *n = (int)m->batchStats.size();
-    int flags = 0;
-    for (int i = 0; i < *n && i < cap && out; i++)
-    {
-        out[i] = m->batchStats[i];
-        flags |= (int)out[i].error_flags;
-    }
-    if (flags)
-        return fail(CHS_ERR_CAPACITY, "device table overflow, flags=" + std::to_string(flags));
+    return copy_call_stats(m, m->callId, out, cap, n);
+}
+
+int chs_last_batch_ticket(chs_map *m, int64_t *ticket)
+{
+    if (!m || !ticket)
+        return fail(CHS_ERR_INVALID, "null argument");
+    *ticket = m->callId;
     return CHS_OK;
+}
+
+// Wait for ONE chs_integrate_batch call (not for the calls issued after it) and return its per-frame counters: lets a caller
+// keep the next batch's copies and kernels in flight while it reads the previous batch's result.
+int chs_wait_batch(chs_map *m, int64_t ticket, chs_frame_stats *out, int cap, int *n)
+{
+    if (!m || !n)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    chs_map::CallStats *cs = call_stats(m, (int)ticket);
+    if (!cs)
+        return copy_call_stats(m, (int)ticket, out, cap, n);
+    int rc;
+    for (int spin = 0; cs->pending > 0; spin++)
+    {
+        if ((rc = poll_inflight(m, false)))
+            return rc;
+        if (cs->pending <= 0)
+            break;
+        if (spin > 2000000)
+        {
+            // the snapshot is written by the last CTA of the call's last kernel: fall back to a full synchronisation
+            if ((rc = poll_inflight(m, true)))
+                return rc;
+            break;
+        }
+        _mm_pause();
+    }
+    return copy_call_stats(m, (int)ticket, out, cap, n);
 }
 
 int chs_get_frame_stats(chs_map *m, chs_frame_stats *out)
@@ -1747,6 +1881,22 @@ int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], co
                 }
             }
     *n = count;
+    return CHS_OK;
+}
+
+int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4])
+{
+    if (!out || div_pairs < 0)
+        return fail(CHS_ERR_INVALID, "null argument");
+    unsigned long long *d = nullptr;
+    CHS_CUDA(cudaMalloc((void **)&d, 4 * sizeof(unsigned long long)));
+    CHS_CUDA(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+    CHS_CUDA(launch_selftest_arithmetic(d, (unsigned long long)div_pairs, nullptr));
+    unsigned long long h[4];
+    CHS_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    for (int i = 0; i < 4; i++)
+        out[i] = (int64_t)h[i];
     return CHS_OK;
 }
 

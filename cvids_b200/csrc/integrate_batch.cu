@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, Devi
     {
         int *c = reinterpret_cast<int *>(bp.bctr);
         for (int i = threadIdx.x; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
-            c[i] = i == (int)(offsetof(BatchCounters, chunks_at_start) / 4) ? map.ctr->n_chunks : 0;
+            c[i] = 0;
     }
     const FrameParams &fp = bp.frames[blockIdx.y];
     if ((int)blockIdx.x < tiles)
@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     constexpr int BPL = NB / GL;
     __shared__ FrameParams sF[kMaxBatch];
     load_frames(sF, bp);
+    // chunks created by this batch will occupy the pool slots from here on (this kernel runs on the map's stream, after every
+    // earlier batch; the prepare kernel may run ahead on the copy stream)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        bp.bctr->chunks_at_start = map.ctr->n_chunks;
     const int K = bp.K;
     const int total = bp.n[0] * bp.n[1] * bp.n[2];
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,19 +212,26 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
         if (!(exists && ((flags >> b) & 1ull)))
             fm &= afterBand;
         const bool keepB = (exists && (bandM[k] | fm) != 0u) || (virt && bandM[k] != 0u);
-        const unsigned bm = __ballot_sync(0xffffffffu, keepB);
-        int ubase = 0;
-        if (lane == 0 && bm)
-            ubase = atomicAdd(&bp.bctr->unit_count, __popc(bm));
-        ubase = __shfl_sync(0xffffffffu, ubase, 0);
+        // units with many frames go to the front of the list, the others to the back: batch_bricks_kernel hands tasks out front to
+        // back, so the long tasks start first and the short ones fill the tail
+        const bool heavy = keepB && 2 * __popc(bandM[k] | fm) > K;
+        const unsigned hm = __ballot_sync(0xffffffffu, heavy), lm = __ballot_sync(0xffffffffu, keepB && !heavy);
+        int hbase = 0, lbase = 0;
+        if (lane == 0)
+        {
+            if (hm)
+                hbase = atomicAdd(&bp.bctr->unit_count, __popc(hm));
+            if (lm)
+                lbase = atomicAdd(&bp.bctr->light_count, __popc(lm));
+        }
+        hbase = __shfl_sync(0xffffffffu, hbase, 0);
+        lbase = __shfl_sync(0xffffffffu, lbase, 0);
         if (keepB)
         {
-            const int pos = ubase + __popc(bm & ((1u << lane) - 1));
-            if (pos < bp.units_cap)
-                bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
-                                          (int)(bandM[k] | (fm << 16)));
-            else
-                atomicOr(&map.ctr->error_flags, kErrWorkFull);
+            const unsigned below = (1u << lane) - 1;
+            const int pos = heavy ? hbase + __popc(hm & below) : bp.units_cap - 1 - (lbase + __popc(lm & below));
+            bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
+                                      (int)(bandM[k] | (fm << 16)));
         }
     }
 }
@@ -309,7 +320,7 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
         h->n_chunks = g->n_chunks;
         h->n_dirty = g->n_dirty;
         h->error_flags = g->error_flags;
-        h->unit_count = c->unit_count;
+        h->unit_count = c->unit_count + c->light_count;
         h->new_count = c->new_count;
         h->K = bp.K;
     }
@@ -544,8 +555,14 @@ __device__ __forceinline__ int get_or_create_chunk(const BatchParams &bp, const 
 // A warp per half brick; tasks are handed out by an atomic counter because their cost (1 .. K frames) varies. Units of
 // chunks that do not exist yet start from the initial state; the chunk is created when (and only if) a frame hits
 // ("created and untouched => garbage collected", Chisel.h:76-80,102-110 / :133-143,170-173,202-207, never allocates anything).
+#ifndef CHS_BRICK_THREADS
+#define CHS_BRICK_THREADS 256
+#endif
+#ifndef CHS_BRICK_MIN_CTAS
+#define CHS_BRICK_MIN_CTAS 2
+#endif
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-__global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, DeviceMap map)
+__global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_bricks_kernel(BatchParams bp, DeviceMap map)
 {
     constexpr int BPA = CS / 8;
     __shared__ FrameParams sF[kMaxBatch];
@@ -553,7 +570,8 @@ __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, De
     batch_shared_zero(&sB);
     load_frames(sF, bp);
     const int lane = threadIdx.x & 31;
-    const int nTasks = min(bp.bctr->unit_count, bp.units_cap) * 2;
+    // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
+    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * 2;
     const bool hasCol = COLOR_PATH && map.use_color;
     const float carveMax = sF[0].sdf_carve_max;
     while (true)
@@ -564,7 +582,8 @@ __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, De
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= nTasks)
             break;
-        const int4 unit = bp.units[g >> 1];
+        const int u = g >> 1;
+        const int4 unit = bp.units[u < nHeavy ? u : bp.units_cap - 1 - (u - nHeavy)];
         const int half = g & 1;
         int x, y, z;
         const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
@@ -684,6 +703,57 @@ __global__ void __launch_bounds__(256, 2) batch_bricks_kernel(BatchParams bp, De
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Self-test of the range-check-free reciprocal and quotient against the IEEE intrinsics (chs_selftest_arithmetic).
+__global__ void selftest_rcp_kernel(unsigned long long *mismatches, unsigned long long *tested)
+{
+    unsigned long long bad = 0, n = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const float z = __uint_as_float((unsigned)i);
+        if (!rcp_in_range(z))
+            continue;
+        n++;
+        bad += __float_as_uint(rcp_rn_inrange(z)) != __float_as_uint(__frcp_rn(z));
+    }
+    atomicAdd(mismatches, bad);
+    atomicAdd(tested, n);
+}
+
+__global__ void selftest_div_kernel(unsigned long long *mismatches, unsigned long long *tested, unsigned long long pairs)
+{
+    unsigned long long bad = 0, n = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long h = mix64(i * 0x9E3779B97F4A7C15ull + 1);
+        float a = __uint_as_float((unsigned)h), b = __uint_as_float((unsigned)(h >> 32));
+        if ((i & 3) == 1)
+        {
+            // the shape DistVoxel::Integrate produces: (w * sdf + wu * d) / (wu + w) with small weights
+            const float w = (float)((h >> 8) & 63), wu = 0.5f * (float)(1 + ((h >> 14) & 15));
+            const float sdf = 0.4f * (__uint_as_float(0x3f800000u | ((unsigned)(h >> 20) & 0x7fffffu)) - 1.5f);
+            const float d = 0.4f * (__uint_as_float(0x3f800000u | ((unsigned)(h >> 41) & 0x7fffffu)) - 1.5f);
+            a = __fadd_rn(__fmul_rn(w, sdf), __fmul_rn(wu, d));
+            b = __fadd_rn(wu, w);
+        }
+        else if ((i & 3) == 2)
+            a = (i & 4) ? 0.0f : -0.0f;
+        if (!div_in_range(a, b))
+            continue;
+        n++;
+        bad += __float_as_uint(div_rn_inrange(a, b)) != __float_as_uint(__fdiv_rn(a, b));
+    }
+    atomicAdd(mismatches, bad);
+    atomicAdd(tested, n);
+}
+
+cudaError_t launch_selftest_arithmetic(unsigned long long *dCounters, unsigned long long divPairs, cudaStream_t st)
+{
+    selftest_rcp_kernel<<<148 * 8, 256, 0, st>>>(dCounters, dCounters + 1);
+    selftest_div_kernel<<<148 * 8, 256, 0, st>>>(dCounters + 2, dCounters + 3, divPairs);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host launcher
 
 template <typename Kern>
@@ -697,48 +767,56 @@ static int batch_resident(Kern kernel, int threads)
 }
 
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st)
+static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
+                                        cudaEvent_t prepared, cudaStream_t st)
 {
     static int residentBricks = 0;
     if (!residentBricks)
-        residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, 256);
+        residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, CHS_BRICK_THREADS);
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
     const long long lanes = info.unionCandidates * std::min<long long>(NB, 32);
     const unsigned gCand = (unsigned)std::max(1ll, (lanes + 255) / 256);
-    const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * 2 + 7) / 8, residentBricks));
+    const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * 2 + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
+    static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
     cudaError_t e;
-    if (info.profiling && (e = cudaEventRecord(evt[0], st)) != cudaSuccess)
+    if (info.profiling && (e = cudaEventRecord(evt[0], stPrep)) != cudaSuccess)
         return e;
     const int tilesX = (info.W + 63) / 64, tiles = tilesX * ((info.H + 63) / 64);
     const int packBlocks = info.colorPath ? std::max(1, std::min(148, (info.cW * info.cH / 4 + 255) / 256)) : 0;
-    batch_prepare_kernel<<<dim3(tiles + packBlocks, bp.K), 256, 0, st>>>(bp, map, tilesX, tiles);
-    if (info.profiling && (e = cudaEventRecord(evt[1], st)) != cudaSuccess)
+    batch_prepare_kernel<<<dim3(tiles + packBlocks, bp.K), 256, 0, stPrep>>>(bp, map, tilesX, tiles);
+    if (info.profiling && (e = cudaEventRecord(evt[1], stPrep)) != cudaSuccess)
+        return e;
+    if ((e = cudaEventRecord(prepared, stPrep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, prepared, 0)) != cudaSuccess)
         return e;
     batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
     if (info.profiling && ((e = cudaEventRecord(evt[2], st)) != cudaSuccess || (e = cudaEventRecord(evt[7], st)) != cudaSuccess))
         return e;
-    batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, 256, 0, st>>>(bp, map);
+    batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)
         return e;
     return cudaGetLastError();
 }
 
 template <int CS>
-static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st)
+static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
+                                   cudaEvent_t prepared, cudaStream_t st)
 {
     if (info.colorPath)
-        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, st) : launch_batch_variant<CS, true, false>(bp, map, info, evt, st);
-    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, st) : launch_batch_variant<CS, false, false>(bp, map, info, evt, st);
+        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, stPrep, prepared, st)
+                             : launch_batch_variant<CS, true, false>(bp, map, info, evt, stPrep, prepared, st);
+    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, stPrep, prepared, st)
+                         : launch_batch_variant<CS, false, false>(bp, map, info, evt, stPrep, prepared, st);
 }
 
-cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st)
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
+                         cudaEvent_t prepared, cudaStream_t st)
 {
     switch (map.cs)
     {
-    case 8: return launch_batch_cs<8>(bp, map, info, evt, st);
-    case 16: return launch_batch_cs<16>(bp, map, info, evt, st);
-    default: return launch_batch_cs<32>(bp, map, info, evt, st);
+    case 8: return launch_batch_cs<8>(bp, map, info, evt, stPrep, prepared, st);
+    case 16: return launch_batch_cs<16>(bp, map, info, evt, stPrep, prepared, st);
+    default: return launch_batch_cs<32>(bp, map, info, evt, stPrep, prepared, st);
     }
 }
 

@@ -26,7 +26,7 @@ constexpr int kMaxBatch = 16;
 struct BatchCounters
 {
     int unit_count, new_count, tickets, next_task;
-    int chunks_at_start, pad[3];
+    int chunks_at_start, light_count, pad[2];
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch], pad2[kMaxBatch];
     unsigned long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
 };
@@ -65,8 +65,13 @@ struct BatchLaunchInfo
     long long newHint;
     bool colorPath, perPixel, profiling;
 };
-// events (profiling): [0] start, [1] after prepare, [2] after candidates, [7] after new chunks, [3] after bricks
-cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t st);
+// The prepare kernel runs on stPrep and records `prepared`; candidates and bricks run on st after waiting for it.
+// events (profiling): [0] start, [1] after prepare (both on stPrep), [2] = [7] after candidates, [3] after bricks (on st)
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
+                         cudaEvent_t prepared, cudaStream_t st);
+
+// dCounters[4] (zeroed): rcp mismatches, rcp tested, div mismatches, div tested
+cudaError_t launch_selftest_arithmetic(unsigned long long *dCounters, unsigned long long divPairs, cudaStream_t st);
 
 // table maintenance (capi.cu)
 void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st);

@@ -149,6 +149,10 @@ int chs_integrate_batch(chs_map *map, const chs_integrator *integ, int n_frames,
                         const chs_camera *cam, int channels, const chs_camera *color_cam);
 /* per-frame counters of the last chs_integrate_batch call; *n = its frame count. Synchronises. */
 int chs_get_batch_stats(chs_map *map, chs_frame_stats *out, int cap, int *n);
+/* Pipelined use: ticket of the last chs_integrate_batch call, and a wait for ONE call (later calls stay in flight; the
+ * counters of the last 4 calls are kept). chs_integrate_batch itself returns as soon as its host buffers have been copied. */
+int chs_last_batch_ticket(chs_map *map, int64_t *ticket);
+int chs_wait_batch(chs_map *map, int64_t ticket, chs_frame_stats *out, int cap, int *n);
 int chs_get_frame_stats(chs_map *map, chs_frame_stats *out);   /* synchronises */
 int chs_get_timings(chs_map *map, chs_timings *out);           /* synchronises */
 
@@ -176,6 +180,11 @@ int chs_import_chunks(chs_map *map, int64_t n, const int32_t *ids, const float *
 int chs_set_dirty(chs_map *map, int64_t n, const int32_t *ids);
 int chs_num_dirty(chs_map *map, int64_t *n);                   /* synchronises */
 int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
+
+/* Device self-test of the two range-check-free arithmetic forms the fused kernels use (cvids_b200/csrc/integrate_device.cuh)
+ * against the IEEE intrinsics: the reciprocal over EVERY binary32 value of its guarded range, the quotient over div_pairs
+ * pseudo-random operand pairs. out = {rcp mismatches, rcp values tested, div mismatches, div pairs tested}. */
+int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4]);
 
 /* Host-side exact restatements the facade needs (no device work). */
 int chs_frustum(const float pose[12], const chs_camera *cam, float corners[24], float lines[72], float planes[24]);

@@ -163,3 +163,39 @@ def test_batch_sharded_union_equals_single_map():
     order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
     merged = tuple(np.concatenate([p[k] for p in parts])[order] for k in range(4))
     common.assert_state_equal(merged, (ids_w, sdf_w, w_w, c_w))
+
+
+def test_fast_reciprocal_and_quotient_are_correctly_rounded():
+    """The straight-line voxel update replaces __frcp_rn / __fdiv_rn by their range-check-free fast paths inside a guarded
+    operand range: exhaustive comparison for the reciprocal, 2^30 operand pairs for the quotient."""
+    from cvids_b200 import capi
+    r = capi.selftest_arithmetic(1 << 30)
+    assert r["rcp_tested"] > (1 << 30) and r["rcp_mismatches"] == 0, r
+    assert r["div_tested"] > (1 << 27) and r["div_mismatches"] == 0, r
+
+
+def test_pipelined_batches_with_tickets():
+    """Issue batch k + 1 before reading batch k's counters (chs_wait_batch): same map and counters as the blocking way."""
+    setup = Setup(16, 0.05, True)
+    cam = common.SMALL_CAM
+    frames = list(common.orbit_stream(cam, 12, total=30, color=True, seed=21))
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    blocking, piped = [], []
+    for i in range(0, 12, 3):
+        grp = frames[i:i + 3]
+        a.m.integrate_batch(a.integ, [g[0] for g in grp], [g[2] for g in grp], cam.as_array(), [g[1] for g in grp])
+        blocking += a.m.batch_stats()
+    prev = None
+    for i in range(0, 12, 3):
+        grp = frames[i:i + 3]
+        b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], cam.as_array(), [g[1] for g in grp])
+        t = b.m.last_batch_ticket()
+        if prev is not None:
+            piped += b.m.wait_batch(prev)
+        prev = t
+    piped += b.m.wait_batch(prev)
+    assert len(piped) == 12
+    for x, y in zip(blocking, piped):
+        for k in COUNTERS:
+            assert x[k] == y[k]
+    common.assert_state_equal(a.state(), b.state())
