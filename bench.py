@@ -430,7 +430,13 @@ def run_cuda(args):
         t_kernels = t_integrate + t_new
         achieved = bytes_alg / t_kernels / 1e9 if t_kernels > 0 else 0.0
         h2d = (4 * W * H + channels * W * H) * B
-        kname = "batch_bricks_kernel<16,color> + batch_new_chunks_kernel<16,color>" if B > 1 else "integrate_bricks_kernel<16,color> + integrate_new_chunks_kernel<16,color>"
+        kname = "batch_bricks_kernel<16,1,0>" if B > 1 else "integrate_bricks_kernel<16,color> + integrate_new_chunks_kernel<16,color>"
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kname)
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"] if (tr and B == 10) else None
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": upd_total / t_dev / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": 1000.0 * t_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -455,10 +461,11 @@ def run_cuda(args):
                     "timing": "wall clock; per step chs_integrate_batch(pinned host frames), then chs_wait_batch of the PREVIOUS step's counters "
                               "(depth-2 pipeline: copies of step k overlap kernels of step k-1)" if B > 1 else
                               "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
-            "gpu_launches": (5 if B > 1 else 5) * steps,
+            "gpu_launches": (3 if B > 1 else 5) * steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r01_traffic.json)" if traffic else None,
                          "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_kernels / steps,
                          "bricks_ms_per_launch": 1000.0 * t_integrate / steps, "new_chunks_ms_per_launch": 1000.0 * t_new / steps,
                          "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps,

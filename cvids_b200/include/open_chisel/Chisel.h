@@ -5,9 +5,18 @@
 // Semantics kept: UpdateMeshes re-meshes on every 10th call only (Chisel.cpp:50-59; counter per instance instead of
 // process-global, quirk Q4); every new-and-untouched chunk is garbage collected (the deterministic reading of quirk Q2).
 // Not kept: the reference's printf chatter and its per-frame PrintMemoryStatistics scan (Chisel.h:62,109-111).
+//
+// Frame batching (extension, off by default; SetFrameBatching(n) or the environment variable CHISEL_B200_BATCH=n, n <= 16):
+// IntegrateDepthScan[Color] copies the frame into a queue and returns; the queue goes to the device as ONE
+// chs_integrate_batch call (fused multi-frame kernels, bit-identical to frame-by-frame integration) when it holds n frames,
+// when the integrator / camera settings change, or when anything reads the device map -- UpdateMeshes on a call that actually
+// re-meshes (every 10th), GetMeshesToUpdate, HasChunk / GetChunk / GetChunks, Reset. chisel_ros calls UpdateMeshes after
+// every frame but re-meshes on every 10th call only, so with n = 10 a live stream runs entirely through the fused path.
 #ifndef CHISEL_B200_CHISEL_H_
 #define CHISEL_B200_CHISEL_H_
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -27,18 +36,59 @@ namespace chisel
 class Chisel
 {
   public:
-    Chisel() : updateCalls(0), dirtyVersion(-1) {}
-    Chisel(const Eigen::Vector3i &chunkSize, float voxelResolution, bool useColor) : chunkManager(chunkSize, voxelResolution, useColor), updateCalls(0), dirtyVersion(-1) {}
+    Chisel() : updateCalls(0), dirtyVersion(-1), batchFrames(1) {}
+    Chisel(const Eigen::Vector3i &chunkSize, float voxelResolution, bool useColor) : chunkManager(chunkSize, voxelResolution, useColor), updateCalls(0), dirtyVersion(-1), batchFrames(1)
+    {
+        InitBatching();
+    }
     // multi-GPU / explicit-stream variant (not in the reference): this instance keeps the chunk IDs it owns
     Chisel(const Eigen::Vector3i &chunkSize, float voxelResolution, bool useColor, int device, int rank, int world, void *stream = nullptr)
-        : chunkManager(chunkSize, voxelResolution, useColor, device, rank, world, stream), updateCalls(0), dirtyVersion(-1)
+        : chunkManager(chunkSize, voxelResolution, useColor, device, rank, world, stream), updateCalls(0), dirtyVersion(-1), batchFrames(1)
     {
+        InitBatching();
     }
-    virtual ~Chisel() {}
+    Chisel(const Chisel &) = delete;                 // the flush hook installed in the ChunkManager points at this object
+    Chisel &operator=(const Chisel &) = delete;
+    virtual ~Chisel() { chunkManager.SetBeforeDeviceRead(std::function<void()>()); }
 
     const ChunkManager &GetChunkManager() const { return chunkManager; }
     ChunkManager &GetMutableChunkManager() { return chunkManager; }
-    void SetChunkManager(const ChunkManager &manager) { chunkManager = manager; }
+    void SetChunkManager(const ChunkManager &manager)
+    {
+        Flush();
+        chunkManager = manager;
+        chunkManager.SetBeforeDeviceRead([this]() { Flush(); });
+    }
+
+    // Queue up to n frames (1 = off: every frame goes to the device at once). See the header comment.
+    void SetFrameBatching(int n)
+    {
+        Flush();
+        batchFrames = n < 1 ? 1 : (n > 16 ? 16 : n);
+    }
+    int GetFrameBatching() const { return batchFrames; }
+    // Send the queued frames to the device now.
+    void Flush() const
+    {
+        if (queue.empty())
+            return;
+        std::vector<chs_frame> fr(queue.size());
+        for (size_t i = 0; i < queue.size(); i++)
+        {
+            const Queued &q = queue[i];
+            fr[i].depth = q.depth.data();
+            fr[i].color = q.color.empty() ? nullptr : q.color.data();
+            fr[i].trunc_per_pixel = q.trunc.empty() ? nullptr : q.trunc.data();
+            std::memcpy(fr[i].pose, q.pose, sizeof(q.pose));
+            std::memcpy(fr[i].color_pose, q.cpose, sizeof(q.cpose));
+        }
+        chs_integrator integ = qInteg;
+        integ.trunc_per_pixel = nullptr;              // per frame, in chs_frame
+        const int n = static_cast<int>(fr.size());
+        queue.clear();
+        b200::Check(chs_integrate_batch(chunkManager.Handle(), &integ, n, fr.data(), CHS_MEM_HOST, &qCam, qChannels, qColorPath ? &qCcam : nullptr),
+                    "chs_integrate_batch");
+    }
 
     template <class DataType>
     void IntegrateDepthScan(const ProjectionIntegrator &integrator, const std::shared_ptr<const DepthImage<DataType>> &depthImage, const Transform &extrinsic,
@@ -48,8 +98,13 @@ class Chisel
         const chs_camera cam = camera.ToC();
         float pose[12];
         b200::PoseToArray(extrinsic, pose);
-        b200::Check(chs_integrate_depth(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam), "chs_integrate_depth");
         chunkManager.Touch();
+        if (batchFrames > 1)
+        {
+            Enqueue(integ, cam, cam, false, 0, DepthAsFloat(*depthImage), nullptr, pose, pose);
+            return;
+        }
+        b200::Check(chs_integrate_depth(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam), "chs_integrate_depth");
     }
 
     template <class DataType, class ColorType>
@@ -63,10 +118,16 @@ class Chisel
         float pose[12], cpose[12];
         b200::PoseToArray(depthExtrinsic, pose);
         b200::PoseToArray(colorExtrinsic, cpose);
+        chunkManager.Touch();
+        if (batchFrames > 1)
+        {
+            Enqueue(integ, cam, ccam, true, static_cast<int>(colorImage->GetNumChannels()), DepthAsFloat(*depthImage),
+                    reinterpret_cast<const uint8_t *>(colorImage->GetData()), pose, cpose);
+            return;
+        }
         b200::Check(chs_integrate_depth_color(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam,
                                               reinterpret_cast<const uint8_t *>(colorImage->GetData()), static_cast<int>(colorImage->GetNumChannels()), cpose, &ccam),
                     "chs_integrate_depth_color");
-        chunkManager.Touch();
     }
 
     // The point-cloud fusion mode (Chisel.cpp:107-157) is outside the hot path this library accelerates.
@@ -110,6 +171,7 @@ class Chisel
 
     void Reset()
     {
+        queue.clear();                               // queued frames would be integrated and then dropped with the map
         chunkManager.Reset();
         meshesToUpdate.clear();
         dirtyVersion = -1;
@@ -118,6 +180,7 @@ class Chisel
     // Host mirror of the device dirty set (Chisel.h:221-224), refreshed when a frame was integrated since the last call.
     const ChunkSet &GetMeshesToUpdate() const
     {
+        Flush();
         int64_t n = 0;
         b200::Check(chs_num_dirty(chunkManager.Handle(), &n), "chs_num_dirty");
         if (dirtyVersion != n || n == 0)
@@ -149,11 +212,61 @@ class Chisel
         return depthScratch.data();
     }
 
+    void InitBatching()
+    {
+        chunkManager.SetBeforeDeviceRead([this]() { Flush(); });
+        if (const char *e = std::getenv("CHISEL_B200_BATCH"))
+            SetFrameBatching(std::atoi(e));
+    }
+
+    struct Queued
+    {
+        std::vector<float> depth, trunc;
+        std::vector<uint8_t> color;
+        float pose[12], cpose[12];
+    };
+    static bool SameCamera(const chs_camera &a, const chs_camera &b) { return std::memcmp(&a, &b, sizeof(chs_camera)) == 0; }
+    static bool SameIntegrator(const chs_integrator &a, const chs_integrator &b)
+    {
+        return a.trunc_kind == b.trunc_kind && a.trunc_param == b.trunc_param && a.weight == b.weight && a.carving_enabled == b.carving_enabled &&
+               a.carving_dist == b.carving_dist;
+    }
+    // The caller reuses its image buffers (CR ChiselServer.cpp:285-295): the queue owns copies.
+    void Enqueue(const chs_integrator &integ, const chs_camera &cam, const chs_camera &ccam, bool colorPath, int channels, const float *depth, const uint8_t *color,
+                 const float *pose, const float *cpose)
+    {
+        if (!queue.empty() && (!SameIntegrator(integ, qInteg) || !SameCamera(cam, qCam) || !SameCamera(ccam, qCcam) || colorPath != qColorPath || channels != qChannels))
+            Flush();
+        qInteg = integ;
+        qCam = cam;
+        qCcam = ccam;
+        qColorPath = colorPath;
+        qChannels = channels;
+        queue.emplace_back();
+        Queued &q = queue.back();
+        const size_t npx = static_cast<size_t>(cam.width) * cam.height;
+        q.depth.assign(depth, depth + npx);
+        if (integ.trunc_kind == CHS_TRUNC_PER_PIXEL && integ.trunc_per_pixel)
+            q.trunc.assign(integ.trunc_per_pixel, integ.trunc_per_pixel + npx);
+        if (colorPath)
+            q.color.assign(color, color + static_cast<size_t>(ccam.width) * ccam.height * channels);
+        std::memcpy(q.pose, pose, sizeof(q.pose));
+        std::memcpy(q.cpose, cpose, sizeof(q.cpose));
+        if (static_cast<int>(queue.size()) >= batchFrames)
+            Flush();
+    }
+
     ChunkManager chunkManager;
     mutable ChunkSet meshesToUpdate;
     int updateCalls;
     mutable int64_t dirtyVersion;
     std::vector<float> truncScratch, depthScratch;
+    int batchFrames;
+    mutable std::vector<Queued> queue;
+    chs_integrator qInteg;
+    chs_camera qCam, qCcam;
+    bool qColorPath;
+    int qChannels;
 };
 typedef std::shared_ptr<Chisel> ChiselPtr;
 typedef std::shared_ptr<const Chisel> ChiselConstPtr;

@@ -6,6 +6,7 @@
 // the MeshMap that Chisel::UpdateMeshes maintains with the reference's publication rule (ChunkManager.cpp:101-127).
 #ifndef CHISEL_B200_CHUNKMANAGER_H_
 #define CHISEL_B200_CHUNKMANAGER_H_
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -65,6 +66,13 @@ class ChunkManager
 
     chs_map *Handle() const { return handle.get(); }
     void Touch() { version++; }                                  // the device map changed: host mirrors are stale
+    // Frame batching (Chisel::SetFrameBatching): frames queued in the facade must reach the device before anything reads it.
+    void SetBeforeDeviceRead(const std::function<void()> &f) { beforeDeviceRead = f; }
+    void Sync() const
+    {
+        if (beforeDeviceRead)
+            beforeDeviceRead();
+    }
 
     const Eigen::Vector3i &GetChunkSize() const { return chunkSize; }
     float GetResolution() const { return voxelResolutionMeters; }
@@ -73,6 +81,7 @@ class ChunkManager
 
     bool HasChunk(const ChunkID &id) const
     {
+        Sync();
         int found = 0;
         const int32_t cid[3] = {id(0), id(1), id(2)};
         b200::Check(chs_has_chunk(handle.get(), cid, &found), "chs_has_chunk");
@@ -83,6 +92,7 @@ class ChunkManager
     // unordered_map::at semantics: throws std::out_of_range for a missing chunk (ChunkManager.h:84-87)
     ChunkPtr GetChunk(const ChunkID &id) const
     {
+        Sync();
         ChunkPtr c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor);
         const size_t V = c->GetTotalNumVoxels();
         std::vector<float> sdf(V), w(V);
@@ -106,6 +116,7 @@ class ChunkManager
     // Whole-map host mirror (one bulk transfer), refreshed only if the device map changed since the last call.
     const ChunkMap &GetChunks() const
     {
+        Sync();
         if (chunksVersion != version)
         {
             chunks.clear();
@@ -140,6 +151,7 @@ class ChunkManager
     void RecomputeMeshes(const ChunkSet & /*dirty: the device holds the authoritative set*/) { RecomputeDirtyMeshes(); }
     void RecomputeDirtyMeshes()
     {
+        Sync();
         b200::Check(chs_update_meshes(handle.get()), "chs_update_meshes");
         chs_mesh_counts mc;
         b200::Check(chs_mesh_counts_last(handle.get(), &mc), "chs_mesh_counts_last");
@@ -213,6 +225,7 @@ class ChunkManager
     long version;
     mutable ChunkMap chunks;
     mutable long chunksVersion;
+    std::function<void()> beforeDeviceRead;
 };
 typedef std::shared_ptr<ChunkManager> ChunkManagerPtr;
 typedef std::shared_ptr<const ChunkManager> ChunkManagerConstPtr;

@@ -73,12 +73,15 @@ def test_same_client_against_the_reference(tmp_path, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1, 10])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_facade_client_on_device(tmp_path, case):
+def test_facade_client_on_device(tmp_path, case, batch):
+    """batch = 10: the facade queues frames (CHISEL_B200_BATCH) and sends them through the fused multi-frame path; the client
+    is unchanged and must see the same map, dirty set and meshes."""
     exe = facade_util.build_facade_client()
     stream, frames = _stream(tmp_path, case)
     dump = str(tmp_path / "b200.dump")
-    subprocess.run([exe, stream, dump], check=True)
+    subprocess.run([exe, stream, dump], check=True, env=dict(os.environ, CHISEL_B200_BATCH=str(batch)))
     d = facade_util.read_dump(dump)
     drv = _oracle_expectation(case, frames)
     _compare(d, drv, CASES[case]["color"])
