@@ -434,7 +434,7 @@ def run_cuda(args):
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kname)
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"] if (tr and B == 10) else None
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"] if (tr and B == 10 and world == 1) else None
         except Exception:
             pass
         line = {

@@ -72,10 +72,12 @@ class Chisel
     {
         if (queue.empty())
             return;
-        std::vector<chs_frame> fr(queue.size());
-        for (size_t i = 0; i < queue.size(); i++)
+        std::vector<Queued> pending;
+        pending.swap(queue);                          // re-entrancy: the queue is empty while the call below runs
+        std::vector<chs_frame> fr(pending.size());
+        for (size_t i = 0; i < pending.size(); i++)
         {
-            const Queued &q = queue[i];
+            const Queued &q = pending[i];
             fr[i].depth = q.depth.data();
             fr[i].color = q.color.empty() ? nullptr : q.color.data();
             fr[i].trunc_per_pixel = q.trunc.empty() ? nullptr : q.trunc.data();
@@ -85,7 +87,6 @@ class Chisel
         chs_integrator integ = qInteg;
         integ.trunc_per_pixel = nullptr;              // per frame, in chs_frame
         const int n = static_cast<int>(fr.size());
-        queue.clear();
         b200::Check(chs_integrate_batch(chunkManager.Handle(), &integ, n, fr.data(), CHS_MEM_HOST, &qCam, qChannels, qColorPath ? &qCcam : nullptr),
                     "chs_integrate_batch");
     }

@@ -199,3 +199,22 @@ def test_pipelined_batches_with_tickets():
         for k in COUNTERS:
             assert x[k] == y[k]
     common.assert_state_equal(a.state(), b.state())
+
+
+def test_batch_inverse_truncator_8cube_one_then_ten():
+    """The facade's pattern for an 11-frame chisel_ros stream: one frame alone (flushed by the first UpdateMeshes), then ten
+    in one batch; InverseTruncator, 8^3 chunks (a chunk is one brick)."""
+    setup = Setup(8, 0.1, True, trunc_kind=common.TRUNC_INVERSE, trunc_param=2.0, carve_dist=0.0)
+    frames = list(common.orbit_stream(common.SMALL_CAM, 11, total=30, color=True, seed=3))
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    camv = common.SMALL_CAM.as_array()
+    for grp in (frames[:1], frames[1:]):
+        a.m.integrate_batch(a.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+        want = []
+        for depth, col, pose in grp:
+            b.integrate(depth, pose, camv, col)
+            want.append(b.counters())
+        for j, (g, w) in enumerate(zip(a.m.batch_stats(), want)):
+            for k in COUNTERS:
+                assert g[k] == w[k], "frame %d of the group counter %s: cuda batch %d oracle %d" % (j, k, g[k], w[k])
+    common.assert_state_equal(a.state(), b.state())
