@@ -17,7 +17,7 @@
 //   batch_prepare_kernel      grid.y = frame: Hi-Z tiles (+ per-pixel truncation) and the packed colour image of every frame
 //   batch_candidates_kernel   thread per (chunk of the UNION candidate box, 8^3 brick): exact Frustum::Intersects and the
 //                             conservative depth-range class per frame -> per-brick frame masks; warp-ballot compaction
-//   batch_bricks_kernel       warp per half brick: state of 8 voxels per lane in registers, straight-line update per frame of the
+//   batch_bricks_kernel       warp per quarter brick (8 x 8 x 2 voxels): state of 4 voxels per lane in registers, straight-line update per frame of the
 //                             brick's frame mask, one store per changed voxel at the end; tasks from an atomic queue. Bricks of
 //                             chunks that do not exist yet start from the initial state in registers and create the chunk
 //                             (hash insert + pool bump, no voxel traffic: free pool slots are kept initialised) on the first hit
@@ -33,6 +33,20 @@ namespace chs
 
 static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams is copied word-wise into shared memory");
 constexpr int kVirtualSlot = 0xFFFFFF;      // unit of a chunk that does not exist yet
+
+// z slices of a brick per task: 4 = half brick (8 voxels per lane), 2 = quarter brick (4 voxels per lane)
+#ifndef CHS_BRICK_SLICES
+#define CHS_BRICK_SLICES 2                   // measured on B200 (configs[1], 10 frames): 94 us vs 113 us with 4
+#endif
+#ifndef CHS_BRICK_THREADS
+#define CHS_BRICK_THREADS 256
+#endif
+#ifndef CHS_BRICK_MIN_CTAS
+#define CHS_BRICK_MIN_CTAS 3
+#endif
+constexpr int kNS = CHS_BRICK_SLICES;        // z slices per task
+constexpr int kVPL = 2 * kNS;                // voxels per lane: kNS slices x the lane's two y rows
+constexpr int kParts = 8 / kNS;              // tasks per brick
 
 // All frames of the batch into shared memory: afterwards `sF[f]` is read with warp-uniform shared loads.
 __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &bp)
@@ -340,7 +354,7 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
 }
 
 // ------------------------------------------------------------------------------------------------------
-// One frame applied to the lane's eight voxels of a half brick (z slices 4*half .. 4*half+3, y rows ly and ly+4), state in
+// One frame applied to the lane's kVPL voxels of a brick part (z slices kNS*half .. kNS*half+kNS-1, y rows ly and ly+4), state in
 // registers. Same arithmetic as process_batch<MODE 0> (ProjectionIntegrator.h:51-183); colour and depth cameras coincide.
 //
 // FAST = true: straight-line code. The reciprocal of the projection and the quotient of DistVoxel::Integrate use the
@@ -350,17 +364,17 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
 // Returns false (FAST only) when an operand is out of range.
 template <int CS, bool COLOR_PATH, bool PER_PIXEL, bool FAST>
 __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const DeviceMap &map, const BrickLane &L, int half, bool hasCol,
-                                                    float2 (&dv)[8], unsigned (&cv)[8], unsigned &wroteD, unsigned &wroteC,
+                                                    float2 (&dv)[kVPL], unsigned (&cv)[kVPL], unsigned &wroteD, unsigned &wroteC,
                                                     int &nUpd, int &nCarve, int &nCol, bool &carvable)
 {
     const CameraDev &c = fp.cam;
-    int pix[8];
-    float cz[8];
+    int pix[kVPL];
+    float cz[kVPL];
     bool ok = true;
 #pragma unroll
-    for (int s = 0; s < 4; s++)
+    for (int s = 0; s < kNS; s++)
     {
-        const float pz = __fadd_rn(__fadd_rn(__fmul_rn((float)(L.vz0 + 4 * half + s), map.res), map.half), L.orgz);
+        const float pz = __fadd_rn(__fadd_rn(__fmul_rn((float)(L.vz0 + kNS * half + s), map.res), map.half), L.orgz);
         const float d2 = __fsub_rn(pz, c.t[2]);
         const float m20 = __fmul_rn(c.R[6], d2), m21 = __fmul_rn(c.R[7], d2), m22 = __fmul_rn(c.R[8], d2);
 #pragma unroll
@@ -381,10 +395,10 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
     }
     if (FAST && !__all_sync(0xffffffffu, ok))
         return false;
-    float depth[8], trunc[8];
-    unsigned cpx[8];
+    float depth[kVPL], trunc[kVPL];
+    unsigned cpx[kVPL];
 #pragma unroll
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < kVPL; k++)
     {
         depth[k] = pix[k] >= 0 ? __ldg(fp.depth + pix[k]) : __int_as_float(0x7fc00000);
         // the colour of a voxel is frozen once its colour weight reaches 8 (:153): no fetch for those
@@ -395,9 +409,9 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
     {
         // predicates and the operands of the division for all eight voxels
         unsigned band = 0u, crv = 0u;
-        float sd[8], num[8], den[8], wu[8];
+        float sd[kVPL], num[kVPL], den[kVPL], wu[kVPL];
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < kVPL; k++)
         {
             const float d = depth[k];
             const bool skip = (pix[k] < 0) || (COLOR_PATH ? (d != d || d > 100.0f) : (d > 50.0f));
@@ -426,12 +440,12 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
         if (COLOR_PATH && hasCol)
         {
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < kVPL; k++)
                 colM |= ((((band >> k) & 1u) && (cv[k] >> 24) < 8u) ? 1u : 0u) << k;                         // :153
         }
         const bool anyCol = COLOR_PATH && __any_sync(0xffffffffu, colM != 0u);
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < kVPL; k++)
         {
             const bool inBand = (band >> k) & 1u, canCarve = (crv >> k) & 1u;
             const float q = div_rn_inrange(num[k], den[k]);
@@ -461,7 +475,7 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
     }
     if constexpr (!FAST)
 #pragma unroll
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < kVPL; k++)
     {
         const float d = depth[k];
         const bool skip = (pix[k] < 0) || (COLOR_PATH ? (d != d || d > 100.0f) : (d > 50.0f));
@@ -503,7 +517,7 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
     return true;
 }
 
-// Pool slot of chunk `key`, creating the chunk if it does not exist (lane 0 of a warp whose half brick of a VIRTUAL unit was
+// Pool slot of chunk `key`, creating the chunk if it does not exist (lane 0 of a warp whose brick part of a VIRTUAL unit was
 // hit). Several warps of one new chunk race: the one whose CAS claims the hash entry bumps the pool, fills the side arrays and
 // publishes the slot; the others wait for the value (vals of empty entries hold -1). No voxel is written here: pool slots at
 // and above n_chunks always hold the initial state {99999, 0} / colour 0 (capi.cu keeps that invariant), which is exactly
@@ -552,15 +566,9 @@ __device__ __forceinline__ int get_or_create_chunk(const BatchParams &bp, const 
     }
 }
 
-// A warp per half brick; tasks are handed out by an atomic counter because their cost (1 .. K frames) varies. Units of
+// A warp per brick part (kNS z slices); tasks are handed out by an atomic counter because their cost (1 .. K frames) varies. Units of
 // chunks that do not exist yet start from the initial state; the chunk is created when (and only if) a frame hits
 // ("created and untouched => garbage collected", Chisel.h:76-80,102-110 / :133-143,170-173,202-207, never allocates anything).
-#ifndef CHS_BRICK_THREADS
-#define CHS_BRICK_THREADS 256
-#endif
-#ifndef CHS_BRICK_MIN_CTAS
-#define CHS_BRICK_MIN_CTAS 2
-#endif
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_bricks_kernel(BatchParams bp, DeviceMap map)
 {
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
     load_frames(sF, bp);
     const int lane = threadIdx.x & 31;
     // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
-    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * 2;
+    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * kParts;
     const bool hasCol = COLOR_PATH && map.use_color;
     const float carveMax = sF[0].sdf_carve_max;
     while (true)
@@ -582,9 +590,9 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= nTasks)
             break;
-        const int u = g >> 1;
+        const int u = g / kParts;
         const int4 unit = bp.units[u < nHeavy ? u : bp.units_cap - 1 - (u - nHeavy)];
-        const int half = g & 1;
+        const int half = g % kParts;                     // which group of kNS z slices of the brick
         int x, y, z;
         const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
         unpack_id(key, &x, &y, &z);
@@ -595,15 +603,15 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
         unsigned mask = bandM | ((unsigned)unit.w >> 16);
         const float orgx = __fmul_rn((float)(CS * x), map.res), orgy = __fmul_rn((float)(CS * y), map.res), orgz = __fmul_rn((float)(CS * z), map.res);
         const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
-        const int idx0 = ((bz * 8 + 4 * half) * CS + (by * 8 + (lane >> 3))) * CS + bx * 8 + (lane & 7);
-        float2 dv[8];
-        unsigned cv[8];
+        const int idx0 = ((bz * 8 + kNS * half) * CS + (by * 8 + (lane >> 3))) * CS + bx * 8 + (lane & 7);
+        float2 dv[kVPL];
+        unsigned cv[kVPL];
         if (!virt)
         {
             const float2 *dist = dist_ptr(map, slot);
             const unsigned *col = hasCol ? reinterpret_cast<const unsigned *>(color_ptr(map, slot)) : nullptr;
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < kVPL; k++)
             {
                 const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
                 dv[k] = dist[idx];
@@ -613,7 +621,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
         else
         {
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < kVPL; k++)
             {
                 dv[k] = make_float2(99999.0f, 0.0f);                // Chunk::Chunk initial state (DistVoxel.cpp:29-33)
                 cv[k] = 0u;
@@ -631,7 +639,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
                 // free-space frame: it can only carve, and only voxels with weight > 0 && sdf < 1e-5 (:90 / :169)
                 bool c = false;
 #pragma unroll
-                for (int k = 0; k < 8; k++)
+                for (int k = 0; k < kVPL; k++)
                     c |= dv[k].y > 0.0f && dv[k].x < carveMax;
                 if (!__any_sync(0xffffffffu, c))
                     continue;
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
             float2 *dist = dist_ptr(map, slot);
             unsigned *col = hasCol ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < kVPL; k++)
             {
                 const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
                 if ((wroteD >> k) & 1u)
@@ -776,7 +784,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
     const long long lanes = info.unionCandidates * std::min<long long>(NB, 32);
     const unsigned gCand = (unsigned)std::max(1ll, (lanes + 255) / 256);
-    const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * 2 + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
+    const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
     cudaError_t e;
