@@ -197,6 +197,8 @@ struct chs_map
     long long *dVertOffsets = nullptr, *dGridOffsets = nullptr;
     size_t meshChunkCap = 0;
     float *dVerts = nullptr, *dNormals = nullptr, *dColors = nullptr, *dGrids = nullptr;
+    unsigned char *dCfgScratch = nullptr;
+    size_t cfgScratchCap = 0;
     long long vertCap = 0, gridCap = 0;
     chs_mesh_counts lastMesh{};
     int lastMeshChunks = 0;
@@ -1087,7 +1089,7 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dColorPacked, m->dHiz,
                     m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
-                    m->dColors, m->dGrids, m->dSlotBatch, m->bset[0].depth, m->bset[0].trunc, m->bset[0].color, m->bset[0].packed, m->bset[0].hiz,
+                    m->dColors, m->dGrids, m->dCfgScratch, m->dSlotBatch, m->bset[0].depth, m->bset[0].trunc, m->bset[0].color, m->bset[0].packed, m->bset[0].hiz,
                     m->bset[1].depth, m->bset[1].trunc, m->bset[1].color, m->bset[1].packed, m->bset[1].hiz};
     for (void *p : bufs)
         if (p)
@@ -1694,7 +1696,10 @@ int chs_update_meshes(chs_map *m)
             return rc;
         m->meshChunkCap = want;
     }
+    if ((rc = grow_buffer(&m->dCfgScratch, &m->cfgScratchCap, (size_t)nd * m->dm.V, st)))
+        return rc;
     MeshParams mp{};
+    mp.cfg_scratch = m->dCfgScratch;
     mp.dirty_list = m->dm.dirty_list;
     mp.n_dirty = (int)nd;
     mp.mesh_slots = m->dMeshSlots;

@@ -88,6 +88,7 @@ struct MeshParams
     int *grid_counts;                        // [n] occupied cells per remeshed chunk, then exclusive offsets
     long long *vert_offsets;                 // [n+1]
     long long *grid_offsets;                 // [n+1]
+    unsigned char *cfg_scratch;              // [n * V] cube configuration of every cell in the reference's cell order (0: no triangle)
     float *vertices, *normals, *colors, *grids;
     long long cap_vertices, cap_grids;
     float w_observed_min;                    // largest float T with double(T) <= 1e-12: weight > 1e-12 <=> weight > T

@@ -41,6 +41,11 @@ __global__ void mesh_select_kernel(MeshParams mp, DeviceMap map)
         mp.mesh_slots[base + __popc(mask & ((1u << lane) - 1))] = slot;
 }
 
+// cube corner offsets, ChunkManager.cpp:67-69: x 0 1 1 0 0 1 1 0 ; y 0 0 1 1 0 0 1 1 ; z 0 0 0 0 1 1 1 1
+__device__ __forceinline__ int corner_dx(int i) { return (0x66 >> i) & 1; }
+__device__ __forceinline__ int corner_dy(int i) { return (0xCC >> i) & 1; }
+__device__ __forceinline__ int corner_dz(int i) { return (0xF0 >> i) & 1; }
+
 // Cell k of the reference's traversal (ChunkManager.cpp:393-441) -> voxel index of the cell's corner 0.
 template <int CS>
 __device__ __forceinline__ void cell_of_rank(int k, int *x, int *y, int *z)
@@ -109,10 +114,6 @@ __device__ void load_halo(const DeviceMap &map, int slot, float wMin, float *til
     __syncthreads();
 }
 
-// cube corner offsets, ChunkManager.cpp:67-69: x 0 1 1 0 0 1 1 0 ; y 0 0 1 1 0 0 1 1 ; z 0 0 0 0 1 1 1 1
-__device__ __forceinline__ int corner_dx(int i) { return (0x66 >> i) & 1; }
-__device__ __forceinline__ int corner_dy(int i) { return (0xCC >> i) & 1; }
-__device__ __forceinline__ int corner_dz(int i) { return (0xF0 >> i) & 1; }
 
 // returns the cube configuration, or -1 if any corner is unobserved
 template <int CS>
@@ -133,51 +134,98 @@ __device__ __forceinline__ int cell_config(const float *tileS, const unsigned ch
     return ok ? cfg : -1;
 }
 
+// Rank of cell (x, y, z) in the reference's traversal (ChunkManager.cpp:393-441): interior z,y,x; +X face; +Y face; +Z face.
+// Inverse of cell_of_rank.
+template <int CS>
+__device__ __forceinline__ int rank_of_cell(int x, int y, int z)
+{
+    constexpr int M = CS - 1;
+    constexpr int nInterior = M * M * M, nX = M * CS, nY = M * M;
+    if (z == M)
+        return nInterior + nX + nY + y * CS + x;
+    if (x == M)
+        return nInterior + z * CS + y;
+    if (y == M)
+        return nInterior + nX + z * M + x;
+    return (z * M + y) * M + x;
+}
+
+// Pass 1 of a re-mesh: classify every cell ONCE. The halo tile holds one byte per voxel (bit 0 = meshable corner,
+// !(weight <= 0.5); bit 2 = sdf < 0), cells are visited in memory order (conflict-free shared loads, shifts instead of the
+// divisions cell_of_rank needs), and the cube configuration of every cell that produces triangles is written, in the
+// reference's cell order, to a per-chunk scratch row that mesh_emit_kernel reads back -- it never classifies again.
 template <int CS>
 __global__ void __launch_bounds__(256) mesh_count_kernel(MeshParams mp, DeviceMap map)
 {
-    extern __shared__ float tile[];
+    extern __shared__ unsigned char smemB[];
+    constexpr int V = CS * CS * CS, H = CS + 1, H3 = H * H * H;
+    unsigned char *tileB = smemB;                       // [H3]
+    unsigned char *sCfg = smemB + ((H3 + 15) & ~15);    // [V] by reference rank
     __shared__ int nbr[8];
     __shared__ int red[2][8];
-    constexpr int V = CS * CS * CS, CPT = V / 256, H3 = (CS + 1) * (CS + 1) * (CS + 1);
-    float *tileS = tile;
-    unsigned char *tileW = reinterpret_cast<unsigned char *>(tile + H3);
+    const int t = threadIdx.x;
     const int n = map.ctr->mesh_chunks;
     for (int c = blockIdx.x; c < n; c += gridDim.x)
     {
-        load_halo<CS>(map, mp.mesh_slots[c], mp.w_observed_min, tileS, tileW, nbr);
-        int tris = 0, grids = 0;
-        for (int j = 0; j < CPT; j++)
+        const int slot = mp.mesh_slots[c];
+        const int idx = map.slot_ids[3 * slot], idy = map.slot_ids[3 * slot + 1], idz = map.slot_ids[3 * slot + 2];
+        if (t < 8)
+            nbr[t] = (t == 0) ? slot : hash_lookup(map, pack_id(idx + (t & 1), idy + ((t >> 1) & 1), idz + (t >> 2)));
+        __syncthreads();
+        for (int i = t; i < H3; i += 256)
         {
-            int x, y, z;
-            float sdf[8];
-            cell_of_rank<CS>(threadIdx.x * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
-            if (cfg >= 0)
+            const int x = i % H, y = (i / H) % H, z = i / (H * H);
+            const int s = nbr[(x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0)];
+            unsigned char cls = 0;
+            if (s >= 0)
             {
-                const int nt = cTriCount[cfg];
-                tris += nt;
-                grids += nt > 0;
+                const int vx = x == CS ? 0 : x, vy = y == CS ? 0 : y, vz = z == CS ? 0 : z;
+                const float2 d = dist_ptr(map, s)[(vz * CS + vy) * CS + vx];
+                cls = (unsigned char)((!(d.y <= 0.5f) ? 1 : 0) | ((d.x < 0.0f) ? 4 : 0));
             }
+            tileB[i] = cls;
+        }
+        __syncthreads();
+        int tris = 0, grids = 0;
+        for (int i = t; i < V; i += 256)
+        {
+            const int x = i % CS, y = (i / CS) % CS, z = i / (CS * CS);
+            int cfg = 0, ok = 1;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                const int b = tileB[((z + corner_dz(k)) * H + (y + corner_dy(k))) * H + (x + corner_dx(k))];
+                ok &= b;
+                cfg |= ((b >> 2) & 1) << k;                      // MarchingCubes::CalculateVertexConfiguration (MarchingCubes.h:106-116)
+            }
+            const int nt = (ok & 1) ? cTriCount[cfg] : 0;
+            sCfg[rank_of_cell<CS>(x, y, z)] = (unsigned char)(nt ? cfg : 0);     // configurations 0 and 255 have no triangle either
+            tris += nt;
+            grids += nt > 0;
         }
         for (int o = 16; o > 0; o >>= 1)
         {
             tris += __shfl_xor_sync(0xffffffffu, tris, o);
             grids += __shfl_xor_sync(0xffffffffu, grids, o);
         }
-        if ((threadIdx.x & 31) == 0)
+        if ((t & 31) == 0)
         {
-            red[0][threadIdx.x >> 5] = tris;
-            red[1][threadIdx.x >> 5] = grids;
+            red[0][t >> 5] = tris;
+            red[1][t >> 5] = grids;
         }
         __syncthreads();
-        if (threadIdx.x < 2)
+        if (t < 2)
         {
-            int s = 0;
+            int sum = 0;
             for (int k = 0; k < 8; k++)
-                s += red[threadIdx.x][k];
-            (threadIdx.x == 0 ? mp.tri_counts : mp.grid_counts)[c] = s;
+                sum += red[t][k];
+            (t == 0 ? mp.tri_counts : mp.grid_counts)[c] = sum;
         }
+        // the chunk's configuration row, coalesced
+        uint4 *dst = reinterpret_cast<uint4 *>(mp.cfg_scratch + (size_t)c * V);
+        const uint4 *src = reinterpret_cast<const uint4 *>(sCfg);
+        for (int i = t; i < V / 16; i += 256)
+            dst[i] = src[i];
         __syncthreads();
     }
 }
@@ -471,31 +519,31 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
     extern __shared__ float tile[];
     __shared__ int nbr[8];
     __shared__ int warpTot[2][8];
+    __shared__ int sBaseT[257], sBaseG[257];
     constexpr int V = CS * CS * CS, CPT = V / 256, H3 = (CS + 1) * (CS + 1) * (CS + 1);
     float *tileS = tile;
     unsigned char *tileW = reinterpret_cast<unsigned char *>(tile + H3);
+    unsigned char *sCfg = reinterpret_cast<unsigned char *>(tile) + ((5 * H3 + 15) & ~15);   // [V] configurations by reference rank (16-byte aligned)
     const int n = map.ctr->mesh_chunks;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int c = blockIdx.x; c < n; c += gridDim.x)
     {
         const int slot = mp.mesh_slots[c];
-        load_halo<CS>(map, slot, mp.w_observed_min, tileS, tileW, nbr);
-        // pass 1: this thread's triangle / grid totals over its CPT consecutive cells
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(mp.cfg_scratch + (size_t)c * V);
+            uint4 *dst = reinterpret_cast<uint4 *>(sCfg);
+            for (int i = t; i < V / 16; i += 256)
+                dst[i] = src[i];
+        }
+        load_halo<CS>(map, slot, mp.w_observed_min, tileS, tileW, nbr);              // ends with a barrier
+        // exclusive prefix sums, over the reference's cell order, of triangles and occupied cells (thread t owns ranks t*CPT ..)
         int tris = 0, grids = 0;
         for (int j = 0; j < CPT; j++)
         {
-            int x, y, z;
-            float sdf[8];
-            cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
-            if (cfg >= 0)
-            {
-                const int nt = cTriCount[cfg];
-                tris += nt;
-                grids += nt > 0;
-            }
+            const int nt = cTriCount[sCfg[t * CPT + j]];
+            tris += nt;
+            grids += nt > 0;
         }
-        // block-wide exclusive prefix sums (warp shuffles, then across the 8 warps)
         int incT = tris, incG = grids;
         for (int o = 1; o < 32; o <<= 1)
         {
@@ -518,23 +566,54 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
             baseT += warpTot[0][w];
             baseG += warpTot[1][w];
         }
+        sBaseT[t] = baseT;
+        sBaseG[t] = baseG;
+        if (t == 255)
+        {
+            sBaseT[256] = baseT + tris;
+            sBaseG[256] = baseG + grids;
+        }
+        __syncthreads();
+        const int nActive = sBaseG[256];
         const long long vBase = mp.vert_offsets[c], vEnd = mp.vert_offsets[c + 1];
-        long long vOut = vBase + 3ll * baseT;
-        long long gOut = mp.grid_offsets[c] + baseG;
+        const long long gBase = mp.grid_offsets[c];
         const int idx = map.slot_ids[3 * slot], idy = map.slot_ids[3 * slot + 1], idz = map.slot_ids[3 * slot + 2];
         const P3 org = {__fmul_rn((float)(CS * idx), map.res), __fmul_rn((float)(CS * idy), map.res), __fmul_rn((float)(CS * idz), map.res)};
-        // pass 2: positions and flat normals, in the reference's emission order
-        for (int j = 0; j < CPT; j++)
+        // pass 2: one occupied cell per thread and round (balanced: 1..5 triangles each), positions and flat normals written where
+        // the reference's emission order puts them
+        for (int g = t; g < nActive; g += 256)
         {
+            // owner thread of occupied cell g: the last tau with sBaseG[tau] <= g
+            int lo = 0, hi = 255;
+            while (lo < hi)
+            {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sBaseG[mid] <= g)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            int rank = lo * CPT, triBase = sBaseT[lo], cfg = 0;
+            for (int left = g - sBaseG[lo];; rank++)
+            {
+                cfg = sCfg[rank];
+                if (cfg)
+                {
+                    if (left == 0)
+                        break;
+                    left--;
+                    triBase += cTriCount[cfg];
+                }
+            }
             int x, y, z;
+            cell_of_rank<CS>(rank, &x, &y, &z);
             float sdf[8];
-            cell_of_rank<CS>(t * CPT + j, &x, &y, &z);
-            const int cfg = cell_config<CS>(tileS, tileW, x, y, z, sdf);
-            if (cfg < 0)
-                continue;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                sdf[i] = tileS[((z + corner_dz(i)) * (CS + 1) + (y + corner_dy(i))) * (CS + 1) + (x + corner_dx(i))];
             const int nt = cTriCount[cfg];
-            if (nt == 0)
-                continue;
+            long long vOut = vBase + 3ll * triBase;
+            const long long gOut = gBase + g;
             // coords = centroid + origin (ChunkManager.cpp:400 etc.), centroid_k = float(k)*res + res/2 (:61)
             const P3 c0 = {__fadd_rn(__fadd_rn(__fmul_rn((float)x, map.res), map.half), org.x),
                            __fadd_rn(__fadd_rn(__fmul_rn((float)y, map.res), map.half), org.y),
@@ -545,7 +624,6 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(MeshParams mp, DeviceMap
                 mp.grids[3 * gOut + 1] = c0.y;
                 mp.grids[3 * gOut + 2] = c0.z;
             }
-            gOut++;
             const unsigned long long row = cTriPacked[cfg];
             for (int tri = 0; tri < nt; tri++)
             {
@@ -638,7 +716,9 @@ void launch_mesh_select(const MeshParams &mp, const DeviceMap &map, cudaStream_t
 template <int CS>
 static void mesh_launch_cs(const MeshParams &mp, const DeviceMap &map, int grid, cudaStream_t st, bool emit)
 {
-    const size_t smem = (sizeof(float) + 1) * (CS + 1) * (CS + 1) * (CS + 1) + 16;   // SDF tile + class-byte tile
+    constexpr size_t H3 = (size_t)(CS + 1) * (CS + 1) * (CS + 1), V = (size_t)CS * CS * CS;
+    // emit: SDF tile + class-byte tile + configuration row; count: class-byte tile + configuration row
+    const size_t smem = emit ? ((5 * H3 + 15) & ~(size_t)15) + V : ((H3 + 15) & ~(size_t)15) + V;
     if (emit)
     {
         if (smem > 48 * 1024)
