@@ -94,22 +94,43 @@ __device__ void load_halo(const DeviceMap &map, int slot, float wMin, float *til
     if (t < 8)
         nbrSlots[t] = (t == 0) ? slot : hash_lookup(map, pack_id(idx + (t & 1), idy + ((t >> 1) & 1), idz + (t >> 2)));
     __syncthreads();
-    for (int i = t; i < H * H * H; i += blockDim.x)
+    // linear walk over the tile, 256 voxels per round; (x, y, z) advance incrementally (no division in the loop) and four
+    // rounds are batched so that four loads per thread are in flight
+    constexpr int H3 = H * H * H, dX = 256 % H, dY = (256 / H) % H, dZ = (256 / H) / H;
+    int x = t % H, y = (t / H) % H, z = t / (H * H);
+    for (int i0 = t; i0 < H3; i0 += 1024)
     {
-        const int x = i % H, y = (i / H) % H, z = i / (H * H);
-        const int n = (x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0);
-        const int s = nbrSlots[n];
-        float sdf = 0.0f;
-        unsigned char cls = 0;
-        if (s >= 0)
+        float2 d[4];
+        bool have[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
         {
-            const int vx = x == CS ? 0 : x, vy = y == CS ? 0 : y, vz = z == CS ? 0 : z;
-            const float2 d = dist_ptr(map, s)[(vz * CS + vy) * CS + vx];
-            sdf = d.x;
-            cls = (unsigned char)((!(d.y <= 0.5f) ? 1 : 0) | ((d.y > wMin) ? 2 : 0));
+            have[r] = false;
+            d[r] = make_float2(0.0f, 0.0f);
+            if (i0 + 256 * r < H3)
+            {
+                const int s = nbrSlots[(x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0)];
+                if (s >= 0)
+                {
+                    have[r] = true;
+                    d[r] = dist_ptr(map, s)[((z == CS ? 0 : z) * CS + (y == CS ? 0 : y)) * CS + (x == CS ? 0 : x)];
+                }
+            }
+            x += dX;
+            int c = x >= H;
+            x -= c * H;
+            y += dY + c;
+            c = y >= H;
+            y -= c * H;
+            z += dZ + c;
         }
-        tileS[i] = sdf;
-        tileW[i] = cls;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (i0 + 256 * r < H3)
+            {
+                tileS[i0 + 256 * r] = have[r] ? d[r].x : 0.0f;
+                tileW[i0 + 256 * r] = have[r] ? (unsigned char)((!(d[r].y <= 0.5f) ? 1 : 0) | ((d[r].y > wMin) ? 2 : 0)) : (unsigned char)0;
+            }
     }
     __syncthreads();
 }
@@ -172,18 +193,40 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(MeshParams mp, DeviceMa
         if (t < 8)
             nbr[t] = (t == 0) ? slot : hash_lookup(map, pack_id(idx + (t & 1), idy + ((t >> 1) & 1), idz + (t >> 2)));
         __syncthreads();
-        for (int i = t; i < H3; i += 256)
         {
-            const int x = i % H, y = (i / H) % H, z = i / (H * H);
-            const int s = nbr[(x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0)];
-            unsigned char cls = 0;
-            if (s >= 0)
+            constexpr int dX = 256 % H, dY = (256 / H) % H, dZ = (256 / H) / H;
+            int x = t % H, y = (t / H) % H, z = t / (H * H);
+            for (int i0 = t; i0 < H3; i0 += 1024)
             {
-                const int vx = x == CS ? 0 : x, vy = y == CS ? 0 : y, vz = z == CS ? 0 : z;
-                const float2 d = dist_ptr(map, s)[(vz * CS + vy) * CS + vx];
-                cls = (unsigned char)((!(d.y <= 0.5f) ? 1 : 0) | ((d.x < 0.0f) ? 4 : 0));
+                float2 d[4];
+                bool have[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    have[r] = false;
+                    d[r] = make_float2(0.0f, 0.0f);
+                    if (i0 + 256 * r < H3)
+                    {
+                        const int s = nbr[(x == CS ? 1 : 0) | (y == CS ? 2 : 0) | (z == CS ? 4 : 0)];
+                        if (s >= 0)
+                        {
+                            have[r] = true;
+                            d[r] = dist_ptr(map, s)[((z == CS ? 0 : z) * CS + (y == CS ? 0 : y)) * CS + (x == CS ? 0 : x)];
+                        }
+                    }
+                    x += dX;
+                    int c = x >= H;
+                    x -= c * H;
+                    y += dY + c;
+                    c = y >= H;
+                    y -= c * H;
+                    z += dZ + c;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (i0 + 256 * r < H3)
+                        tileB[i0 + 256 * r] = have[r] ? (unsigned char)((!(d[r].y <= 0.5f) ? 1 : 0) | ((d[r].x < 0.0f) ? 4 : 0)) : (unsigned char)0;
             }
-            tileB[i] = cls;
         }
         __syncthreads();
         int tris = 0, grids = 0;
