@@ -415,6 +415,41 @@ def run_cuda(args):
     t_e2e = time.perf_counter() - t0
     m.close()
 
+    # ---------------- leg B': the same pipeline fed with 16UC1 millimetre depth (the sensor's own encoding; converted on the
+    # device like chisel_ros converts it on the host). Different input VALUES (quantised to 1 mm), hence reported beside, not as, e2e.
+    e2e_mm = None
+    if world == 1 and B > 1 and not args.quick:
+        h_mm = torch.empty((n_unique, H, W), dtype=torch.int16).pin_memory()
+        for i, fr in enumerate(frames):
+            q = np.clip(np.nan_to_num(fr[0], nan=0.0) * 1000.0, 0, 65535).astype(np.uint16)
+            h_mm[i].copy_(torch.from_numpy(q.view(np.int16)))
+        m = new_map()
+
+        def step_mm(step):
+            ids = frame_ids(step)
+            ds = [h_mm[i].numpy().view(np.uint16) for i in ids]
+            cs = [sharding.unpack_frame(h_frames[i].numpy(), W, H, channels)[1] for i in ids]
+            m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs)
+
+        for i in range(warm):
+            step_mm(i)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        upd_mm, prev = 0, None
+        for k in range(steps):
+            step_mm(warm + k)
+            tk = m.last_batch_ticket()
+            if prev is not None:
+                upd_mm += sum(st["n_upd"] for st in m.wait_batch(prev))
+            prev = tk
+        upd_mm += sum(st["n_upd"] for st in m.wait_batch(prev))
+        torch.cuda.synchronize(dev)
+        t_mm = time.perf_counter() - t0
+        m.close()
+        e2e_mm = {"value": upd_mm / t_mm / 1e9, "unit": UNIT, "frames_per_s": steps * B / t_mm, "ms_per_step": 1000.0 * t_mm / steps,
+                  "h2d_bytes_per_step": (2 * W * H + channels * W * H) * B,
+                  "note": "depth handed over as uint16 millimetres (chs_frame.depth_mm), same pipeline as e2e"}
+
     # ---------------- reduce over ranks -------------------------------------------------------------------------
     vals = torch.tensor([t_dev, t_e2e, wall_a, t_integrate, t_warm, t_single], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(upd_local), float(upd_e2e), float(bytes_alg), float(total_chunks), float(upd_single)], dtype=torch.float64, device=dev)
@@ -461,6 +496,7 @@ def run_cuda(args):
                     "timing": "wall clock; per step chs_integrate_batch(pinned host frames), then chs_wait_batch of the PREVIOUS step's counters "
                               "(depth-2 pipeline: copies of step k overlap kernels of step k-1)" if B > 1 else
                               "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
+            "e2e_depth_mm": e2e_mm,
             "gpu_launches": (3 if B > 1 else 5) * steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",

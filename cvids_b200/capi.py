@@ -57,7 +57,7 @@ class chs_frame_stats(C.Structure):
 
 
 class chs_frame(C.Structure):
-    _fields_ = [("depth", C.c_void_p), ("color", C.c_void_p), ("trunc_per_pixel", C.c_void_p),
+    _fields_ = [("depth", C.c_void_p), ("depth_mm", C.c_void_p), ("color", C.c_void_p), ("trunc_per_pixel", C.c_void_p),
                 ("pose", C.c_float * 12), ("color_pose", C.c_float * 12)]
 
 
@@ -317,9 +317,13 @@ class Chisel:
             arr[i].pose[:] = p.tolist()
             arr[i].color_pose[:] = cp.tolist()
             if device_ptrs is None:
-                d = np.ascontiguousarray(depths[i], np.float32)
+                if np.asarray(depths[i]).dtype == np.uint16:           # millimetres (ROS 16UC1): converted on the device
+                    d = np.ascontiguousarray(depths[i], np.uint16)
+                    arr[i].depth_mm = d.ctypes.data
+                else:
+                    d = np.ascontiguousarray(depths[i], np.float32)
+                    arr[i].depth = d.ctypes.data
                 keep.append(d)
-                arr[i].depth = d.ctypes.data
                 if use_color:
                     c = np.ascontiguousarray(colors[i], np.uint8)
                     keep.append(c)

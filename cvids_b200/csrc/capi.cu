@@ -165,6 +165,8 @@ struct chs_map
         FrameParams *dFrames = nullptr;
         BatchCounters *dBctr = nullptr;
         float *depth = nullptr, *trunc = nullptr;
+        uint16_t *depthMm = nullptr;
+        size_t depthMmCap = 0;
         uint8_t *color = nullptr;
         unsigned *packed = nullptr;
         float2 *hiz = nullptr;
@@ -800,6 +802,9 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     const bool computeTrunc = integ->trunc_kind == CHS_TRUNC_QUADRATIC || integ->trunc_kind == CHS_TRUNC_INVERSE;
     const bool perPixel = integ->trunc_kind != CHS_TRUNC_CONSTANT;
     const bool hostMem = mem == CHS_MEM_HOST;
+    bool anyMm = false;
+    for (int f = 0; f < K; f++)
+        anyMm |= frames[f].depth_mm != nullptr;
     const int setIdx = (m->batchId + 1) & 1;
     chs_map::BatchSet &bs = m->bset[setIdx];
     cudaStream_t cs = m->copyStream;
@@ -807,7 +812,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     if (bs.used)
         CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
     {
-        const bool grow = tiles * kMaxBatch > bs.hizCap || (hostMem && npx * kMaxBatch > bs.depthCap) ||
+        const bool grow = tiles * kMaxBatch > bs.hizCap || ((hostMem || anyMm) && npx * kMaxBatch > bs.depthCap) || (anyMm && hostMem && npx * kMaxBatch > bs.depthMmCap) ||
                           ((computeTrunc || (perPixel && hostMem)) && npx * kMaxBatch > bs.truncCap) ||
                           (colorPath && ((hostMem && cpx * channels * kMaxBatch > bs.colorCap) || cpx * kMaxBatch > bs.packedCap));
         if (grow)
@@ -819,7 +824,9 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     if ((rc = grow_buffer(&bs.hiz, &bs.hizCap, tiles * kMaxBatch, cs)))
         return rc;
-    if (hostMem && (rc = grow_buffer(&bs.depth, &bs.depthCap, npx * kMaxBatch, cs)))
+    if ((hostMem || anyMm) && (rc = grow_buffer(&bs.depth, &bs.depthCap, npx * kMaxBatch, cs)))
+        return rc;
+    if (anyMm && hostMem && (rc = grow_buffer(&bs.depthMm, &bs.depthMmCap, npx * kMaxBatch, cs)))
         return rc;
     if ((computeTrunc || (perPixel && hostMem)) && (rc = grow_buffer(&bs.trunc, &bs.truncCap, npx * kMaxBatch, cs)))
         return rc;
@@ -843,7 +850,19 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         FrameParams &fp = fps[f];
         fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], bs.hiz + tiles * f, &fp);
         fp.hiz_ticket = m->dHizTickets + setIdx * kMaxBatch + f;
-        if (hostMem)
+        if (frames[f].depth_mm)
+        {
+            // millimetres: half the bytes over PCIe; batch_prepare converts into the float image
+            if (hostMem)
+            {
+                CHS_CUDA(cudaMemcpyAsync(bs.depthMm + npx * f, frames[f].depth_mm, npx * sizeof(uint16_t), cudaMemcpyHostToDevice, cs));
+                fp.depth_u16 = bs.depthMm + npx * f;
+            }
+            else
+                fp.depth_u16 = frames[f].depth_mm;
+            fp.depth = bs.depth + npx * f;
+        }
+        else if (hostMem)
         {
             CHS_CUDA(cudaMemcpyAsync(bs.depth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, cs));
             fp.depth = bs.depth + npx * f;
@@ -1089,7 +1108,7 @@ int chs_destroy(chs_map *m)
         cudaFreeAsync(p, m->stream);
     void *bufs[] = {m->dm.keys, m->dm.vals, m->dm.slot_ids, m->dm.brick_flags, m->dm.slot_epoch, m->dm.dirty_keys, m->dm.dirty_list, m->dDepth, m->dTrunc, m->dColor, m->dColorPacked, m->dHiz,
                     m->dUnits, m->dNews, m->dMeshSlots, m->dTriCounts, m->dGridCounts, m->dVertOffsets, m->dGridOffsets, m->dVerts, m->dNormals,
-                    m->dColors, m->dGrids, m->dCfgScratch, m->dSlotBatch, m->bset[0].depth, m->bset[0].trunc, m->bset[0].color, m->bset[0].packed, m->bset[0].hiz,
+                    m->dColors, m->dGrids, m->dCfgScratch, m->dSlotBatch, m->bset[0].depthMm, m->bset[1].depthMm, m->bset[0].depth, m->bset[0].trunc, m->bset[0].color, m->bset[0].packed, m->bset[0].hiz,
                     m->bset[1].depth, m->bset[1].trunc, m->bset[1].color, m->bset[1].packed, m->bset[1].hiz};
     for (void *p : bufs)
         if (p)
@@ -1210,17 +1229,20 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
     const bool colorPath = ccam != nullptr;
     if (colorPath && (channels < 1 || channels > 4 || ccam->width <= 0 || ccam->height <= 0))
         return fail(CHS_ERR_INVALID, "bad colour arguments");
-    bool fusable = true;
+    bool fusable = true, anyMm = false;
     for (int f = 0; f < n; f++)
     {
-        if (!frames[f].depth || (colorPath && !frames[f].color) || (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !frames[f].trunc_per_pixel))
+        if ((!frames[f].depth && !frames[f].depth_mm) || (colorPath && !frames[f].color) || (integ->trunc_kind == CHS_TRUNC_PER_PIXEL && !frames[f].trunc_per_pixel))
             return fail(CHS_ERR_INVALID, "frame without depth / colour / truncation image");
+        anyMm |= frames[f].depth_mm != nullptr;
         if (!finite12(frames[f].pose) || (colorPath && !finite12(frames[f].color_pose)))
             return fail(CHS_ERR_INVALID, "non-finite pose (quirk Q14: rejected at the boundary)");
         // the fused kernels reuse the depth projection for the colour lookup
         if (colorPath && (std::memcmp(frames[f].pose, frames[f].color_pose, sizeof(float) * 12) != 0 || std::memcmp(cam, ccam, 4 * sizeof(float) + 2 * sizeof(int)) != 0))
             fusable = false;
     }
+    if (anyMm && !fusable)
+        return fail(CHS_ERR_INVALID, "depth_mm frames need the colour camera to coincide with the depth camera (they only run through the fused kernels)");
     CHS_CUDA(cudaSetDevice(m->device));
     int rc = poll_inflight(m, false);
     if (rc)
@@ -1236,8 +1258,10 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
     {
         const int K = std::min(n - f, (int)kMaxBatch);
         rc = CHS_ERR_NOT_FOUND;
-        if (fusable && K >= 2)
+        if (fusable && (K >= 2 || anyMm))
             rc = integrate_batch_fused(m, integ, K, frames + f, mem, cam, channels, ccam, colorPath, f);
+        if (rc == CHS_ERR_NOT_FOUND && anyMm)
+            return fail(CHS_ERR_INVALID, "depth_mm frames too far apart to share a candidate box");
         if (rc == CHS_ERR_NOT_FOUND)
         {
             // frame by frame (single frame, separate colour camera, or frames too far apart to share a candidate box)

@@ -191,7 +191,9 @@ struct FrameParams
 {
     CameraDev cam;            // depth camera + pose
     CameraDev ccam;           // colour camera + pose
-    const float *depth;       // W*H
+    const float *depth;       // W*H metres
+    const uint16_t *depth_u16;// W*H millimetres (ROS 16UC1) or nullptr: frame_prepare converts it into `depth`, (1.0f / 1000.0f) * value
+                              // as ROSImgToDepthImg does (CR Conversions.h:141-152)
     const float *trunc_img;   // W*H or nullptr (constant truncator)
     const uint8_t *color;     // cW*cH*channels, as the caller handed it over
     unsigned *color_packed;   // cW*cH packed r | g << 8 | b << 16, written by frame_prepare (ColorImage::At, OC ColorImage.h:61-101)

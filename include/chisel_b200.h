@@ -135,7 +135,9 @@ int chs_integrate_depth_color(chs_map *map, const chs_integrator *integ, const f
 /* One frame of a batch. Pointers live in the memory space named by `mem` of the call. */
 typedef struct
 {
-    const float *depth;            /* width*height float metres */
+    const float *depth;            /* width*height float metres (ignored when depth_mm is set) */
+    const uint16_t *depth_mm;      /* or: width*height uint16 millimetres, the ROS 16UC1 depth encoding. Converted on the device exactly as
+                                      chisel_ros does on the host, (1.0f / 1000.0f) * value (CR Conversions.h:141-152): half the bytes to move */
     const uint8_t *color;          /* colour path only: color_cam.width*height*channels */
     const float *trunc_per_pixel;  /* CHS_TRUNC_PER_PIXEL only */
     float pose[12];

@@ -218,3 +218,32 @@ def test_batch_inverse_truncator_8cube_one_then_ten():
             for k in COUNTERS:
                 assert g[k] == w[k], "frame %d of the group counter %s: cuda batch %d oracle %d" % (j, k, g[k], w[k])
     common.assert_state_equal(a.state(), b.state())
+
+
+def test_batch_depth_in_millimetres_converted_on_device():
+    """16UC1 depth (ROS): the device conversion equals chisel_ros's host loop, depth = (1.0f / 1000.0f) * mm
+    (CR Conversions.h:141-152); zero (no reading) stays 0.0 m like there."""
+    setup = Setup(16, 0.04, True)
+    cam = common.SMALL_CAM
+    frames = list(common.orbit_stream(cam, 6, total=30, color=True, seed=13))
+    mm = []
+    for depth, _, _ in frames:
+        q = np.clip(np.nan_to_num(depth, nan=0.0) * 1000.0, 0, 65535).astype(np.uint16)
+        q[::17, ::13] = 0
+        mm.append(q)
+    k = np.float32(1.0) / np.float32(1000.0)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    camv = cam.as_array()
+    want = []
+    for q, (_, col, pose) in zip(mm, frames):
+        b.integrate((k * q.astype(np.float32)).astype(np.float32), pose, camv, col)
+        want.append(b.counters())
+    a.m.integrate_batch(a.integ, mm[:1], [frames[0][2]], camv, [frames[0][1]])          # a single frame also goes through the fused kernels
+    got = a.m.batch_stats()
+    a.m.integrate_batch(a.integ, mm[1:], [f[2] for f in frames[1:]], camv, [f[1] for f in frames[1:]])
+    got += a.m.batch_stats()
+    for j, (g, w) in enumerate(zip(got, want)):
+        for c in COUNTERS:
+            assert g[c] == w[c], "frame %d counter %s: %d vs %d" % (j, c, g[c], w[c])
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
