@@ -271,6 +271,8 @@ def run_cuda(args):
         else:
             m.integrate_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
 
+    align = torch.zeros(1, device=dev)
+
     def timed_leg(b, n_warm, n_steps, do_flush):
         """CUDA events around every step on the stream the kernels run on; returns (device seconds, wall seconds, clocks)."""
         m = new_map()
@@ -285,6 +287,10 @@ def run_cuda(args):
         if do_flush:
             for k in range(n_steps):
                 flush_l2(k)
+                if world > 1:
+                    # align the ranks IN STREAM ORDER before the step starts: without it the skew between the ranks' flushes is
+                    # waited out by the step's broadcast, inside the timed bracket
+                    dist.all_reduce(align)
                 ev[k][0].record(stream)
                 step_device(m, n_warm + k, b)
                 ev[k][1].record(stream)
