@@ -391,7 +391,8 @@ def run_cuda(args):
             if B == 1:
                 m.integrate_depth_scan_color(integ, ds[0], poses[ids[0]], camv, cs[0])
             else:
-                m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs)
+                # the pinned frames are never modified: CHS_MEM_HOST_ASYNC lets the call return right after enqueueing
+                m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs, host_async=True)
         if not read:
             return 0
         return sum(st["n_upd"] for st in m.batch_stats()) if B > 1 else m.frame_stats()["n_upd"]
@@ -435,7 +436,7 @@ def run_cuda(args):
             ids = frame_ids(step)
             ds = [h_mm[i].numpy().view(np.uint16) for i in ids]
             cs = [sharding.unpack_frame(h_frames[i].numpy(), W, H, channels)[1] for i in ids]
-            m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs)
+            m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs, host_async=True)
 
         for i in range(warm):
             step_mm(i)
@@ -499,7 +500,7 @@ def run_cuda(args):
                                           "new_chunks": float(np.mean([p[5] for p in per_step]))}},
             "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * B / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * B,
-                    "timing": "wall clock; per step chs_integrate_batch(pinned host frames), then chs_wait_batch of the PREVIOUS step's counters "
+                    "timing": "wall clock; per step chs_integrate_batch(pinned host frames, CHS_MEM_HOST_ASYNC), then chs_wait_batch of the PREVIOUS step's counters "
                               "(depth-2 pipeline: copies of step k overlap kernels of step k-1)" if B > 1 else
                               "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
             "e2e_depth_mm": e2e_mm,

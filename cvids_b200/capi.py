@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(HERE, "libchisel_b200.so")
 
 CHS_OK, CHS_ERR_INVALID, CHS_ERR_CUDA, CHS_ERR_CAPACITY, CHS_ERR_NOT_FOUND = range(5)
 TRUNC_CONSTANT, TRUNC_QUADRATIC, TRUNC_INVERSE, TRUNC_PER_PIXEL = range(4)
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 
 
 class ChiselError(RuntimeError):
@@ -301,7 +301,7 @@ class Chisel:
                                                        C.byref(cam), device_ptrs[1], channels, _ptr(cp), C.byref(ccam)))
 
     def integrate_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
-                        device_ptrs=None, channels=None, truncs=None):
+                        device_ptrs=None, channels=None, truncs=None, host_async=False):
         """n consecutive frames in one call (chs_integrate_batch): the same result as n calls of integrate_depth_scan[_color]
         in order. depths/colors: lists of host arrays, or with device_ptrs=[(depth_ptr, color_ptr|None, trunc_ptr|None), ...]
         device memory. colors=None (and no colour device pointers): the depth path."""
@@ -338,7 +338,10 @@ class Chisel:
                 arr[i].color = device_ptrs[i][1]
                 arr[i].trunc_per_pixel = device_ptrs[i][2] if len(device_ptrs[i]) > 2 else None
         integ = integrator.as_struct(device_ptr=0) if integrator.trunc_kind == TRUNC_PER_PIXEL else integrator.as_struct()
-        _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, MEM_HOST if device_ptrs is None else MEM_DEVICE,
+        mem = MEM_DEVICE if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
+        if host_async:
+            self._keep = (self._keep or [])[-64:] + [keep]          # the buffers must outlive the call
+        _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, mem,
                                              C.byref(cam), int(channels or 0), C.byref(ccam) if ccam is not None else None))
 
     def last_batch_ticket(self) -> int:

@@ -764,6 +764,24 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
     return CHS_OK;
 }
 
+// K host images of `bytes` bytes each -> K consecutive device images. Callers usually keep their frames in one ring or array,
+// i.e. at a constant stride: then the K copies are ONE strided copy (one DMA descriptor chain instead of K submissions).
+static int copy_images_h2d(void *dst, const void *const *src, int K, size_t bytes, cudaStream_t st)
+{
+    bool strided = K > 1;
+    const ptrdiff_t stride = K > 1 ? (const char *)src[1] - (const char *)src[0] : 0;
+    for (int f = 1; f < K && strided; f++)
+        strided = (const char *)src[f] - (const char *)src[f - 1] == stride;
+    if (strided && stride >= (ptrdiff_t)bytes)
+    {
+        CHS_CUDA(cudaMemcpy2DAsync(dst, bytes, src[0], (size_t)stride, bytes, (size_t)K, cudaMemcpyHostToDevice, st));
+        return CHS_OK;
+    }
+    for (int f = 0; f < K; f++)
+        CHS_CUDA(cudaMemcpyAsync((char *)dst + bytes * f, src[f], bytes, cudaMemcpyHostToDevice, st));
+    return CHS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // chs_integrate_batch: n consecutive frames of one sensor stream (same image size, intrinsics and integrator). Sub-batches of
 // up to kMaxBatch frames go through the fused kernels (integrate_batch.cu); the map afterwards is bit-identical to n calls of
@@ -801,7 +819,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     const size_t tiles = hiz_tiles(cam);
     const bool computeTrunc = integ->trunc_kind == CHS_TRUNC_QUADRATIC || integ->trunc_kind == CHS_TRUNC_INVERSE;
     const bool perPixel = integ->trunc_kind != CHS_TRUNC_CONSTANT;
-    const bool hostMem = mem == CHS_MEM_HOST;
+    const bool hostMem = mem == CHS_MEM_HOST || mem == CHS_MEM_HOST_ASYNC;
     bool anyMm = false;
     for (int f = 0; f < K; f++)
         anyMm |= frames[f].depth_mm != nullptr;
@@ -854,49 +872,60 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         {
             // millimetres: half the bytes over PCIe; batch_prepare converts into the float image
             if (hostMem)
-            {
-                CHS_CUDA(cudaMemcpyAsync(bs.depthMm + npx * f, frames[f].depth_mm, npx * sizeof(uint16_t), cudaMemcpyHostToDevice, cs));
                 fp.depth_u16 = bs.depthMm + npx * f;
-            }
             else
                 fp.depth_u16 = frames[f].depth_mm;
             fp.depth = bs.depth + npx * f;
         }
         else if (hostMem)
-        {
-            CHS_CUDA(cudaMemcpyAsync(bs.depth + npx * f, frames[f].depth, npx * sizeof(float), cudaMemcpyHostToDevice, cs));
             fp.depth = bs.depth + npx * f;
-        }
         else
             fp.depth = frames[f].depth;
         fp.trunc_img = nullptr;
         if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL)
         {
-            if (hostMem)
-            {
-                CHS_CUDA(cudaMemcpyAsync(bs.trunc + npx * f, frames[f].trunc_per_pixel, npx * sizeof(float), cudaMemcpyHostToDevice, cs));
-                fp.trunc_img = bs.trunc + npx * f;
-            }
-            else
-                fp.trunc_img = frames[f].trunc_per_pixel;
+            fp.trunc_img = hostMem ? bs.trunc + npx * f : frames[f].trunc_per_pixel;
         }
         else if (computeTrunc)
             fp.trunc_img = bs.trunc + npx * f;                      // written by batch_prepare
         if (colorPath)
         {
-            if (hostMem)
-            {
-                CHS_CUDA(cudaMemcpyAsync(bs.color + cpx * channels * f, frames[f].color, cpx * channels, cudaMemcpyHostToDevice, cs));
-                fp.color = bs.color + cpx * channels * f;
-            }
-            else
-                fp.color = frames[f].color;
+            fp.color = hostMem ? bs.color + cpx * channels * f : frames[f].color;
             fp.color_packed = bs.packed + cpx * f;
         }
         fp.frame_id = ++m->frameId;
     }
     if (hostMem)
+    {
+        // runs of frames of the same kind (float / millimetre depth) go in one strided copy each
+        const void *src[kMaxBatch];
+        for (int f0 = 0; f0 < K;)
+        {
+            const bool mm = frames[f0].depth_mm != nullptr;
+            int f1 = f0;
+            for (; f1 < K && (frames[f1].depth_mm != nullptr) == mm; f1++)
+                src[f1 - f0] = mm ? (const void *)frames[f1].depth_mm : (const void *)frames[f1].depth;
+            if ((rc = mm ? copy_images_h2d(bs.depthMm + npx * f0, src, f1 - f0, npx * sizeof(uint16_t), cs)
+                         : copy_images_h2d(bs.depth + npx * f0, src, f1 - f0, npx * sizeof(float), cs)))
+                return rc;
+            f0 = f1;
+        }
+        if (integ->trunc_kind == CHS_TRUNC_PER_PIXEL)
+        {
+            for (int f = 0; f < K; f++)
+                src[f] = frames[f].trunc_per_pixel;
+            if ((rc = copy_images_h2d(bs.trunc, src, K, npx * sizeof(float), cs)))
+                return rc;
+        }
+        if (colorPath)
+        {
+            for (int f = 0; f < K; f++)
+                src[f] = frames[f].color;
+            if ((rc = copy_images_h2d(bs.color, src, K, cpx * channels, cs)))
+                return rc;
+        }
         CHS_CUDA(cudaEventRecord(bs.copied, cs));
+    }
     // the frame table: pageable source, staged by the driver before the call returns
     CHS_CUDA(cudaMemcpyAsync(bs.dFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
 
@@ -955,8 +984,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     if (m->profiling)
         m->frameTimed = true;
     m->haveFrame = true;
-    // the caller may reuse its host buffers as soon as we return
-    if (hostMem)
+    // the caller may reuse its host buffers as soon as we return (unless it promised not to: CHS_MEM_HOST_ASYNC)
+    if (mem == CHS_MEM_HOST)
         CHS_CUDA(cudaEventSynchronize(bs.copied));
     return CHS_OK;
 }
@@ -1269,7 +1298,7 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
             {
                 chs_integrator one = *integ;
                 one.trunc_per_pixel = frames[j].trunc_per_pixel;
-                if ((rc = integrate_common(m, &one, frames[j].depth, mem, frames[j].pose, cam, frames[j].color, channels, frames[j].color_pose, ccam, colorPath, j)))
+                if ((rc = integrate_common(m, &one, frames[j].depth, mem == CHS_MEM_HOST_ASYNC ? CHS_MEM_HOST : mem, frames[j].pose, cam, frames[j].color, channels, frames[j].color_pose, ccam, colorPath, j)))
                     return rc;
             }
         }

@@ -51,7 +51,10 @@ enum
 };
 
 enum { CHS_TRUNC_CONSTANT = 0, CHS_TRUNC_QUADRATIC = 1, CHS_TRUNC_INVERSE = 2, CHS_TRUNC_PER_PIXEL = 3 };
-enum { CHS_MEM_HOST = 0, CHS_MEM_DEVICE = 1 };
+/* CHS_MEM_HOST_ASYNC (chs_integrate_batch only): host buffers (ideally pinned) that the caller leaves untouched until the
+ * call's ticket has been waited for (chs_wait_batch / any synchronising call); the call returns right after enqueueing, so
+ * the copies of successive batches run back to back on the copy engine. */
+enum { CHS_MEM_HOST = 0, CHS_MEM_DEVICE = 1, CHS_MEM_HOST_ASYNC = 2 };
 
 typedef struct
 {
