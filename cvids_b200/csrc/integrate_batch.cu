@@ -389,7 +389,8 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
             const float invZ = FAST ? rcp_rn_inrange(cz[k]) : __frcp_rn(cz[k]);                // == 1.0f / z, correctly rounded
             const float u = __fadd_rn(__fmul_rn(__fmul_rn(c.fx, cx), invZ), c.cx);
             const float v = __fadd_rn(__fmul_rn(__fmul_rn(c.fy, cy), invZ), c.cy);
-            const bool on = u >= 0.0f && v >= 0.0f && u < c.Wf && v < c.Hf && !(cz[k] < 0.0f);
+            // bitwise, not short-circuit: five compares feeding one predicate instead of four branches
+            const bool on = (u >= 0.0f) & (v >= 0.0f) & (u < c.Wf) & (v < c.Hf) & !(cz[k] < 0.0f);
             pix[k] = on ? (int)u + (int)v * c.W : -1;
         }
     }
@@ -414,18 +415,19 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
         for (int k = 0; k < kVPL; k++)
         {
             const float d = depth[k];
-            const bool skip = (pix[k] < 0) || (COLOR_PATH ? (d != d || d > 100.0f) : (d > 50.0f));
+            // !(d <= cutoff) is "NaN or beyond the cutoff" (:134, :141); the depth path keeps NaN (its comparisons then all fail)
+            const bool skip = (pix[k] < 0) | (COLOR_PATH ? !(d <= 100.0f) : (d > 50.0f));
             sd[k] = __fsub_rn(d, cz[k]);
-            const bool inBand = !skip && fabsf(sd[k]) < __fadd_rn(trunc[k], fp.diag);                       // :82 / :143
-            const bool canCarve = !skip && !inBand && fp.carve && sd[k] > __fadd_rn(trunc[k], fp.carve_dist)  // :88 / :166
-                                  && dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max;                           // :90 / :169
+            const bool inBand = !skip & (fabsf(sd[k]) < __fadd_rn(trunc[k], fp.diag));                      // :82 / :143
+            const bool canCarve = !skip & !inBand & (fp.carve != 0) & (sd[k] > __fadd_rn(trunc[k], fp.carve_dist))  // :88 / :166
+                                  & (dv[k].y > 0.0f) & (dv[k].x < fp.sdf_carve_max);                         // :90 / :169
             band |= (inBand ? 1u : 0u) << k;
             crv |= (canCarve ? 1u : 0u) << k;
             wu[k] = COLOR_PATH ? (PER_PIXEL ? fp.weight : fp.wu_const) : 1.0f;
             if (COLOR_PATH && PER_PIXEL)
             {
                 const float t5 = __fmul_rn(5.0f, trunc[k]);                                                  // ConstantWeighter.h:43-46
-                ok &= !inBand || div_in_range(fp.weight, t5);
+                ok &= !inBand | div_in_range(fp.weight, t5);
                 wu[k] = div_rn_inrange(fp.weight, inBand ? t5 : 1.0f);
             }
             num[k] = inBand ? __fadd_rn(__fmul_rn(dv[k].y, dv[k].x), __fmul_rn(wu[k], sd[k])) : 0.0f;      // DistVoxel.h:52-60
@@ -466,7 +468,7 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
             }
             dv[k].x = inBand ? upd.x : (canCarve ? carved.x : dv[k].x);
             dv[k].y = inBand ? upd.y : (canCarve ? carved.y : dv[k].y);
-            carvable |= (inBand || canCarve) && dv[k].y > 0.0f && dv[k].x < fp.sdf_carve_max;
+            carvable |= (inBand | canCarve) & (dv[k].y > 0.0f) & (dv[k].x < fp.sdf_carve_max);
         }
         wroteD |= band | crv;
         nUpd += __popc(band);
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
                 bool c = false;
 #pragma unroll
                 for (int k = 0; k < kVPL; k++)
-                    c |= dv[k].y > 0.0f && dv[k].x < carveMax;
+                    c |= (dv[k].y > 0.0f) & (dv[k].x < carveMax);
                 if (!__any_sync(0xffffffffu, c))
                     continue;
             }
