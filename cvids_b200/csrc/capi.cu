@@ -641,6 +641,24 @@ static void fill_frame_params(chs_map *m, const chs_integrator *integ, const flo
             fp.planes[p][k] = pl.fg.plane[p].n[k];
         fp.planes[p][3] = pl.fg.plane[p].d;
     }
+    {
+        // view pyramid for culling (classify_box): u >= -3  <=>  fx x + (cx + 3) z >= 0 for z > 0, etc., in camera coordinates;
+        // n_world = R n_cam, d = -n_world . t
+        const float m = 3.0f;
+        const float nc[5][3] = {{cam->fx, 0.0f, cam->cx + m}, {-cam->fx, 0.0f, (float)cam->width + m - cam->cx},
+                                {0.0f, cam->fy, cam->cy + m}, {0.0f, -cam->fy, (float)cam->height + m - cam->cy}, {0.0f, 0.0f, 1.0f}};
+        for (int p = 0; p < 5; p++)
+        {
+            float d = 0.0f;
+            for (int r = 0; r < 3; r++)
+            {
+                const float nw = pose[r * 4 + 0] * nc[p][0] + pose[r * 4 + 1] * nc[p][1] + pose[r * 4 + 2] * nc[p][2];
+                fp.view_planes[p][r] = nw;
+                d -= nw * pose[r * 4 + 3];
+            }
+            fp.view_planes[p][3] = d;
+        }
+    }
     size_t off = 0;
     fp.hiz_levels = kHizLevels;
     for (int l = 0; l < kHizLevels; l++)

@@ -211,7 +211,9 @@ struct FrameParams
     float wu_const;           // constant truncator: weight / (5 * trunc), formed on the host in binary32
     // candidate enumeration
     int lo[3], n[3];
-    float planes[6][4];
+    float planes[6][4];       // the reference's (quirky) frustum planes, for the exact Frustum::Intersects
+    float view_planes[5][4];  // the camera's real view pyramid in world space (left, right, top, bottom with a 3 pixel margin, z >= 0):
+                              // n.x + d >= 0 inside. Culling only: a box entirely outside one of them projects off the image.
     float2 *hiz[kHizLevels];  // {min lo, max hi} per tile
     int hizW[kHizLevels], hizH[kHizLevels];
     int hiz_levels;           // levels in use: the coarsest one has at most 3x3 tiles (or is level kHizLevels - 1)

@@ -146,6 +146,22 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
         chunkBand |= __shfl_xor_sync(0xffffffffu, chunkBand, o);
         chunkFree |= __shfl_xor_sync(0xffffffffu, chunkFree, o);
     }
+    // Does the chunk exist? One lookup per chunk that stage 1 could not dismiss, BEFORE the per-brick stage: most of the view
+    // pyramid is free space without chunks, and a chunk that does not exist only matters if some frame may hit it.
+    int slot = -1;
+    unsigned long long flags = 0ull;
+    if (leader && (chunkBand || (chunkFree && carve)))
+    {
+        slot = hash_lookup(map, pack_id(x, y, z));
+        if (slot >= 0 && chunkFree && carve)
+            flags = map.brick_flags[slot];
+    }
+    const int leaderLane = (int)(lane & ~(unsigned)(GL - 1));
+    slot = __shfl_sync(0xffffffffu, slot, leaderLane);
+    flags = __shfl_sync(0xffffffffu, flags, leaderLane);
+    // free-space frames can only carve observed voxels: they matter for an existing chunk with a carvable brick, or after a band
+    // frame of this batch (which may create one)
+    const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
     // stage 2: the lane's brick(s) in the surviving frames
     unsigned bandM[BPL], freeM[BPL];
 #pragma unroll
@@ -154,11 +170,11 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     if (NB == 1)
     {
         bandM[0] = chunkBand;
-        freeM[0] = chunkFree;
+        freeM[0] = freeTodo;
     }
     else
     {
-        unsigned todo = chunkBand | (carve ? chunkFree : 0u);
+        unsigned todo = chunkBand | freeTodo;
         while (todo)
         {
             const int f = __ffs(todo) - 1;
@@ -185,17 +201,6 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
             u |= __shfl_xor_sync(0xffffffffu, u, o);
         chunkBand = u;
     }
-    int slot = -1;
-    unsigned long long flags = 0ull;
-    if (leader && (chunkBand || (chunkFree && carve)))
-    {
-        slot = hash_lookup(map, pack_id(x, y, z));
-        if (slot >= 0 && chunkFree && carve)
-            flags = map.brick_flags[slot];
-    }
-    const int leaderLane = (int)(lane & ~(unsigned)(GL - 1));
-    slot = __shfl_sync(0xffffffffu, slot, leaderLane);
-    flags = __shfl_sync(0xffffffffu, flags, leaderLane);
 
     // per-frame candidate counts: lane f of the warp accumulates frame f
     int myCount = 0;
