@@ -170,6 +170,76 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# side lines (not the headline): BASELINE configs[4] shape (8 agents) and configs[3] shape (1 cm hall, meshing-heavy)
+
+def side_lines(torch, capi, dev, stream, flush_l2, pool_chunks):
+    out = {}
+    # --- 8 agents x 640x480 depth only, 2 cm: the eight frames of a time step are one batch (arrival order) ---
+    cfg = scenes.CONFIG5
+    integ = capi.ProjectionIntegrator(capi.TRUNC_CONSTANT, cfg.truncation, cfg.weight, cfg.carve, cfg.carve_dist)
+    camv = cfg.cam.as_array()
+    n_t, warm_t = 8, 2
+    frames = [[scenes.stream_frame(cfg, t, agent=a) for a in range(cfg.agents)] for t in range(n_t)]
+    dd = [[torch.from_numpy(f[0]).to(dev) for f in grp] for grp in frames]
+    m = capi.Chisel(cfg.chunk, cfg.resolution, False, stream=stream.cuda_stream, initial_chunks=pool_chunks)
+    t_dev, upd = 0.0, 0
+    for t in range(n_t):
+        flush_l2(t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        m.integrate_batch(integ, None, [f[2] for f in frames[t]], camv, device_ptrs=[(d.data_ptr(), None) for d in dd[t]])
+        e1.record(stream)
+        sts = m.batch_stats()
+        if t >= warm_t:
+            t_dev += e0.elapsed_time(e1) / 1000.0
+            upd += sum(s["n_upd"] for s in sts)
+    out["eight_agents_2cm"] = {"workload": "configs[4] shape: 8 agents x 640x480 depth, 2 cm; step = the 8 frames of one time step in one batch",
+                               "value": upd / t_dev / 1e9, "unit": UNIT, "frames_per_s": 8 * (n_t - warm_t) / t_dev,
+                               "ms_per_step": 1000.0 * t_dev / (n_t - warm_t), "steps": n_t - warm_t, "map_chunks": m.frame_stats()["total_chunks"]}
+    m.close()
+    # --- 1 cm hall, lawn-mower sweep, then ONE re-mesh of everything dirty (meshing-heavy) ---
+    hall = scenes.hall(seed=3)
+    cam = scenes.Camera(525.0, 525.0, 319.5, 239.5, 640, 480, near=0.05, far=5.0)
+    res = 0.01
+    integ = capi.ProjectionIntegrator(capi.TRUNC_CONSTANT, float(np.float32(4.0) * np.float32(res)), 1.0, True, 0.05)
+    poses = [scenes.yaw_pose(0.35 * (i % 6), (-20.0 + 1.0 * (i // 6) + 0.15 * (i % 6), -20.0 + 0.9 * (i % 6), 0.0)) for i in range(24)]
+    dd = [torch.from_numpy(scenes.render(hall, cam, p)[0]).to(dev) for p in poses]
+    m = capi.Chisel(16, res, False, stream=stream.cuda_stream, initial_chunks=pool_chunks)
+    m.set_profiling(True)
+    t_dev, upd = 0.0, 0
+    for i in range(0, 24, 8):
+        flush_l2(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        m.integrate_batch(integ, None, poses[i:i + 8], cam.as_array(), device_ptrs=[(d.data_ptr(), None) for d in dd[i:i + 8]])
+        e1.record(stream)
+        sts = m.batch_stats()
+        t_dev += e0.elapsed_time(e1) / 1000.0
+        upd += sum(s["n_upd"] for s in sts)
+        tm = m.timings()
+        kern = {k: kern.get(k, 0.0) + tm[k + "_ms"] / 3.0 for k in ("prepare", "candidates", "integrate")} if i else \
+            {k: tm[k + "_ms"] / 3.0 for k in ("prepare", "candidates", "integrate")}
+        cand = sum(s["candidates"] for s in sts)
+    dirty = m.get_meshes_to_update()
+    m._lib.chs_update_meshes(m._h)
+    for _ in range(2):
+        m.set_dirty(dirty)
+        flush_l2(1)
+        assert m._lib.chs_update_meshes(m._h) == 0
+    mt, mc = m.timings(), m.last_mesh_counts()
+    b_mc = mc["n_chunks"] * 17 ** 3 * 8 + mc["n_vertices"] * 24 + mc["n_grids"] * 12
+    out["hall_1cm"] = {"workload": "configs[3] shape: 50x50x5 m pillar hall, 1 cm voxels, 640x480 depth, 24 frames in batches of 8, then one re-mesh of the whole dirty set",
+                       "integration": {"value": upd / t_dev / 1e9, "unit": UNIT, "frames_per_s": 24 / t_dev, "voxel_updates_per_frame": upd / 24,
+                                       "ms_per_8_frame_batch": {"prepare": kern["prepare"], "candidates": kern["candidates"], "bricks": kern["integrate"]},
+                                       "candidate_chunks_last_batch": cand},
+                       "remesh": {"dirty_ids": int(len(dirty)), "remeshed_chunks": mc["n_chunks"], "triangles": mc["n_vertices"] // 3,
+                                  "device_ms": mt["mesh_ms"], "count_ms": mt["mesh_count_ms"], "emit_ms": mt["mesh_emit_ms"],
+                                  "algorithmic_bytes": b_mc, "achieved_gbs": b_mc / (mt["mesh_ms"] * 1e-3) / 1e9 if mt["mesh_ms"] > 0 else None}}
+    m.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # CUDA arm
 
 def run_cuda(args):
@@ -527,6 +597,11 @@ def run_cuda(args):
             "wall_s_timed_region": wall_a,
             "mesh": mesh_info,
         }
+        if world == 1 and not args.quick and not args.no_side_lines:
+            try:
+                line["side_lines"] = side_lines(torch, capi, dev, stream, flush_l2, args.pool_chunks)
+            except Exception as ex:                              # side lines must never cost the headline
+                line["side_lines"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu:
             n_cpu = min(steps * B, args.cpu_frames)
             r = cpu_arm(frames, 0, n_cpu, budget_s=args.cpu_budget)
@@ -547,6 +622,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-side-lines", action="store_true", help="skip the 8-agent and 1 cm hall side lines")
     ap.add_argument("--quick", action="store_true", help="A/B runs: only the flushed device leg and the profiling leg are meaningful")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--pool-chunks", type=int, default=98304,

@@ -562,7 +562,10 @@ static int plan_frame(chs_map *m, const float pose[12], const chs_camera *cam, F
 
 // Capacity: known counts + bounds of launches whose counters have not come back yet + this launch (`cand` new chunks,
 // `dirtyBound` dirty IDs at most); work lists for `cand` chunks.
-static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound)
+// poolLater (fused path): if the pool cannot hold the worst case (every candidate becomes a chunk -- 48 KB each, far too
+// pessimistic for large candidate boxes), do not grow it here: *poolLater is set and the caller sizes the pool from the exact
+// number of chunks the candidates kernel found possible, before it launches the kernel that creates them.
+static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound, bool *poolLater = nullptr)
 {
     cudaStream_t st = m->stream;
     int rc = poll_inflight(m, false);
@@ -574,6 +577,8 @@ static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound)
         chunkUb += f.newBound;
         dirtyUb += f.dirtyBound;
     }
+    if (poolLater)
+        *poolLater = false;
     if (chunkUb > m->dm.capacity || (size_t)chunkUb * 2 > m->hashSize || (size_t)dirtyUb * 2 > m->dirtySize)
     {
         // tighten the bound before growing: wait for outstanding counters
@@ -582,7 +587,12 @@ static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound)
         // head-room for several launches in flight: the bound per launch is the candidate count
         const long long wantChunks = m->knownChunks + 4 * cand + m->knownChunks / 4;
         const long long wantDirty = m->knownDirty + 4 * dirtyBound + m->knownDirty / 4;
-        if ((rc = ensure_pool(m, wantChunks)) || (rc = ensure_hash(m, wantChunks)) || (rc = ensure_dirty(m, wantDirty)))
+        const bool defer = poolLater && m->knownChunks + cand > m->dm.capacity && cand > 32768;
+        if (defer)
+            *poolLater = true;
+        else if ((rc = ensure_pool(m, wantChunks)))
+            return rc;
+        if ((rc = ensure_hash(m, defer ? m->knownChunks + cand : wantChunks)) || (rc = ensure_dirty(m, wantDirty)))
             return rc;
     }
     const int bpa = m->cfg.chunk_size / 8;
@@ -829,7 +839,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     if (unionCand > (1ll << 26))
         return CHS_ERR_NOT_FOUND;                                   // frames too far apart to share a box: the caller falls back to single frames
-    if ((rc = ensure_capacity(m, unionCand, dirtyBound)))
+    bool poolLater = false;
+    if ((rc = ensure_capacity(m, unionCand, dirtyBound, &poolLater)))
         return rc;
 
     const size_t npx = (size_t)cam->width * cam->height;
@@ -996,7 +1007,30 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     info.colorPath = colorPath;
     info.perPixel = perPixel;
     info.profiling = m->profiling;
-    CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st));
+    if (!poolLater)
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 3));
+    else
+    {
+        // large candidate box and a pool that could not take the worst case: run prepare + candidates, read how many chunks the
+        // batch can create at most (its virtual candidates), size the pool for exactly that, then run the brick kernel
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 1));
+        BatchCounters hc;
+        CHS_CUDA(cudaMemcpyAsync(&hc, bs.dBctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+        CHS_CUDA(cudaStreamSynchronize(st));
+        m->inflight.pop_back();                                     // everything before this batch has completed: retire it first
+        if ((rc = poll_inflight(m, true)))
+            return rc;
+        Counters cc;
+        CHS_CUDA(cudaMemcpyAsync(&cc, m->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CHS_CUDA(cudaStreamSynchronize(st));
+        m->knownChunks = cc.n_chunks;
+        if ((rc = ensure_pool(m, (long long)cc.n_chunks + hc.new_count + 1024)))
+            return rc;
+        inf.newBound = hc.new_count;
+        m->inflight.push_back(inf);
+        bp.slot_batch = m->dSlotBatch;                              // the pool's side arrays may have moved
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 2));
+    }
     CHS_CUDA(cudaEventRecord(bs.released, st));
     bs.used = true;
     if (m->profiling)

@@ -783,7 +783,7 @@ static int batch_resident(Kern kernel, int threads)
 
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                                        cudaEvent_t prepared, cudaStream_t st)
+                                        cudaEvent_t prepared, cudaStream_t st, int phases)
 {
     static int residentBricks = 0;
     if (!residentBricks)
@@ -795,6 +795,8 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
     cudaError_t e;
+    if (phases & 1)
+    {
     if (info.profiling && (e = cudaEventRecord(evt[0], stPrep)) != cudaSuccess)
         return e;
     const int tilesX = (info.W + 63) / 64, tiles = tilesX * ((info.H + 63) / 64);
@@ -805,7 +807,12 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     if ((e = cudaEventRecord(prepared, stPrep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, prepared, 0)) != cudaSuccess)
         return e;
     batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
-    if (info.profiling && ((e = cudaEventRecord(evt[2], st)) != cudaSuccess || (e = cudaEventRecord(evt[7], st)) != cudaSuccess))
+    if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
+        return e;
+    }
+    if (!(phases & 2))
+        return cudaGetLastError();
+    if (info.profiling && (e = cudaEventRecord(evt[7], st)) != cudaSuccess)
         return e;
     batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)
@@ -815,23 +822,23 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
 
 template <int CS>
 static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                                   cudaEvent_t prepared, cudaStream_t st)
+                                   cudaEvent_t prepared, cudaStream_t st, int phases)
 {
     if (info.colorPath)
-        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, stPrep, prepared, st)
-                             : launch_batch_variant<CS, true, false>(bp, map, info, evt, stPrep, prepared, st);
-    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, stPrep, prepared, st)
-                         : launch_batch_variant<CS, false, false>(bp, map, info, evt, stPrep, prepared, st);
+        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, stPrep, prepared, st, phases)
+                             : launch_batch_variant<CS, true, false>(bp, map, info, evt, stPrep, prepared, st, phases);
+    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, stPrep, prepared, st, phases)
+                         : launch_batch_variant<CS, false, false>(bp, map, info, evt, stPrep, prepared, st, phases);
 }
 
 cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                         cudaEvent_t prepared, cudaStream_t st)
+                         cudaEvent_t prepared, cudaStream_t st, int phases)
 {
     switch (map.cs)
     {
-    case 8: return launch_batch_cs<8>(bp, map, info, evt, stPrep, prepared, st);
-    case 16: return launch_batch_cs<16>(bp, map, info, evt, stPrep, prepared, st);
-    default: return launch_batch_cs<32>(bp, map, info, evt, stPrep, prepared, st);
+    case 8: return launch_batch_cs<8>(bp, map, info, evt, stPrep, prepared, st, phases);
+    case 16: return launch_batch_cs<16>(bp, map, info, evt, stPrep, prepared, st, phases);
+    default: return launch_batch_cs<32>(bp, map, info, evt, stPrep, prepared, st, phases);
     }
 }
 

@@ -67,8 +67,9 @@ struct BatchLaunchInfo
 };
 // The prepare kernel runs on stPrep and records `prepared`; candidates and bricks run on st after waiting for it.
 // events (profiling): [0] start, [1] after prepare (both on stPrep), [2] = [7] after candidates, [3] after bricks (on st)
+// phases: bit 0 = prepare + candidates, bit 1 = bricks (3 = the whole batch; the host may size the pool between the two)
 cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                         cudaEvent_t prepared, cudaStream_t st);
+                         cudaEvent_t prepared, cudaStream_t st, int phases);
 
 // dCounters[4] (zeroed): rcp mismatches, rcp tested, div mismatches, div tested
 cudaError_t launch_selftest_arithmetic(unsigned long long *dCounters, unsigned long long divPairs, cudaStream_t st);

@@ -247,3 +247,49 @@ def test_batch_depth_in_millimetres_converted_on_device():
             assert g[c] == w[c], "frame %d counter %s: %d vs %d" % (j, c, g[c], w[c])
     common.assert_state_equal(a.state(), b.state())
     assert np.array_equal(a.dirty(), b.dirty())
+
+
+def test_full_size_config2_batch_equals_frame_by_frame():
+    """BASELINE configs[1] at full size (752x480, 2 cm, colour, NaN pixels): 20 frames as two fused batches of 10 leave exactly
+    the map, dirty set, per-frame counters and meshes that 20 single-frame calls leave (the oracle is too slow at this size; the
+    single-frame path is pinned to it at small sizes)."""
+    cfg = scenes.CONFIG2
+    setup = Setup(cfg.chunk, cfg.resolution, True)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    camv = cfg.cam.as_array()
+    frames = [scenes.stream_frame(cfg, f) for f in range(20)]
+    single = []
+    for depth, col, pose in frames:
+        a.integrate(depth, pose, camv, col)
+        single.append(a.counters())
+    got = []
+    for i in (0, 10):
+        grp = frames[i:i + 10]
+        b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+        got += b.m.batch_stats()
+    for j, (g, w) in enumerate(zip(got, single)):
+        for k in COUNTERS:
+            assert g[k] == w[k], "frame %d counter %s: batch %d single %d" % (j, k, g[k], w[k])
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
+    a.remesh()
+    b.remesh()
+    common.assert_meshes_equal(a.meshes(), b.meshes())
+
+
+def test_full_size_config5_eight_agents_one_batch_per_time_step():
+    """BASELINE configs[4] shape at full size: 8 agents, 640x480 depth only, 2 cm; the eight frames of a time step form one batch
+    (different poses, one union candidate box). Equal to frame-by-frame integration in arrival order."""
+    cfg = scenes.CONFIG5
+    setup = Setup(cfg.chunk, cfg.resolution, False)
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "cuda")
+    camv = cfg.cam.as_array()
+    for t in range(3):
+        grp = [scenes.stream_frame(cfg, t, agent=ag) for ag in range(8)]
+        for depth, _, pose in grp:
+            a.integrate(depth, pose, camv)
+        b.m.integrate_batch(b.integ, [g[0] for g in grp], [g[2] for g in grp], camv)
+        st = b.m.batch_stats()
+        assert len(st) == 8 and all(s["error_flags"] == 0 for s in st)
+    common.assert_state_equal(a.state(), b.state())
+    assert np.array_equal(a.dirty(), b.dirty())
