@@ -300,11 +300,10 @@ class Chisel:
             _check(self._lib.chs_integrate_depth_color(self._h, C.byref(integ), device_ptrs[0], MEM_DEVICE, _ptr(p),
                                                        C.byref(cam), device_ptrs[1], channels, _ptr(cp), C.byref(ccam)))
 
-    def integrate_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
-                        device_ptrs=None, channels=None, truncs=None, host_async=False):
-        """n consecutive frames in one call (chs_integrate_batch): the same result as n calls of integrate_depth_scan[_color]
-        in order. depths/colors: lists of host arrays, or with device_ptrs=[(depth_ptr, color_ptr|None, trunc_ptr|None), ...]
-        device memory. colors=None (and no colour device pointers): the depth path."""
+    def prepare_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
+                      device_ptrs=None, channels=None, truncs=None, host_async=False):
+        """Marshal the arguments of one chs_integrate_batch call once (a streaming caller that owns a ring of frame buffers
+        does this at start-up); integrate_prepared() then only makes the call. See integrate_batch for the arguments."""
         cam = make_camera(cam)
         n = len(poses)
         use_color = (colors is not None) or (device_ptrs is not None and len(device_ptrs) and device_ptrs[0][1] is not None)
@@ -314,8 +313,8 @@ class Chisel:
         for i in range(n):
             p = _pose(poses[i])
             cp = p if (color_poses is None or color_poses[i] is None) else _pose(color_poses[i])
-            arr[i].pose[:] = p.tolist()
-            arr[i].color_pose[:] = cp.tolist()
+            C.memmove(arr[i].pose, p.ctypes.data, 48)
+            C.memmove(arr[i].color_pose, cp.ctypes.data, 48)
             if device_ptrs is None:
                 if np.asarray(depths[i]).dtype == np.uint16:           # millimetres (ROS 16UC1): converted on the device
                     d = np.ascontiguousarray(depths[i], np.uint16)
@@ -339,10 +338,23 @@ class Chisel:
                 arr[i].trunc_per_pixel = device_ptrs[i][2] if len(device_ptrs[i]) > 2 else None
         integ = integrator.as_struct(device_ptr=0) if integrator.trunc_kind == TRUNC_PER_PIXEL else integrator.as_struct()
         mem = MEM_DEVICE if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
+        return (integ, n, arr, mem, cam, int(channels or 0), ccam, keep)
+
+    def integrate_prepared(self, prepared):
+        integ, n, arr, mem, cam, channels, ccam, _keep = prepared
+        _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, mem, C.byref(cam), channels,
+                                             C.byref(ccam) if ccam is not None else None))
+
+    def integrate_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
+                        device_ptrs=None, channels=None, truncs=None, host_async=False):
+        """n consecutive frames in one call (chs_integrate_batch): the same result as n calls of integrate_depth_scan[_color]
+        in order. depths/colors: lists of host arrays (float32 metres, or uint16 millimetres), or with
+        device_ptrs=[(depth_ptr, color_ptr|None, trunc_ptr|None), ...] device memory. colors=None (and no colour device
+        pointers): the depth path. host_async: the host buffers stay untouched until the call's ticket has been waited for."""
+        prepared = self.prepare_batch(integrator, depths, poses, cam, colors, color_poses, color_cam, device_ptrs, channels, truncs, host_async)
         if host_async:
-            self._keep = (self._keep or [])[-64:] + [keep]          # the buffers must outlive the call
-        _check(self._lib.chs_integrate_batch(self._h, C.byref(integ), n, arr, mem,
-                                             C.byref(cam), int(channels or 0), C.byref(ccam) if ccam is not None else None))
+            self._keep = (self._keep or [])[-64:] + [prepared]      # the buffers must outlive the call
+        self.integrate_prepared(prepared)
 
     def last_batch_ticket(self) -> int:
         t = C.c_int64()
