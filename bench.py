@@ -68,17 +68,20 @@ class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
+    def __init__(self, indices, enabled=True):
+        """indices: the GPUs of the job. ONE sampler (rank 0) queries all of them in one nvidia-smi call: a poller per rank
+        contends with the kernel launches of eight processes for the driver."""
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.indices, self.samples, self._halt, self.enabled = list(indices), [], threading.Event(), enabled
 
     def run(self):
-        while not self._halt.is_set():
+        while self.enabled and not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                for row in out.split("\n"):
+                    if row.strip():
+                        self.samples.append([x.strip() for x in row.split(",")])
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -293,7 +296,22 @@ def run_cuda(args):
         for i, fr in enumerate(frames):
             h_frames[i].copy_(torch.from_numpy(sharding.pack_frame(fr[0], fr[1])))
         d_frames.copy_(h_frames)
-    recv = torch.empty((B, fbytes), dtype=torch.uint8, device=dev)
+    # N > 1, sharded ingest: the frames of a step enter the node through ALL ranks -- rank r ingests the r-th of N equal byte
+    # ranges of the step's contiguous [depth | colour] x B block (over its own PCIe link in the e2e leg) and ONE all-gather
+    # replicates the block. Every byte is still broadcast over NVLink from its ingest rank, all ingest ranks at once, and all
+    # ranks finish together (a ring broadcast from a single root reaches the last of 8 ranks only after ~300 us). Set-up,
+    # outside every timed region: every rank gets a copy of the synthetic stream so that it can play the ingest rank of its range.
+    share = ((B * fbytes + world - 1) // world + 15) // 16 * 16          # bytes per rank and step
+    if world > 1:
+        dist.broadcast(d_frames, 0)
+        if rank != 0:
+            h_frames = torch.empty((n_unique, fbytes), dtype=torch.uint8).pin_memory()
+            h_frames.copy_(d_frames)
+        torch.cuda.synchronize(dev)
+    recv = torch.empty(max(B * fbytes, share * world) + fbytes, dtype=torch.uint8, device=dev)   # all-gather output = the step's block
+    mine = torch.empty(max(share, fbytes), dtype=torch.uint8, device=dev)                        # this rank's range when it needs staging
+    d_flat = d_frames.view(-1)
+    h_flat = h_frames.view(-1) if h_frames is not None else None
     # L2 flush between timed steps: write a 256 MiB buffer, then read another one, so that L2 ends up full of CLEAN
     # foreign lines (a write-only flush leaves ~126 MB of dirty lines whose write-back would be charged to the step)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
@@ -319,34 +337,57 @@ def run_cuda(args):
 
     prepared_dev = {}
 
-    def source_of(step, b):
-        """(tensor to broadcast or None, needs staging copy) for a step of b frames."""
+    def my_range(step, b):
+        """This rank's byte range of the step's block: (offset into the flat stream, valid bytes), or None when the frames of the
+        step are not contiguous in the stream (the orbit wraps inside the step)."""
         ids = frame_ids(step, b)
-        if world == 1:
-            return ids, None, False
-        contiguous = ids[-1] - ids[0] == b - 1            # consecutive frames are contiguous in d_frames unless the orbit wraps
-        if rank == 0 and contiguous:
-            return ids, d_frames[ids[0]:ids[0] + b], False
-        return ids, recv[:b], rank == 0
+        lo = min(rank * share, b * fbytes)
+        n = min((rank + 1) * share, b * fbytes) - lo
+        if ids[-1] - ids[0] != b - 1:
+            return None, lo, n
+        return ids[0] * fbytes + lo, lo, n
+
+    def exchange(step, b):
+        if b == 1:
+            i = frame_ids(step, 1)[0]
+            sharding.broadcast_frame(d_frames[i:i + 1] if rank == 0 else recv[:fbytes].view(1, fbytes), 0)
+            return
+        off, lo, n = my_range(step, b)
+        if off is not None and n == share:
+            block = d_flat[off:off + share]                   # a full range of the resident stream: no staging copy
+        else:
+            if n > 0:
+                if off is not None:
+                    mine[:n].copy_(d_flat[off:off + n])
+                else:
+                    whole = d_frames[frame_ids(step, b)].view(-1)
+                    mine[:n].copy_(whole[lo:lo + n])
+            block = mine[:share]
+        dist.all_gather_into_tensor(recv[:share * world], block)
 
     def prepared_for(m, step, b):
         key = (b, step)
         if key not in prepared_dev:
-            ids, src, _ = source_of(step, b)
-            base = src.data_ptr() if world > 1 else d_frames.data_ptr()
-            ptrs = [(base + j * fbytes, base + j * fbytes + dbytes) for j in range(b)] if world > 1 else \
-                [(base + i * fbytes, base + i * fbytes + dbytes) for i in ids]
+            ids = frame_ids(step, b)
+            if world > 1:
+                base = recv.data_ptr() if (b > 1 or rank != 0) else d_frames[ids[0]:ids[0] + 1].data_ptr()   # b == 1: root integrates in place
+                ptrs = [(base + j * fbytes, base + j * fbytes + dbytes) for j in range(b)]
+            else:
+                base = d_frames.data_ptr()
+                ptrs = [(base + i * fbytes, base + i * fbytes + dbytes) for i in ids]
             prepared_dev[key] = ptrs[0] if b == 1 else m.prepare_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
         return prepared_dev[key]
 
-    def step_device(m, step, b=B):
-        """One step = b consecutive frames, inputs resident in HBM (rank 0) -> [NCCL broadcast] -> fused integration. The call's
-        arguments (device pointers, poses) are marshalled once per (b, step) -- harness work, not part of the path."""
-        ids, src, stage = source_of(step, b)
+    mid_events = []
+
+    def step_device(m, step, b=B, mid=None):
+        """One step = b consecutive frames, inputs resident in HBM on their ingest ranks -> [NCCL all-gather] -> fused integration.
+        The call's arguments (device pointers, poses) are marshalled once per (b, step) -- harness work, not part of the path."""
+        ids = frame_ids(step, b)
         if world > 1:
-            if stage:
-                recv[:b].copy_(d_frames[ids])
-            sharding.broadcast_frame(src, 0)
+            exchange(step, b)
+            if mid is not None:
+                mid.record(stream)
         pre = prepared_for(m, step, b)
         if b == 1:
             m.integrate_depth_scan_color(integ, None, poses[ids[0]], camv, None, device_ptrs=pre, channels=channels)
@@ -364,7 +405,7 @@ def run_cuda(args):
             step_device(m, i, b)
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(range(world), enabled=(rank == 0))
         sampler.start()
         barrier()
         t0 = time.perf_counter()
@@ -376,8 +417,11 @@ def run_cuda(args):
                     # waited out by the step's broadcast, inside the timed bracket
                     dist.all_reduce(align)
                 ev[k][0].record(stream)
-                step_device(m, n_warm + k, b)
+                mid = torch.cuda.Event(enable_timing=True) if world > 1 else None
+                step_device(m, n_warm + k, b, mid)
                 ev[k][1].record(stream)
+                if mid is not None:
+                    mid_events.append((ev[k][0], mid, ev[k][1]))
         else:
             ev[0][0].record(stream)
             for k in range(n_steps):
@@ -392,6 +436,14 @@ def run_cuda(args):
 
     # ---------------- leg A: device-resident inputs, CUDA events per step, L2 flushed between steps -------------
     t_dev, wall_a, clocks = timed_leg(B, warm, steps, True)
+    bracket = None
+    if mid_events:
+        bracket = {"broadcast_us": 1000.0 * float(np.mean([a.elapsed_time(b_) for a, b_, _ in mid_events])),
+                   "integrate_us": 1000.0 * float(np.mean([b_.elapsed_time(c_) for _, b_, c_ in mid_events]))}
+        mid_events.clear()
+        allb = [None] * world
+        dist.all_gather_object(allb, bracket)
+        bracket = {"per_rank_exchange_us": [round(x["broadcast_us"], 1) for x in allb], "per_rank_integrate_us": [round(x["integrate_us"], 1) for x in allb]}
     # ---------------- leg A': same, no flush (the map working set stays in L2 as it does in a live stream) -------
     t_warm, _, _ = timed_leg(B, warm, steps, False) if not args.quick else (t_dev, 0, 0)
     # ---------------- leg S: one frame per call (chs_integrate_depth_color, the reference's call granularity) ----
@@ -471,16 +523,22 @@ def run_cuda(args):
     def step_host(step, read=True):
         ids = frame_ids(step)
         if world > 1:
-            if rank == 0:
-                for j, i in enumerate(ids):
-                    recv[j].copy_(h_frames[i], non_blocking=True)
-            sharding.broadcast_frame(recv[:B], 0)
-            base = recv.data_ptr()
-            ptrs = [(base + j * fbytes, base + j * fbytes + dbytes) for j in range(B)]
+            # every rank copies ITS byte range of the step from pinned host memory over its own PCIe link, then one all-gather
             if B == 1:
-                m.integrate_depth_scan_color(integ, None, poses[ids[0]], camv, None, device_ptrs=ptrs[0], channels=channels)
+                if rank == 0:
+                    mine[:fbytes].copy_(h_frames[ids[0]], non_blocking=True)
+                sharding.broadcast_frame((mine if rank == 0 else recv)[:fbytes].view(1, fbytes), 0)
+                p0 = (mine if rank == 0 else recv).data_ptr()
+                m.integrate_depth_scan_color(integ, None, poses[ids[0]], camv, None, device_ptrs=(p0, p0 + dbytes), channels=channels)
             else:
-                m.integrate_batch(integ, None, [poses[i] for i in ids], camv, device_ptrs=ptrs, channels=channels)
+                off, lo, n = my_range(step, B)
+                if n > 0:
+                    if off is not None:
+                        mine[:n].copy_(h_flat[off:off + n], non_blocking=True)
+                    else:
+                        mine[:n].copy_(h_frames[ids].view(-1)[lo:lo + n], non_blocking=True)
+                dist.all_gather_into_tensor(recv[:share * world], mine[:share])
+                m.integrate_prepared(prepared_for(m, step, B))
         else:
             ds, cs, ps = views_of(step)
             if B == 1:
@@ -597,17 +655,17 @@ def run_cuda(args):
             "single_frame_calls": {"value": upd_single_total / t_single / 1e9 if t_single > 0 else None, "unit": UNIT,
                                    "frames_per_s": s_steps / t_single if t_single > 0 else None, "ms_per_frame": 1000.0 * t_single / max(s_steps, 1),
                                    "note": "one frame per call (chs_integrate_depth_color, the reference's call granularity), frames %d..%d, L2 flushed" % (s_warm, s_warm + s_steps - 1)},
-            "config": {"workload": WORKLOAD % B, "parallelism": "chunk-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "1 GPU",
+            "config": {"workload": WORKLOAD % B, "parallelism": "chunk-hash shard x%d; every step's frame block ingested in %d equal byte ranges (one per rank), replicated by one NCCL all-gather" % (world, world) if world > 1 else "1 GPU",
                        "l2": "256 MiB write + 256 MiB read between steps, excluded from the step time" if flush is not None else
                              "no flush: frame stream (%d MB) > L2, map working set stays in L2" % ((h2d * nfr) >> 20),
-                       "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
+                       "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total, "rank0_bracket": bracket,
                        "rank0_per_step": {"candidate_chunks": float(np.mean([p[2] for p in per_step])),
                                           "brick_units": float(np.mean([p[1] for p in per_step])),
                                           "new_chunk_candidates": float(np.mean([p[6] for p in per_step])),
                                           "updated_chunks": float(np.mean([p[4] for p in per_step])),
                                           "new_chunks": float(np.mean([p[5] for p in per_step]))}},
             "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * B / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * B,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * B * world,
                     "timing": "wall clock; per step chs_integrate_batch(pinned host frames, CHS_MEM_HOST_ASYNC), then chs_wait_batch of the PREVIOUS step's counters "
                               "(depth-2 pipeline: copies of step k overlap kernels of step k-1)" if B > 1 else
                               "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
