@@ -16,9 +16,9 @@ counters, wall clock per step. `roofline`: algorithmic bytes of the integrate ke
 against MEASURED_PEAKS.json. `cpu_baseline`: the reference CPU OpenChisel (oracle/_ref, else the C port) on a
 bounded sample of the same frames on this box's host cores.
 
-N > 1: one process per GPU; the chunk-ID hash space is partitioned (owner = chs_owner(id) % N), rank 0 holds the
-stream and broadcasts each frame with NCCL, every rank integrates the chunks it owns. Total work is fixed =>
-"scaling": "strong". Time is the max over ranks.
+N > 1: one process per GPU; the chunk-ID hash space is partitioned (owner = chs_owner(id) % N). Every step's frame block is
+ingested in N equal byte ranges, one per rank, and replicated with ONE NCCL all-gather; every rank then
+integrates the chunks it owns. Total work is fixed => "scaling": "strong". Time is the max over ranks.
 """
 from __future__ import annotations
 
