@@ -6,14 +6,17 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- the single-agent EuRoC-shape 752x480 synthetic depth+colour
 stream of the analytic room, 2 cm voxels, 16^3 chunks, truncation 4 voxels, ConstantWeighter(1), carving on;
-one STEP = one frame through IntegrateDepthScanColor (chs_integrate_depth_color). Frames W .. W+K-1 of the 200-frame
-orbit are timed after W warm-up frames from an empty map.
+one STEP = --batch (default 10) consecutive frames handed over in ONE chs_integrate_batch call (the fused multi-frame
+kernels; bit-identical to IntegrateDepthScanColor frame by frame; 10 = the period of the reference's UpdateMeshes gate,
+i.e. what the drop-in facade queues without any observable difference). --batch 1: one frame per call. Steps
+W .. W+K-1 of the 200-frame orbit are timed after W warm-up steps from an empty map.
 
 Metric: TSDF voxel updates per second (GVox/s; a "voxel update" is one DistVoxel::Integrate, SURVEY.md 8(d)), with
 frames/s alongside. `value`: inputs resident in HBM, device time from CUDA events per step, L2 flushed between
-steps (flush excluded). `e2e`: the same call with pinned HOST frames (H2D inside) plus the D2H read of the frame's
-counters, wall clock per step. `roofline`: algorithmic bytes of the integrate kernel / its event-timed duration,
-against MEASURED_PEAKS.json. `cpu_baseline`: the reference CPU OpenChisel (oracle/_ref, else the C port) on a
+steps (flush excluded). `e2e`: the same call with pinned HOST frames (H2D inside) plus the D2H read of every step's
+per-frame counters (depth-2 pipeline), wall clock per step. `roofline`: algorithmic bytes of the brick kernel / its
+event-timed duration, against MEASURED_PEAKS.json; `traffic` from the committed ncu capture. `single_frame_calls`,
+`l2_warm`, `e2e_depth_mm`, `mesh`, `side_lines`: context, see DESIGN.md section 7. `cpu_baseline`: the reference CPU OpenChisel (oracle/_ref, else the C port) on a
 bounded sample of the same frames on this box's host cores.
 
 N > 1: one process per GPU; the chunk-ID hash space is partitioned (owner = chs_owner(id) % N). Every step's frame block is
