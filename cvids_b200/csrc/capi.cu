@@ -1003,7 +1003,6 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     info.cW = colorPath ? ccam->width : 0;
     info.cH = colorPath ? ccam->height : 0;
     info.unionCandidates = unionCand;
-    info.newHint = m->haveFrame ? std::max<long long>(64, 2ll * m->lastFrame.new_count * K) : unionCand;
     info.colorPath = colorPath;
     info.perPixel = perPixel;
     info.profiling = m->profiling;

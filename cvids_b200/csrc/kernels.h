@@ -62,7 +62,6 @@ struct BatchLaunchInfo
 {
     int W, H, cW, cH;               // depth / colour image size (identical for all frames of a batch)
     long long unionCandidates;      // chunk IDs in the union box
-    long long newHint;
     bool colorPath, perPixel, profiling;
 };
 // The prepare kernel runs on stPrep and records `prepared`; candidates and bricks run on st after waiting for it.

@@ -1,10 +1,11 @@
 // mesh.cu -- incremental marching cubes over the dirty chunk set (sm_100a).
 //
 //   mesh_select_kernel  dirty ID list -> pool slots of the IDs that exist (warp-ballot compaction)
-//   mesh_count_kernel   per chunk: halo tile in shared memory, cube configuration per cell, triangle / grid counts
+//   mesh_count_kernel   per chunk: one-byte halo tile in shared memory, cube configuration of every cell ONCE (memory order),
+//                       written by reference rank to a per-chunk configuration row; triangle / grid counts
 //   mesh_scan_kernel    exclusive prefix sums over chunks -> vertex and grid offsets
-//   mesh_emit_kernel    per chunk: same classification, block prefix sum in the REFERENCE'S cell order, emission of
-//                       vertices + flat normals + grids, then gradient normals and colours per vertex
+//   mesh_emit_kernel    per chunk: configuration row + SDF halo tile, block prefix sum in the REFERENCE'S cell order, one
+//                       occupied cell per thread -> vertices + flat normals + grids, then gradient normals and colours per vertex
 //
 // Replaces ChunkManager::RecomputeMeshes / RecomputeMesh / GenerateMesh / Extract{Inside,Border}VoxelMesh
 // (OC ChunkManager.cpp:91-169, 259-447), MarchingCubes::MeshCube & friends (OC MarchingCubes.h:73-146),
@@ -135,25 +136,6 @@ __device__ void load_halo(const DeviceMap &map, int slot, float wMin, float *til
     __syncthreads();
 }
 
-
-// returns the cube configuration, or -1 if any corner is unobserved
-template <int CS>
-__device__ __forceinline__ int cell_config(const float *tileS, const unsigned char *tileW, int x, int y, int z, float *sdf)
-{
-    constexpr int H = CS + 1;
-    int cfg = 0;
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-    {
-        const int ti = ((z + corner_dz(i)) * H + (y + corner_dy(i))) * H + (x + corner_dx(i));
-        const float v = tileS[ti];
-        sdf[i] = v;
-        ok &= (tileW[ti] & 1) != 0;
-        cfg |= (v < 0.0f) ? (1 << i) : 0;                   // MarchingCubes::CalculateVertexConfiguration (MarchingCubes.h:106-116)
-    }
-    return ok ? cfg : -1;
-}
 
 // Rank of cell (x, y, z) in the reference's traversal (ChunkManager.cpp:393-441): interior z,y,x; +X face; +Y face; +Z face.
 // Inverse of cell_of_rank.
