@@ -76,7 +76,7 @@ EXPORTS = (
     "chs_get_batch_stats", "chs_last_batch_ticket", "chs_wait_batch", "chs_get_frame_stats",
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
-    "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic",
+    "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic", "chs_host_alloc", "chs_host_free",
 )
 
 _lib = None
@@ -126,6 +126,9 @@ def load_library(build_if_missing: bool = True):
     lib.chs_frustum.argtypes = [vp, C.POINTER(chs_camera), vp, vp, vp]
     lib.chs_candidate_ids.argtypes = [i32, C.c_float, vp, C.POINTER(chs_camera), vp, i64, C.POINTER(i64)]
     lib.chs_selftest_arithmetic.argtypes = [i64, C.POINTER(i64 * 4)]
+    lib.chs_host_alloc.restype = C.c_void_p
+    lib.chs_host_alloc.argtypes = [C.c_size_t]
+    lib.chs_host_free.argtypes = [vp]
     lib.chs_truncation.restype = C.c_float
     lib.chs_truncation.argtypes = [i32, C.c_float, C.c_float]
     lib.chs_owner.restype = C.c_uint32

@@ -1993,6 +1993,23 @@ int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], co
     return CHS_OK;
 }
 
+void *chs_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void chs_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
 int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4])
 {
     if (!out || div_pairs < 0)

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <chisel_b200.h>
@@ -49,7 +50,11 @@ class Chisel
     }
     Chisel(const Chisel &) = delete;                 // the flush hook installed in the ChunkManager points at this object
     Chisel &operator=(const Chisel &) = delete;
-    virtual ~Chisel() { chunkManager.SetBeforeDeviceRead(std::function<void()>()); }
+    virtual ~Chisel()
+    {
+        chunkManager.SetBeforeDeviceRead(std::function<void()>());
+        chs_host_free(ring);
+    }
 
     const ChunkManager &GetChunkManager() const { return chunkManager; }
     ChunkManager &GetMutableChunkManager() { return chunkManager; }
@@ -70,23 +75,24 @@ class Chisel
     // Send the queued frames to the device now.
     void Flush() const
     {
-        if (queue.empty())
+        if (queued == 0)
             return;
-        std::vector<Queued> pending;
-        pending.swap(queue);                          // re-entrancy: the queue is empty while the call below runs
-        std::vector<chs_frame> fr(pending.size());
-        for (size_t i = 0; i < pending.size(); i++)
+        const int n = queued;
+        queued = 0;                                   // re-entrancy: the queue is empty while the call below runs
+        std::vector<chs_frame> fr(n);
+        for (int i = 0; i < n; i++)
         {
-            const Queued &q = pending[i];
-            fr[i].depth = q.depth.data();
-            fr[i].color = q.color.empty() ? nullptr : q.color.data();
-            fr[i].trunc_per_pixel = q.trunc.empty() ? nullptr : q.trunc.data();
-            std::memcpy(fr[i].pose, q.pose, sizeof(q.pose));
-            std::memcpy(fr[i].color_pose, q.cpose, sizeof(q.cpose));
+            const unsigned char *slot = ring + slotBytes * i;
+            std::memset(&fr[i], 0, sizeof(chs_frame));
+            fr[i].depth = reinterpret_cast<const float *>(slot);
+            fr[i].color = qColorPath ? slot + colorOff : nullptr;
+            fr[i].trunc_per_pixel = qInteg.trunc_kind == CHS_TRUNC_PER_PIXEL ? reinterpret_cast<const float *>(slot + truncOff) : nullptr;
+            std::memcpy(fr[i].pose, &poses[24 * i], 12 * sizeof(float));
+            std::memcpy(fr[i].color_pose, &poses[24 * i + 12], 12 * sizeof(float));
         }
         chs_integrator integ = qInteg;
         integ.trunc_per_pixel = nullptr;              // per frame, in chs_frame
-        const int n = static_cast<int>(fr.size());
+        // the slots are page-locked and equally spaced: the whole queue crosses PCIe as one strided copy per image kind
         b200::Check(chs_integrate_batch(chunkManager.Handle(), &integ, n, fr.data(), CHS_MEM_HOST, &qCam, qChannels, qColorPath ? &qCcam : nullptr),
                     "chs_integrate_batch");
     }
@@ -172,7 +178,7 @@ class Chisel
 
     void Reset()
     {
-        queue.clear();                               // queued frames would be integrated and then dropped with the map
+        queued = 0;                                  // queued frames would be integrated and then dropped with the map
         chunkManager.Reset();
         meshesToUpdate.clear();
         dirtyVersion = -1;
@@ -220,40 +226,49 @@ class Chisel
             SetFrameBatching(std::atoi(e));
     }
 
-    struct Queued
-    {
-        std::vector<float> depth, trunc;
-        std::vector<uint8_t> color;
-        float pose[12], cpose[12];
-    };
     static bool SameCamera(const chs_camera &a, const chs_camera &b) { return std::memcmp(&a, &b, sizeof(chs_camera)) == 0; }
     static bool SameIntegrator(const chs_integrator &a, const chs_integrator &b)
     {
         return a.trunc_kind == b.trunc_kind && a.trunc_param == b.trunc_param && a.weight == b.weight && a.carving_enabled == b.carving_enabled &&
                a.carving_dist == b.carving_dist;
     }
-    // The caller reuses its image buffers (CR ChiselServer.cpp:285-295): the queue owns copies.
+    // The caller reuses its image buffers (CR ChiselServer.cpp:285-295): the queue owns copies, in page-locked slots.
     void Enqueue(const chs_integrator &integ, const chs_camera &cam, const chs_camera &ccam, bool colorPath, int channels, const float *depth, const uint8_t *color,
                  const float *pose, const float *cpose)
     {
-        if (!queue.empty() && (!SameIntegrator(integ, qInteg) || !SameCamera(cam, qCam) || !SameCamera(ccam, qCcam) || colorPath != qColorPath || channels != qChannels))
+        if (queued > 0 && (!SameIntegrator(integ, qInteg) || !SameCamera(cam, qCam) || !SameCamera(ccam, qCcam) || colorPath != qColorPath || channels != qChannels))
             Flush();
         qInteg = integ;
         qCam = cam;
         qCcam = ccam;
         qColorPath = colorPath;
         qChannels = channels;
-        queue.emplace_back();
-        Queued &q = queue.back();
         const size_t npx = static_cast<size_t>(cam.width) * cam.height;
-        q.depth.assign(depth, depth + npx);
-        if (integ.trunc_kind == CHS_TRUNC_PER_PIXEL && integ.trunc_per_pixel)
-            q.trunc.assign(integ.trunc_per_pixel, integ.trunc_per_pixel + npx);
+        const size_t depthBytes = (npx * sizeof(float) + 255) & ~static_cast<size_t>(255);
+        const size_t colorBytes = colorPath ? ((static_cast<size_t>(ccam.width) * ccam.height * channels + 255) & ~static_cast<size_t>(255)) : 0;
+        const size_t truncBytes = integ.trunc_kind == CHS_TRUNC_PER_PIXEL ? depthBytes : 0;
+        const size_t need = depthBytes + colorBytes + truncBytes;
+        if (need != slotBytes || !ring)
+        {
+            Flush();                                  // nothing is queued with another layout
+            chs_host_free(ring);
+            slotBytes = need;
+            colorOff = depthBytes;
+            truncOff = depthBytes + colorBytes;
+            ring = static_cast<unsigned char *>(chs_host_alloc(slotBytes * 16));
+            if (!ring)
+                throw std::runtime_error("chisel_b200: cannot allocate the page-locked frame queue");
+            poses.resize(24 * 16);
+        }
+        unsigned char *slot = ring + slotBytes * queued;
+        std::memcpy(slot, depth, npx * sizeof(float));
         if (colorPath)
-            q.color.assign(color, color + static_cast<size_t>(ccam.width) * ccam.height * channels);
-        std::memcpy(q.pose, pose, sizeof(q.pose));
-        std::memcpy(q.cpose, cpose, sizeof(q.cpose));
-        if (static_cast<int>(queue.size()) >= batchFrames)
+            std::memcpy(slot + colorOff, color, static_cast<size_t>(ccam.width) * ccam.height * channels);
+        if (truncBytes)
+            std::memcpy(slot + truncOff, integ.trunc_per_pixel, npx * sizeof(float));
+        std::memcpy(&poses[24 * queued], pose, 12 * sizeof(float));
+        std::memcpy(&poses[24 * queued + 12], cpose, 12 * sizeof(float));
+        if (++queued >= batchFrames)
             Flush();
     }
 
@@ -263,7 +278,10 @@ class Chisel
     mutable int64_t dirtyVersion;
     std::vector<float> truncScratch, depthScratch;
     int batchFrames;
-    mutable std::vector<Queued> queue;
+    mutable int queued = 0;
+    unsigned char *ring = nullptr;                   // 16 page-locked slots [depth | colour | per-pixel truncation]
+    size_t slotBytes = 0, colorOff = 0, truncOff = 0;
+    std::vector<float> poses;
     chs_integrator qInteg;
     chs_camera qCam, qCcam;
     bool qColorPath;

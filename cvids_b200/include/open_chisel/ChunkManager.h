@@ -6,6 +6,7 @@
 // the MeshMap that Chisel::UpdateMeshes maintains with the reference's publication rule (ChunkManager.cpp:101-127).
 #ifndef CHISEL_B200_CHUNKMANAGER_H_
 #define CHISEL_B200_CHUNKMANAGER_H_
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -168,16 +169,41 @@ class ChunkManager
                 continue;
             MeshPtr m = had ? allMeshes[id] : std::make_shared<Mesh>();
             m->Clear();
-            for (int64_t k = voff[i]; k < voff[i + 1]; k++)
+            const size_t nv = static_cast<size_t>(voff[i + 1] - voff[i]), ng = static_cast<size_t>(goff[i + 1] - goff[i]);
+            m->vertices.resize(nv);
+            m->normals.resize(nv);
+            m->indices.resize(nv);
+            if (mc.has_colors)
+                m->colors.resize(nv);
+            m->grids.resize(ng);
+            if (sizeof(Vec3) == 3 * sizeof(float))
             {
-                m->vertices.push_back(Vec3(v[3 * k], v[3 * k + 1], v[3 * k + 2]));
-                m->normals.push_back(Vec3(nr[3 * k], nr[3 * k + 1], nr[3 * k + 2]));
-                if (mc.has_colors)
-                    m->colors.push_back(Vec3(col[3 * k], col[3 * k + 1], col[3 * k + 2]));
-                m->indices.push_back(static_cast<VertIndex>(k - voff[i]));          // MarchingCubes.h:91-93
+                // Vec3 is three packed floats: whole arrays at once
+                if (nv)
+                {
+                    std::memcpy(static_cast<void *>(m->vertices.data()), &v[3 * voff[i]], nv * sizeof(Vec3));
+                    std::memcpy(static_cast<void *>(m->normals.data()), &nr[3 * voff[i]], nv * sizeof(Vec3));
+                    if (mc.has_colors)
+                        std::memcpy(static_cast<void *>(m->colors.data()), &col[3 * voff[i]], nv * sizeof(Vec3));
+                }
+                if (ng)
+                    std::memcpy(static_cast<void *>(m->grids.data()), &g[3 * goff[i]], ng * sizeof(Vec3));
             }
-            for (int64_t k = goff[i]; k < goff[i + 1]; k++)
-                m->grids.push_back(Vec3(g[3 * k], g[3 * k + 1], g[3 * k + 2]));
+            else
+            {
+                for (size_t k = 0; k < nv; k++)
+                {
+                    const int64_t q = voff[i] + static_cast<int64_t>(k);
+                    m->vertices[k] = Vec3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+                    m->normals[k] = Vec3(nr[3 * q], nr[3 * q + 1], nr[3 * q + 2]);
+                    if (mc.has_colors)
+                        m->colors[k] = Vec3(col[3 * q], col[3 * q + 1], col[3 * q + 2]);
+                }
+                for (size_t k = 0; k < ng; k++)
+                    m->grids[k] = Vec3(g[3 * (goff[i] + k)], g[3 * (goff[i] + k) + 1], g[3 * (goff[i] + k) + 2]);
+            }
+            for (size_t k = 0; k < nv; k++)
+                m->indices[k] = static_cast<VertIndex>(k);                          // MarchingCubes.h:91-93
             allMeshes[id] = m;
         }
     }

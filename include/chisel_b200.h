@@ -191,6 +191,11 @@ int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
  * pseudo-random operand pairs. out = {rcp mismatches, rcp values tested, div mismatches, div pairs tested}. */
 int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4]);
 
+/* Page-locked host memory for frame queues (the facade's batching queue lives in it): H2D copies from it run at full PCIe
+ * speed and asynchronously. NULL on failure. */
+void *chs_host_alloc(size_t bytes);
+void chs_host_free(void *p);
+
 /* Host-side exact restatements the facade needs (no device work). */
 int chs_frustum(const float pose[12], const chs_camera *cam, float corners[24], float lines[72], float planes[24]);
 int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], const chs_camera *cam,

@@ -3,7 +3,9 @@
 // same file compiles against (a) the reference's own headers + sources and (b) the drop-in facade under
 // cvids_b200/include + libchisel_b200.so. tests/test_facade.py builds both and compares their dumps.
 //
-//   chisel_client <stream.bin> <dump.bin>
+//   chisel_client <stream.bin> <dump.bin> [time]
+// With "time" the frames are read into memory first, the per-frame loop is exactly ChiselServer::IntegrateLastDepthImage
+// (integrate, then UpdateMeshes -- the every-10th gate decides) and its wall time is printed (tools/dropin_demo.py).
 #include <open_chisel/Chisel.h>
 #include <open_chisel/truncation/ConstantTruncator.h>
 #include <open_chisel/truncation/InverseTruncator.h>
@@ -11,6 +13,7 @@
 #include <open_chisel/weighting/ConstantWeighter.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -81,12 +84,39 @@ int main(int argc, char **argv)
     const size_t npx = (size_t)h.width * h.height;
     chisel::Frustum frustum;
     int remeshes = 0;
+    const bool timed = argc > 3 && std::strcmp(argv[3], "time") == 0;
+    std::vector<float> allPoses, allDepth;
+    std::vector<uint8_t> allColor;
+    if (timed)
+    {
+        allPoses.resize((size_t)h.frames * 12);
+        allDepth.resize((size_t)h.frames * npx);
+        allColor.resize((size_t)h.frames * npx * (h.channels > 0 ? h.channels : 0));
+        for (int f = 0; f < h.frames; f++)
+        {
+            if (fread(&allPoses[(size_t)f * 12], sizeof(float), 12, in) != 12) return 5;
+            if (fread(&allDepth[(size_t)f * npx], sizeof(float), npx, in) != npx) return 5;
+            if (h.channels > 0 && fread(&allColor[(size_t)f * npx * h.channels], 1, npx * h.channels, in) != npx * h.channels) return 5;
+        }
+    }
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < h.frames; f++)
     {
         float pose[12];
-        if (fread(pose, sizeof(float), 12, in) != 12) return 5;
-        if (fread(lastDepthImage->GetMutableData(), sizeof(float), npx, in) != npx) return 5;
-        if (h.channels > 0 && fread(lastColorImage->GetMutableData(), 1, npx * h.channels, in) != npx * h.channels) return 5;
+        if (timed)
+        {
+            // what the ROS callbacks do: copy the message into the one reused image buffer (CR ChiselServer.cpp:266-295)
+            std::memcpy(pose, &allPoses[(size_t)f * 12], sizeof(pose));
+            std::memcpy(lastDepthImage->GetMutableData(), &allDepth[(size_t)f * npx], npx * sizeof(float));
+            if (h.channels > 0)
+                std::memcpy(lastColorImage->GetMutableData(), &allColor[(size_t)f * npx * h.channels], npx * h.channels);
+        }
+        else
+        {
+            if (fread(pose, sizeof(float), 12, in) != 12) return 5;
+            if (fread(lastDepthImage->GetMutableData(), sizeof(float), npx, in) != npx) return 5;
+            if (h.channels > 0 && fread(lastColorImage->GetMutableData(), 1, npx * h.channels, in) != npx * h.channels) return 5;
+        }
         chisel::Transform lastPose;
         for (int r = 0; r < 3; r++)
         {
@@ -103,10 +133,21 @@ int main(int argc, char **argv)
         cameraModel.SetupFrustum(lastPose, &frustum);
         // the reference gates re-meshing on a process-global call counter (Chisel.cpp:50-59): call it every frame like
         // ChiselServer::IntegrateLastDepthImage does and let the gate decide
+        if (timed)
+        {
+            chiselMap->UpdateMeshes();
+            continue;
+        }
         const size_t before = chiselMap->GetMeshesToUpdate().size();
         chiselMap->UpdateMeshes();
         if (before > 0 && chiselMap->GetMeshesToUpdate().size() == 0)
             remeshes++;
+    }
+    if (timed)
+    {
+        (void)chiselMap->GetMeshesToUpdate().size();             // everything the loop queued has reached the map
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "TIMING frames %d seconds %.6f fps %.3f\n", h.frames, sec, h.frames / sec);
     }
     fclose(in);
 
