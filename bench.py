@@ -304,7 +304,7 @@ def run_cuda(args):
     # replicates the block. Every byte is still broadcast over NVLink from its ingest rank, all ingest ranks at once, and all
     # ranks finish together (a ring broadcast from a single root reaches the last of 8 ranks only after ~300 us). Set-up,
     # outside every timed region: every rank gets a copy of the synthetic stream so that it can play the ingest rank of its range.
-    share = ((B * fbytes + world - 1) // world + 15) // 16 * 16          # bytes per rank and step
+    share = sharding.ingest_share(B * fbytes, world)                     # bytes per rank and step
     if world > 1:
         dist.broadcast(d_frames, 0)
         if rank != 0:
@@ -344,8 +344,7 @@ def run_cuda(args):
         """This rank's byte range of the step's block: (offset into the flat stream, valid bytes), or None when the frames of the
         step are not contiguous in the stream (the orbit wraps inside the step)."""
         ids = frame_ids(step, b)
-        lo = min(rank * share, b * fbytes)
-        n = min((rank + 1) * share, b * fbytes) - lo
+        lo, n = sharding.ingest_range(b * fbytes, rank, world)
         if ids[-1] - ids[0] != b - 1:
             return None, lo, n
         return ids[0] * fbytes + lo, lo, n
@@ -366,7 +365,7 @@ def run_cuda(args):
                     whole = d_frames[frame_ids(step, b)].view(-1)
                     mine[:n].copy_(whole[lo:lo + n])
             block = mine[:share]
-        dist.all_gather_into_tensor(recv[:share * world], block)
+        sharding.all_gather_block(recv[:share * world], block)
 
     def prepared_for(m, step, b):
         key = (b, step)
@@ -540,7 +539,7 @@ def run_cuda(args):
                         mine[:n].copy_(h_flat[off:off + n], non_blocking=True)
                     else:
                         mine[:n].copy_(h_frames[ids].view(-1)[lo:lo + n], non_blocking=True)
-                dist.all_gather_into_tensor(recv[:share * world], mine[:share])
+                sharding.all_gather_block(recv[:share * world], mine[:share])
                 m.integrate_prepared(prepared_for(m, step, B))
         else:
             ds, cs, ps = views_of(step)

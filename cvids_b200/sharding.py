@@ -4,6 +4,8 @@ same code runs over NCCL on the GPU box and over gloo in the CPU tests.
 
   owner(id)   = chs_owner(id) % world          (the device kernels apply the same rule: chunk_candidates_kernel)
   frame       = one contiguous byte buffer [depth float32 W*H | colour uint8 W*H*C] -> ONE broadcast per frame
+  step block  = the frames of a step, contiguous; ingested in `world` equal byte ranges (rank r ingests range r) and
+                replicated by ONE all-gather: every rank has the whole block when the collective ends
   results     = per-rank maps are disjoint; their union is the map (tests: equal to the 1-rank map bit for bit)
 """
 from __future__ import annotations
@@ -57,6 +59,33 @@ def unpack_frame(buf: np.ndarray, width: int, height: int, channels: int):
     depth = buf[:n].view(np.float32).reshape(height, width)
     color = buf[n:n + channels * width * height].reshape(height, width, channels) if channels else None
     return depth, color
+
+
+def ingest_share(total_bytes: int, world: int) -> int:
+    """Bytes per rank of a step block split into `world` equal ranges (16-byte aligned; the last range may be short or empty)."""
+    return ((total_bytes + world - 1) // world + 15) // 16 * 16
+
+
+def ingest_range(total_bytes: int, rank: int, world: int):
+    """(offset, valid bytes) of rank's range inside the step block."""
+    share = ingest_share(total_bytes, world)
+    lo = min(rank * share, total_bytes)
+    return lo, min((rank + 1) * share, total_bytes) - lo
+
+
+def all_gather_block(out, mine):
+    """Replicate a step block: `mine` = this rank's range padded to ingest_share bytes, `out` = world * share bytes (the block
+    followed by padding). One collective; NCCL all_gather_into_tensor on the device, list all_gather elsewhere (gloo)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        out[:mine.numel()].copy_(mine)
+        return out
+    if out.is_cuda:
+        dist.all_gather_into_tensor(out, mine)
+    else:
+        dist.all_gather(list(out.view(world, -1).unbind(0)), mine)
+    return out
 
 
 def broadcast_frame(buf, src: int = 0):

@@ -109,3 +109,30 @@ def test_color_integrate_integer_identity():
         n = (w * np.arange(256, dtype=np.uint64)[:, None] + np.arange(256, dtype=np.uint64)[None, :])
         got = ((n * recip[w + 1]) >> np.uint64(20)).astype(np.uint8)
         assert np.array_equal(ref, got), w
+
+
+def test_batch_entry_points_validate_arguments_without_a_device():
+    """chs_integrate_batch / chs_wait_batch reject bad arguments before touching CUDA; the pinned allocator fails cleanly
+    (NULL) where there is no device."""
+    import ctypes as C
+    from cvids_b200 import capi
+    lib = capi.load_library()
+    integ = capi.ProjectionIntegrator().as_struct()
+    cam = capi.make_camera([100, 100, 32, 24, 64, 48, 0.05, 5.0])
+    fr = (capi.chs_frame * 1)()
+    assert lib.chs_integrate_batch(None, C.byref(integ), 1, fr, capi.MEM_HOST, C.byref(cam), 3, C.byref(cam)) == capi.CHS_ERR_INVALID
+    n = C.c_int()
+    assert lib.chs_wait_batch(None, 1, None, 0, C.byref(n)) == capi.CHS_ERR_INVALID
+    t = C.c_int64()
+    assert lib.chs_last_batch_ticket(None, C.byref(t)) == capi.CHS_ERR_INVALID
+    import torch
+    if not torch.cuda.is_available():
+        assert not lib.chs_host_alloc(1024)
+    lib.chs_host_free(None)
+
+
+def test_chs_frame_layout_matches_the_header():
+    """The ctypes mirror of chs_frame (four pointers, two 3x4 poses) has the C struct's size."""
+    import ctypes as C
+    from cvids_b200 import capi
+    assert C.sizeof(capi.chs_frame) == 4 * C.sizeof(C.c_void_p) + 2 * 12 * C.sizeof(C.c_float)

@@ -50,6 +50,42 @@ def _worker(rank, world, port, tmpdir):
     dist.destroy_process_group()
 
 
+def _ingest_worker(rank, world, port, tmpdir):
+    """Sharded ingest of a step block (bench.py, N > 1): every rank contributes ITS byte range, one all-gather, and every rank
+    ends up with the whole block of frames."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from cvids_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fbytes = sharding.frame_nbytes(40, 30, 3)
+    for b in (1, 3, 10):
+        total = b * fbytes
+        block = torch.from_numpy(np.random.RandomState(b).randint(0, 256, total).astype(np.uint8))     # the same stream on every rank
+        share = sharding.ingest_share(total, world)
+        lo, n = sharding.ingest_range(total, rank, world)
+        mine = torch.full((share,), 255, dtype=torch.uint8)
+        mine[:n] = block[lo:lo + n]                                                                     # only this rank's range is read
+        out = torch.zeros(share * world, dtype=torch.uint8)
+        sharding.all_gather_block(out, mine)
+        assert torch.equal(out[:total], block), "rank %d: block of %d frames not reconstructed" % (rank, b)
+    spans = [sharding.ingest_range(1000, r, 3) for r in range(3)]
+    assert spans[0][0] == 0 and sum(s[1] for s in spans) == 1000 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(2))
+    if rank == 0:
+        np.save(os.path.join(tmpdir, "ingest_ok.npy"), np.array([1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_ingest_all_gather(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_ingest_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ingest_ok.npy")
+
+
 def test_gloo_world2_broadcast_partition_merge(tmp_path):
     import torch.multiprocessing as mp
     port = 29600 + os.getpid() % 300
