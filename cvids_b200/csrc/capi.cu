@@ -854,9 +854,11 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         anyMm |= frames[f].depth_mm != nullptr;
     const int setIdx = (m->batchId + 1) & 1;
     chs_map::BatchSet &bs = m->bset[setIdx];
-    cudaStream_t cs = m->copyStream;
+    // Host frames: copies and prepare run on the copy stream, beside the kernels of the previous batch. Device frames are ordered by
+    // the map's stream anyway (the caller produced them there), so everything stays on it: no cross-stream hand-overs.
+    cudaStream_t cs = hostMem ? m->copyStream : st;
     // the set is free once the kernels of the batch that used it last (two batches ago) are done
-    if (bs.used)
+    if (bs.used && hostMem)
         CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
     {
         const bool grow = tiles * kMaxBatch > bs.hizCap || ((hostMem || anyMm) && npx * kMaxBatch > bs.depthCap) || (anyMm && hostMem && npx * kMaxBatch > bs.depthMmCap) ||
@@ -883,12 +885,6 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             return rc;
         if ((rc = grow_buffer(&bs.packed, &bs.packedCap, cpx * kMaxBatch, cs)))
             return rc;
-    }
-    if (mem == CHS_MEM_DEVICE)
-    {
-        // device inputs are ordered by the map's stream (the caller produced them there): prepare must not run ahead of them
-        CHS_CUDA(cudaEventRecord(m->callEvent, st));
-        CHS_CUDA(cudaStreamWaitEvent(cs, m->callEvent, 0));
     }
     FrameParams fps[kMaxBatch];
     std::memset(fps, 0, sizeof(fps));

@@ -804,7 +804,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     batch_prepare_kernel<<<dim3(tiles + packBlocks, bp.K), 256, 0, stPrep>>>(bp, map, tilesX, tiles);
     if (info.profiling && (e = cudaEventRecord(evt[1], stPrep)) != cudaSuccess)
         return e;
-    if ((e = cudaEventRecord(prepared, stPrep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, prepared, 0)) != cudaSuccess)
+    if (stPrep != st && ((e = cudaEventRecord(prepared, stPrep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, prepared, 0)) != cudaSuccess))
         return e;
     batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
