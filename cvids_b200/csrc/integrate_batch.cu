@@ -15,12 +15,14 @@
 // reads and writes each touched voxel once instead of K times, and gives every warp K frames of independent work.
 //
 //   batch_prepare_kernel      grid.y = frame: Hi-Z tiles (+ per-pixel truncation) and the packed colour image of every frame
-//   batch_candidates_kernel   thread per (chunk of the UNION candidate box, 8^3 brick): exact Frustum::Intersects and the
-//                             conservative depth-range class per frame -> per-brick frame masks; warp-ballot compaction
-//   batch_bricks_kernel       warp per quarter brick (8 x 8 x 2 voxels): state of 4 voxels per lane in registers, straight-line update per frame of the
-//                             brick's frame mask, one store per changed voxel at the end; tasks from an atomic queue. Bricks of
-//                             chunks that do not exist yet start from the initial state in registers and create the chunk
-//                             (hash insert + pool bump, no voxel traffic: free pool slots are kept initialised) on the first hit
+//   batch_candidates_kernel   a group of lanes per chunk of the UNION candidate box: exact Frustum::Intersects and the
+//                             conservative depth-range class per frame (chunk level over frames, then brick level for the
+//                             survivors) -> per-brick frame masks; warp-ballot compaction, long units first
+//   batch_bricks_kernel       warp per quarter brick (8 x 8 x 2 voxels): state of 4 voxels per lane in registers, straight-line
+//                             update per frame of the brick's frame mask, one store per changed voxel at the end; tasks from an
+//                             atomic queue. Bricks of chunks that do not exist yet start from the initial state in registers and
+//                             create the chunk (hash insert + pool bump, no voxel traffic: free pool slots are kept
+//                             initialised) on the first hit
 #include <algorithm>
 #include <cstddef>
 
@@ -83,8 +85,8 @@ __global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, Devi
 //   2. brick level, lanes spread over BRICKS: classify the lane's brick for the frames that survived stage 1.
 //        bandM  frames in which some voxel of the brick may fall inside the truncation band
 //        freeM  frames in which the brick lies in free space (only carving of observed voxels can act)
-//      A free-space frame is kept when the brick can hold a carvable voxel: its flag is set already, or a band frame of
-//      this batch may create one (conservative: any band frame of the batch).
+//      A free-space frame is kept when the brick can hold a carvable voxel by then: its flag is set already, or an EARLIER band
+//      frame of this batch may create one (batch_bricks_kernel then checks the actual register state before spending the frame).
 // Chunk indices go through a multiplicative permutation so that the few surviving chunks spread over all CTAs.
 template <int CS>
 __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, DeviceMap map)
@@ -363,8 +365,8 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
 // registers. Same arithmetic as process_batch<MODE 0> (ProjectionIntegrator.h:51-183); colour and depth cameras coincide.
 //
 // FAST = true: straight-line code. The reciprocal of the projection and the quotient of DistVoxel::Integrate use the
-// range-check-free correctly rounded forms (integrate_device.cuh), every update is computed for all eight voxels and selected
-// by predicate, so the eight dependency chains interleave. The caller's warp votes guarantee the operand ranges; if a vote
+// range-check-free correctly rounded forms (integrate_device.cuh), every update is computed for all kVPL voxels and selected
+// by predicate, so their dependency chains interleave. The caller's warp votes guarantee the operand ranges; if a vote
 // fails, nothing has been modified yet and the frame is redone with FAST = false (__frcp_rn / __fdiv_rn, branches).
 // Returns false (FAST only) when an operand is out of range.
 template <int CS, bool COLOR_PATH, bool PER_PIXEL, bool FAST>
@@ -413,7 +415,7 @@ __device__ __forceinline__ bool frame_on_half_brick(const FrameParams &fp, const
     }
     if constexpr (FAST)
     {
-        // predicates and the operands of the division for all eight voxels
+        // predicates and the operands of the division for all kVPL voxels
         unsigned band = 0u, crv = 0u;
         float sd[kVPL], num[kVPL], den[kVPL], wu[kVPL];
 #pragma unroll
