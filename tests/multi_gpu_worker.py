@@ -56,6 +56,36 @@ def main():
         assert all(len(p[0][0]) > 0 for p in parts)
         print("MULTI_GPU_OK world=%d chunks=%d triangles=%d" % (world, len(merged[0]), sum(len(m["vertices"]) for m in root_meshes.values()) // 3), flush=True)
     dist.barrier()
+
+    # ---- the fused multi-frame path, fed the way bench.py feeds it at N > 1: every rank ingests ITS byte range of the step's frame
+    # block, ONE all-gather replicates the block, one chs_integrate_batch per rank. Union of the shards == the oracle's map.
+    fbytes = nbytes
+    block_host = torch.empty(n * fbytes, dtype=torch.uint8)
+    if rank == 0:
+        for i in range(n):
+            block_host[i * fbytes:(i + 1) * fbytes].copy_(torch.from_numpy(sharding.pack_frame(frames[i][0], frames[i][1])))
+    stream_all = block_host.to(dev)
+    dist.broadcast(stream_all, 0)                                   # set-up: every rank can play the ingest rank of its range
+    shard2 = common.Driver(setup, "cuda", device=local, rank=rank, world=world)
+    for first, cnt in ((0, 3), (3, 5)):                            # two steps: 3 frames, then 5
+        total = cnt * fbytes
+        share = sharding.ingest_share(total, world)
+        lo, nb = sharding.ingest_range(total, rank, world)
+        mine = torch.zeros(share, dtype=torch.uint8, device=dev)
+        mine[:nb].copy_(stream_all[first * fbytes + lo:first * fbytes + lo + nb])
+        out = torch.zeros(share * world, dtype=torch.uint8, device=dev)
+        sharding.all_gather_block(out, mine)
+        torch.cuda.synchronize(dev)
+        base = out.data_ptr()
+        ptrs = [(base + j * fbytes, base + j * fbytes + 4 * cam.width * cam.height) for j in range(cnt)]
+        shard2.m.integrate_batch(shard2.integ, None, [poses[first + j] for j in range(cnt)], cam.as_array(), device_ptrs=ptrs, channels=3)
+        assert len(shard2.m.batch_stats()) == cnt
+    parts = sharding.gather_to_root((shard2.state(), shard2.dirty()), 0)
+    if rank == 0:
+        merged = sharding.merge_states([p[0] for p in parts])
+        common.assert_state_equal(merged, oracle.state(), "union of %d NCCL shards, fused batches" % world)
+        print("MULTI_GPU_BATCH_OK world=%d chunks=%d" % (world, len(merged[0])), flush=True)
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -1,5 +1,6 @@
 """GPU suite, needs >= 2 devices (skipped on a 1-GPU box): real NCCL run of the sharded path -- frame broadcast, ownership
-sharded integration, distributed re-mesh with ghost-chunk exchange, mesh gather -- against the CPU oracle."""
+sharded integration, distributed re-mesh with ghost-chunk exchange, mesh gather -- against the CPU oracle; then the fused
+multi-frame path fed by sharded ingest + one all-gather."""
 import os
 import subprocess
 import sys
@@ -26,3 +27,5 @@ def test_nccl_sharded_integration_and_meshing():
                           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_OK world=%d" % world in out.stdout
+    # second phase of the worker: fused multi-frame batches fed by sharded ingest + one all-gather (bench.py's N > 1 path)
+    assert "MULTI_GPU_BATCH_OK world=%d" % world in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
