@@ -156,7 +156,12 @@ class Chisel
         }
     }
 
-    bool SaveAllMeshesToPLY(const std::string &filename)
+    bool SaveAllMeshesToPLY(const std::string &filename) { return SaveAllMeshes(filename, false); }
+    // extension: the same mesh as binary_little_endian PLY (io/PLY.h)
+    bool SaveAllMeshesToPLYBinary(const std::string &filename) { return SaveAllMeshes(filename, true); }
+
+  protected:
+    bool SaveAllMeshes(const std::string &filename, bool binary)
     {
         // Chisel.cpp:69-105: concatenate every chunk mesh, indices 0..n-1
         MeshPtr full = std::make_shared<Mesh>();
@@ -173,8 +178,10 @@ class Chisel
             for (const Vec3 &n : it.second->normals)
                 full->normals.push_back(n);
         }
-        return SaveMeshPLYASCII(filename, full);
+        return binary ? SaveMeshPLYBinary(filename, full) : SaveMeshPLYASCII(filename, full);
     }
+
+  public:
 
     void Reset()
     {

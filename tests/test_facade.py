@@ -92,3 +92,29 @@ def test_facade_client_on_device(tmp_path, case, batch):
     ply = open(dump + ".ply").read().split("\n")
     nverts = sum(len(m["vertices"]) for m in d["meshes"].values())
     assert ply[0] == "ply" and ("element vertex %d" % nverts) in ply[2]
+
+
+def test_ply_writers_ascii_and_binary_agree(tmp_path):
+    """Host-only: SaveMeshPLYASCII (the reference's layout, OC/src/io/PLY.cpp:29-88) and the binary_little_endian variant hold
+    the same vertices, colours and faces."""
+    exe = str(tmp_path / "ply_test")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(facade_util.ROOT, "oracle", "eigen_shim"), "-I", os.path.join(facade_util.ROOT, "include"),
+                           "-I", os.path.join(facade_util.ROOT, "cvids_b200", "include"), os.path.join(facade_util.ROOT, "tests", "cpp", "ply_test.cpp"), "-o", exe])
+    a, b = str(tmp_path / "a.ply"), str(tmp_path / "b.ply")
+    subprocess.check_call([exe, a, b])
+    lines = open(a).read().split("\n")
+    assert lines[0] == "ply" and lines[1] == "format ascii 1.0" and lines[2] == "element vertex 21"
+    end = lines.index("end_header")
+    verts = np.array([[float(x) for x in l.split()] for l in lines[end + 1:end + 22]])
+    faces = np.array([[int(x) for x in l.split()] for l in lines[end + 22:end + 29]])
+    raw = open(b, "rb").read()
+    hdr_end = raw.index(b"end_header\n") + len(b"end_header\n")
+    assert b"format binary_little_endian 1.0" in raw[:hdr_end] and b"element vertex 21" in raw[:hdr_end] and b"element face 7" in raw[:hdr_end]
+    vt = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
+    bv = np.frombuffer(raw, dtype=vt, count=21, offset=hdr_end)
+    ft = np.dtype([("n", "u1"), ("idx", "<i4", 3)])
+    bf = np.frombuffer(raw, dtype=ft, count=7, offset=hdr_end + 21 * vt.itemsize)
+    assert len(raw) == hdr_end + 21 * 15 + 7 * 13
+    assert np.allclose(bv["xyz"], verts[:, :3], rtol=1e-5, atol=1e-6)          # the ASCII file holds 6 significant digits
+    assert np.array_equal(bv["rgb"], verts[:, 3:].astype(np.uint8))
+    assert np.all(bf["n"] == 3) and np.array_equal(bf["idx"], faces[:, 1:])
