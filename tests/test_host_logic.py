@@ -136,3 +136,30 @@ def test_chs_frame_layout_matches_the_header():
     import ctypes as C
     from cvids_b200 import capi
     assert C.sizeof(capi.chs_frame) == 4 * C.sizeof(C.c_void_p) + 2 * 12 * C.sizeof(C.c_float)
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """Compile a C program against include/chisel_b200.h that prints sizeof / offsetof of every ABI struct and compare with the
+    ctypes mirrors in cvids_b200/capi.py (catches silent ABI drift between the header and the Python harness)."""
+    import ctypes as C
+    import subprocess
+    from cvids_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"chs_config": capi.chs_config, "chs_camera": capi.chs_camera, "chs_integrator": capi.chs_integrator,
+               "chs_frame_stats": capi.chs_frame_stats, "chs_mesh_counts": capi.chs_mesh_counts, "chs_timings": capi.chs_timings,
+               "chs_frame": capi.chs_frame}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "chisel_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines += ['return 0; }']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    got = dict(l.rsplit(" ", 1) for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().split("\n"))
+    for name, cls in structs.items():
+        assert int(got["%s sizeof" % name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, "%s.%s" % (name, field)
