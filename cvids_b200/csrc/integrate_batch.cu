@@ -77,6 +77,39 @@ __global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, Devi
         color_pack_body(fp, (blockIdx.x - tiles) * blockDim.x + threadIdx.x, (gridDim.x - tiles) * blockDim.x);
 }
 
+// Emit the unit of brick b of chunk (x, y, z): `active` lanes hold one brick each. Free-space frames can only carve: the brick must
+// hold an observed voxel -- its flag says so, or an EARLIER band frame of this batch may create one (batch_bricks_kernel checks
+// the actual register state before it spends a frame on it). Units with many frames go to the front of the list, the others to
+// the back: batch_bricks_kernel hands tasks out front to back, so the long tasks start first and the short ones fill the tail.
+__device__ __forceinline__ void emit_brick_unit(const BatchParams &bp, bool active, unsigned long long key, int slot, bool exists, bool virt, bool carve,
+                                                unsigned long long flags, int b, unsigned band, unsigned freeFrames, int K, unsigned lane)
+{
+    const unsigned afterBand = band ? ~((band & (0u - band)) | ((band & (0u - band)) - 1u)) : 0u;
+    unsigned fm = carve ? freeFrames : 0u;
+    if (!(exists && ((flags >> b) & 1ull)))
+        fm &= afterBand;
+    const bool keepB = active && ((exists && (band | fm) != 0u) || (virt && band != 0u));
+    const bool heavy = keepB && 2 * __popc(band | fm) > K;
+    const unsigned hm = __ballot_sync(0xffffffffu, heavy), lm = __ballot_sync(0xffffffffu, keepB && !heavy);
+    int hbase = 0, lbase = 0;
+    if (lane == 0)
+    {
+        if (hm)
+            hbase = atomicAdd(&bp.bctr->unit_count, __popc(hm));
+        if (lm)
+            lbase = atomicAdd(&bp.bctr->light_count, __popc(lm));
+    }
+    hbase = __shfl_sync(0xffffffffu, hbase, 0);
+    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+    if (keepB)
+    {
+        const unsigned below = (1u << lane) - 1;
+        const int pos = heavy ? hbase + __popc(hm & below) : bp.units_cap - 1 - (lbase + __popc(lm & below));
+        bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
+                                  (int)(band | (fm << 16)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // A group of GL lanes per chunk of the union box (GL = bricks per chunk, at most 32), two stages:
 //   1. chunk level, lanes spread over FRAMES: is the chunk inside frame f's candidate ID box and does it pass
@@ -224,37 +257,7 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     const unsigned long long key = pack_id(x, y, z);
 #pragma unroll
     for (int k = 0; k < BPL; k++)
-    {
-        const int b = gl + k * GL;
-        // free-space frames can only carve: the brick must hold an observed voxel -- its flag says so, or an EARLIER band frame
-        // of this batch may create one (batch_bricks_kernel checks the actual register state before it spends a frame on it)
-        const unsigned afterBand = bandM[k] ? ~((bandM[k] & (0u - bandM[k])) | ((bandM[k] & (0u - bandM[k])) - 1u)) : 0u;
-        unsigned fm = carve ? freeM[k] : 0u;
-        if (!(exists && ((flags >> b) & 1ull)))
-            fm &= afterBand;
-        const bool keepB = (exists && (bandM[k] | fm) != 0u) || (virt && bandM[k] != 0u);
-        // units with many frames go to the front of the list, the others to the back: batch_bricks_kernel hands tasks out front to
-        // back, so the long tasks start first and the short ones fill the tail
-        const bool heavy = keepB && 2 * __popc(bandM[k] | fm) > K;
-        const unsigned hm = __ballot_sync(0xffffffffu, heavy), lm = __ballot_sync(0xffffffffu, keepB && !heavy);
-        int hbase = 0, lbase = 0;
-        if (lane == 0)
-        {
-            if (hm)
-                hbase = atomicAdd(&bp.bctr->unit_count, __popc(hm));
-            if (lm)
-                lbase = atomicAdd(&bp.bctr->light_count, __popc(lm));
-        }
-        hbase = __shfl_sync(0xffffffffu, hbase, 0);
-        lbase = __shfl_sync(0xffffffffu, lbase, 0);
-        if (keepB)
-        {
-            const unsigned below = (1u << lane) - 1;
-            const int pos = heavy ? hbase + __popc(hm & below) : bp.units_cap - 1 - (lbase + __popc(lm & below));
-            bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
-                                      (int)(bandM[k] | (fm << 16)));
-        }
-    }
+        emit_brick_unit(bp, true, key, slot, exists, virt, carve, flags, gl + k * GL, bandM[k], freeM[k], K, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------
