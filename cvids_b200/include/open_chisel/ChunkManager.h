@@ -170,12 +170,7 @@ class ChunkManager
             MeshPtr m = had ? allMeshes[id] : std::make_shared<Mesh>();
             m->Clear();
             const size_t nv = static_cast<size_t>(voff[i + 1] - voff[i]), ng = static_cast<size_t>(goff[i + 1] - goff[i]);
-            m->vertices.resize(nv);
-            m->normals.resize(nv);
-            m->indices.resize(nv);
-            if (mc.has_colors)
-                m->colors.resize(nv);
-            m->grids.resize(ng);
+            m->Resize(nv, ng, mc.has_colors != 0);
             if (sizeof(Vec3) == 3 * sizeof(float))
             {
                 // Vec3 is three packed floats: whole arrays at once
@@ -202,8 +197,6 @@ class ChunkManager
                 for (size_t k = 0; k < ng; k++)
                     m->grids[k] = Vec3(g[3 * (goff[i] + k)], g[3 * (goff[i] + k) + 1], g[3 * (goff[i] + k) + 2]);
             }
-            for (size_t k = 0; k < nv; k++)
-                m->indices[k] = static_cast<VertIndex>(k);                          // MarchingCubes.h:91-93
             allMeshes[id] = m;
         }
     }
