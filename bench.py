@@ -175,6 +175,38 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# parity check inside the bench: the frames the bench times, against the CPU oracle
+
+PARITY_KEYS = ("candidates", "n_upd", "n_carve", "n_col", "n_new", "updated_chunks")
+
+
+def oracle_counters(frames):
+    """Per-frame counters of the CPU oracle (the plain-C restatement, bit-identical to the compiled reference) and the oracle itself."""
+    from oracle import pyoracle
+    o = pyoracle.OracleChisel(CFG.chunk, CFG.resolution, True)
+    o.setup_integrator(pyoracle.TRUNC_CONSTANT, CFG.truncation, CFG.weight, CFG.carve, CFG.carve_dist)
+    cam = CFG.cam.as_array()
+    out = []
+    for depth, col, pose in frames:
+        o.integrate_color(depth, pose, cam, col)
+        out.append(o.frame_counters())
+    return out, o
+
+
+def state_equal(a, b):
+    """Bit-exact comparison of two (ids, sdf, weight, rgbw) states; returns a list of what differs."""
+    bad = []
+    if a[0].shape != b[0].shape or not np.array_equal(a[0], b[0]):
+        return ["chunk-ID set (%d vs %d chunks)" % (len(a[0]), len(b[0]))]
+    for name, x, y in (("sdf", a[1], b[1]), ("weight", a[2], b[2]), ("colour", a[3], b[3])):
+        xv = np.ascontiguousarray(x).view(np.uint32) if x.dtype == np.float32 else x
+        yv = np.ascontiguousarray(y).view(np.uint32) if y.dtype == np.float32 else y
+        if not np.array_equal(xv, yv):
+            bad.append("%s (%d voxels)" % (name, int((xv != yv).sum())))
+    return bad
+
 # ---------------------------------------------------------------------------------------------------------------
 # side lines (not the headline): BASELINE configs[4] shape (8 agents) and configs[3] shape (1 cm hall, meshing-heavy)
 
@@ -459,11 +491,15 @@ def run_cuda(args):
     bytes_alg = 0
     t_integrate = t_prepare = t_cand = t_new = 0.0
     per_step = []
+    parity_steps = min(args.parity_steps, warm + steps, max(1, n_unique // B))
+    got_counters = []                              # per-frame counters of the first parity_steps steps (this rank's chunks)
     for i in range(warm + steps):
         if i >= warm:
             flush_l2(i)
         step_device(m, i)
         sts = m.batch_stats() if B > 1 else [m.frame_stats()]
+        if i < parity_steps:
+            got_counters += [[int(st[k]) for k in PARITY_KEYS] for st in sts]
         if i * B < s_warm + s_steps:
             upd_single += sum(st["n_upd"] for j, st in enumerate(sts) if s_warm <= i * B + j < s_warm + s_steps)
         if i >= warm:
@@ -477,6 +513,39 @@ def run_cuda(args):
             per_step.append((sum(st["n_upd"] for st in sts), sts[-1]["brick_units"], sum(st["candidates"] for st in sts), tm["integrate_ms"],
                              sum(st["updated_chunks"] for st in sts), sum(st["n_new"] for st in sts), sts[-1]["new_candidates"]))
     total_chunks = m.frame_stats()["total_chunks"]
+    # ---- parity check: the first parity_steps steps of exactly this path against the CPU oracle (counters summed over ranks;
+    # at N = 1 also the whole voxel state and the dirty set, bit for bit, from a second map fed the same steps)
+    parity = None
+    if parity_steps > 0:
+        gc = torch.tensor(got_counters, dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(gc, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            t0 = time.perf_counter()
+            want, orc = oracle_counters([frames[i] for s_ in range(parity_steps) for i in frame_ids(s_)])
+            gcl = gc.cpu().tolist()
+            bad = []
+            for j, (g, w) in enumerate(zip(gcl, want)):
+                for k, name in enumerate(PARITY_KEYS):
+                    if g[k] != w[name]:
+                        bad.append("frame %d %s: cuda %d oracle %d" % (j, name, g[k], w[name]))
+            parity = {"frames": len(want), "counters": list(PARITY_KEYS), "counters_equal": not bad, "oracle": "oracle/chisel_oracle.c (C restatement, pinned to the compiled reference)"}
+            if world == 1:
+                pm = new_map()
+                for s_ in range(parity_steps):
+                    step_device(pm, s_)
+                diff = state_equal(pm.state(), orc.state())
+                if not np.array_equal(pm.dirty_ids(), orc.dirty_ids()):
+                    diff.append("dirty set")
+                parity["state_bit_exact"] = not diff
+                parity["chunks"] = int(len(orc.state()[0]))
+                bad += diff
+                pm.close()
+            parity["seconds"] = round(time.perf_counter() - t0, 1)
+            if bad:
+                # a fast kernel whose results differ from the reference's is not done: no bench line
+                print(json.dumps({"parity_check": parity, "mismatch": bad[:20]}), flush=True)
+                raise SystemExit("bench.py: PARITY MISMATCH against the oracle: " + "; ".join(bad[:5]))
     # meshing: re-mesh of everything the run left dirty (Chisel::UpdateMeshes without its every-10th gate): once cold (first
     # launch, cold L2), then the same dirty set again twice (steady state; the dirty set is restored with chs_set_dirty)
     dirty = m.get_meshes_to_update()
@@ -683,6 +752,7 @@ def run_cuda(args):
                          "note": "algorithmic bytes = B_int of SURVEY 8(d) summed over the step's frames; with %d frames fused the voxel state "
                                  "moves through HBM once per step, so DRAM traffic is BELOW the algorithmic bytes" % B},
             "wall_s_timed_region": wall_a,
+            "parity_check": parity,
             "mesh": mesh_info,
         }
         if world == 1 and not args.quick and not args.no_side_lines:
@@ -716,6 +786,8 @@ def main():
     ap.add_argument("--pool-chunks", type=int, default=98304,
                     help="pre-sized chunk pool (chunks) so that no slab / hash growth lands inside the timed region")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
+    ap.add_argument("--parity-steps", type=int, default=2,
+                    help="steps (from the empty map) whose per-frame counters, voxel state and dirty set are compared with the CPU oracle; 0 = off")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -1002,6 +1003,35 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     info.colorPath = colorPath;
     info.perPixel = perPixel;
     info.profiling = m->profiling;
+    // the fast brick kernel's per-frame constants and its preconditions (integrate_batch.cu: batch_bricks_fast_kernel)
+    BrickFrames brickFrames;
+    info.fastBricks = !perPixel && cam->width < (1 << 22) && cam->height < (1 << 22) && std::getenv("CHS_NO_FAST_BRICKS") == nullptr;
+    for (int f = 0; f < K && info.fastBricks; f++)
+    {
+        const FrameParams &fp = fps[f];
+        BrickFrame &b = brickFrames.f[f];
+        std::memset(&b, 0, sizeof(b));
+        std::memcpy(b.R, fp.cam.R, sizeof(b.R));
+        std::memcpy(b.t, fp.cam.t, sizeof(b.t));
+        b.fx = fp.cam.fx;
+        b.fy = fp.cam.fy;
+        b.cx = fp.cam.cx == 0.0f ? 0.0f : fp.cam.cx;           // -0.0f -> +0.0f: identical pixel decisions (see BrickFrame)
+        b.cy = fp.cam.cy == 0.0f ? 0.0f : fp.cam.cy;
+        b.Wf = fp.cam.Wf;
+        b.Hf = fp.cam.Hf;
+        b.W = fp.cam.W;
+        b.pix_bias = (int)(0u - (0x4B000000u * (unsigned)fp.cam.W + 0x4B000000u));
+        b.thr_band = fp.trunc_param + fp.diag;                  // binary32 sums, as the kernels form them (__fadd_rn)
+        b.thr_carve = fp.carve ? fp.trunc_param + fp.carve_dist : INFINITY;
+        b.wu = colorPath ? fp.wu_const : 1.0f;
+        b.cutoff = fp.depth_cutoff;
+        b.depth = fp.depth;
+        b.color = fp.color_packed;
+        b.carve_max = fp.sdf_carve_max;
+        info.fastBricks = (!colorPath || fp.same_cam) && b.wu >= 0.125f && b.wu <= 1024.0f && b.thr_band <= 256.0f && std::isfinite(b.thr_band) &&
+                          (b.thr_carve == b.thr_carve);
+    }
+    info.brickFrames = &brickFrames;
     if (!poolLater)
         CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 3));
     else

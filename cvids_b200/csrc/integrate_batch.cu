@@ -35,6 +35,7 @@ namespace chs
 
 static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams is copied word-wise into shared memory");
 constexpr int kVirtualSlot = 0xFFFFFF;      // unit of a chunk that does not exist yet
+constexpr int kNoSlot = -2;                 // hash value of a key whose chunk could not be allocated (pool exhausted); -1 = "being created"
 
 // z slices of a brick per task: 4 = half brick (8 voxels per lane), 2 = quarter brick (4 voxels per lane)
 #ifndef CHS_BRICK_SLICES
@@ -548,9 +549,12 @@ __device__ __forceinline__ int get_or_create_chunk(const BatchParams &bp, const 
                 int s = atomicAdd(&map.ctr->n_chunks, 1);
                 if (s >= map.capacity)
                 {
+                    // pool exhausted (the host sizes it ahead of need, so this is a bug or an out-of-memory map): reported
+                    // through error_flags. The key stays in the table with the value kNoSlot: no chunk, nothing is stored, and the
+                    // waiters give up as well -- never alias another chunk's slot.
                     atomicOr(&map.ctr->error_flags, kErrPoolFull);
                     atomicSub(&map.ctr->n_chunks, 1);
-                    s = 0;                                          // reported through error_flags; keep the kernel well defined
+                    s = kNoSlot;
                 }
                 else
                 {
@@ -569,7 +573,7 @@ __device__ __forceinline__ int get_or_create_chunk(const BatchParams &bp, const 
         if (k == key)
         {
             int s;
-            while ((s = *reinterpret_cast<volatile int *>(&map.vals[i])) < 0)
+            while ((s = *reinterpret_cast<volatile int *>(&map.vals[i])) == -1)
                 __nanosleep(20);
             __threadfence();
             return s;
@@ -675,6 +679,8 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
             if (lane == 0)
                 slot = get_or_create_chunk(bp, map, key, x, y, z);
             slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < 0)
+                continue;                                           // pool exhausted: the unit is dropped, error_flags says so
         }
         {
             float2 *dist = dist_ptr(map, slot);
@@ -710,6 +716,413 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
             } while (old != assumed);
             first = (assumed >> 32) != (unsigned long long)(unsigned)bp.batch_id;
             newBits = updMask & ~(unsigned)(cur & 0xffffffffull);
+        }
+        first = __shfl_sync(0xffffffffu, first, 0);
+        newBits = __shfl_sync(0xffffffffu, newBits, 0);
+        if (first && lane < 27)
+            dirty_insert(map, pack_id(x + lane / 9 - 1, y + (lane / 3) % 3 - 1, z + lane % 3 - 1));
+        if (lane < kMaxBatch && ((newBits >> lane) & 1u))
+            atomicAdd(&sB.chunks[lane], 1);
+    }
+    batch_flush(bp, &sB);
+    batch_snapshot(bp, map);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// batch_bricks_fast_kernel -- the brick kernel for the common case (constant truncator, colour camera == depth camera, weight
+// update in [2^-3, 2^10]); everything else goes through batch_bricks_kernel above. Same tasks, same results, about half the
+// instructions per voxel and no dependent gather latency between the frames of a task:
+//   * the frame's constants come from the kernel's parameter block (constant bank, warp-uniform loads): no per-CTA staging,
+//     no shared-memory reads in the loop;
+//   * SOFTWARE PIPELINE over the frames of a task: projection + depth/colour gathers of frame f+1 are issued BEFORE the
+//     update of frame f (the pixel a voxel projects to does not depend on the voxel's state), so a task's chain is one gather
+//     latency plus K x ALU instead of K x (gather latency + ALU);
+//   * straight-line, predicate-selected update. What the reference decides with a branch is evaluated with exactly its
+//     operations; the operand-range preconditions of the guard-free reciprocal / quotient are
+//     established ONCE per task from the loaded state (weights in [0, 2^20], |sdf| <= 2^17) plus one chained compare per
+//     voxel and frame, and anything outside them (also a numerator that is exactly zero) redoes the frame with the IEEE
+//     intrinsics (exact_frame) -- nothing has been modified at that point;
+//   * on-image test on the bit patterns (u >= 0 && u < W  <=>  bits(u) < bits(W) for u != -0, which cannot occur once the
+//     principal point's -0 is canonicalised), pixel index from two round-toward-zero magic-number adds instead of F2I;
+//   * carving, rare in practice, is detected by one chained compare per voxel and handled out of line;
+//   * per-lane change flags instead of per-voxel masks: a lane that changed anything stores its kVPL voxels (same sectors).
+#ifndef CHS_FAST_THREADS
+#define CHS_FAST_THREADS 256
+#endif
+#ifndef CHS_FAST_MIN_CTAS
+#define CHS_FAST_MIN_CTAS 2
+#endif
+
+struct VoxState
+{
+    float sdf[kVPL], w[kVPL];
+    unsigned cv[kVPL];
+    unsigned cnt;          // this frame's per-lane counts: n_upd | n_carve << 10 | n_col << 20 (the order of BatchShared's arrays)
+    unsigned touchedC;     // != 0: a colour voxel of the lane changed
+};
+
+// What project_gather leaves for apply_frame.
+struct Fetch
+{
+    float d[kVPL];         // depth under the voxel's projection; NaN when the voxel is not on the image (then nothing can happen)
+    float cz[kVPL];        // camera-space z
+    unsigned c[kVPL];      // packed colour pixel (only fetched while the voxel's colour weight is below 8)
+    unsigned slow;         // != 0: some camera-space z of the lane is outside the guard-free reciprocal's range
+};
+
+// guard-free correctly rounded quotient for 2^-40 <= |a| < 2^40, 2^-40 <= b < 2^40 (a != 0: the callers send zero numerators
+// through the exact path, so the sign-of-zero fix of div_rn_inrange is not needed here)
+__device__ __forceinline__ float div_rn_fast(float a, float b)
+{
+    float r = mufu_rcp(b);
+    r = __fmaf_rn(r, __fmaf_rn(-b, r, 1.0f), r);
+    const float q = __fmul_rn(a, r);
+    return __fmaf_rn(r, __fmaf_rn(-b, q, a), q);
+}
+
+// 32-bit read-only load under a predicate, without a branch: `dflt` when the predicate is false (the address is not touched)
+__device__ __forceinline__ unsigned ldg_if(const unsigned *p, bool pred, unsigned dflt)
+{
+    unsigned r = dflt;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "+r"(r) : "l"(p), "r"((int)pred));
+    return r;
+}
+
+// Projection of the lane's kVPL voxels into frame F and the gathers under them (PinholeCamera.cpp:38-45, 61-64;
+// ProjectionIntegrator.h:64-72 / :117-131). px, py[2], pz[kNS]: world coordinates of the lane's voxel centres.
+template <bool COLOR_PATH>
+__device__ __forceinline__ void project_gather(const BrickFrame &F, float px, const float (&py)[2], const float (&pz)[kNS], bool hasCol,
+                                               const unsigned (&cv)[kVPL], Fetch &o)
+{
+    const float d0 = __fsub_rn(px, F.t[0]);
+    const float m00 = __fmul_rn(F.R[0], d0), m01 = __fmul_rn(F.R[1], d0), m02 = __fmul_rn(F.R[2], d0);
+    float m1[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        const float d1 = __fsub_rn(py[h], F.t[1]);
+        m1[h][0] = __fmul_rn(F.R[3], d1);
+        m1[h][1] = __fmul_rn(F.R[4], d1);
+        m1[h][2] = __fmul_rn(F.R[5], d1);
+    }
+    const unsigned wBits = __float_as_uint(F.Wf), hBits = __float_as_uint(F.Hf);
+    unsigned slow = 0u;
+#pragma unroll
+    for (int s = 0; s < kNS; s++)
+    {
+        const float d2 = __fsub_rn(pz[s], F.t[2]);
+        const float m20 = __fmul_rn(F.R[6], d2), m21 = __fmul_rn(F.R[7], d2), m22 = __fmul_rn(F.R[8], d2);
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+            const int k = s * 2 + h;
+            // c_j = R(0,j) d0 + (R(1,j) d1 + R(2,j) d2): Eigen's order
+            const float cx = __fadd_rn(m00, __fadd_rn(m1[h][0], m20));
+            const float cy = __fadd_rn(m01, __fadd_rn(m1[h][1], m21));
+            const float cz = __fadd_rn(m02, __fadd_rn(m1[h][2], m22));
+            o.cz[k] = cz;
+            // 2^-64 <= cz < 2^64: the guard-free reciprocal is exact there. Negative z (sign bit set, also -0 and negative NaN) is
+            // skipped by the reference anyway (z < 0, or 1/z = -inf puts u, v off the image); +0, positive tiny / huge / NaN
+            // values go through the exact path.
+            const unsigned zb = __float_as_uint(cz);
+            const bool inR = (zb - 0x1F800000u) < 0x40000000u;
+            slow |= (!inR && (int)zb >= 0) ? 1u : 0u;
+            const float invZ = rcp_rn_inrange(cz);
+            const float u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, cx), invZ), F.cx);
+            const float v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, cy), invZ), F.cy);
+            // u >= 0 && u < W && v >= 0 && v < H on the bit patterns (u, v are never -0: see BrickFrame)
+            const bool on = inR & (__float_as_uint(u) < wBits) & (__float_as_uint(v) < hBits);
+            // (int)u + (int)v * W: 2^23 + floor(x) has floor(x) in its low mantissa bits for 0 <= x < 2^23
+            const unsigned iu = __float_as_uint(__fadd_rz(u, 8388608.0f)), iv = __float_as_uint(__fadd_rz(v, 8388608.0f));
+            const unsigned pix = iv * (unsigned)F.W + (unsigned)F.pix_bias + iu;
+            // predicated loads (no branch): NaN depth / colour 0 for voxels that are not on the image. The colour of a voxel is
+            // frozen once its colour weight reaches 8 (:153); weights only grow, so a voxel that is below 8 now may need this
+            // frame's pixel, one that is not never will
+            o.d[k] = __uint_as_float(ldg_if(reinterpret_cast<const unsigned *>(F.depth) + pix, on, 0x7fc00000u));
+            o.c[k] = (COLOR_PATH && hasCol) ? ldg_if(F.color + pix, on & (cv[k] < 0x08000000u), 0u) : 0u;
+        }
+    }
+    o.slow = slow;
+}
+
+// One frame applied to the lane's voxels (ProjectionIntegrator.h:72-97 / :131-179, DistVoxel.h:52-60, ColorVoxel.h:65-85).
+// Returns false -- before anything is modified -- when an operand is outside the guard-free forms' ranges.
+template <bool COLOR_PATH>
+__device__ __forceinline__ bool apply_frame(const BrickFrame &F, const Fetch &g, bool hasCol, VoxState &v)
+{
+    float sd[kVPL], num[kVPL], den[kVPL];
+    bool band[kVPL];
+    bool far = false, tiny = false, anyCol = false;
+#pragma unroll
+    for (int k = 0; k < kVPL; k++)
+    {
+        sd[k] = __fsub_rn(g.d[k], g.cz[k]);                                              // :80 / :139
+        // depth path: skip depth > 50 (:74); colour path: skip NaN (:134) and depth > 100 (:141). A NaN depth (also: voxel off
+        // the image) fails every comparison below in both paths.
+        const bool valid = g.d[k] <= F.cutoff;
+        band[k] = valid & (fabsf(sd[k]) < F.thr_band);                                   // :82 / :143
+        far |= sd[k] > F.thr_carve;                                                      // :88 / :166 (superset: the rest is tested out of line)
+        num[k] = __fadd_rn(__fmul_rn(v.w[k], v.sdf[k]), __fmul_rn(F.wu, sd[k]));         // DistVoxel.h:52-60
+        den[k] = __fadd_rn(F.wu, v.w[k]);
+        tiny |= fabsf(num[k]) < 9.094947017729282e-13f;                                  // 2^-40 (also exactly zero)
+        if (COLOR_PATH)
+            anyCol |= band[k] & (v.cv[k] < 0x08000000u);
+    }
+    if (__any_sync(0xffffffffu, tiny | (g.slow != 0u)))
+        return false;
+    unsigned cnt = 0u;
+    if (__any_sync(0xffffffffu, far))
+    {
+        // carving: weight > 0 && sdf < 1e-5 (:90 / :169); colour path: weight < 5 resets, else weight -= 1 (:171-175)
+#pragma unroll
+        for (int k = 0; k < kVPL; k++)
+        {
+            const bool crv = (g.d[k] <= F.cutoff) & !band[k] & (sd[k] > F.thr_carve) & (v.w[k] > 0.0f) & (v.sdf[k] < F.carve_max);
+            const bool dec = COLOR_PATH && !(v.w[k] < 5.0f);
+            const float cs = dec ? v.sdf[k] : 99999.0f, cw = dec ? __fsub_rn(v.w[k], 1.0f) : 0.0f;
+            v.sdf[k] = crv ? cs : v.sdf[k];
+            v.w[k] = crv ? cw : v.w[k];
+            cnt += crv ? (1u << 10) : 0u;
+        }
+    }
+    if (COLOR_PATH && hasCol && __any_sync(0xffffffffu, anyCol))
+    {
+#pragma unroll
+        for (int k = 0; k < kVPL; k++)
+        {
+            const bool colOk = band[k] & (v.cv[k] < 0x08000000u);                        // :153
+            const unsigned cw = v.cv[k] >> 24;
+            const unsigned mrec = cRecip20[min(cw, 7u) + 1];
+            // r and b share one multiply-add (16-bit lanes: w * old + new <= 2040)
+            const unsigned nrb = cw * (v.cv[k] & 0x00FF00FFu) + (g.c[k] & 0x00FF00FFu);
+            const unsigned ng = cw * __byte_perm(v.cv[k], 0u, 0x4441) + __byte_perm(g.c[k], 0u, 0x4441);
+            const unsigned r = ((nrb & 0xFFFFu) * mrec) >> 20, b = ((nrb >> 16) * mrec) >> 20, gg = (ng * mrec) >> 20;
+            // r | g << 8 | b << 16 | (w + 1) << 24 (r, g, b <= 255: their upper bytes are the zero bytes of the permutes)
+            const unsigned nv = __byte_perm(__byte_perm(__byte_perm(r, gg, 0x1140), b, 0x3410), v.cv[k] + 0x01000000u, 0x7210);
+            v.cv[k] = colOk ? nv : v.cv[k];
+            cnt += colOk ? (1u << 20) : 0u;
+        }
+        v.touchedC |= cnt & (0x3FFu << 20);
+    }
+#pragma unroll
+    for (int k = 0; k < kVPL; k++)
+    {
+        const float q = div_rn_fast(num[k], den[k]);
+        const float w2 = __fadd_rn(v.w[k], F.wu);
+        v.sdf[k] = band[k] ? q : v.sdf[k];
+        v.w[k] = band[k] ? w2 : v.w[k];
+        cnt += band[k] ? 1u : 0u;
+    }
+    v.cnt = cnt;
+    return true;
+}
+
+// The frame redone with the IEEE intrinsics and per-voxel branches (frame_on_half_brick<..., FAST = false>): rare, out of line.
+template <int CS, bool COLOR_PATH>
+__device__ __noinline__ VoxState exact_frame(const FrameParams *fpp, const DeviceMap *mapp, VoxState v, int packedBrick, float orgx, float orgy, float orgz, bool hasCol)
+{
+    const int lane = threadIdx.x & 31;
+    const int bx = packedBrick & 0xFF, by = (packedBrick >> 8) & 0xFF, bz = (packedBrick >> 16) & 0xFF, half = packedBrick >> 24;
+    const FrameParams &fp = *fpp;
+    const DeviceMap &map = *mapp;
+    const BrickLane L = brick_lane_setup(fp, map, orgx, orgy, orgz, bx, by, bz, lane);
+    float2 dv[kVPL];
+#pragma unroll
+    for (int k = 0; k < kVPL; k++)
+        dv[k] = make_float2(v.sdf[k], v.w[k]);
+    unsigned wd = 0u, wc = 0u;
+    int nUpd = 0, nCarve = 0, nCol = 0;
+    bool carvable = false;
+    frame_on_half_brick<CS, COLOR_PATH, false, false>(fp, map, L, half, hasCol, dv, v.cv, wd, wc, nUpd, nCarve, nCol, carvable);
+#pragma unroll
+    for (int k = 0; k < kVPL; k++)
+    {
+        v.sdf[k] = dv[k].x;
+        v.w[k] = dv[k].y;
+    }
+    v.cnt = (unsigned)nUpd | ((unsigned)nCarve << 10) | ((unsigned)nCol << 20);
+    v.touchedC |= wc;
+    return v;
+}
+
+template <int CS, bool COLOR_PATH>
+__global__ void __launch_bounds__(CHS_FAST_THREADS, CHS_FAST_MIN_CTAS)
+batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_constant__ DeviceMap map, const __grid_constant__ BrickFrames bf)
+{
+    constexpr int BPA = CS / 8;
+    __shared__ BatchShared sB;
+    batch_shared_zero(&sB);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
+    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * kParts;
+    const bool hasCol = COLOR_PATH && map.use_color;
+    const float carveMax = bf.f[0].carve_max;
+    int g = 0;
+    if (lane == 0)
+        g = atomicAdd(&bp.bctr->next_task, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    while (g < nTasks)
+    {
+        // the next task's index is requested now and consumed at the end of this task: the atomic's round trip is hidden
+        int gNext = 0;
+        if (lane == 0)
+            gNext = atomicAdd(&bp.bctr->next_task, 1);
+        const int u = g / kParts;
+        const int4 unit = bp.units[u < nHeavy ? u : bp.units_cap - 1 - (u - nHeavy)];
+        const int half = g % kParts;                     // which group of kNS z slices of the brick
+        int x, y, z;
+        const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
+        unpack_id(key, &x, &y, &z);
+        int slot = unit.z & 0xFFFFFF;
+        const int b = unit.z >> 24;
+        const bool virt = slot == kVirtualSlot;
+        const unsigned bandM = (unsigned)unit.w & 0xFFFFu;
+        unsigned mask = bandM | ((unsigned)unit.w >> 16);
+        const float orgx = __fmul_rn((float)(CS * x), map.res), orgy = __fmul_rn((float)(CS * y), map.res), orgz = __fmul_rn((float)(CS * z), map.res);
+        const int bx = b % BPA, by = (b / BPA) % BPA, bz = b / (BPA * BPA);
+        const int idx0 = ((bz * 8 + kNS * half) * CS + (by * 8 + (lane >> 3))) * CS + bx * 8 + (lane & 7);
+        VoxState v;
+        v.touchedC = 0u;
+        v.cnt = 0u;
+        if (!virt)
+        {
+            const float2 *dist = dist_ptr(map, slot);
+            const unsigned *col = hasCol ? reinterpret_cast<const unsigned *>(color_ptr(map, slot)) : nullptr;
+#pragma unroll
+            for (int k = 0; k < kVPL; k++)
+            {
+                const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
+                const float2 d = dist[idx];
+                v.sdf[k] = d.x;
+                v.w[k] = d.y;
+                v.cv[k] = hasCol ? col[idx] : 0u;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < kVPL; k++)
+            {
+                v.sdf[k] = 99999.0f;                                // Chunk::Chunk initial state (DistVoxel.cpp:29-33)
+                v.w[k] = 0.0f;
+                v.cv[k] = 0u;
+            }
+        }
+        // world coordinates of the lane's voxel centres: centre_k = float(k) * res + res/2 (ChunkManager.cpp:52,61), p = centre +
+        // origin (ProjectionIntegrator.h:64). Lane = (x = lane & 7, y rows lane >> 3 and + 4), kNS z slices.
+        const float px = __fadd_rn(__fadd_rn(__fmul_rn((float)(bx * 8 + (lane & 7)), map.res), map.half), orgx);
+        float py[2], pz[kNS];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            py[h] = __fadd_rn(__fadd_rn(__fmul_rn((float)(by * 8 + (lane >> 3) + 4 * h), map.res), map.half), orgy);
+#pragma unroll
+        for (int s = 0; s < kNS; s++)
+            pz[s] = __fadd_rn(__fadd_rn(__fmul_rn((float)(bz * 8 + kNS * half + s), map.res), map.half), orgz);
+        // first frame's gathers go out before the voxel state is needed
+        int f = __ffs(mask) - 1;
+        mask &= mask - 1;
+        Fetch cur, nxt;
+        project_gather<COLOR_PATH>(bf.f[f], px, py, pz, hasCol, v.cv, cur);
+        // preconditions of the guard-free quotient over the whole task: 0 <= weight <= 2^20 (bit pattern compare: negative and
+        // NaN weights fail), |sdf| <= 2^17. Weights grow by at most 16 * 2^10 and |sdf| stays below max(|sdf|, band) inside a task.
+        bool stateOk = true;
+#pragma unroll
+        for (int k = 0; k < kVPL; k++)
+            stateOk &= (__float_as_uint(v.w[k]) <= 0x49800000u) & (fabsf(v.sdf[k]) <= 131072.0f);
+        const bool exactTask = !__all_sync(0xffffffffu, stateOk);
+        unsigned touchedD = 0u, updMask = 0u;
+        // One step: issue projection + gathers of the next frame of the mask into `b`, then apply frame f from `a`. The two
+        // buffers swap roles every step (the loop below is unrolled by two), so nothing is copied.
+        auto step = [&](const Fetch &a, Fetch &b) -> bool
+        {
+            int fn = -1;
+            if (mask)
+            {
+                fn = __ffs(mask) - 1;
+                mask &= mask - 1;
+                project_gather<COLOR_PATH>(bf.f[fn], px, py, pz, hasCol, v.cv, b);
+            }
+            bool run = true;
+            if (!((bandM >> f) & 1u))
+            {
+                // free-space frame: it can only carve, and only voxels with weight > 0 && sdf < 1e-5 (:90 / :169)
+                bool c = false;
+#pragma unroll
+                for (int k = 0; k < kVPL; k++)
+                    c |= (v.w[k] > 0.0f) & (v.sdf[k] < carveMax);
+                run = __any_sync(0xffffffffu, c);
+            }
+            if (run)
+            {
+                if (exactTask || !apply_frame<COLOR_PATH>(bf.f[f], a, hasCol, v))
+                    v = exact_frame<CS, COLOR_PATH>(bp.frames + f, &map, v, bx | (by << 8) | (bz << 16) | (half << 24), orgx, orgy, orgz, hasCol);
+                const unsigned tot = __reduce_add_sync(0xffffffffu, v.cnt);
+                touchedD |= v.cnt;
+                if (tot)
+                {
+                    updMask |= 1u << f;
+                    if (lane < 3)
+                    {
+                        const unsigned n = (tot >> (10 * lane)) & 0x3FFu;
+                        if (n)
+                            atomicAdd(&sB.upd[lane * kMaxBatch + f], (int)n);      // upd, carve, col are consecutive arrays of BatchShared
+                    }
+                }
+            }
+            f = fn;
+            return fn >= 0;
+        };
+        while (step(cur, nxt) && step(nxt, cur))
+        {
+        }
+        g = __shfl_sync(0xffffffffu, gNext, 0);
+        if (!updMask)
+            continue;                                               // nothing changed: no store, no chunk, no dirty mark
+        if (virt)
+        {
+            if (lane == 0)
+                slot = get_or_create_chunk(bp, map, key, x, y, z);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < 0)
+                continue;                                           // pool exhausted: the unit is dropped, error_flags says so
+        }
+        bool carvable = false;
+        {
+            float2 *dist = dist_ptr(map, slot);
+            unsigned *col = hasCol ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
+#pragma unroll
+            for (int k = 0; k < kVPL; k++)
+            {
+                const int idx = idx0 + (k >> 1) * CS * CS + (k & 1) * 4 * CS;
+                if (touchedD)
+                    dist[idx] = make_float2(v.sdf[k], v.w[k]);
+                if (hasCol && v.touchedC)
+                    col[idx] = v.cv[k];
+                carvable |= (v.w[k] > 0.0f) & (v.sdf[k] < carveMax);
+            }
+        }
+        if (__any_sync(0xffffffffu, carvable) && lane == 0)
+            atomicOr(&map.brick_flags[slot], 1ull << b);
+        // (batch id << 32) | frames of this batch that updated the chunk: the first warp of the batch marks the 27 neighbour IDs
+        // dirty (Chisel.h:89-101, 175-189); every newly set frame bit counts the chunk once for that frame
+        unsigned newBits = 0u;
+        int first = 0;
+        if (lane == 0)
+        {
+            const unsigned long long tag = (unsigned long long)(unsigned)bp.batch_id << 32;
+            unsigned long long old = bp.slot_batch[slot], assumed, curv;
+            do
+            {
+                assumed = old;
+                curv = ((assumed >> 32) == (unsigned long long)(unsigned)bp.batch_id) ? assumed : tag;
+                const unsigned long long nw = curv | updMask;
+                if (nw == assumed)
+                    break;
+                old = atomicCAS(&bp.slot_batch[slot], assumed, nw);
+            } while (old != assumed);
+            first = (assumed >> 32) != (unsigned long long)(unsigned)bp.batch_id;
+            newBits = updMask & ~(unsigned)(curv & 0xffffffffull);
         }
         first = __shfl_sync(0xffffffffu, first, 0);
         newBits = __shfl_sync(0xffffffffu, newBits, 0);
@@ -819,7 +1232,17 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         return cudaGetLastError();
     if (info.profiling && (e = cudaEventRecord(evt[7], st)) != cudaSuccess)
         return e;
-    batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
+    if (!PER_PIXEL && info.fastBricks)
+    {
+        static int residentFast = 0;
+        if (!residentFast)
+            residentFast = batch_resident(batch_bricks_fast_kernel<CS, COLOR_PATH>, CHS_FAST_THREADS);
+        const unsigned gFast = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_FAST_THREADS / 32 - 1) / (CHS_FAST_THREADS / 32), residentFast));
+        bp.total_ctas = (int)gFast;
+        batch_bricks_fast_kernel<CS, COLOR_PATH><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
+    }
+    else
+        batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)
         return e;
     return cudaGetLastError();

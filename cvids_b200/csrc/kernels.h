@@ -58,11 +58,39 @@ struct BatchParams
     unsigned long long *slot_batch; // [capacity] (batch id << 32) | mask of the batch's frames that updated the chunk
 };
 
+// What the fast brick kernel needs of one frame, 128 bytes, passed BY VALUE in the kernel's parameter block (constant bank): a
+// warp reads the frame it is working on with warp-uniform constant loads, nothing is staged through shared memory.
+struct alignas(16) BrickFrame
+{
+    float R[9];                     // row-major rotation, camera -> world
+    float t[3];
+    float fx, fy, cx, cy;           // cx, cy with -0.0f canonicalised to +0.0f (same pixel decisions; lets the on-image test be a
+                                    // compare of the float bit patterns)
+    float Wf, Hf;
+    int W;
+    int pix_bias;                   // -(M * W + M) mod 2^32, M = 0x4B000000: turns the magic-number floors into the pixel index
+    float thr_band;                 // trunc + diag          (ProjectionIntegrator.h:82 / :143)
+    float thr_carve;                // trunc + carvingDist   (:88 / :166); +inf when carving is off
+    float wu;                       // weight update: 1.0f (depth path, quirk Q7) or weight / (5 * trunc)
+    float cutoff;                   // 50 / 100
+    const float *depth;
+    const unsigned *color;          // packed r | g << 8 | b << 16
+    float carve_max;                // sdf < 1e-5 as a binary32 threshold
+    int pad[3];
+};
+static_assert(sizeof(BrickFrame) == 128, "BrickFrame is read as eight 16-byte constant loads");
+struct BrickFrames
+{
+    BrickFrame f[kMaxBatch];
+};
+
 struct BatchLaunchInfo
 {
     int W, H, cW, cH;               // depth / colour image size (identical for all frames of a batch)
     long long unionCandidates;      // chunk IDs in the union box
     bool colorPath, perPixel, profiling;
+    bool fastBricks;                // every frame satisfies the preconditions of batch_bricks_fast_kernel (brick_frames is filled)
+    const BrickFrames *brickFrames; // host pointer; copied into the kernel's parameter block
 };
 // The prepare kernel runs on stPrep and records `prepared`; candidates and bricks run on st after waiting for it.
 // events (profiling): [0] start, [1] after prepare (both on stPrep), [2] = [7] after candidates, [3] after bricks (on st)

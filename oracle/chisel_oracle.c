@@ -955,6 +955,23 @@ int orc_chunk_voxels(void *h, const int *id, float *sdf, float *weight, uint8_t 
     if (rgbw && m->chunks[idx].rgbw) memcpy(rgbw, m->chunks[idx].rgbw, 4 * m->V);
     return 1;
 }
+/* State injection for the import / checkpoint-resume parity tests (the reference has no such entry: its chunks are public
+ * objects a caller can fill, ChunkManager.h:79-87 AddChunk + Chunk::GetVoxelsMutable). Creates the chunk if absent. */
+void orc_set_chunk_voxels(void *h, const int *id, const float *sdf, const float *weight, const uint8_t *rgbw)
+{
+    Map *m = (Map *)h;
+    int idx = idmap_get(&m->chunkMap, id);
+    if (idx < 0)
+    {
+        uint8_t *zero = (uint8_t *)calloc(4, m->V);
+        add_chunk(m, id, sdf, weight, rgbw ? rgbw : zero);
+        free(zero);
+        return;
+    }
+    memcpy(m->chunks[idx].sdf, sdf, sizeof(float) * m->V);
+    memcpy(m->chunks[idx].weight, weight, sizeof(float) * m->V);
+    if (rgbw && m->chunks[idx].rgbw) memcpy(m->chunks[idx].rgbw, rgbw, 4 * m->V);
+}
 int orc_num_dirty(void *h) { return (int)((Map *)h)->dirty.n; }
 void orc_dirty_ids(void *h, int *out) { sorted_keys(&((Map *)h)->dirty, out); }
 int orc_num_meshes(void *h) { return (int)((Map *)h)->meshMap.n; }

@@ -40,6 +40,7 @@ void orc_update_meshes(void *h, int unused);
 int orc_num_chunks(void *h);
 void orc_chunk_ids(void *h, int *out);
 int orc_chunk_voxels(void *h, const int *id, float *sdf, float *weight, uint8_t *rgbw);
+void orc_set_chunk_voxels(void *h, const int *id, const float *sdf, const float *weight, const uint8_t *rgbw); /* test-only state injection */
 int orc_num_dirty(void *h);
 void orc_dirty_ids(void *h, int *out);
 int orc_num_meshes(void *h);

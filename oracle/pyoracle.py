@@ -278,6 +278,16 @@ class OracleChisel(RefChisel):
                                       np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(color), cW, cH, ch,
                                       _as_pose(cpose), np.ascontiguousarray(ccam, np.float32), 0)
 
+    def import_chunks(self, ids, sdf, weight, rgbw=None):
+        """Test-only state injection (same signature as capi.Chisel.import_chunks): overwrite / create the chunks `ids`."""
+        ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1, 3))
+        fn = self._lib.orc_set_chunk_voxels
+        fn.argtypes = [C.c_void_p, _i32p, _f32p, _f32p, C.c_void_p]
+        for i, cid in enumerate(ids):
+            c = np.ascontiguousarray(rgbw[i], np.uint8) if rgbw is not None else None
+            fn(self._h, np.ascontiguousarray(cid), np.ascontiguousarray(sdf[i], np.float32), np.ascontiguousarray(weight[i], np.float32),
+               c.ctypes.data if c is not None else None)
+
     def candidate_ids(self, pose, cam) -> np.ndarray:
         cap = 1 << 16
         while True:

@@ -293,3 +293,61 @@ def test_full_size_config5_eight_agents_one_batch_per_time_step():
         assert len(st) == 8 and all(s["error_flags"] == 0 for s in st)
     common.assert_state_equal(a.state(), b.state())
     assert np.array_equal(a.dirty(), b.dirty())
+
+
+def _axis_pose(t):
+    m = np.zeros((3, 4), np.float32)
+    m[0, 0] = m[1, 1] = m[2, 2] = 1.0
+    m[:, 3] = t
+    return m
+
+
+def test_batch_exact_fallback_paths():
+    """Inputs built to leave the ranges of the fast brick kernel's guard-free arithmetic, so that its exact fallback runs:
+    a power-of-two voxel size and an axis-aligned camera on a voxel centre make (a) camera-space z of a voxel layer exactly +0
+    (reciprocal out of range), (b) depth - z exactly 0 on a layer inside the band (numerator of DistVoxel::Integrate exactly 0).
+    Part of the image sees a surface 6 cm in front of the camera so that the z = 0 layer lies inside the band."""
+    cam = common.SMALL_CAM
+    frames = []
+    for i in range(6):
+        pose = _axis_pose((0.03125, 0.03125 * (1 + 2 * i), 0.03125 + 0.0625 * (i % 3)))
+        d = np.full((cam.height, cam.width), 1.0 + 0.0625 * (i % 2), np.float32)
+        d[:60, :80] = 0.0625
+        d[::7, ::5] = np.nan
+        col = np.full((cam.height, cam.width, 3), 100 + 10 * i, np.uint8)
+        frames.append((d, col, pose))
+    a, b = _run_batched(Setup(16, 0.0625, True), frames, cam, 3)
+    ids, sdf, w, _ = b.state()
+    assert int(((sdf == 0) & (w > 0)).sum()) > 100                  # the zero-numerator case really occurred
+
+
+def test_batch_state_outside_fast_preconditions():
+    """Voxel state outside the fast kernel's per-task preconditions (weight > 2^20, |sdf| > 2^17, negative weight) arrives through
+    chs_import_chunks; the batch that follows must treat it exactly like the oracle does."""
+    setup = Setup(16, 0.05, True)
+    cam = common.SMALL_CAM
+    frames = list(common.orbit_stream(cam, 6, total=30, color=True, seed=5))
+    a, b = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    camv = cam.as_array()
+    for depth, col, pose in frames[:2]:
+        a.integrate(depth, pose, camv, col)
+        b.integrate(depth, pose, camv, col)
+    ids, sdf, w, rgbw = b.state()
+    rng = np.random.RandomState(11)
+    sdf, w = sdf.copy(), w.copy()
+    obs = np.argwhere(w > 0)
+    pick = obs[rng.choice(len(obs), 600, replace=False)]
+    for j, (c, v) in enumerate(pick):
+        if j % 3 == 0:
+            w[c, v] = np.float32(3.0e6)
+        elif j % 3 == 1:
+            sdf[c, v] = np.float32(-2.5e5)
+        else:
+            w[c, v] = np.float32(-1.5)
+    a.m.import_chunks(ids, sdf, w, rgbw)
+    b.m.import_chunks(ids, sdf, w, rgbw)
+    grp = frames[2:]
+    a.m.integrate_batch(a.integ, [g[0] for g in grp], [g[2] for g in grp], camv, [g[1] for g in grp])
+    for depth, col, pose in grp:
+        b.integrate(depth, pose, camv, col)
+    common.assert_state_equal(a.state(), b.state())
