@@ -489,7 +489,7 @@ def run_cuda(args):
     m.set_profiling(True)
     upd_local = upd_single = 0
     bytes_alg = 0
-    t_integrate = t_prepare = t_cand = t_new = 0.0
+    t_integrate = t_prepare = t_cand = t_new = t_span = 0.0
     per_step = []
     parity_steps = min(args.parity_steps, warm + steps, max(1, n_unique // B))
     got_counters = []                              # per-frame counters of the first parity_steps steps (this rank's chunks)
@@ -510,6 +510,7 @@ def run_cuda(args):
             t_prepare += tm["prepare_ms"] / 1000.0
             t_cand += tm["candidates_ms"] / 1000.0
             t_new += tm["new_chunks_ms"] / 1000.0
+            t_span += tm.get("bricks_span_ms", 0.0) / 1000.0
             per_step.append((sum(st["n_upd"] for st in sts), sts[-1]["brick_units"], sum(st["candidates"] for st in sts), tm["integrate_ms"],
                              sum(st["updated_chunks"] for st in sts), sum(st["n_new"] for st in sts), sts[-1]["new_candidates"]))
     total_chunks = m.frame_stats()["total_chunks"]
@@ -741,13 +742,13 @@ def run_cuda(args):
                               "(depth-2 pipeline: copies of step k overlap kernels of step k-1)" if B > 1 else
                               "wall clock around chs_integrate_depth_color(host) + chs_get_frame_stats"},
             "e2e_depth_mm": e2e_mm,
-            "gpu_launches": (3 if B > 1 else 5) * steps,
+            "gpu_launches": (4 if B > 1 else 5) * steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r01_traffic.json)" if traffic else None,
                          "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_kernels / steps,
-                         "bricks_ms_per_launch": 1000.0 * t_integrate / steps, "new_chunks_ms_per_launch": 1000.0 * t_new / steps,
+                         "bricks_ms_per_launch": 1000.0 * t_integrate / steps, "bricks_span_ms_per_launch": 1000.0 * t_span / steps, "new_chunks_ms_per_launch": 1000.0 * t_new / steps,
                          "prepare_ms_per_launch": 1000.0 * t_prepare / steps, "candidates_ms_per_launch": 1000.0 * t_cand / steps,
                          "note": "algorithmic bytes = B_int of SURVEY 8(d) summed over the step's frames; with %d frames fused the voxel state "
                                  "moves through HBM once per step, so DRAM traffic is BELOW the algorithmic bytes" % B},

@@ -67,7 +67,7 @@ class chs_mesh_counts(C.Structure):
 
 class chs_timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("prepare_ms", "candidates_ms", "new_chunks_ms", "integrate_ms", "frame_ms",
-                                         "mesh_count_ms", "mesh_emit_ms", "mesh_ms")]
+                                         "mesh_count_ms", "mesh_emit_ms", "mesh_ms", "bricks_span_ms")]
 
 
 EXPORTS = (

@@ -172,7 +172,7 @@ struct chs_map
         unsigned *packed = nullptr;
         float2 *hiz = nullptr;
         size_t depthCap = 0, truncCap = 0, colorCap = 0, packedCap = 0, hizCap = 0;
-        cudaEvent_t copied = nullptr, prepared = nullptr, released = nullptr;
+        cudaEvent_t copied = nullptr, prepared = nullptr, released = nullptr, packDone = nullptr, fork = nullptr;
         bool used = false;
     } bset[2];
     cudaStream_t copyStream = nullptr;
@@ -181,6 +181,7 @@ struct chs_map
     HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
     unsigned long long *dSlotBatch = nullptr;  // [capacity]
     int batchId = 0, batchRingNext = 0;
+    long long lastBricksSpanNs = 0;
     // per-frame counters of the most recent chs_integrate_batch calls (a call is identified by its ticket)
     struct CallStats
     {
@@ -404,6 +405,7 @@ static chs_map::CallStats *call_stats(chs_map *m, int callId)
 
 static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base, int callId)
 {
+    m->lastBricksSpanNs = b.bricks_span_ns;
     m->knownChunks = b.n_chunks;
     m->knownDirty = b.n_dirty;
     const int K = std::min(std::max(b.K, 0), kMaxBatch);
@@ -597,7 +599,8 @@ static int ensure_capacity(chs_map *m, long long cand, long long dirtyBound, boo
             return rc;
     }
     const int bpa = m->cfg.chunk_size / 8;
-    if ((rc = grow_buffer(&m->dUnits, &m->unitsCap, (size_t)cand * bpa * bpa * bpa, st)) || (rc = grow_buffer(&m->dNews, &m->newsCap, (size_t)cand, st)))
+    // the fused path keeps its units in two buffers of cand * bricks entries (four cost buckets)
+    if ((rc = grow_buffer(&m->dUnits, &m->unitsCap, 2 * (size_t)cand * bpa * bpa * bpa, st)) || (rc = grow_buffer(&m->dNews, &m->newsCap, (size_t)cand, st)))
         return rc;
     return CHS_OK;
 }
@@ -979,7 +982,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         bp.n[k] = uhi[k] - ulo[k] + 1;
     }
     bp.units = m->dUnits;
-    bp.units_cap = (int)std::min<size_t>(m->unitsCap, 0x1fffffff);
+    bp.units_cap = (int)std::min<size_t>(m->unitsCap / 2, 0x1fffffff);
     {
         // smallest odd stride >= 7919 that is coprime to the box size
         long long stride = 7919;
@@ -1003,6 +1006,17 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     info.colorPath = colorPath;
     info.perPixel = perPixel;
     info.profiling = m->profiling;
+    {
+        // coarse Hi-Z levels in the candidates kernel's shared memory when they fit; then the Hi-Z kernel can be the TMA one
+        int coarse = 0;
+        for (int l = 4; l < fps[0].hiz_levels; l++)
+            coarse += fps[0].hizW[l] * fps[0].hizH[l];
+        bp.coarse_in_shared = coarse <= 48 ? 1 : 0;
+        bool tma = bp.coarse_in_shared && !perPixel && !anyMm && (cam->width % 4) == 0 && std::getenv("CHS_NO_TMA_HIZ") == nullptr;
+        for (int f = 0; f < K && tma; f++)
+            tma = (reinterpret_cast<size_t>(fps[f].depth) & 15) == 0;
+        info.hizTma = tma;
+    }
     // the fast brick kernel's per-frame constants and its preconditions (integrate_batch.cu: batch_bricks_fast_kernel)
     BrickFrames brickFrames;
     info.fastBricks = !perPixel && cam->width < (1 << 22) && cam->height < (1 << 22) && std::getenv("CHS_NO_FAST_BRICKS") == nullptr;
@@ -1032,13 +1046,16 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
                           (b.thr_carve == b.thr_carve);
     }
     info.brickFrames = &brickFrames;
+    // colour packing runs beside the candidates kernel: on the copy stream (host frames: it follows the copies and the Hi-Z kernel
+    // there; device frames: forked from the map's stream)
+    BatchStreams streams{cs, m->copyStream, st, bs.prepared, bs.packDone, bs.fork};
     if (!poolLater)
-        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 3));
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 3));
     else
     {
         // large candidate box and a pool that could not take the worst case: run prepare + candidates, read how many chunks the
         // batch can create at most (its virtual candidates), size the pool for exactly that, then run the brick kernel
-        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 1));
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 1));
         BatchCounters hc;
         CHS_CUDA(cudaMemcpyAsync(&hc, bs.dBctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
         CHS_CUDA(cudaStreamSynchronize(st));
@@ -1054,7 +1071,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         inf.newBound = hc.new_count;
         m->inflight.push_back(inf);
         bp.slot_batch = m->dSlotBatch;                              // the pool's side arrays may have moved
-        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, cs, bs.prepared, st, 2));
+        CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 2));
     }
     CHS_CUDA(cudaEventRecord(bs.released, st));
     bs.used = true;
@@ -1181,6 +1198,8 @@ int chs_create(const chs_config *cfg, chs_map **out)
         CHS_CUDA(cudaEventCreateWithFlags(&bs.copied, cudaEventDisableTiming));
         CHS_CUDA(cudaEventCreateWithFlags(&bs.prepared, cudaEventDisableTiming));
         CHS_CUDA(cudaEventCreateWithFlags(&bs.released, cudaEventDisableTiming));
+        CHS_CUDA(cudaEventCreateWithFlags(&bs.packDone, cudaEventDisableTiming));
+        CHS_CUDA(cudaEventCreateWithFlags(&bs.fork, cudaEventDisableTiming));
     }
     CHS_CUDA(cudaHostAlloc((void **)&m->hBatchSnap, sizeof(HostBatchSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hBatchSnap, 0, sizeof(HostBatchSnapshot) * chs_map::kRing);
@@ -1230,6 +1249,8 @@ int chs_destroy(chs_map *m)
         if (bs.copied) cudaEventDestroy(bs.copied);
         if (bs.prepared) cudaEventDestroy(bs.prepared);
         if (bs.released) cudaEventDestroy(bs.released);
+        if (bs.packDone) cudaEventDestroy(bs.packDone);
+        if (bs.fork) cudaEventDestroy(bs.fork);
     }
     cudaFree(m->dHizTickets);
     if (m->callEvent)
@@ -1483,6 +1504,12 @@ int chs_get_timings(chs_map *m, chs_timings *out)
         CHS_CUDA(cudaEventElapsedTime(&out->new_chunks_ms, m->evt[2], m->evt[7]));
         CHS_CUDA(cudaEventElapsedTime(&out->integrate_ms, m->evt[7], m->evt[3]));
         CHS_CUDA(cudaEventElapsedTime(&out->frame_ms, m->evt[0], m->evt[3]));
+    }
+    {
+        int rc = poll_inflight(m, true);
+        if (rc)
+            return rc;
+        out->bricks_span_ms = (float)((double)m->lastBricksSpanNs * 1e-6);
     }
     if (m->meshTimed)
     {

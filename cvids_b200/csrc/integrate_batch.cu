@@ -35,6 +35,7 @@ namespace chs
 
 static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams is copied word-wise into shared memory");
 constexpr int kVirtualSlot = 0xFFFFFF;      // unit of a chunk that does not exist yet
+constexpr int kCoarseTiles = 48;            // Hi-Z tiles of the levels >= 4 of one frame that batch_candidates_kernel keeps in shared memory
 constexpr int kNoSlot = -2;                 // hash value of a key whose chunk could not be allocated (pool exhausted); -1 = "being created"
 
 // z slices of a brick per task: 4 = half brick (8 voxels per lane), 2 = quarter brick (4 voxels per lane)
@@ -62,8 +63,8 @@ __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &
     __syncthreads();
 }
 
-// grid = (tiles + pack blocks, K): the first `tiles` CTAs of a frame build its Hi-Z levels, the others pack its colour image
-__global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, DeviceMap map, int tilesX, int tiles)
+// grid = (64x64 pixel tiles, K): Hi-Z levels (+ per-pixel truncation, millimetre conversion) of every frame of the batch
+__global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMap map, int tilesX)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0)
     {
@@ -72,16 +73,171 @@ __global__ void __launch_bounds__(256) batch_prepare_kernel(BatchParams bp, Devi
             c[i] = 0;
     }
     const FrameParams &fp = bp.frames[blockIdx.y];
-    if ((int)blockIdx.x < tiles)
-        frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
-    else
-        color_pack_body(fp, (blockIdx.x - tiles) * blockDim.x + threadIdx.x, (gridDim.x - tiles) * blockDim.x);
+    frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
+}
+
+// grid = (pack blocks, K): packed colour image of every frame (ColorImage::At once per pixel). Only the brick kernel reads it, so
+// this runs beside the candidates kernel.
+__global__ void __launch_bounds__(256) batch_pack_kernel(BatchParams bp)
+{
+    const FrameParams &fp = bp.frames[blockIdx.y];
+    color_pack_body(fp, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ---- Hi-Z with TMA bulk copies -----------------------------------------------------------------------------------------
+// The common case (float depth, constant truncator, W % 4 == 0, 16-byte aligned image): a PERSISTENT grid; every CTA walks
+// (frame, 64x64 tile) items with a three-stage ring of shared-memory tiles filled by cp.async.bulk row copies (the TMA
+// engine; one mbarrier per stage counts the bytes), so that each CTA keeps up to 48 KB of DRAM reads in flight without a
+// register or a thread waiting on them. Levels 0..3 go to global memory; the coarser levels are built by the candidates
+// kernel in shared memory (no "last block of the frame" serialisation).
+constexpr int kHizStages = 3;
+constexpr int kHizPitch = 68;                          // floats per shared row: 64 + 4 (rows stay 16-byte aligned)
+constexpr int kHizThreads = 128;
+constexpr size_t kHizSmem = (size_t)kHizStages * 64 * kHizPitch * sizeof(float);
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)), "l"(srcGlobal),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams bp, int tilesX, int tilesPerFrame, int nItems)
+{
+    extern __shared__ __align__(128) unsigned char hizSmem[];
+    float *stage = reinterpret_cast<float *>(hizSmem);
+    __shared__ __align__(8) unsigned long long full[kHizStages];
+    __shared__ float2 s0[64], s1[16], s2[4];
+    const int t = threadIdx.x, lane = t & 31;
+    if (blockIdx.x == 0)
+    {
+        int *c = reinterpret_cast<int *>(bp.bctr);
+        for (int i = t; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
+            c[i] = 0;
+    }
+    if (t == 0)
+    {
+        for (int s = 0; s < kHizStages; s++)
+            mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nMine = ((int)blockIdx.x < nItems) ? (nItems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // warp 0 issues the row copies of item j into stage s: lane r rows r and r + 32
+    auto issue = [&](int j, int s)
+    {
+        const int item = (int)blockIdx.x + j * (int)gridDim.x;
+        const FrameParams &fp = bp.frames[item / tilesPerFrame];
+        const int tile = item % tilesPerFrame, x0 = (tile % tilesX) * 64, y0 = (tile / tilesX) * 64;
+        const int W = fp.cam.W, H = fp.cam.H;
+        const unsigned rowBytes = (unsigned)min(64, W - x0) * 4u;
+        const int nRows = min(64, H - y0);
+        if (lane == 0)
+            mbar_expect_tx(&full[s], rowBytes * (unsigned)nRows);
+        __syncwarp();
+        float *dst = stage + (size_t)s * 64 * kHizPitch;
+        for (int r = lane; r < nRows; r += 32)
+            bulk_g2s(dst + r * kHizPitch, fp.depth + (size_t)(y0 + r) * W + x0, rowBytes, &full[s]);
+    };
+    if (t < 32)
+        for (int j = 0; j < min(kHizStages, nMine); j++)
+            issue(j, j);
+    const int tile8 = t >> 1, sub = t & 1;                 // 64 tiles of 8x8 pixels, 2 threads per tile (4 rows each)
+    for (int j = 0; j < nMine; j++)
+    {
+        const int s = j % kHizStages;
+        const int item = (int)blockIdx.x + j * (int)gridDim.x;
+        const FrameParams &fp = bp.frames[item / tilesPerFrame];
+        const int tile = item % tilesPerFrame, bx = tile % tilesX, by = tile / tilesX;
+        const int W = fp.cam.W, H = fp.cam.H;
+        mbar_wait(&full[s], (unsigned)(j / kHizStages) & 1u);
+        const float *src = stage + (size_t)s * 64 * kHizPitch;
+        const int lx = (tile8 & 7) * 8, ly = (tile8 >> 3) * 8 + sub * 4;
+        float lo = INFINITY, hi = -INFINITY;
+        if (bx * 64 + lx < W)
+        {
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                const bool in = by * 64 + ly + r < H;
+                const float nanv = __int_as_float(0x7fc00000);
+                const float4 *row = reinterpret_cast<const float4 *>(src + (ly + r) * kHizPitch + lx);
+                v[2 * r] = in ? row[0] : make_float4(nanv, nanv, nanv, nanv);
+                v[2 * r + 1] = (in && bx * 64 + lx + 4 < W) ? row[1] : make_float4(nanv, nanv, nanv, nanv);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                hiz_accumulate(fp, v[k].x, fp.trunc_param, &lo, &hi);
+                hiz_accumulate(fp, v[k].y, fp.trunc_param, &lo, &hi);
+                hiz_accumulate(fp, v[k].z, fp.trunc_param, &lo, &hi);
+                hiz_accumulate(fp, v[k].w, fp.trunc_param, &lo, &hi);
+            }
+        }
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, 1));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+        const int tx = bx * 8 + (tile8 & 7), ty = by * 8 + (tile8 >> 3);
+        if (sub == 0)
+        {
+            s0[tile8] = make_float2(lo, hi);
+            if (tx < fp.hizW[0] && ty < fp.hizH[0])
+                fp.hiz[0][ty * fp.hizW[0] + tx] = make_float2(lo, hi);
+        }
+        __syncthreads();                                    // also: every thread is done reading the stage
+        if (t < 32 && j + kHizStages < nMine)
+            issue(j + kHizStages, s);
+        if (t < 16)
+        {
+            const int ax = t & 3, ay = t >> 2;
+            float2 a = s0[(ay * 2) * 8 + ax * 2], b = s0[(ay * 2) * 8 + ax * 2 + 1], c = s0[(ay * 2 + 1) * 8 + ax * 2], d = s0[(ay * 2 + 1) * 8 + ax * 2 + 1];
+            const float2 v = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
+            s1[t] = v;
+            const int gx = bx * 4 + ax, gy = by * 4 + ay;
+            if (gx < fp.hizW[1] && gy < fp.hizH[1])
+                fp.hiz[1][gy * fp.hizW[1] + gx] = v;
+        }
+        __syncthreads();
+        if (t < 4)
+        {
+            const int ax = t & 1, ay = t >> 1;
+            float2 a = s1[(ay * 2) * 4 + ax * 2], b = s1[(ay * 2) * 4 + ax * 2 + 1], c = s1[(ay * 2 + 1) * 4 + ax * 2], d = s1[(ay * 2 + 1) * 4 + ax * 2 + 1];
+            const float2 v = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
+            s2[t] = v;
+            const int gx = bx * 2 + ax, gy = by * 2 + ay;
+            if (gx < fp.hizW[2] && gy < fp.hizH[2])
+                fp.hiz[2][gy * fp.hizW[2] + gx] = v;
+        }
+        __syncthreads();
+        if (t == 0)
+        {
+            const float2 v = make_float2(fminf(fminf(s2[0].x, s2[1].x), fminf(s2[2].x, s2[3].x)), fmaxf(fmaxf(s2[0].y, s2[1].y), fmaxf(s2[2].y, s2[3].y)));
+            fp.hiz[3][by * fp.hizW[3] + bx] = v;
+        }
+    }
 }
 
 // Emit the unit of brick b of chunk (x, y, z): `active` lanes hold one brick each. Free-space frames can only carve: the brick must
-// hold an observed voxel -- its flag says so, or an EARLIER band frame of this batch may create one (batch_bricks_kernel checks
-// the actual register state before it spends a frame on it). Units with many frames go to the front of the list, the others to
-// the back: batch_bricks_kernel hands tasks out front to back, so the long tasks start first and the short ones fill the tail.
+// hold an observed voxel -- its flag says so, or an EARLIER band frame of this batch may create one (the brick kernels check
+// the actual register state before they spend a frame on it). Units are ordered by COST (frames to apply), in four buckets:
+// the brick kernels hand tasks out bucket by bucket, so the long tasks start first and the shortest ones fill the tail.
+__device__ __forceinline__ int unit_bucket(int frames, int K) { return 4 * frames > 3 * K ? 0 : (2 * frames > K ? 1 : (4 * frames > K ? 2 : 3)); }
+
 __device__ __forceinline__ void emit_brick_unit(const BatchParams &bp, bool active, unsigned long long key, int slot, bool exists, bool virt, bool carve,
                                                 unsigned long long flags, int b, unsigned band, unsigned freeFrames, int K, unsigned lane)
 {
@@ -90,25 +246,53 @@ __device__ __forceinline__ void emit_brick_unit(const BatchParams &bp, bool acti
     if (!(exists && ((flags >> b) & 1ull)))
         fm &= afterBand;
     const bool keepB = active && ((exists && (band | fm) != 0u) || (virt && band != 0u));
-    const bool heavy = keepB && 2 * __popc(band | fm) > K;
-    const unsigned hm = __ballot_sync(0xffffffffu, heavy), lm = __ballot_sync(0xffffffffu, keepB && !heavy);
-    int hbase = 0, lbase = 0;
-    if (lane == 0)
+    const int bucket = keepB ? unit_bucket(__popc(band | fm), K) : -1;
+    unsigned bm[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        bm[q] = __ballot_sync(0xffffffffu, bucket == q);
+    int base = 0;
+    const unsigned laneMask = lane == 0 ? bm[0] : (lane == 1 ? bm[1] : (lane == 2 ? bm[2] : bm[3]));     // lanes 0..3 reserve for buckets 0..3
+    if (lane < 4 && laneMask)
     {
-        if (hm)
-            hbase = atomicAdd(&bp.bctr->unit_count, __popc(hm));
-        if (lm)
-            lbase = atomicAdd(&bp.bctr->light_count, __popc(lm));
+        int *ctr = lane == 0 ? &bp.bctr->unit_count : (lane == 1 ? &bp.bctr->bucket1 : (lane == 2 ? &bp.bctr->bucket2 : &bp.bctr->light_count));
+        base = atomicAdd(ctr, __popc(laneMask));
     }
-    hbase = __shfl_sync(0xffffffffu, hbase, 0);
-    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+    const int myBase = __shfl_sync(0xffffffffu, base, bucket & 3);
     if (keepB)
     {
-        const unsigned below = (1u << lane) - 1;
-        const int pos = heavy ? hbase + __popc(hm & below) : bp.units_cap - 1 - (lbase + __popc(lm & below));
+        const unsigned mine = bucket == 0 ? bm[0] : (bucket == 1 ? bm[1] : (bucket == 2 ? bm[2] : bm[3]));
+        const int rank = myBase + __popc(mine & ((1u << lane) - 1));
+        // buckets 0 / 2 grow from the front of their buffer, 1 / 3 from the back
+        const int pos = ((bucket & 1) ? bp.units_cap - 1 - rank : rank) + (bucket >> 1) * bp.units_cap;
         bp.units[pos] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32), (exists ? slot : kVirtualSlot) | (b << 24),
                                   (int)(band | (fm << 16)));
     }
+}
+
+// Unit number u of the batch in cost order (bucket 0 first). nb[q]: units in bucket q.
+struct UnitCounts
+{
+    int n0, n01, n012, total;
+};
+__device__ __forceinline__ UnitCounts unit_counts(const BatchParams &bp)
+{
+    UnitCounts c;
+    c.n0 = bp.bctr->unit_count;
+    c.n01 = c.n0 + bp.bctr->bucket1;
+    c.n012 = c.n01 + bp.bctr->bucket2;
+    c.total = c.n012 + bp.bctr->light_count;
+    return c;
+}
+__device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCounts &c, int u)
+{
+    if (u < c.n0)
+        return u;
+    if (u < c.n01)
+        return bp.units_cap - 1 - (u - c.n0);
+    if (u < c.n012)
+        return bp.units_cap + (u - c.n01);
+    return 2 * bp.units_cap - 1 - (u - c.n012);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -129,7 +313,50 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
     constexpr int GL = NB >= 32 ? 32 : NB;
     constexpr int BPL = NB / GL;
     __shared__ FrameParams sF[kMaxBatch];
+    __shared__ float2 sCoarse[kMaxBatch][kCoarseTiles];
     load_frames(sF, bp);
+    if (bp.coarse_in_shared)
+    {
+        // Hi-Z levels >= 4 (tiles of 128 pixels and up, until at most 3x3 tiles cover the image) of every frame, from level 3:
+        // a few dozen tiles per frame, rebuilt by every CTA in shared memory instead of by the last block of the Hi-Z kernel
+        const int K = bp.K;
+        int off = 0;
+        for (int l = 4; l < sF[0].hiz_levels; l++)
+        {
+            const int w = sF[0].hizW[l], h = sF[0].hizH[l], pw = sF[0].hizW[l - 1], ph = sF[0].hizH[l - 1];
+            for (int i = threadIdx.x; i < K * w * h; i += blockDim.x)
+            {
+                const int f = i / (w * h), r = i - f * (w * h), ox = r % w, oy = r / w;
+                const float2 *prev = (l == 4) ? sF[f].hiz[3] : &sCoarse[f][off - pw * ph];
+                float mn = INFINITY, mx = -INFINITY;
+                for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++)
+                    {
+                        const int qx = ox * 2 + dx, qy = oy * 2 + dy;
+                        if (qx < pw && qy < ph)
+                        {
+                            const float2 v = prev[qy * pw + qx];
+                            mn = fminf(mn, v.x);
+                            mx = fmaxf(mx, v.y);
+                        }
+                    }
+                sCoarse[f][off + r] = make_float2(mn, mx);
+            }
+            __syncthreads();
+            off += w * h;
+        }
+        // point the frames' coarse levels at the shared copies (generic addresses; classify_box<true> reads them with plain loads)
+        if (threadIdx.x < K)
+        {
+            int o = 0;
+            for (int l = 4; l < sF[0].hiz_levels; l++)
+            {
+                sF[threadIdx.x].hiz[l] = &sCoarse[threadIdx.x][o];
+                o += sF[0].hizW[l] * sF[0].hizH[l];
+            }
+        }
+        __syncthreads();
+    }
     // chunks created by this batch will occupy the pool slots from here on (this kernel runs on the map's stream, after every
     // earlier batch; the prepare kernel may run ahead on the copy stream)
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -170,7 +397,7 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
                 if (!frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
                     continue;
                 candM |= 1u << f;
-                const int code = classify_box(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
+                const int code = classify_box<true>(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
                 chunkBand |= (code == 2 ? 1u : 0u) << f;
                 chunkFree |= (code == 1 ? 1u : 0u) << f;
             }
@@ -221,8 +448,8 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
             {
                 const int b = gl + k * GL;
                 const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
-                const int code = classify_box(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
-                                              bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
+                const int code = classify_box<true>(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
+                                                    bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
                 bandM[k] |= (code == 2 ? 1u : 0u) << f;
                 freeM[k] |= (code == 1 ? 1u : 0u) << f;
             }
@@ -287,10 +514,24 @@ __device__ __forceinline__ void batch_count_frame(BatchShared *s, int f, int nUp
     }
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void batch_span_start(const BatchParams &bp)
+{
+    if (threadIdx.x == 0)
+        atomicMax(&bp.bctr->span_start_inv, ~global_timer_ns());
+}
+
 __device__ __forceinline__ void batch_flush(const BatchParams &bp, BatchShared *s)
 {
     __syncthreads();
     const int t = threadIdx.x;
+    if (t == 0)
+        atomicMax(&bp.bctr->span_end, global_timer_ns());
     if (t < bp.K)
     {
         BatchCounters *c = bp.bctr;
@@ -345,9 +586,10 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
         h->n_chunks = g->n_chunks;
         h->n_dirty = g->n_dirty;
         h->error_flags = g->error_flags;
-        h->unit_count = c->unit_count + c->light_count;
+        h->unit_count = c->unit_count + c->bucket1 + c->bucket2 + c->light_count;
         h->new_count = c->new_count;
         h->K = bp.K;
+        h->bricks_span_ns = (long long)(c->span_end - ~c->span_start_inv);
     }
     if (t < kMaxBatch)
     {
@@ -591,11 +833,13 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
     constexpr int BPA = CS / 8;
     __shared__ FrameParams sF[kMaxBatch];
     __shared__ BatchShared sB;
+    batch_span_start(bp);
     batch_shared_zero(&sB);
     load_frames(sF, bp);
     const int lane = threadIdx.x & 31;
     // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
-    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * kParts;
+    const UnitCounts uc = unit_counts(bp);
+    const int nTasks = uc.total * kParts;
     const bool hasCol = COLOR_PATH && map.use_color;
     const float carveMax = sF[0].sdf_carve_max;
     while (true)
@@ -607,7 +851,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
         if (g >= nTasks)
             break;
         const int u = g / kParts;
-        const int4 unit = bp.units[u < nHeavy ? u : bp.units_cap - 1 - (u - nHeavy)];
+        const int4 unit = bp.units[unit_position(bp, uc, u)];
         const int half = g % kParts;                     // which group of kNS z slices of the brick
         int x, y, z;
         const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
@@ -780,17 +1024,21 @@ __device__ __forceinline__ float div_rn_fast(float a, float b)
     return __fmaf_rn(r, __fmaf_rn(-b, q, a), q);
 }
 
-// 32-bit read-only load under a predicate, without a branch: `dflt` when the predicate is false (the address is not touched)
+// 32-bit read-only load under a predicate, without a branch: `dflt` when the predicate is false (the address is not touched).
+// Default and load write the same register inside one asm block, so that no copy of the loaded value (= a wait for the load)
+// lands behind it.
 __device__ __forceinline__ unsigned ldg_if(const unsigned *p, bool pred, unsigned dflt)
 {
-    unsigned r = dflt;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "+r"(r) : "l"(p), "r"((int)pred));
+    unsigned r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.b32 %0, %3;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(r) : "l"(p), "r"((int)pred), "r"(dflt));
     return r;
 }
 
 // Projection of the lane's kVPL voxels into frame F and the gathers under them (PinholeCamera.cpp:38-45, 61-64;
 // ProjectionIntegrator.h:64-72 / :117-131). px, py[2], pz[kNS]: world coordinates of the lane's voxel centres.
-template <bool COLOR_PATH>
+// FIRST: the first frame of a task, issued while the voxel state is still on its way from memory -- the colour pixel is then
+// fetched without looking at the colour weight.
+template <bool COLOR_PATH, bool FIRST>
 __device__ __forceinline__ void project_gather(const BrickFrame &F, float px, const float (&py)[2], const float (&pz)[kNS], bool hasCol,
                                                const unsigned (&cv)[kVPL], Fetch &o)
 {
@@ -821,12 +1069,12 @@ __device__ __forceinline__ void project_gather(const BrickFrame &F, float px, co
             const float cy = __fadd_rn(m01, __fadd_rn(m1[h][1], m21));
             const float cz = __fadd_rn(m02, __fadd_rn(m1[h][2], m22));
             o.cz[k] = cz;
-            // 2^-64 <= cz < 2^64: the guard-free reciprocal is exact there. Negative z (sign bit set, also -0 and negative NaN) is
-            // skipped by the reference anyway (z < 0, or 1/z = -inf puts u, v off the image); +0, positive tiny / huge / NaN
-            // values go through the exact path.
+            // 2^-64 <= cz < 2^64: the guard-free reciprocal is exact there. Anything else (voxels behind or in the plane of the
+            // camera, absurd coordinates) sends the warp's frame through the exact path; bricks that straddle the camera plane
+            // are rare (they lie in free space unless a surface is closer than the band).
             const unsigned zb = __float_as_uint(cz);
             const bool inR = (zb - 0x1F800000u) < 0x40000000u;
-            slow |= (!inR && (int)zb >= 0) ? 1u : 0u;
+            slow |= inR ? 0u : 1u;
             const float invZ = rcp_rn_inrange(cz);
             const float u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, cx), invZ), F.cx);
             const float v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, cy), invZ), F.cy);
@@ -839,7 +1087,7 @@ __device__ __forceinline__ void project_gather(const BrickFrame &F, float px, co
             // frozen once its colour weight reaches 8 (:153); weights only grow, so a voxel that is below 8 now may need this
             // frame's pixel, one that is not never will
             o.d[k] = __uint_as_float(ldg_if(reinterpret_cast<const unsigned *>(F.depth) + pix, on, 0x7fc00000u));
-            o.c[k] = (COLOR_PATH && hasCol) ? ldg_if(F.color + pix, on & (cv[k] < 0x08000000u), 0u) : 0u;
+            o.c[k] = (COLOR_PATH && hasCol) ? ldg_if(F.color + pix, FIRST ? on : (on & (cv[k] < 0x08000000u)), 0u) : 0u;
         }
     }
     o.slow = slow;
@@ -945,31 +1193,61 @@ __device__ __noinline__ VoxState exact_frame(const FrameParams *fpp, const Devic
     return v;
 }
 
-template <int CS, bool COLOR_PATH>
+template <int CS, bool COLOR_PATH, bool HAS_COL>
 __global__ void __launch_bounds__(CHS_FAST_THREADS, CHS_FAST_MIN_CTAS)
 batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_constant__ DeviceMap map, const __grid_constant__ BrickFrames bf)
 {
     constexpr int BPA = CS / 8;
+    constexpr int kSlabCache = 256;                     // slab base pointers kept in shared memory (256 K chunks); beyond: global
     __shared__ BatchShared sB;
+    __shared__ float2 *sDist[kSlabCache];
+    __shared__ uchar4 *sCol[kSlabCache];
+    batch_span_start(bp);
     batch_shared_zero(&sB);
+    constexpr bool hasCol = COLOR_PATH && HAS_COL;          // HAS_COL: the map stores colour voxels (compile time: no duplicated code paths)
+    {
+        const int nSlabs = min((map.capacity + kSlabChunks - 1) >> kSlabChunksLog2, kSlabCache);
+        for (int i = threadIdx.x; i < nSlabs; i += blockDim.x)
+        {
+            sDist[i] = map.dist_slabs[i];
+            sCol[i] = hasCol ? map.color_slabs[i] : nullptr;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
-    const int nHeavy = bp.bctr->unit_count, nTasks = (nHeavy + bp.bctr->light_count) * kParts;
-    const bool hasCol = COLOR_PATH && map.use_color;
+    const UnitCounts uc = unit_counts(bp);
+    const int nTasks = uc.total * kParts;
     const float carveMax = bf.f[0].carve_max;
-    int g = 0;
-    if (lane == 0)
-        g = atomicAdd(&bp.bctr->next_task, 1);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    while (g < nTasks)
+    // Task queue, two entries deep, kept in lanes 0 and 1: entry p is requested (atomicAdd) at a task boundary, its unit record is
+    // loaded at the next boundary and it is consumed at the one after, so neither round trip is ever waited for. Tasks are handed
+    // out in cost order (bucket 0 first).
+    int qg = 0x7fffffff;
+    int4 qu = make_int4(0, 0, 0, 0);
     {
-        // the next task's index is requested now and consumed at the end of this task: the atomic's round trip is hidden
-        int gNext = 0;
+        int base = 0;
         if (lane == 0)
-            gNext = atomicAdd(&bp.bctr->next_task, 1);
-        const int u = g / kParts;
-        const int4 unit = bp.units[u < nHeavy ? u : bp.units_cap - 1 - (u - nHeavy)];
+            base = atomicAdd(&bp.bctr->next_task, 2);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < 2)
+            qg = base + lane;
+        if (lane == 0 && qg < nTasks)
+            qu = bp.units[unit_position(bp, uc, qg / kParts)];
+    }
+    for (int t = 0;; t++)
+    {
+        const int p = t & 1;
+        const int g = __shfl_sync(0xffffffffu, qg, p);
+        if (g >= nTasks)
+            break;
+        int4 unit;
+        unit.x = __shfl_sync(0xffffffffu, qu.x, p);
+        unit.y = __shfl_sync(0xffffffffu, qu.y, p);
+        unit.z = __shfl_sync(0xffffffffu, qu.z, p);
+        unit.w = __shfl_sync(0xffffffffu, qu.w, p);
+        if (lane == p)
+            qg = atomicAdd(&bp.bctr->next_task, 1);                     // consumed two boundaries from now
+        if (lane == 1 - p && qg < nTasks)
+            qu = bp.units[unit_position(bp, uc, qg / kParts)];         // requested at the previous boundary, consumed at the next
         const int half = g % kParts;                     // which group of kNS z slices of the brick
         int x, y, z;
         const unsigned long long key = ((unsigned long long)(unsigned)unit.y << 32) | (unsigned long long)(unsigned)unit.x;
@@ -987,8 +1265,10 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
         v.cnt = 0u;
         if (!virt)
         {
-            const float2 *dist = dist_ptr(map, slot);
-            const unsigned *col = hasCol ? reinterpret_cast<const unsigned *>(color_ptr(map, slot)) : nullptr;
+            const int sl = slot >> kSlabChunksLog2;
+            const size_t off = (size_t)(slot & (kSlabChunks - 1)) * map.V;
+            const float2 *dist = (sl < kSlabCache ? sDist[sl] : map.dist_slabs[sl]) + off;
+            const unsigned *col = hasCol ? reinterpret_cast<const unsigned *>((sl < kSlabCache ? sCol[sl] : map.color_slabs[sl]) + off) : nullptr;
 #pragma unroll
             for (int k = 0; k < kVPL; k++)
             {
@@ -1023,7 +1303,7 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
         int f = __ffs(mask) - 1;
         mask &= mask - 1;
         Fetch cur, nxt;
-        project_gather<COLOR_PATH>(bf.f[f], px, py, pz, hasCol, v.cv, cur);
+        project_gather<COLOR_PATH, true>(bf.f[f], px, py, pz, hasCol, v.cv, cur);
         // preconditions of the guard-free quotient over the whole task: 0 <= weight <= 2^20 (bit pattern compare: negative and
         // NaN weights fail), |sdf| <= 2^17. Weights grow by at most 16 * 2^10 and |sdf| stays below max(|sdf|, band) inside a task.
         bool stateOk = true;
@@ -1041,7 +1321,7 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
             {
                 fn = __ffs(mask) - 1;
                 mask &= mask - 1;
-                project_gather<COLOR_PATH>(bf.f[fn], px, py, pz, hasCol, v.cv, b);
+                project_gather<COLOR_PATH, false>(bf.f[fn], px, py, pz, hasCol, v.cv, b);
             }
             bool run = true;
             if (!((bandM >> f) & 1u))
@@ -1076,7 +1356,6 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
         while (step(cur, nxt) && step(nxt, cur))
         {
         }
-        g = __shfl_sync(0xffffffffu, gNext, 0);
         if (!updMask)
             continue;                                               // nothing changed: no store, no chunk, no dirty mark
         if (virt)
@@ -1089,8 +1368,10 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
         }
         bool carvable = false;
         {
-            float2 *dist = dist_ptr(map, slot);
-            unsigned *col = hasCol ? reinterpret_cast<unsigned *>(color_ptr(map, slot)) : nullptr;
+            const int sl = slot >> kSlabChunksLog2;
+            const size_t off = (size_t)(slot & (kSlabChunks - 1)) * map.V;
+            float2 *dist = (sl < kSlabCache ? sDist[sl] : map.dist_slabs[sl]) + off;
+            unsigned *col = hasCol ? reinterpret_cast<unsigned *>((sl < kSlabCache ? sCol[sl] : map.color_slabs[sl]) + off) : nullptr;
 #pragma unroll
             for (int k = 0; k < kVPL; k++)
             {
@@ -1200,8 +1481,7 @@ static int batch_resident(Kern kernel, int threads)
 }
 
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
-static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                                        cudaEvent_t prepared, cudaStream_t st, int phases)
+static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
 {
     static int residentBricks = 0;
     if (!residentBricks)
@@ -1212,20 +1492,51 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
+    cudaStream_t st = bs.main;
     cudaError_t e;
     if (phases & 1)
     {
-    if (info.profiling && (e = cudaEventRecord(evt[0], stPrep)) != cudaSuccess)
+    if (info.profiling && (e = cudaEventRecord(evt[0], bs.prep)) != cudaSuccess)
         return e;
     const int tilesX = (info.W + 63) / 64, tiles = tilesX * ((info.H + 63) / 64);
     const int packBlocks = info.colorPath ? std::max(1, std::min(148, (info.cW * info.cH / 4 + 255) / 256)) : 0;
-    batch_prepare_kernel<<<dim3(tiles + packBlocks, bp.K), 256, 0, stPrep>>>(bp, map, tilesX, tiles);
-    if (info.profiling && (e = cudaEventRecord(evt[1], stPrep)) != cudaSuccess)
+    if (packBlocks && bs.pack != bs.prep)
+    {
+        // device frames: fork the packing off the main stream so that it runs beside Hi-Z + candidates
+        if ((e = cudaEventRecord(bs.fork, st)) != cudaSuccess || (e = cudaStreamWaitEvent(bs.pack, bs.fork, 0)) != cudaSuccess)
+            return e;
+        batch_pack_kernel<<<dim3(packBlocks, bp.K), 256, 0, bs.pack>>>(bp);
+        if ((e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
+            return e;
+    }
+    if (info.hizTma)
+    {
+        static bool attr = false;
+        if (!attr)
+        {
+            if ((e = cudaFuncSetAttribute(batch_hiz_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHizSmem)) != cudaSuccess)
+                return e;
+            attr = true;
+        }
+        const int nItems = tiles * bp.K;
+        batch_hiz_tma_kernel<<<std::min(nItems, 148 * 4), kHizThreads, kHizSmem, bs.prep>>>(bp, tilesX, tiles, nItems);
+    }
+    else
+        batch_hiz_kernel<<<dim3(tiles, bp.K), 256, 0, bs.prep>>>(bp, map, tilesX);
+    if (info.profiling && (e = cudaEventRecord(evt[1], bs.prep)) != cudaSuccess)
         return e;
-    if (stPrep != st && ((e = cudaEventRecord(prepared, stPrep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, prepared, 0)) != cudaSuccess))
+    if (bs.prep != st && ((e = cudaEventRecord(bs.prepared, bs.prep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, bs.prepared, 0)) != cudaSuccess))
         return e;
+    if (packBlocks && bs.pack == bs.prep)
+    {
+        batch_pack_kernel<<<dim3(packBlocks, bp.K), 256, 0, bs.pack>>>(bp);
+        if (bs.pack != st && (e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
+            return e;
+    }
     batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
     if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
+        return e;
+    if (packBlocks && bs.pack != st && (e = cudaStreamWaitEvent(st, bs.packed, 0)) != cudaSuccess)
         return e;
     }
     if (!(phases & 2))
@@ -1236,10 +1547,13 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     {
         static int residentFast = 0;
         if (!residentFast)
-            residentFast = batch_resident(batch_bricks_fast_kernel<CS, COLOR_PATH>, CHS_FAST_THREADS);
+            residentFast = batch_resident(batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH>, CHS_FAST_THREADS);
         const unsigned gFast = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_FAST_THREADS / 32 - 1) / (CHS_FAST_THREADS / 32), residentFast));
         bp.total_ctas = (int)gFast;
-        batch_bricks_fast_kernel<CS, COLOR_PATH><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
+        if (COLOR_PATH && map.use_color)
+            batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
+        else
+            batch_bricks_fast_kernel<CS, COLOR_PATH, false><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
     }
     else
         batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
@@ -1249,24 +1563,22 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
 }
 
 template <int CS>
-static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                                   cudaEvent_t prepared, cudaStream_t st, int phases)
+static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
 {
     if (info.colorPath)
-        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, stPrep, prepared, st, phases)
-                             : launch_batch_variant<CS, true, false>(bp, map, info, evt, stPrep, prepared, st, phases);
-    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, stPrep, prepared, st, phases)
-                         : launch_batch_variant<CS, false, false>(bp, map, info, evt, stPrep, prepared, st, phases);
+        return info.perPixel ? launch_batch_variant<CS, true, true>(bp, map, info, evt, bs, phases)
+                             : launch_batch_variant<CS, true, false>(bp, map, info, evt, bs, phases);
+    return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, bs, phases)
+                         : launch_batch_variant<CS, false, false>(bp, map, info, evt, bs, phases);
 }
 
-cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                         cudaEvent_t prepared, cudaStream_t st, int phases)
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
 {
     switch (map.cs)
     {
-    case 8: return launch_batch_cs<8>(bp, map, info, evt, stPrep, prepared, st, phases);
-    case 16: return launch_batch_cs<16>(bp, map, info, evt, stPrep, prepared, st, phases);
-    default: return launch_batch_cs<32>(bp, map, info, evt, stPrep, prepared, st, phases);
+    case 8: return launch_batch_cs<8>(bp, map, info, evt, bs, phases);
+    case 16: return launch_batch_cs<16>(bp, map, info, evt, bs, phases);
+    default: return launch_batch_cs<32>(bp, map, info, evt, bs, phases);
     }
 }
 

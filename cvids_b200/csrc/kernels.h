@@ -25,10 +25,11 @@ constexpr int kMaxBatch = 16;
 
 struct BatchCounters
 {
-    int unit_count, new_count, tickets, next_task;
-    int chunks_at_start, light_count, pad[2];
+    int unit_count, new_count, tickets, next_task;     // unit_count: units of cost bucket 0 (most frames)
+    int chunks_at_start, light_count, bucket1, bucket2; // units of buckets 3 (fewest frames), 1 and 2
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch], pad2[kMaxBatch];
     unsigned long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
+    unsigned long long span_start_inv, span_end;       // brick kernel: max over CTAs of ~(start time) and of the end time (%globaltimer, ns)
 };
 
 // Written into a pinned slot by the last CTA of a batch: head, payload, system fence, tail. Valid for batch b when
@@ -39,6 +40,7 @@ struct HostBatchSnapshot
     int unit_count, new_count, K, pad;
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch];
     long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
+    long long bricks_span_ns;       // first CTA start -> last CTA end of the brick kernel, from %globaltimer (no launch / event overhead)
     int tail, pad3[3];
 };
 
@@ -48,7 +50,8 @@ struct BatchParams
     int K;
     int lo[3], n[3];                // union of the K candidate ID boxes
     int4 *units;                    // bricks: {id key low, id key high, slot | brick << 24, band frames | free-space frames << 16};
-                                    // slot 0xFFFFFF: the chunk does not exist yet
+                                    // slot 0xFFFFFF: the chunk does not exist yet. TWO buffers of units_cap entries: cost buckets 0 / 1
+                                    // grow from the front / back of the first, buckets 2 / 3 from the front / back of the second
     int units_cap;
     int cand_stride;                // multiplicative permutation of the union box enumeration (coprime to its size)
     int batch_id;                   // > 0, increases by one per batch
@@ -56,6 +59,7 @@ struct BatchParams
     BatchCounters *bctr;
     HostBatchSnapshot *host_slot;   // pinned, device-mapped
     unsigned long long *slot_batch; // [capacity] (batch id << 32) | mask of the batch's frames that updated the chunk
+    int coarse_in_shared;           // the candidates kernel builds the Hi-Z levels >= 4 in shared memory (they fit: <= 48 tiles per frame)
 };
 
 // What the fast brick kernel needs of one frame, 128 bytes, passed BY VALUE in the kernel's parameter block (constant bank): a
@@ -89,14 +93,22 @@ struct BatchLaunchInfo
     int W, H, cW, cH;               // depth / colour image size (identical for all frames of a batch)
     long long unionCandidates;      // chunk IDs in the union box
     bool colorPath, perPixel, profiling;
+    bool hizTma;                    // Hi-Z by the TMA bulk-copy kernel (float depth, constant truncator, aligned rows)
     bool fastBricks;                // every frame satisfies the preconditions of batch_bricks_fast_kernel (brick_frames is filled)
     const BrickFrames *brickFrames; // host pointer; copied into the kernel's parameter block
 };
-// The prepare kernel runs on stPrep and records `prepared`; candidates and bricks run on st after waiting for it.
-// events (profiling): [0] start, [1] after prepare (both on stPrep), [2] = [7] after candidates, [3] after bricks (on st)
+// Streams of one batch. The Hi-Z kernel runs on `prep` and records `prepared`; the candidates kernel waits for it on `main`. The
+// colour packing kernel (only the brick kernel reads its output) runs on `pack` BESIDE the candidates kernel and records
+// `packed`, which the brick kernel waits for. pack == prep: it simply follows the Hi-Z kernel there (host frames: both follow
+// the copies on the copy stream). pack != prep (device frames, prep == main): forked from `main` with `fork`.
+struct BatchStreams
+{
+    cudaStream_t prep, pack, main;
+    cudaEvent_t prepared, packed, fork;
+};
+// events (profiling): [0] start, [1] after the Hi-Z kernel (both on prep), [2] = [7] after candidates, [3] after bricks (on main)
 // phases: bit 0 = prepare + candidates, bit 1 = bricks (3 = the whole batch; the host may size the pool between the two)
-cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, cudaStream_t stPrep,
-                         cudaEvent_t prepared, cudaStream_t st, int phases);
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases);
 
 // dCounters[4] (zeroed): rcp mismatches, rcp tested, div mismatches, div tested
 cudaError_t launch_selftest_arithmetic(unsigned long long *dCounters, unsigned long long divPairs, cudaStream_t st);

@@ -115,6 +115,8 @@ typedef struct
 {
     float prepare_ms, candidates_ms, new_chunks_ms, integrate_ms, frame_ms;   /* integrate_ms: the brick kernel (existing chunks) */
     float mesh_count_ms, mesh_emit_ms, mesh_ms;
+    float bricks_span_ms;        /* fused path: first CTA start -> last CTA end of the brick kernel of the last finished batch, from the device's
+                                    %globaltimer (kernel time without launch and event-record overhead; integrate_ms is the event-timed figure) */
 } chs_timings;
 
 const char *chs_last_error_string(void);

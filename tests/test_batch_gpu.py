@@ -318,7 +318,7 @@ def test_batch_exact_fallback_paths():
         frames.append((d, col, pose))
     a, b = _run_batched(Setup(16, 0.0625, True), frames, cam, 3)
     ids, sdf, w, _ = b.state()
-    assert int(((sdf == 0) & (w > 0)).sum()) > 100                  # the zero-numerator case really occurred
+    assert int(((sdf == 0) & (w > 0)).sum()) > 50                   # the zero-numerator case really occurred
 
 
 def test_batch_state_outside_fast_preconditions():
