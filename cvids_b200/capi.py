@@ -77,6 +77,8 @@ EXPORTS = (
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic", "chs_host_alloc", "chs_host_free",
+    "chs_comm_unique_id", "chs_comm_init", "chs_comm_attach", "chs_comm_destroy", "chs_integrate_batch_distributed",
+    "chs_comm_sync_dirty", "chs_update_meshes_distributed",
 )
 
 _lib = None
@@ -123,6 +125,13 @@ def load_library(build_if_missing: bool = True):
     lib.chs_set_dirty.argtypes = [vp, i64, vp]
     lib.chs_num_dirty.argtypes = [vp, C.POINTER(i64)]
     lib.chs_dirty_ids.argtypes = [vp, vp, i64]
+    lib.chs_comm_unique_id.argtypes = [vp]
+    lib.chs_comm_init.argtypes = [vp, vp]
+    lib.chs_comm_attach.argtypes = [vp, vp]
+    lib.chs_comm_destroy.argtypes = [vp]
+    lib.chs_integrate_batch_distributed.argtypes = [vp, C.POINTER(chs_integrator), i32, C.POINTER(chs_frame), i32, C.POINTER(chs_camera), i32, C.POINTER(chs_camera)]
+    lib.chs_comm_sync_dirty.argtypes = [vp]
+    lib.chs_update_meshes_distributed.argtypes = [vp, i32]
     lib.chs_frustum.argtypes = [vp, C.POINTER(chs_camera), vp, vp, vp]
     lib.chs_candidate_ids.argtypes = [i32, C.c_float, vp, C.POINTER(chs_camera), vp, i64, C.POINTER(i64)]
     lib.chs_selftest_arithmetic.argtypes = [i64, C.POINTER(i64 * 4)]
@@ -253,6 +262,7 @@ class Chisel:
                  stream: int | None = None, initial_chunks: int = 0):
         self._lib = load_library()
         self.chunk, self.resolution, self.use_color = chunk, float(np.float32(resolution)), bool(use_color)
+        self.rank, self.world = int(rank), max(int(world), 1)
         cfg = chs_config(chunk, resolution, int(use_color), device, rank, world, initial_chunks, stream)
         h = C.c_void_p()
         _check(self._lib.chs_create(C.byref(cfg), C.byref(h)))
@@ -358,6 +368,83 @@ class Chisel:
         if host_async:
             self._keep = (self._keep or [])[-64:] + [prepared]      # the buffers must outlive the call
         self.integrate_prepared(prepared)
+
+    # ---- multi-GPU (one process per GPU; every call below is collective over the map's world) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId through the library: call on ONE rank and hand the 128 bytes to every rank (any side channel)."""
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().chs_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self._lib.chs_comm_init(self._h, buf))
+
+    def comm_init_torch(self, group=None):
+        """Convenience for harnesses that already run torch.distributed: rank 0 makes the NCCL unique id, the process group
+        (any backend) carries its 128 bytes to the other ranks, every rank joins the library's own communicator."""
+        import torch.distributed as dist
+        box = [self.comm_unique_id() if dist.get_rank(group) == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.comm_init(box[0])
+
+    def comm_destroy(self):
+        _check(self._lib.chs_comm_destroy(self._h))
+
+    def integrate_batch_distributed(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, device_ptrs=None, channels=None,
+                                    host_async=False):
+        """One step of len(poses) frames spread over the ranks (chs_integrate_batch_distributed): poses of ALL frames; depths /
+        colors / device_ptrs entries only for the frames this rank ingests (None elsewhere)."""
+        n = len(poses)
+        per = n // self.world
+        lo = self.rank * per
+        cam_s = make_camera(cam)
+        use_color = (colors is not None) or (device_ptrs is not None and device_ptrs[lo][1] is not None)
+        arr = (chs_frame * max(n, 1))()
+        keep = []
+        for i in range(n):
+            p = _pose(poses[i])
+            C.memmove(arr[i].pose, p.ctypes.data, 48)
+            C.memmove(arr[i].color_pose, p.ctypes.data, 48)
+            if not (lo <= i < lo + per):
+                continue
+            if device_ptrs is None:
+                if np.asarray(depths[i]).dtype == np.uint16:
+                    d = np.ascontiguousarray(depths[i], np.uint16)
+                    arr[i].depth_mm = d.ctypes.data
+                else:
+                    d = np.ascontiguousarray(depths[i], np.float32)
+                    arr[i].depth = d.ctypes.data
+                keep.append(d)
+                if use_color:
+                    c = np.ascontiguousarray(colors[i], np.uint8)
+                    keep.append(c)
+                    arr[i].color = c.ctypes.data
+                    channels = c.shape[2] if c.ndim == 3 else 1
+            else:
+                arr[i].depth = device_ptrs[i][0]
+                arr[i].color = device_ptrs[i][1]
+        integ = integrator.as_struct()
+        mem = MEM_DEVICE if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
+        if host_async:
+            self._keep = (self._keep or [])[-64:] + [keep]
+        _check(self._lib.chs_integrate_batch_distributed(self._h, C.byref(integ), n, arr, mem, C.byref(cam_s), int(channels or 0),
+                                                         C.byref(cam_s) if use_color else None))
+
+    def sync_dirty(self):
+        _check(self._lib.chs_comm_sync_dirty(self._h))
+
+    def recompute_meshes_distributed(self, root: int = 0):
+        """Distributed Chisel::UpdateMeshes (chs_update_meshes_distributed). On the root the gathered meshes of ALL ranks are merged
+        into the host MeshMap with the reference's publication rule; returns the re-meshed chunks this rank received."""
+        _check(self._lib.chs_update_meshes_distributed(self._h, root))
+        got = self.download_last_meshes()
+        if self.rank == root:
+            for cid, mesh in got.items():
+                if cid in self.chunk_manager.all_meshes or len(mesh["grids"]) > 0:
+                    self.chunk_manager.all_meshes[cid] = mesh
+        return got
 
     def last_batch_ticket(self) -> int:
         t = C.c_int64()

@@ -206,6 +206,23 @@ struct chs_map
     long long vertCap = 0, gridCap = 0;
     chs_mesh_counts lastMesh{};
     int lastMeshChunks = 0;
+    // multi-GPU (capi_comm.inc)
+    void *comm = nullptr;                      // ncclComm_t
+    bool ownComm = false;
+    chs_map *ghost = nullptr;                  // scratch one-rank map the distributed re-mesh runs on
+    long long *dCommScratch = nullptr;
+    size_t commScratchCap = 0;
+    int distFirst = 0, distCount = 0;          // distributed batch in progress: the frames [distFirst, distFirst + distCount) are ingested here
+    struct Gathered                            // the root's copy of all ranks' meshes of the last distributed re-mesh
+    {
+        int *ids = nullptr;
+        long long *vertOffsets = nullptr, *gridOffsets = nullptr;
+        float *verts = nullptr, *normals = nullptr, *colors = nullptr, *grids = nullptr;
+        size_t idsCap = 0, voCap = 0, goCap = 0, vCap = 0, nCap = 0, cCap = 0, gCap = 0;
+        long long nChunks = 0, nVerts = 0, nGrids = 0;
+    } gathered;
+    bool meshGathered = false;                 // chs_download_meshes serves the gathered union (root of a distributed re-mesh)
+    bool meshFromGhost = false;                // ... or this rank's part, held by the ghost map (other ranks)
 };
 
 namespace chs
@@ -487,6 +504,33 @@ static int poll_inflight(chs_map *m, bool block)
                 cs->pending -= 1;
             }
         m->inflight.pop_front();
+    }
+    return CHS_OK;
+}
+
+// Keep at most `depth` launches in flight: wait for the OLDEST ones only (their counter snapshots arrive in pinned memory), never
+// drain the stream -- the GPU keeps the younger launches to work on while the host waits. Without this bound a caller that
+// enqueues faster than the GPU works piles up worst-case capacity reservations (one candidate box of chunks per launch in flight)
+// until ensure_capacity has to synchronise with everything.
+static int wait_inflight_below(chs_map *m, size_t depth)
+{
+    unsigned spins = 0;
+    while (m->inflight.size() >= depth)
+    {
+        int rc = poll_inflight(m, false);
+        if (rc)
+            return rc;
+        if (m->inflight.size() < depth)
+            break;
+        _mm_pause();
+        if ((++spins & 0xFFFu) == 0)
+        {
+            const cudaError_t q = cudaStreamQuery(m->stream);
+            if (q == cudaSuccess)
+                return poll_inflight(m, true);                      // stream idle: everything has arrived (or is reported missing)
+            if (q != cudaErrorNotReady)
+                return fail(CHS_ERR_CUDA, std::string("stream error while waiting for a batch: ") + cudaGetErrorString(q));
+        }
     }
     return CHS_OK;
 }
@@ -798,7 +842,7 @@ static int integrate_common(chs_map *m, const chs_integrator *integ, const float
 
 // K host images of `bytes` bytes each -> K consecutive device images. Callers usually keep their frames in one ring or array,
 // i.e. at a constant stride: then the K copies are ONE strided copy (one DMA descriptor chain instead of K submissions).
-static int copy_images_h2d(void *dst, const void *const *src, int K, size_t bytes, cudaStream_t st)
+static int copy_images_h2d(void *dst, const void *const *src, int K, size_t bytes, cudaStream_t st, cudaMemcpyKind kind = cudaMemcpyHostToDevice)
 {
     bool strided = K > 1;
     const ptrdiff_t stride = K > 1 ? (const char *)src[1] - (const char *)src[0] : 0;
@@ -806,13 +850,17 @@ static int copy_images_h2d(void *dst, const void *const *src, int K, size_t byte
         strided = (const char *)src[f] - (const char *)src[f - 1] == stride;
     if (strided && stride >= (ptrdiff_t)bytes)
     {
-        CHS_CUDA(cudaMemcpy2DAsync(dst, bytes, src[0], (size_t)stride, bytes, (size_t)K, cudaMemcpyHostToDevice, st));
+        CHS_CUDA(cudaMemcpy2DAsync(dst, bytes, src[0], (size_t)stride, bytes, (size_t)K, kind, st));
         return CHS_OK;
     }
     for (int f = 0; f < K; f++)
-        CHS_CUDA(cudaMemcpyAsync((char *)dst + bytes * f, src[f], bytes, cudaMemcpyHostToDevice, st));
+        CHS_CUDA(cudaMemcpyAsync((char *)dst + bytes * f, src[f], bytes, kind, st));
     return CHS_OK;
 }
+
+// capi_comm.inc
+static int exchange_frames(chs_map *m, void *depth, size_t depthBytesPerFrame, void *color, size_t colorBytesPerFrame, cudaStream_t st);
+static int world_any_mm(chs_map *m, bool *anyMm);
 
 // ---------------------------------------------------------------------------------------------------------
 // chs_integrate_batch: n consecutive frames of one sensor stream (same image size, intrinsics and integrator). Sub-batches of
@@ -843,6 +891,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     if (unionCand > (1ll << 26))
         return CHS_ERR_NOT_FOUND;                                   // frames too far apart to share a box: the caller falls back to single frames
+    if ((rc = wait_inflight_below(m, 4)))
+        return rc;
     bool poolLater = false;
     if ((rc = ensure_capacity(m, unionCand, dirtyBound, &poolLater)))
         return rc;
@@ -852,10 +902,17 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     const size_t tiles = hiz_tiles(cam);
     const bool computeTrunc = integ->trunc_kind == CHS_TRUNC_QUADRATIC || integ->trunc_kind == CHS_TRUNC_INVERSE;
     const bool perPixel = integ->trunc_kind != CHS_TRUNC_CONSTANT;
-    const bool hostMem = mem == CHS_MEM_HOST || mem == CHS_MEM_HOST_ASYNC;
+    // distributed batch (chs_integrate_batch_distributed): only the frames [distFirst, distFirst + distCount) carry images; they
+    // are staged like host frames (device frames: copied device to device) and the other ranks' images arrive by all-gather
+    const bool dist = m->distCount > 0;
+    const int locFirst = dist ? m->distFirst : 0, locEnd = dist ? m->distFirst + m->distCount : K;
+    const bool devSrc = mem == CHS_MEM_DEVICE;
+    const bool hostMem = mem == CHS_MEM_HOST || mem == CHS_MEM_HOST_ASYNC || dist;
     bool anyMm = false;
-    for (int f = 0; f < K; f++)
+    for (int f = locFirst; f < locEnd; f++)
         anyMm |= frames[f].depth_mm != nullptr;
+    if (dist && world_any_mm(m, &anyMm))
+        return CHS_ERR_CUDA;
     const int setIdx = (m->batchId + 1) & 1;
     chs_map::BatchSet &bs = m->bset[setIdx];
     // Host frames: copies and prepare run on the copy stream, beside the kernels of the previous batch. Device frames are ordered by
@@ -864,6 +921,12 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     // the set is free once the kernels of the batch that used it last (two batches ago) are done
     if (bs.used && hostMem)
         CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
+    if (dist && devSrc)
+    {
+        // the caller produced its device frames on the map's stream: the copy stream picks them up from there
+        CHS_CUDA(cudaEventRecord(bs.fork, st));
+        CHS_CUDA(cudaStreamWaitEvent(cs, bs.fork, 0));
+    }
     {
         const bool grow = tiles * kMaxBatch > bs.hizCap || ((hostMem || anyMm) && npx * kMaxBatch > bs.depthCap) || (anyMm && hostMem && npx * kMaxBatch > bs.depthMmCap) ||
                           ((computeTrunc || (perPixel && hostMem)) && npx * kMaxBatch > bs.truncCap) ||
@@ -897,7 +960,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         FrameParams &fp = fps[f];
         fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], bs.hiz + tiles * f, &fp);
         fp.hiz_ticket = m->dHizTickets + setIdx * kMaxBatch + f;
-        if (frames[f].depth_mm)
+        if (dist ? anyMm : frames[f].depth_mm != nullptr)
         {
             // millimetres: half the bytes over PCIe; batch_prepare converts into the float image
             if (hostMem)
@@ -928,14 +991,17 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     {
         // runs of frames of the same kind (float / millimetre depth) go in one strided copy each
         const void *src[kMaxBatch];
-        for (int f0 = 0; f0 < K;)
+        const cudaMemcpyKind kind = (dist && devSrc) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        for (int f0 = locFirst; f0 < locEnd;)
         {
             const bool mm = frames[f0].depth_mm != nullptr;
+            if (dist && mm != anyMm)
+                return fail(CHS_ERR_INVALID, "distributed batches need one depth encoding for all frames");
             int f1 = f0;
-            for (; f1 < K && (frames[f1].depth_mm != nullptr) == mm; f1++)
+            for (; f1 < locEnd && (frames[f1].depth_mm != nullptr) == mm; f1++)
                 src[f1 - f0] = mm ? (const void *)frames[f1].depth_mm : (const void *)frames[f1].depth;
-            if ((rc = mm ? copy_images_h2d(bs.depthMm + npx * f0, src, f1 - f0, npx * sizeof(uint16_t), cs)
-                         : copy_images_h2d(bs.depth + npx * f0, src, f1 - f0, npx * sizeof(float), cs)))
+            if ((rc = mm ? copy_images_h2d(bs.depthMm + npx * f0, src, f1 - f0, npx * sizeof(uint16_t), cs, kind)
+                         : copy_images_h2d(bs.depth + npx * f0, src, f1 - f0, npx * sizeof(float), cs, kind)))
                 return rc;
             f0 = f1;
         }
@@ -943,17 +1009,20 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         {
             for (int f = 0; f < K; f++)
                 src[f] = frames[f].trunc_per_pixel;
-            if ((rc = copy_images_h2d(bs.trunc, src, K, npx * sizeof(float), cs)))
+            if ((rc = copy_images_h2d(bs.trunc, src, K, npx * sizeof(float), cs, kind)))
                 return rc;
         }
         if (colorPath)
         {
-            for (int f = 0; f < K; f++)
-                src[f] = frames[f].color;
-            if ((rc = copy_images_h2d(bs.color, src, K, cpx * channels, cs)))
+            for (int f = locFirst; f < locEnd; f++)
+                src[f - locFirst] = frames[f].color;
+            if ((rc = copy_images_h2d(bs.color + cpx * channels * locFirst, src, locEnd - locFirst, cpx * channels, cs, kind)))
                 return rc;
         }
         CHS_CUDA(cudaEventRecord(bs.copied, cs));
+        if (dist && (rc = exchange_frames(m, anyMm ? (void *)bs.depthMm : (void *)bs.depth, npx * (anyMm ? sizeof(uint16_t) : sizeof(float)),
+                                          colorPath ? bs.color : nullptr, cpx * channels, cs)))
+            return rc;
     }
     // the frame table: pageable source, staged by the driver before the call returns
     CHS_CUDA(cudaMemcpyAsync(bs.dFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
@@ -1260,6 +1329,13 @@ int chs_destroy(chs_map *m)
     cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
+    chs_comm_destroy(m);
+    if (m->dCommScratch)
+        cudaFree(m->dCommScratch);
+    for (void *p : {(void *)m->gathered.ids, (void *)m->gathered.vertOffsets, (void *)m->gathered.gridOffsets, (void *)m->gathered.verts,
+                    (void *)m->gathered.normals, (void *)m->gathered.colors, (void *)m->gathered.grids})
+        if (p)
+            cudaFree(p);
     frame_graph_destroy(m->frameGraph);
     if (m->h2dDone)
         cudaEventDestroy(m->h2dDone);
@@ -1829,6 +1905,8 @@ int chs_dirty_ids(chs_map *m, int32_t *ids, int64_t cap)
 // Chisel::UpdateMeshes without its every-10th gate (OC Chisel.cpp:50-59): RecomputeMeshes(meshesToUpdate), clear.
 int chs_update_meshes(chs_map *m)
 {
+    if (m)
+        m->meshGathered = m->meshFromGhost = false;
     if (!m)
         return fail(CHS_ERR_INVALID, "null map");
     int rc = sync_counts(m);
@@ -1941,6 +2019,32 @@ int chs_download_meshes(chs_map *m, int32_t *ids, int64_t *vertOffsets, int64_t 
         return fail(CHS_ERR_INVALID, "null map");
     CHS_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
+    if (m->meshGathered)
+    {
+        // root of a distributed re-mesh: the union of all ranks' meshes (capi_comm.inc)
+        const chs_map::Gathered &G = m->gathered;
+        if (ids && G.nChunks)
+            CHS_CUDA(cudaMemcpyAsync(ids, G.ids, sizeof(int) * 3 * (size_t)G.nChunks, cudaMemcpyDeviceToHost, st));
+        if (vertOffsets)
+            CHS_CUDA(cudaMemcpyAsync(vertOffsets, G.vertOffsets, sizeof(int64_t) * (size_t)(G.nChunks + 1), cudaMemcpyDeviceToHost, st));
+        if (gridOffsets)
+            CHS_CUDA(cudaMemcpyAsync(gridOffsets, G.gridOffsets, sizeof(int64_t) * (size_t)(G.nChunks + 1), cudaMemcpyDeviceToHost, st));
+        if (G.nVerts)
+        {
+            if (vertices)
+                CHS_CUDA(cudaMemcpyAsync(vertices, G.verts, sizeof(float) * 3 * (size_t)G.nVerts, cudaMemcpyDeviceToHost, st));
+            if (normals)
+                CHS_CUDA(cudaMemcpyAsync(normals, G.normals, sizeof(float) * 3 * (size_t)G.nVerts, cudaMemcpyDeviceToHost, st));
+            if (colors && m->cfg.use_color)
+                CHS_CUDA(cudaMemcpyAsync(colors, G.colors, sizeof(float) * 3 * (size_t)G.nVerts, cudaMemcpyDeviceToHost, st));
+        }
+        if (G.nGrids && grids)
+            CHS_CUDA(cudaMemcpyAsync(grids, G.grids, sizeof(float) * 3 * (size_t)G.nGrids, cudaMemcpyDeviceToHost, st));
+        CHS_CUDA(cudaStreamSynchronize(st));
+        return CHS_OK;
+    }
+    if (m->meshFromGhost && m->ghost)
+        return chs_download_meshes(m->ghost, ids, vertOffsets, gridOffsets, vertices, normals, colors, grids);   // non-root: this rank's part
     const int n = m->lastMeshChunks;
     const long long nv = m->lastMesh.n_vertices, ng = m->lastMesh.n_grids;
     std::vector<int> slots((size_t)n);
@@ -2083,3 +2187,5 @@ float chs_truncation(int kind, float param, float depth) { return host_truncatio
 uint32_t chs_owner(int32_t x, int32_t y, int32_t z) { return owner_hash(x, y, z); }
 
 } // extern "C"
+
+#include "capi_comm.inc"

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) batch_pack_kernel(BatchParams bp)
 // kernel in shared memory (no "last block of the frame" serialisation).
 constexpr int kHizStages = 3;
 constexpr int kHizPitch = 68;                          // floats per shared row: 64 + 4 (rows stay 16-byte aligned)
-constexpr int kHizThreads = 128;
+constexpr int kHizThreads = 256;
 constexpr size_t kHizSmem = (size_t)kHizStages * 64 * kHizPitch * sizeof(float);
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -138,13 +138,18 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     }
     __syncthreads();
     const int nMine = ((int)blockIdx.x < nItems) ? (nItems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // what the arithmetic needs of a frame is the same for all frames of a batch (one integrator, one camera)
+    const FrameParams &f0 = bp.frames[0];
+    const int W = f0.cam.W, H = f0.cam.H;
+    const float cutoff = f0.depth_cutoff, tr = f0.trunc_param, diag = f0.diag, carveDist = f0.carve_dist;
+    const int carve = f0.carve;
+    const int hw0 = f0.hizW[0], hh0 = f0.hizH[0], hw1 = f0.hizW[1], hh1 = f0.hizH[1], hw2 = f0.hizW[2], hh2 = f0.hizH[2], hw3 = f0.hizW[3];
     // warp 0 issues the row copies of item j into stage s: lane r rows r and r + 32
     auto issue = [&](int j, int s)
     {
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
-        const FrameParams &fp = bp.frames[item / tilesPerFrame];
+        const float *depth = bp.frames[item / tilesPerFrame].depth;
         const int tile = item % tilesPerFrame, x0 = (tile % tilesX) * 64, y0 = (tile / tilesX) * 64;
-        const int W = fp.cam.W, H = fp.cam.H;
         const unsigned rowBytes = (unsigned)min(64, W - x0) * 4u;
         const int nRows = min(64, H - y0);
         if (lane == 0)
@@ -152,52 +157,54 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
         __syncwarp();
         float *dst = stage + (size_t)s * 64 * kHizPitch;
         for (int r = lane; r < nRows; r += 32)
-            bulk_g2s(dst + r * kHizPitch, fp.depth + (size_t)(y0 + r) * W + x0, rowBytes, &full[s]);
+            bulk_g2s(dst + r * kHizPitch, depth + (size_t)(y0 + r) * W + x0, rowBytes, &full[s]);
     };
     if (t < 32)
         for (int j = 0; j < min(kHizStages, nMine); j++)
             issue(j, j);
-    const int tile8 = t >> 1, sub = t & 1;                 // 64 tiles of 8x8 pixels, 2 threads per tile (4 rows each)
+    const int tile8 = t >> 2, sub = t & 3;                 // 64 tiles of 8x8 pixels, 4 threads per tile (2 rows each)
     for (int j = 0; j < nMine; j++)
     {
         const int s = j % kHizStages;
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
         const FrameParams &fp = bp.frames[item / tilesPerFrame];
+        float2 *const h0 = fp.hiz[0], *const h1 = fp.hiz[1], *const h2 = fp.hiz[2], *const h3 = fp.hiz[3];
         const int tile = item % tilesPerFrame, bx = tile % tilesX, by = tile / tilesX;
-        const int W = fp.cam.W, H = fp.cam.H;
         mbar_wait(&full[s], (unsigned)(j / kHizStages) & 1u);
         const float *src = stage + (size_t)s * 64 * kHizPitch;
-        const int lx = (tile8 & 7) * 8, ly = (tile8 >> 3) * 8 + sub * 4;
-        float lo = INFINITY, hi = -INFINITY;
+        const int lx = (tile8 & 7) * 8, ly = (tile8 >> 3) * 8 + sub * 2;
+        // two independent min / max chains per thread (one per row)
+        float lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
         if (bx * 64 + lx < W)
         {
-            float4 v[8];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                const bool in = by * 64 + ly + r < H;
-                const float nanv = __int_as_float(0x7fc00000);
-                const float4 *row = reinterpret_cast<const float4 *>(src + (ly + r) * kHizPitch + lx);
-                v[2 * r] = in ? row[0] : make_float4(nanv, nanv, nanv, nanv);
-                v[2 * r + 1] = (in && bx * 64 + lx + 4 < W) ? row[1] : make_float4(nanv, nanv, nanv, nanv);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-            {
-                hiz_accumulate(fp, v[k].x, fp.trunc_param, &lo, &hi);
-                hiz_accumulate(fp, v[k].y, fp.trunc_param, &lo, &hi);
-                hiz_accumulate(fp, v[k].z, fp.trunc_param, &lo, &hi);
-                hiz_accumulate(fp, v[k].w, fp.trunc_param, &lo, &hi);
-            }
+            const float nanv = __int_as_float(0x7fc00000);
+            const float4 nan4 = make_float4(nanv, nanv, nanv, nanv);
+            const bool in0 = by * 64 + ly < H, in1 = by * 64 + ly + 1 < H, right = bx * 64 + lx + 4 < W;
+            const float4 *r0 = reinterpret_cast<const float4 *>(src + ly * kHizPitch + lx);
+            const float4 *r1 = reinterpret_cast<const float4 *>(src + (ly + 1) * kHizPitch + lx);
+            const float4 a = in0 ? r0[0] : nan4, b = (in0 && right) ? r0[1] : nan4;
+            const float4 c = in1 ? r1[0] : nan4, d = (in1 && right) ? r1[1] : nan4;
+            hiz_minmax(a.x, cutoff, &lo0, &hi0); hiz_minmax(c.x, cutoff, &lo1, &hi1);
+            hiz_minmax(a.y, cutoff, &lo0, &hi0); hiz_minmax(c.y, cutoff, &lo1, &hi1);
+            hiz_minmax(a.z, cutoff, &lo0, &hi0); hiz_minmax(c.z, cutoff, &lo1, &hi1);
+            hiz_minmax(a.w, cutoff, &lo0, &hi0); hiz_minmax(c.w, cutoff, &lo1, &hi1);
+            hiz_minmax(b.x, cutoff, &lo0, &hi0); hiz_minmax(d.x, cutoff, &lo1, &hi1);
+            hiz_minmax(b.y, cutoff, &lo0, &hi0); hiz_minmax(d.y, cutoff, &lo1, &hi1);
+            hiz_minmax(b.z, cutoff, &lo0, &hi0); hiz_minmax(d.z, cutoff, &lo1, &hi1);
+            hiz_minmax(b.w, cutoff, &lo0, &hi0); hiz_minmax(d.w, cutoff, &lo1, &hi1);
         }
+        float lo = fminf(lo0, lo1), hi = fmaxf(hi0, hi1);
         lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, 1));
         hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, 2));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
         const int tx = bx * 8 + (tile8 & 7), ty = by * 8 + (tile8 >> 3);
         if (sub == 0)
         {
-            s0[tile8] = make_float2(lo, hi);
-            if (tx < fp.hizW[0] && ty < fp.hizH[0])
-                fp.hiz[0][ty * fp.hizW[0] + tx] = make_float2(lo, hi);
+            const float2 v = hiz_apply_band(lo, hi, tr, diag, carve, carveDist);
+            s0[tile8] = v;
+            if (tx < hw0 && ty < hh0)
+                h0[ty * hw0 + tx] = v;
         }
         __syncthreads();                                    // also: every thread is done reading the stage
         if (t < 32 && j + kHizStages < nMine)
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             const float2 v = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
             s1[t] = v;
             const int gx = bx * 4 + ax, gy = by * 4 + ay;
-            if (gx < fp.hizW[1] && gy < fp.hizH[1])
-                fp.hiz[1][gy * fp.hizW[1] + gx] = v;
+            if (gx < hw1 && gy < hh1)
+                h1[gy * hw1 + gx] = v;
         }
         __syncthreads();
         if (t < 4)
@@ -220,14 +227,20 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             const float2 v = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
             s2[t] = v;
             const int gx = bx * 2 + ax, gy = by * 2 + ay;
-            if (gx < fp.hizW[2] && gy < fp.hizH[2])
-                fp.hiz[2][gy * fp.hizW[2] + gx] = v;
-        }
-        __syncthreads();
-        if (t == 0)
-        {
-            const float2 v = make_float2(fminf(fminf(s2[0].x, s2[1].x), fminf(s2[2].x, s2[3].x)), fmaxf(fmaxf(s2[0].y, s2[1].y), fmaxf(s2[2].y, s2[3].y)));
-            fp.hiz[3][by * fp.hizW[3] + bx] = v;
+            if (gx < hw2 && gy < hh2)
+                h2[gy * hw2 + gx] = v;
+            if (t == 0)
+            {
+                // level 3 from the four level-2 values of this thread's neighbours: recomputed from s1 to save a barrier
+                float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                {
+                    mn = fminf(mn, s1[i].x);
+                    mx = fmaxf(mx, s1[i].y);
+                }
+                h3[by * hw3 + bx] = make_float2(mn, mx);
+            }
         }
     }
 }

@@ -188,6 +188,33 @@ int chs_set_dirty(chs_map *map, int64_t n, const int32_t *ids);
 int chs_num_dirty(chs_map *map, int64_t *n);                   /* synchronises */
 int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
 
+/* ---- multi-GPU: one process per GPU, chunk-ownership shards (chs_config.rank / world, chs_owner), NCCL over NVLink ----
+ * Replaces, for a map spread over several GPUs: the frame hand-over of chisel_ros (CR/src/ChiselServer.cpp:297-367: every agent's
+ * frame lands in ONE map in callback order), Chisel::meshesToUpdate as one set (OC/include/open_chisel/Chisel.h:221-228), the
+ * neighbour-chunk reads of meshing (OC/src/ChunkManager.cpp:319-364, 449-474) and the mesh consumer's view of all meshes
+ * (CR/src/ChiselServer.cpp:613-716). The library loads libnccl.so.2 on first use; nothing NCCL is needed on one GPU.
+ * All of these are COLLECTIVE: every rank of the map's world calls them in the same order. */
+#define CHS_NCCL_ID_BYTES 128
+int chs_comm_unique_id(uint8_t id[CHS_NCCL_ID_BYTES]);      /* ncclGetUniqueId: one rank calls it and hands the bytes to the others out of band */
+int chs_comm_init(chs_map *map, const uint8_t id[CHS_NCCL_ID_BYTES]);   /* ncclCommInitRank(cfg.world, id, cfg.rank) */
+int chs_comm_attach(chs_map *map, void *nccl_comm);         /* or: adopt the caller's ncclComm_t (same size and rank as the map's world) */
+int chs_comm_destroy(chs_map *map);
+/* One step of n_total <= 16 frames (n_total % world == 0), e.g. the frames of all agents of one time step, in arrival order.
+ * frames[0 .. n_total): poses of ALL frames; image pointers only for the frames this rank ingests,
+ * [rank * n_total / world, (rank + 1) * n_total / world) (the other entries' pointers are ignored). The images are all-gathered
+ * over NVLink into the batch staging set on the copy stream (beside the kernels of the previous step) and integrated as one
+ * fused batch, every rank updating the chunks it owns: the union of the ranks' maps equals the single-GPU map of
+ * chs_integrate_batch on the same frames. Colour camera and pose must equal the depth ones; constant / computed truncators only. */
+int chs_integrate_batch_distributed(chs_map *map, const chs_integrator *integ, int n_total, const chs_frame *frames, int mem,
+                                    const chs_camera *cam, int channels, const chs_camera *color_cam);
+/* The dirty set of every rank becomes the union over ranks. */
+int chs_comm_sync_dirty(chs_map *map);
+/* Distributed Chisel::UpdateMeshes: dirty-set union; device-side exchange of the chunks inside the 27-neighbourhood of the dirty
+ * set ("ghost" copies, all-gather-v over NVLink); every rank re-meshes the dirty chunks it owns; the meshes are gathered on
+ * `root`, where chs_mesh_counts_last / chs_download_meshes then return the union (elsewhere: the rank's own part). The dirty
+ * set is cleared. Index for index the meshes of a single-GPU map (one documented exception: DESIGN.md section 8, quirk Q9). */
+int chs_update_meshes_distributed(chs_map *map, int root);
+
 /* Device self-test of the two range-check-free arithmetic forms the fused kernels use (cvids_b200/csrc/integrate_device.cuh)
  * against the IEEE intrinsics: the reciprocal over EVERY binary32 value of its guarded range, the quotient over div_pairs
  * pseudo-random operand pairs. out = {rcp mismatches, rcp values tested, div mismatches, div pairs tested}. */
