@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(HERE, "libchisel_b200.so")
 
 CHS_OK, CHS_ERR_INVALID, CHS_ERR_CUDA, CHS_ERR_CAPACITY, CHS_ERR_NOT_FOUND = range(5)
 TRUNC_CONSTANT, TRUNC_QUADRATIC, TRUNC_INVERSE, TRUNC_PER_PIXEL = range(4)
-MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC, MEM_DEVICE_ASYNC = 0, 1, 2, 3
 
 
 class ChiselError(RuntimeError):
@@ -314,7 +314,7 @@ class Chisel:
                                                        C.byref(cam), device_ptrs[1], channels, _ptr(cp), C.byref(ccam)))
 
     def prepare_batch(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, color_poses=None, color_cam=None,
-                      device_ptrs=None, channels=None, truncs=None, host_async=False):
+                      device_ptrs=None, channels=None, truncs=None, host_async=False, device_async=False):
         """Marshal the arguments of one chs_integrate_batch call once (a streaming caller that owns a ring of frame buffers
         does this at start-up); integrate_prepared() then only makes the call. See integrate_batch for the arguments."""
         cam = make_camera(cam)
@@ -350,7 +350,7 @@ class Chisel:
                 arr[i].color = device_ptrs[i][1]
                 arr[i].trunc_per_pixel = device_ptrs[i][2] if len(device_ptrs[i]) > 2 else None
         integ = integrator.as_struct(device_ptr=0) if integrator.trunc_kind == TRUNC_PER_PIXEL else integrator.as_struct()
-        mem = MEM_DEVICE if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
+        mem = (MEM_DEVICE_ASYNC if device_async else MEM_DEVICE) if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
         return (integ, n, arr, mem, cam, int(channels or 0), ccam, keep)
 
     def integrate_prepared(self, prepared):
@@ -396,6 +396,16 @@ class Chisel:
                                     host_async=False):
         """One step of len(poses) frames spread over the ranks (chs_integrate_batch_distributed): poses of ALL frames; depths /
         colors / device_ptrs entries only for the frames this rank ingests (None elsewhere)."""
+        self.integrate_prepared_distributed(self.prepare_batch_distributed(integrator, depths, poses, cam, colors, device_ptrs, channels, host_async))
+
+    def integrate_prepared_distributed(self, prepared):
+        integ, n, arr, mem, cam_s, channels, use_color, _keep = prepared
+        _check(self._lib.chs_integrate_batch_distributed(self._h, C.byref(integ), n, arr, mem, C.byref(cam_s), channels,
+                                                         C.byref(cam_s) if use_color else None))
+
+    def prepare_batch_distributed(self, integrator: ProjectionIntegrator, depths, poses, cam, colors=None, device_ptrs=None, channels=None,
+                                  host_async=False, device_async=False):
+        """Marshal one chs_integrate_batch_distributed call (see integrate_batch_distributed)."""
         n = len(poses)
         per = n // self.world
         lo = self.rank * per
@@ -426,11 +436,10 @@ class Chisel:
                 arr[i].depth = device_ptrs[i][0]
                 arr[i].color = device_ptrs[i][1]
         integ = integrator.as_struct()
-        mem = MEM_DEVICE if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
+        mem = (MEM_DEVICE_ASYNC if device_async else MEM_DEVICE) if device_ptrs is not None else (MEM_HOST_ASYNC if host_async else MEM_HOST)
         if host_async:
             self._keep = (self._keep or [])[-64:] + [keep]
-        _check(self._lib.chs_integrate_batch_distributed(self._h, C.byref(integ), n, arr, mem, C.byref(cam_s), int(channels or 0),
-                                                         C.byref(cam_s) if use_color else None))
+        return (integ, n, arr, mem, cam_s, int(channels or 0), use_color, keep)
 
     def sync_dirty(self):
         _check(self._lib.chs_comm_sync_dirty(self._h))

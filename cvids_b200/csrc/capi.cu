@@ -906,8 +906,10 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     // are staged like host frames (device frames: copied device to device) and the other ranks' images arrive by all-gather
     const bool dist = m->distCount > 0;
     const int locFirst = dist ? m->distFirst : 0, locEnd = dist ? m->distFirst + m->distCount : K;
-    const bool devSrc = mem == CHS_MEM_DEVICE;
+    const bool devSrc = mem == CHS_MEM_DEVICE || mem == CHS_MEM_DEVICE_ASYNC;
     const bool hostMem = mem == CHS_MEM_HOST || mem == CHS_MEM_HOST_ASYNC || dist;
+    // device frames that are already complete: Hi-Z + colour packing run on the copy stream, beside the kernels of the previous batch
+    const bool devAsync = mem == CHS_MEM_DEVICE_ASYNC && !dist;
     bool anyMm = false;
     for (int f = locFirst; f < locEnd; f++)
         anyMm |= frames[f].depth_mm != nullptr;
@@ -917,11 +919,11 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     chs_map::BatchSet &bs = m->bset[setIdx];
     // Host frames: copies and prepare run on the copy stream, beside the kernels of the previous batch. Device frames are ordered by
     // the map's stream anyway (the caller produced them there), so everything stays on it: no cross-stream hand-overs.
-    cudaStream_t cs = hostMem ? m->copyStream : st;
+    cudaStream_t cs = (hostMem || devAsync) ? m->copyStream : st;
     // the set is free once the kernels of the batch that used it last (two batches ago) are done
-    if (bs.used && hostMem)
+    if (bs.used && (hostMem || devAsync))
         CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
-    if (dist && devSrc)
+    if (dist && mem == CHS_MEM_DEVICE)
     {
         // the caller produced its device frames on the map's stream: the copy stream picks them up from there
         CHS_CUDA(cudaEventRecord(bs.fork, st));
@@ -1432,6 +1434,8 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
     const bool colorPath = ccam != nullptr;
     if (colorPath && (channels < 1 || channels > 4 || ccam->width <= 0 || ccam->height <= 0))
         return fail(CHS_ERR_INVALID, "bad colour arguments");
+    if (mem < CHS_MEM_HOST || mem > CHS_MEM_DEVICE_ASYNC)
+        return fail(CHS_ERR_INVALID, "bad memory space");
     bool fusable = true, anyMm = false;
     for (int f = 0; f < n; f++)
     {
@@ -1472,7 +1476,7 @@ int chs_integrate_batch(chs_map *m, const chs_integrator *integ, int n, const ch
             {
                 chs_integrator one = *integ;
                 one.trunc_per_pixel = frames[j].trunc_per_pixel;
-                if ((rc = integrate_common(m, &one, frames[j].depth, mem == CHS_MEM_HOST_ASYNC ? CHS_MEM_HOST : mem, frames[j].pose, cam, frames[j].color, channels, frames[j].color_pose, ccam, colorPath, j)))
+                if ((rc = integrate_common(m, &one, frames[j].depth, mem == CHS_MEM_HOST_ASYNC ? CHS_MEM_HOST : (mem == CHS_MEM_DEVICE_ASYNC ? CHS_MEM_DEVICE : mem), frames[j].pose, cam, frames[j].color, channels, frames[j].color_pose, ccam, colorPath, j)))
                     return rc;
             }
         }

@@ -54,7 +54,10 @@ enum { CHS_TRUNC_CONSTANT = 0, CHS_TRUNC_QUADRATIC = 1, CHS_TRUNC_INVERSE = 2, C
 /* CHS_MEM_HOST_ASYNC (chs_integrate_batch only): host buffers (ideally pinned) that the caller leaves untouched until the
  * call's ticket has been waited for (chs_wait_batch / any synchronising call); the call returns right after enqueueing, so
  * the copies of successive batches run back to back on the copy engine. */
-enum { CHS_MEM_HOST = 0, CHS_MEM_DEVICE = 1, CHS_MEM_HOST_ASYNC = 2 };
+enum { CHS_MEM_HOST = 0, CHS_MEM_DEVICE = 1, CHS_MEM_HOST_ASYNC = 2, CHS_MEM_DEVICE_ASYNC = 3 };
+/* CHS_MEM_DEVICE_ASYNC (chs_integrate_batch only): device buffers whose contents are COMPLETE when the call is made (not merely
+ * ordered on the map's stream) and stay untouched until the call's ticket has been waited for. The library then prepares the
+ * batch (Hi-Z pyramid, colour packing) on its copy stream, beside the kernels of the previous batch, instead of behind them. */
 
 typedef struct
 {
