@@ -54,7 +54,7 @@ CFG = scenes.CONFIG5                     # configs[4]: 8 agents x 60 frames, 640
 CFG2 = scenes.CONFIG2                    # configs[1]: single agent, 752x480 depth + colour, 2 cm
 AGENTS = CFG.agents
 WORKLOAD = ("configs[4]: scaling sweep, 8 agents x 640x480 depth, analytic room, 2 cm voxels, 16^3 chunks, trunc 4 voxels, carving on, "
-            "IntegrateDepthScan into one shared map; step = the 8 frames of one time step in one fused call")
+            "IntegrateDepthScan into one shared map; step = the 8 frames of each of %d consecutive time step(s), arrival order, in one fused call")
 WORKLOAD2 = ("configs[1]: single-agent EuRoC-shape 752x480 depth+colour stream, analytic room, 2 cm voxels, 16^3 chunks, trunc 4 voxels, "
              "IntegrateDepthScanColor; step = %d consecutive frames in one chs_integrate_batch call")
 PARITY_KEYS = ("candidates", "n_upd", "n_carve", "n_col", "n_new", "updated_chunks")
@@ -115,13 +115,22 @@ def algorithmic_bytes(st: dict, cam, channels: int, use_color: bool, chunk: int)
             + 4 * px + channels * px * int(use_color))
 
 
-def step_frames(cfg, t, agents=None):
-    """The frames of time step t of the multi-agent stream, arrival order = agent order: [(depth, None, pose), ...]."""
-    return [scenes.stream_frame(cfg, t % cfg.n_frames, agent=a) for a in (range(cfg.agents) if agents is None else agents)]
+TS = 2                                   # time steps per step (--time-steps-per-step): a step is TS x 8 frames
+
+
+def step_items(cfg, t):
+    """(time step, agent) of the frames of step t in arrival order: time step by time step, agent by agent."""
+    return [(t * TS + k, a) for k in range(TS) for a in range(cfg.agents)]
+
+
+def step_frames(cfg, t, which=None):
+    """Frames of step t of the multi-agent stream: [(depth, None, pose), ...]; `which`: indices into the step (default: all)."""
+    items = step_items(cfg, t)
+    return [scenes.stream_frame(cfg, items[i][0] % cfg.n_frames, agent=items[i][1]) for i in (range(len(items)) if which is None else which)]
 
 
 def step_poses(cfg, t):
-    return [scenes.orbit_pose(t % cfg.n_frames, cfg.n_frames, a * (2.0 * math.pi / cfg.agents)) for a in range(cfg.agents)]
+    return [scenes.orbit_pose(ts % cfg.n_frames, cfg.n_frames, a * (2.0 * math.pi / cfg.agents)) for ts, a in step_items(cfg, t)]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -201,16 +210,16 @@ def run_reference(args):
         frames += step_frames(CFG, t)
         if time.perf_counter() - t_build > 120:
             break
-    r = cpu_arm(CFG, frames, warm_t * AGENTS, budget_s=args.cpu_budget)
-    steps_done = r["frames_done"] / AGENTS
+    r = cpu_arm(CFG, frames, warm_t * AGENTS * TS, budget_s=args.cpu_budget)
+    steps_done = r["frames_done"] / (AGENTS * TS)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
         "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / max(steps_done, 1e-9), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_step": AGENTS, "frames_per_s": r["fps"],
-        "config": {"workload": WORKLOAD},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_step": AGENTS * TS, "frames_per_s": r["fps"],
+        "config": {"workload": WORKLOAD % TS},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
                          "threads": "1: the reference's depth-only path is serial (Chisel.h:71-72)" if r["kind"] == "reference" else "1 (C port)",
-                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames, %.1f s" % (r["frames_done"], warm_t * AGENTS, r["seconds"])},
+                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames, %.1f s" % (r["frames_done"], warm_t * AGENTS * TS, r["seconds"])},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -239,7 +248,7 @@ class Bench:
         torch.cuda.set_stream(self.stream)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
-            if AGENTS % self.world:
+            if (AGENTS * TS) % self.world:
                 raise SystemExit("bench.py: the 8-agent workload needs --gpus in {1, 2, 4, 8}")
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
         self.flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=self.dev)
@@ -286,8 +295,9 @@ def run_multi_agent(B: Bench, args):
     W, H = cam.width, cam.height
     warm, steps = args.warmup, args.steps
     T = warm + steps
-    per = AGENTS // world
-    mine = list(range(rank * per, (rank + 1) * per))
+    F = AGENTS * TS                                       # frames per step
+    per = F // world
+    mine = list(range(rank * per, (rank + 1) * per))      # indices into the step's arrival order that this rank ingests
     integ = B.integ(cfg)
     # frames this rank ingests (its agents), resident in HBM and in pinned host memory; poses of all agents
     frames = [step_frames(cfg, t, mine) for t in range(T)]
@@ -302,13 +312,13 @@ def run_multi_agent(B: Bench, args):
 
     def dev_ptrs(t):
         base = d_depth[t].data_ptr()
-        out = [(base, None)] * AGENTS                     # only this rank's entries are read
+        out = [(base, None)] * F                          # only this rank's entries are read
         for j, a in enumerate(mine):
             out[a] = (base + 4 * npx * j, None)
         return out
 
     def host_arrays(t):
-        out = [None] * AGENTS
+        out = [None] * F
         for j, a in enumerate(mine):
             out[a] = h_depth[t, j].numpy()
         return out
@@ -500,12 +510,12 @@ def run_multi_agent(B: Bench, args):
     line = {
         "metric": METRIC, "value": upd_total / t_value / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": 1000.0 * t_value / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "frames_per_step": AGENTS, "frames_per_s": steps * AGENTS / t_value,
-        "config": {"workload": WORKLOAD,
-                   "parallelism": ("chunk-hash shard x%d; rank r ingests agents [r*%d, (r+1)*%d); frames all-gathered in place over NVLink by the library "
-                                   "(NCCL on its copy stream, beside the kernels of the previous step)" % (world, per, per)) if world > 1 else "1 GPU",
+        "dtype": "f32", "data": "synthetic", "frames_per_step": F, "frames_per_s": steps * F / t_value,
+        "config": {"workload": WORKLOAD % TS,
+                   "parallelism": ("chunk-hash shard x%d; rank r ingests frames [r*%d, (r+1)*%d) of the step's arrival order and builds their Hi-Z pyramids; images and pyramids "
+                                   "are all-gathered in place over NVLink by the library (NCCL on its copy stream, beside the kernels of the previous step)" % (world, per, per)) if world > 1 else "1 GPU",
                    "l2": "no flush: the timed region streams %d MB of frames (> 126 MB L2 from %d steps on); the map working set stays in L2 as in a live stream"
-                         % ((frame_bytes * AGENTS * steps) >> 20, (126 << 20) // (frame_bytes * AGENTS) + 1),
+                         % ((frame_bytes * F * steps) >> 20, (126 << 20) // (frame_bytes * F) + 1),
                    "timing": "CUDA events on the map's stream around the %d timed steps, barrier + synchronize on both sides, max over ranks; median of %d passes %s ms"
                              % (steps, len(pass_ms), [round(x, 3) for x in pass_ms]),
                    "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
@@ -516,8 +526,8 @@ def run_multi_agent(B: Bench, args):
                    "rank0_per_step": {"candidate_chunks": float(np.mean([p[1] for p in per_step])), "brick_units": float(np.mean([p[0] for p in per_step])),
                                       "updated_chunks": float(np.mean([p[2] for p in per_step])), "new_chunks": float(np.mean([p[3] for p in per_step])),
                                       "new_chunk_candidates": float(np.mean([p[4] for p in per_step]))}},
-        "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * AGENTS / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
-                "h2d_bytes_per_step": frame_bytes * AGENTS, "d2h_bytes_per_step": 88 * AGENTS * world,
+        "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * F / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
+                "h2d_bytes_per_step": frame_bytes * F, "d2h_bytes_per_step": 88 * F * world,
                 "timing": "wall clock, max over ranks; per step chs_integrate_batch%s(pinned host frames, CHS_MEM_HOST_ASYNC; arguments marshalled inside the "
                           "timed region), then chs_wait_batch of the PREVIOUS step's counters (depth-2 pipeline)" % ("_distributed" if world > 1 else "")},
         "gpu_launches": 3 * steps,
@@ -527,8 +537,8 @@ def run_multi_agent(B: Bench, args):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r02_traffic.json)" if traffic else None,
                      "algorithmic_bytes_per_launch": bytes_alg / steps, "kernel_ms_per_launch": 1000.0 * t_kernel / steps,
                      "kernel_span_ms_per_launch": 1000.0 * tk["bricks_span"] / steps,
-                     "note": "rank 0's brick kernel: algorithmic bytes = B_int of SURVEY 8(d) of the chunks this rank owns, summed over the step's 8 frames (every rank "
-                             "reads all 8 frames); duration from CUDA events recorded by the library around the kernel on its stream (kernel_span: first CTA start to "
+                     "note": "rank 0's brick kernel: algorithmic bytes = B_int of SURVEY 8(d) of the chunks this rank owns, summed over the step's frames (every rank "
+                             "reads all of them); duration from CUDA events recorded by the library around the kernel on its stream (kernel_span: first CTA start to "
                              "last CTA end from %globaltimer, i.e. without launch and event-record overhead)"},
         "parity_check": parity,
         "mesh": mesh_info,
@@ -769,7 +779,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-side-lines", action="store_true", help="skip the 1 cm hall side line")
     ap.add_argument("--quick", action="store_true", help="A/B runs: the headline workload only")
-    ap.add_argument("--cpu-steps", type=int, default=2, help="time steps (8 frames each) of the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=1, help="steps of the cpu_baseline sample")
+    ap.add_argument("--time-steps-per-step", type=int, default=2, choices=[1, 2],
+                    help="time steps (8 frames each, one per agent) handed over per call: the fused kernels take up to 16 frames")
     ap.add_argument("--hall-frames", type=int, default=24)
     ap.add_argument("--pool-chunks", type=int, default=98304,
                     help="pre-sized chunk pool (chunks) so that no slab / hash growth lands inside the timed region")
@@ -777,6 +789,8 @@ def main():
     ap.add_argument("--parity-steps", type=int, default=2,
                     help="steps (from the empty map) whose per-frame counters, voxel state and dirty set are compared with the CPU oracle; 0 = off")
     args = ap.parse_args()
+    global TS
+    TS = args.time_steps_per_step
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -475,14 +475,22 @@ static int poll_inflight(chs_map *m, bool block)
         if (f.batch)
         {
             const volatile HostBatchSnapshot *b = &m->hBatchSnap[f.slot];
-            if (b->head != f.frameId || b->tail != f.frameId)
+            bool arrived = b->head == f.frameId && b->tail == f.frameId;
+            HostBatchSnapshot snap;
+            if (arrived)
+            {
+                // no fence on the device side: the checksum tells whether every payload word has landed
+                std::atomic_thread_fence(std::memory_order_acquire);
+                std::memcpy(&snap, (const void *)&m->hBatchSnap[f.slot], sizeof(snap));
+                arrived = snap.head == f.frameId && snap.tail == f.frameId && snap.checksum == batch_snapshot_checksum(snap);
+            }
+            if (!arrived)
             {
                 if (block)
                     return fail(CHS_ERR_CUDA, "batch counter snapshot missing after synchronisation");
                 break;
             }
-            std::atomic_thread_fence(std::memory_order_acquire);
-            retire_batch(m, m->hBatchSnap[f.slot], f.batchIndex, f.callId);
+            retire_batch(m, snap, f.batchIndex, f.callId);
             m->inflight.pop_front();
             continue;
         }
@@ -1117,6 +1125,25 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
                           (b.thr_carve == b.thr_carve);
     }
     info.brickFrames = &brickFrames;
+    // distributed batch: every rank builds the Hi-Z pyramids of the frames it ingests; the others arrive by all-gather right after
+    struct HizGather
+    {
+        chs_map *m;
+        float2 *hiz;
+        size_t bytesPerFrame;
+        cudaStream_t st;
+    } hizGather{m, bs.hiz, tiles * sizeof(float2), cs};
+    if (dist && m->cfg.world > 1 && !computeTrunc && !anyMm)
+    {
+        info.hizFirst = locFirst;
+        info.hizCount = locEnd - locFirst;
+        info.afterHizCtx = &hizGather;
+        info.afterHiz = [](void *p) -> int
+        {
+            HizGather *g = (HizGather *)p;
+            return exchange_frames(g->m, g->hiz, g->bytesPerFrame, nullptr, 0, g->st);
+        };
+    }
     // colour packing runs beside the candidates kernel: on the copy stream (host frames: it follows the copies and the Hi-Z kernel
     // there; device frames: forked from the map's stream)
     BatchStreams streams{cs, m->copyStream, st, bs.prepared, bs.packDone, bs.fork};

@@ -25,6 +25,7 @@
 //                             initialised) on the first hit
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 
 #include "device_map.cuh"
 #include "integrate_device.cuh"
@@ -52,6 +53,12 @@ constexpr int kNS = CHS_BRICK_SLICES;        // z slices per task
 constexpr int kVPL = 2 * kNS;                // voxels per lane: kNS slices x the lane's two y rows
 constexpr int kParts = 8 / kNS;              // tasks per brick
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may START while the
+// kernel before it in the stream is still running; pdl_wait() blocks until that kernel has completed and its writes are visible,
+// pdl_launch_dependents() lets the next kernel of the stream start launching. Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // All frames of the batch into shared memory: afterwards `sF[f]` is read with warp-uniform shared loads.
 __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &bp)
 {
@@ -64,7 +71,7 @@ __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &
 }
 
 // grid = (64x64 pixel tiles, K): Hi-Z levels (+ per-pixel truncation, millimetre conversion) of every frame of the batch
-__global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMap map, int tilesX)
+__global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMap map, int tilesX, int frameBase)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0)
     {
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMa
         for (int i = threadIdx.x; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
             c[i] = 0;
     }
-    const FrameParams &fp = bp.frames[blockIdx.y];
+    const FrameParams &fp = bp.frames[frameBase + blockIdx.y];
     frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
 }
 
@@ -117,7 +124,7 @@ __device__ __forceinline__ void bulk_g2s(void *dstSmem, const void *srcGlobal, u
                  "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams bp, int tilesX, int tilesPerFrame, int nItems)
+__global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams bp, int tilesX, int tilesPerFrame, int nItems, int frameBase)
 {
     extern __shared__ __align__(128) unsigned char hizSmem[];
     float *stage = reinterpret_cast<float *>(hizSmem);
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     auto issue = [&](int j, int s)
     {
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
-        const float *depth = bp.frames[item / tilesPerFrame].depth;
+        const float *depth = bp.frames[frameBase + item / tilesPerFrame].depth;
         const int tile = item % tilesPerFrame, x0 = (tile % tilesX) * 64, y0 = (tile / tilesX) * 64;
         const unsigned rowBytes = (unsigned)min(64, W - x0) * 4u;
         const int nRows = min(64, H - y0);
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     {
         const int s = j % kHizStages;
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
-        const FrameParams &fp = bp.frames[item / tilesPerFrame];
+        const FrameParams &fp = bp.frames[frameBase + item / tilesPerFrame];
         float2 *const h0 = fp.hiz[0], *const h1 = fp.hiz[1], *const h2 = fp.hiz[2], *const h3 = fp.hiz[3];
         const int tile = item % tilesPerFrame, bx = tile % tilesX, by = tile / tilesX;
         mbar_wait(&full[s], (unsigned)(j / kHizStages) & 1u);
@@ -309,25 +316,34 @@ __device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCo
 }
 
 // ------------------------------------------------------------------------------------------------------
-// A group of GL lanes per chunk of the union box (GL = bricks per chunk, at most 32), two stages:
-//   1. chunk level, lanes spread over FRAMES: is the chunk inside frame f's candidate ID box and does it pass
+// batch_candidates_kernel: which bricks of which chunks can change in which frames of the batch.
+// A warp per tile of the union candidate box:
+//   0. the chunk indices of the tile that THIS RANK OWNS are compacted by ballot (32 x world indices are looked at), so that at
+//      N ranks a warp still works on full tiles and the kernel's work divides by N;
+//   1. chunk level, a lane per chunk, frames in a loop: is the chunk inside frame f's candidate ID box and does it pass
 //      Frustum::Intersects (ChunkManager.cpp:182-212, exact)? If so, classify the whole chunk against the frame's Hi-Z tiles.
-//      Most (chunk, frame) pairs end here: behind the surface, off the image, or in free space with nothing to carve.
-//   2. brick level, lanes spread over BRICKS: classify the lane's brick for the frames that survived stage 1.
-//        bandM  frames in which some voxel of the brick may fall inside the truncation band
-//        freeM  frames in which the brick lies in free space (only carving of observed voxels can act)
+//      Most (chunk, frame) pairs end here: behind the surface, off the image, or in free space with nothing to carve. One hash
+//      lookup per chunk that is left (all lanes in parallel);
+//   2. brick level, the whole warp per surviving chunk: lanes = (brick, one of four frames) -> per-brick frame masks
+//        band   frames in which some voxel of the brick may fall inside the truncation band
+//        free   frames in which the brick lies in free space (only carving of observed voxels can act)
 //      A free-space frame is kept when the brick can hold a carvable voxel by then: its flag is set already, or an EARLIER band
-//      frame of this batch may create one (batch_bricks_kernel then checks the actual register state before spending the frame).
-// Chunk indices go through a multiplicative permutation so that the few surviving chunks spread over all CTAs.
+//      frame of this batch may create one (the brick kernels check the actual register state before spending the frame);
+//   3. warp-ballot compaction into the unit lists (four cost buckets).
+// Chunk indices go through a multiplicative permutation so that the surviving chunks spread over all warps.
+constexpr int kCandWarps = 4;                       // warps per CTA
+constexpr int kCandList = 16 * 16;                  // owned chunk indices of one tile (16 x min(world, 16) indices are looked at)
+
 template <int CS>
-__global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, DeviceMap map)
+__global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(BatchParams bp, DeviceMap map)
 {
     constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
-    constexpr int GL = NB >= 32 ? 32 : NB;
-    constexpr int BPL = NB / GL;
     __shared__ FrameParams sF[kMaxBatch];
     __shared__ float2 sCoarse[kMaxBatch][kCoarseTiles];
-    load_frames(sF, bp);
+    __shared__ int sList[kCandWarps][kCandList];
+    pdl_launch_dependents();                       // the brick kernel may start launching: it waits (pdl_wait) before it reads the unit lists
+    load_frames(sF, bp);                           // the frame table was uploaded before the Hi-Z kernel: complete
+    pdl_wait();                                    // the Hi-Z kernel's output is read from here on
     if (bp.coarse_in_shared)
     {
         // Hi-Z levels >= 4 (tiles of 128 pixels and up, until at most 3x3 tiles cover the image) of every frame, from level 3:
@@ -371,134 +387,199 @@ __global__ void __launch_bounds__(256) batch_candidates_kernel(BatchParams bp, D
         __syncthreads();
     }
     // chunks created by this batch will occupy the pool slots from here on (this kernel runs on the map's stream, after every
-    // earlier batch; the prepare kernel may run ahead on the copy stream)
+    // earlier batch; the prepare kernels may run ahead on the copy stream)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         bp.bctr->chunks_at_start = map.ctr->n_chunks;
     const int K = bp.K;
     const int total = bp.n[0] * bp.n[1] * bp.n[2];
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slotIdx = (int)(tid / GL);
-    const int gl = (int)(tid % GL);
+    const int nyz = bp.n[1] * bp.n[2];
     const unsigned lane = threadIdx.x & 31;
-    const bool leader = gl == 0;
+    const int warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    const int world = map.world > 1 ? map.world : 1;
+    const int tileSize = 16 * (world < 16 ? world : 16);              // indices per tile: about 16 of them are owned
+    const int rounds = (tileSize + 31) / 32;
+    const int nTiles = (total + tileSize - 1) / tileSize;
     const bool carve = sF[0].carve != 0;
-    int x = 0, y = 0, z = 0;
-    float bx = 0.0f, by = 0.0f, bz = 0.0f;
-    unsigned candM = 0u, chunkBand = 0u, chunkFree = 0u;
-    const bool inBox = slotIdx < total;
-    if (inBox)
+    const float ext = __fmul_rn((float)CS, map.res);
+    int myCount = 0;                                                   // lane f: candidates of frame f seen by this warp
+    for (int tile = blockIdx.x * kCandWarps + warp; tile < nTiles; tile += gridDim.x * kCandWarps)
     {
-        const int i = (int)(((long long)slotIdx * bp.cand_stride) % total);
-        const int nyz = bp.n[1] * bp.n[2];
-        x = bp.lo[0] + i / nyz;
-        const int r = i - (i / nyz) * nyz;
-        y = bp.lo[1] + r / bp.n[2];
-        z = bp.lo[2] + r % bp.n[2];
-        const bool mine = map.world <= 1 || (owner_hash(x, y, z) % (unsigned)map.world) == (unsigned)map.rank;
-        // chunk box exactly as ChunkManager.cpp:199-201
-        const float ext = __fmul_rn((float)CS, map.res);
-        bx = __fmul_rn((float)(x * CS), map.res);
-        by = __fmul_rn((float)(y * CS), map.res);
-        bz = __fmul_rn((float)(z * CS), map.res);
-        const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
-        if (mine)
-            for (int f = gl; f < K; f += GL)
-            {
-                const FrameParams &fp = sF[f];
-                if ((unsigned)(x - fp.lo[0]) >= (unsigned)fp.n[0] || (unsigned)(y - fp.lo[1]) >= (unsigned)fp.n[1] || (unsigned)(z - fp.lo[2]) >= (unsigned)fp.n[2])
-                    continue;
-                if (!frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
-                    continue;
-                candM |= 1u << f;
-                const int code = classify_box<true>(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
-                chunkBand |= (code == 2 ? 1u : 0u) << f;
-                chunkFree |= (code == 1 ? 1u : 0u) << f;
-            }
-    }
-#pragma unroll
-    for (int o = 1; o < GL; o <<= 1)
-    {
-        candM |= __shfl_xor_sync(0xffffffffu, candM, o);
-        chunkBand |= __shfl_xor_sync(0xffffffffu, chunkBand, o);
-        chunkFree |= __shfl_xor_sync(0xffffffffu, chunkFree, o);
-    }
-    // Does the chunk exist? One lookup per chunk that stage 1 could not dismiss, BEFORE the per-brick stage: most of the view
-    // pyramid is free space without chunks, and a chunk that does not exist only matters if some frame may hit it.
-    int slot = -1;
-    unsigned long long flags = 0ull;
-    if (leader && (chunkBand || (chunkFree && carve)))
-    {
-        slot = hash_lookup(map, pack_id(x, y, z));
-        if (slot >= 0 && chunkFree && carve)
-            flags = map.brick_flags[slot];
-    }
-    const int leaderLane = (int)(lane & ~(unsigned)(GL - 1));
-    slot = __shfl_sync(0xffffffffu, slot, leaderLane);
-    flags = __shfl_sync(0xffffffffu, flags, leaderLane);
-    // free-space frames can only carve observed voxels: they matter for an existing chunk with a carvable brick, or after a band
-    // frame of this batch (which may create one)
-    const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
-    // stage 2: the lane's brick(s) in the surviving frames
-    unsigned bandM[BPL], freeM[BPL];
-#pragma unroll
-    for (int k = 0; k < BPL; k++)
-        bandM[k] = freeM[k] = 0u;
-    if (NB == 1)
-    {
-        bandM[0] = chunkBand;
-        freeM[0] = freeTodo;
-    }
-    else
-    {
-        unsigned todo = chunkBand | freeTodo;
-        while (todo)
+        // 0. owned chunk indices of the tile
+        int nList = 0;
+        for (int r = 0; r < rounds; r++)
         {
-            const int f = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const FrameParams &fp = sF[f];
-#pragma unroll
-            for (int k = 0; k < BPL; k++)
+            const int slotIdx = tile * tileSize + r * 32 + (int)lane;
+            bool own = false;
+            int i = 0;
+            if (r * 32 + (int)lane < tileSize && slotIdx < total)
             {
-                const int b = gl + k * GL;
-                const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
-                const int code = classify_box<true>(fp, bx + (float)(qx * 8) * map.res + map.half, by + (float)(qy * 8) * map.res + map.half,
-                                                    bz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
-                bandM[k] |= (code == 2 ? 1u : 0u) << f;
-                freeM[k] |= (code == 1 ? 1u : 0u) << f;
+                i = (int)(((long long)slotIdx * bp.cand_stride) % total);
+                own = true;
+                if (world > 1)
+                {
+                    const int x = bp.lo[0] + i / nyz, rr = i - (i / nyz) * nyz;
+                    own = (owner_hash(x, bp.lo[1] + rr / bp.n[2], bp.lo[2] + rr % bp.n[2]) % (unsigned)world) == (unsigned)map.rank;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, own);
+            if (own)
+                sList[warp][nList + __popc(m & below)] = i;
+            nList += __popc(m);
+        }
+        __syncwarp();
+        // 16 chunks per pass: lanes c and c + 16 share chunk c and take the even / odd frames (half the dependent chain)
+        for (int base = 0; base < nList; base += 16)
+        {
+            const bool have = base + (int)(lane & 15) < nList;
+            int x = 0, y = 0, z = 0;
+            float bx = 0.0f, by = 0.0f, bz = 0.0f;
+            unsigned candM = 0u, chunkBand = 0u, chunkFree = 0u;
+            if (have)
+            {
+                const int i = sList[warp][base + (lane & 15)];
+                x = bp.lo[0] + i / nyz;
+                const int r = i - (i / nyz) * nyz;
+                y = bp.lo[1] + r / bp.n[2];
+                z = bp.lo[2] + r % bp.n[2];
+                // chunk box exactly as ChunkManager.cpp:199-201
+                bx = __fmul_rn((float)(x * CS), map.res);
+                by = __fmul_rn((float)(y * CS), map.res);
+                bz = __fmul_rn((float)(z * CS), map.res);
+                const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
+                // 1. chunk level
+                for (int f = (int)(lane >> 4); f < K; f += 2)
+                {
+                    const FrameParams &fp = sF[f];
+                    if ((unsigned)(x - fp.lo[0]) >= (unsigned)fp.n[0] || (unsigned)(y - fp.lo[1]) >= (unsigned)fp.n[1] || (unsigned)(z - fp.lo[2]) >= (unsigned)fp.n[2])
+                        continue;
+                    if (!frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
+                        continue;
+                    candM |= 1u << f;
+                    const int code = classify_box<true>(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
+                    chunkBand |= (code == 2 ? 1u : 0u) << f;
+                    chunkFree |= (code == 1 ? 1u : 0u) << f;
+                }
+            }
+            candM |= __shfl_xor_sync(0xffffffffu, candM, 16);
+            chunkBand |= __shfl_xor_sync(0xffffffffu, chunkBand, 16);
+            chunkFree |= __shfl_xor_sync(0xffffffffu, chunkFree, 16);
+            // per-frame candidate counts: lane f of the warp accumulates frame f
+            for (int f = 0; f < K; f++)
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, lane < 16 && ((candM >> f) & 1u));
+                if ((int)lane == f)
+                    myCount += __popc(m);
+            }
+            // Does the chunk exist? One lookup per chunk that stage 1 could not dismiss: most of the view pyramid is free space
+            // without chunks, and a chunk that does not exist only matters if some frame may hit it.
+            int slot = -1;
+            unsigned long long flags = 0ull;
+            if (lane < 16 && (chunkBand || (chunkFree && carve)))
+            {
+                slot = hash_lookup(map, pack_id(x, y, z));
+                if (slot >= 0 && chunkFree && carve)
+                    flags = map.brick_flags[slot];
+            }
+            // free-space frames can only carve observed voxels: they matter for an existing chunk with a carvable brick, or
+            // after a band frame of this batch (which may create one)
+            const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
+            // 2. brick level: the warp takes the surviving chunks one at a time
+            unsigned surv = __ballot_sync(0xffffffffu, lane < 16 && (chunkBand | freeTodo) != 0u);
+            while (surv)
+            {
+                const int src = __ffs(surv) - 1;
+                surv &= surv - 1;
+                const int sx = __shfl_sync(0xffffffffu, x, src), sy = __shfl_sync(0xffffffffu, y, src), sz = __shfl_sync(0xffffffffu, z, src);
+                const float cbx = __shfl_sync(0xffffffffu, bx, src), cby = __shfl_sync(0xffffffffu, by, src), cbz = __shfl_sync(0xffffffffu, bz, src);
+                const unsigned sBand = __shfl_sync(0xffffffffu, chunkBand, src), sFree = __shfl_sync(0xffffffffu, freeTodo, src);
+                const int sSlot = __shfl_sync(0xffffffffu, slot, src);
+                const unsigned long long sFlags = __shfl_sync(0xffffffffu, flags, src);
+                const unsigned long long key = pack_id(sx, sy, sz);
+                const bool exists = sSlot >= 0;
+                auto brick_code = [&](int b, int f) -> int
+                {
+                    const int qx = b % BPA, qy = (b / BPA) % BPA, qz = b / (BPA * BPA);
+                    return classify_box<true>(sF[f], cbx + (float)(qx * 8) * map.res + map.half, cby + (float)(qy * 8) * map.res + map.half,
+                                              cbz + (float)(qz * 8) * map.res + map.half, 7.0f * map.res);
+                };
+                if (NB == 1)
+                {
+                    if (lane == 0 && !exists && sBand)
+                        atomicAdd(&bp.bctr->new_count, 1);
+                    emit_brick_unit(bp, lane == 0, key, sSlot, exists, !exists && sBand != 0u, carve, sFlags, 0, sBand, sFree, K, lane);
+                }
+                else if (NB == 8)
+                {
+                    // lanes = (brick lane & 7, frame slot lane >> 3): the four lowest frames of the to-do mask per round
+                    const int b = lane & 7, j = lane >> 3;
+                    unsigned bandB = 0u, freeB = 0u;
+                    unsigned t = sBand | sFree;
+                    while (t)
+                    {
+                        unsigned pick = 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            const unsigned low = t & (0u - t);
+                            t ^= low;
+                            pick = (q == j) ? low : pick;
+                        }
+                        if (pick)
+                        {
+                            const int code = brick_code(b, __ffs(pick) - 1);
+                            bandB |= code == 2 ? pick : 0u;
+                            freeB |= code == 1 ? pick : 0u;
+                        }
+                    }
+                    bandB |= __shfl_xor_sync(0xffffffffu, bandB, 8);
+                    freeB |= __shfl_xor_sync(0xffffffffu, freeB, 8);
+                    bandB |= __shfl_xor_sync(0xffffffffu, bandB, 16);
+                    freeB |= __shfl_xor_sync(0xffffffffu, freeB, 16);
+                    // the chunk-level band mask that decides creation is the union of the brick-level ones (tighter than stage 1)
+                    unsigned u = bandB;
+                    u |= __shfl_xor_sync(0xffffffffu, u, 1);
+                    u |= __shfl_xor_sync(0xffffffffu, u, 2);
+                    u |= __shfl_xor_sync(0xffffffffu, u, 4);
+                    const bool virt = !exists && u != 0u;
+                    if (lane == 0 && virt)
+                        atomicAdd(&bp.bctr->new_count, 1);
+                    emit_brick_unit(bp, lane < 8, key, sSlot, exists, virt, carve, sFlags, b, bandB, freeB, K, lane);
+                }
+                else
+                {
+                    // 64 bricks: two per lane, frames in a loop
+                    unsigned bandB[2] = {0u, 0u}, freeB[2] = {0u, 0u};
+#pragma unroll
+                    for (int hb = 0; hb < 2; hb++)
+                    {
+                        unsigned t = sBand | sFree;
+                        while (t)
+                        {
+                            const unsigned low = t & (0u - t);
+                            t ^= low;
+                            const int code = brick_code((int)lane + 32 * hb, __ffs(low) - 1);
+                            bandB[hb] |= code == 2 ? low : 0u;
+                            freeB[hb] |= code == 1 ? low : 0u;
+                        }
+                    }
+                    unsigned u = bandB[0] | bandB[1];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                        u |= __shfl_xor_sync(0xffffffffu, u, o);
+                    const bool virt = !exists && u != 0u;
+                    if (lane == 0 && virt)
+                        atomicAdd(&bp.bctr->new_count, 1);
+#pragma unroll
+                    for (int hb = 0; hb < 2; hb++)
+                        emit_brick_unit(bp, true, key, sSlot, exists, virt, carve, sFlags, (int)lane + 32 * hb, bandB[hb], freeB[hb], K, lane);
+                }
             }
         }
-        // the chunk-level band mask that decides creation is the union of the brick-level ones (tighter than stage 1)
-        unsigned u = 0u;
-#pragma unroll
-        for (int k = 0; k < BPL; k++)
-            u |= bandM[k];
-#pragma unroll
-        for (int o = 1; o < GL; o <<= 1)
-            u |= __shfl_xor_sync(0xffffffffu, u, o);
-        chunkBand = u;
-    }
-
-    // per-frame candidate counts: lane f of the warp accumulates frame f
-    int myCount = 0;
-    for (int f = 0; f < K; f++)
-    {
-        const unsigned m = __ballot_sync(0xffffffffu, leader && ((candM >> f) & 1u));
-        if ((int)lane == f)
-            myCount = __popc(m);
+        __syncwarp();
     }
     if ((int)lane < K && myCount)
         atomicAdd(&bp.bctr->candidates[lane], myCount);
-
-    // chunks that do not exist yet (slot < 0) become VIRTUAL units: batch_bricks_kernel creates the chunk if a frame hits
-    const bool exists = slot >= 0;
-    const bool virt = !exists && chunkBand != 0u;
-    const unsigned newMask = __ballot_sync(0xffffffffu, leader && virt);
-    if (lane == 0 && newMask)
-        atomicAdd(&bp.bctr->new_count, __popc(newMask));
-    const unsigned long long key = pack_id(x, y, z);
-#pragma unroll
-    for (int k = 0; k < BPL; k++)
-        emit_brick_unit(bp, true, key, slot, exists, virt, carve, flags, gl + k * GL, bandM[k], freeM[k], K, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -593,30 +674,40 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
             bp.bctr->n_new[t] = sNew[t];
         __syncthreads();
     }
+    // the snapshot is assembled in shared memory (so that its checksum is computed from exactly what is sent), then copied out
+    __shared__ HostBatchSnapshot sSnap;
     if (t == 0)
     {
-        h->head = bp.batch_id;
-        h->n_chunks = g->n_chunks;
-        h->n_dirty = g->n_dirty;
-        h->error_flags = g->error_flags;
-        h->unit_count = c->unit_count + c->bucket1 + c->bucket2 + c->light_count;
-        h->new_count = c->new_count;
-        h->K = bp.K;
-        h->bricks_span_ns = (long long)(c->span_end - ~c->span_start_inv);
+        sSnap.head = bp.batch_id;
+        sSnap.n_chunks = g->n_chunks;
+        sSnap.n_dirty = g->n_dirty;
+        sSnap.error_flags = g->error_flags;
+        sSnap.unit_count = c->unit_count + c->bucket1 + c->bucket2 + c->light_count;
+        sSnap.new_count = c->new_count;
+        sSnap.K = bp.K;
+        sSnap.pad = 0;
+        sSnap.bricks_span_ns = (long long)(c->span_end - ~c->span_start_inv);
+        sSnap.tail = bp.batch_id;
+        sSnap.pad3[0] = sSnap.pad3[1] = sSnap.pad3[2] = 0;
     }
     if (t < kMaxBatch)
     {
-        h->candidates[t] = c->candidates[t];
-        h->n_new[t] = c->n_new[t];
-        h->updated_chunks[t] = c->updated_chunks[t];
-        h->n_upd[t] = (long long)c->n_upd[t];
-        h->n_carve[t] = (long long)c->n_carve[t];
-        h->n_col[t] = (long long)c->n_col[t];
+        sSnap.candidates[t] = c->candidates[t];
+        sSnap.n_new[t] = c->n_new[t];
+        sSnap.updated_chunks[t] = c->updated_chunks[t];
+        sSnap.n_upd[t] = (long long)c->n_upd[t];
+        sSnap.n_carve[t] = (long long)c->n_carve[t];
+        sSnap.n_col[t] = (long long)c->n_col[t];
     }
-    __threadfence_system();
     __syncthreads();
     if (t == 0)
-        h->tail = bp.batch_id;
+        sSnap.checksum = batch_snapshot_checksum(sSnap);
+    __syncthreads();
+    static_assert(sizeof(HostBatchSnapshot) % 4 == 0, "copied word-wise");
+    const int *src = reinterpret_cast<const int *>(&sSnap);
+    volatile int *dst = reinterpret_cast<volatile int *>(h);
+    for (int i = t; i < (int)(sizeof(HostBatchSnapshot) / 4); i += blockDim.x)
+        dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -846,9 +937,10 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
     constexpr int BPA = CS / 8;
     __shared__ FrameParams sF[kMaxBatch];
     __shared__ BatchShared sB;
-    batch_span_start(bp);
     batch_shared_zero(&sB);
     load_frames(sF, bp);
+    pdl_wait();                                    // the candidates kernel's unit lists and counters are read from here on
+    batch_span_start(bp);
     const int lane = threadIdx.x & 31;
     // the list holds every brick of the union box at most once, so heavy (front) and light (back) units cannot collide
     const UnitCounts uc = unit_counts(bp);
@@ -1215,7 +1307,6 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
     __shared__ BatchShared sB;
     __shared__ float2 *sDist[kSlabCache];
     __shared__ uchar4 *sCol[kSlabCache];
-    batch_span_start(bp);
     batch_shared_zero(&sB);
     constexpr bool hasCol = COLOR_PATH && HAS_COL;          // HAS_COL: the map stores colour voxels (compile time: no duplicated code paths)
     {
@@ -1227,6 +1318,8 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
         }
     }
     __syncthreads();
+    pdl_wait();                                    // the candidates kernel's unit lists and counters are read from here on
+    batch_span_start(bp);
     const int lane = threadIdx.x & 31;
     const UnitCounts uc = unit_counts(bp);
     const int nTasks = uc.total * kParts;
@@ -1493,6 +1586,25 @@ static int batch_resident(Kern kernel, int threads)
     return sms * (perSm > 0 ? perSm : 1);
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may begin while its predecessor in the stream drains
+// (it calls pdl_wait() before touching the predecessor's output).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    static const bool off = std::getenv("CHS_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
 {
@@ -1500,8 +1612,9 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     if (!residentBricks)
         residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, CHS_BRICK_THREADS);
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
-    const long long lanes = info.unionCandidates * std::min<long long>(NB, 32);
-    const unsigned gCand = (unsigned)std::max(1ll, (lanes + 255) / 256);
+    // a warp per tile of 16 chunk indices (at N ranks: 16 x N indices, about 16 of them owned)
+    const long long candTiles = (info.unionCandidates + 15) / 16;
+    const unsigned gCand = (unsigned)std::max(1ll, std::min<long long>((candTiles + kCandWarps - 1) / kCandWarps, 148 * 8));
     const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
@@ -1522,6 +1635,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         if ((e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
             return e;
     }
+    const int hizFirst = info.hizCount > 0 ? info.hizFirst : 0, hizCount = info.hizCount > 0 ? info.hizCount : bp.K;
     if (info.hizTma)
     {
         static bool attr = false;
@@ -1531,11 +1645,13 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
                 return e;
             attr = true;
         }
-        const int nItems = tiles * bp.K;
-        batch_hiz_tma_kernel<<<std::min(nItems, 148 * 4), kHizThreads, kHizSmem, bs.prep>>>(bp, tilesX, tiles, nItems);
+        const int nItems = tiles * hizCount;
+        batch_hiz_tma_kernel<<<std::min(nItems, 148 * 4), kHizThreads, kHizSmem, bs.prep>>>(bp, tilesX, tiles, nItems, hizFirst);
     }
     else
-        batch_hiz_kernel<<<dim3(tiles, bp.K), 256, 0, bs.prep>>>(bp, map, tilesX);
+        batch_hiz_kernel<<<dim3(tiles, hizCount), 256, 0, bs.prep>>>(bp, map, tilesX, hizFirst);
+    if (info.afterHiz && info.afterHiz(info.afterHizCtx) != 0)
+        return cudaErrorUnknown;
     if (info.profiling && (e = cudaEventRecord(evt[1], bs.prep)) != cudaSuccess)
         return e;
     if (bs.prep != st && ((e = cudaEventRecord(bs.prepared, bs.prep)) != cudaSuccess || (e = cudaStreamWaitEvent(st, bs.prepared, 0)) != cudaSuccess))
@@ -1546,7 +1662,8 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         if (bs.pack != st && (e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
             return e;
     }
-    batch_candidates_kernel<CS><<<gCand, 256, 0, st>>>(bp, map);
+    if ((e = launch_pdl(batch_candidates_kernel<CS>, dim3(gCand), dim3(32 * kCandWarps), 0, st, bp, map)) != cudaSuccess)
+        return e;
     if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
         return e;
     if (packBlocks && bs.pack != st && (e = cudaStreamWaitEvent(st, bs.packed, 0)) != cudaSuccess)
@@ -1564,12 +1681,14 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         const unsigned gFast = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_FAST_THREADS / 32 - 1) / (CHS_FAST_THREADS / 32), residentFast));
         bp.total_ctas = (int)gFast;
         if (COLOR_PATH && map.use_color)
-            batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
+            e = launch_pdl(batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH>, dim3(gFast), dim3(CHS_FAST_THREADS), 0, st, bp, map, *info.brickFrames);
         else
-            batch_bricks_fast_kernel<CS, COLOR_PATH, false><<<gFast, CHS_FAST_THREADS, 0, st>>>(bp, map, *info.brickFrames);
+            e = launch_pdl(batch_bricks_fast_kernel<CS, COLOR_PATH, false>, dim3(gFast), dim3(CHS_FAST_THREADS), 0, st, bp, map, *info.brickFrames);
     }
     else
-        batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL><<<gBricks, CHS_BRICK_THREADS, 0, st>>>(bp, map);
+        e = launch_pdl(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, dim3(gBricks), dim3(CHS_BRICK_THREADS), 0, st, bp, map);
+    if (e != cudaSuccess)
+        return e;
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)
         return e;
     return cudaGetLastError();

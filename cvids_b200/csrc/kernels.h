@@ -32,8 +32,9 @@ struct BatchCounters
     unsigned long long span_start_inv, span_end;       // brick kernel: max over CTAs of ~(start time) and of the end time (%globaltimer, ns)
 };
 
-// Written into a pinned slot by the last CTA of a batch: head, payload, system fence, tail. Valid for batch b when
-// head == tail == b.
+// Written into a pinned slot by the last CTA of a batch: head, payload, checksum of the payload, tail -- WITHOUT a system-scope
+// fence (a fence makes the kernel wait for a PCIe round trip). Valid for batch b when head == tail == b and the checksum matches
+// the payload the host reads (stores that have not landed yet make it mismatch: the host simply polls again).
 struct HostBatchSnapshot
 {
     int head, n_chunks, n_dirty, error_flags;
@@ -41,8 +42,21 @@ struct HostBatchSnapshot
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch];
     long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
     long long bricks_span_ns;       // first CTA start -> last CTA end of the brick kernel, from %globaltimer (no launch / event overhead)
+    unsigned long long checksum;    // batch_snapshot_checksum of everything between head and here
     int tail, pad3[3];
 };
+
+// 64-bit sum of the payload words, seeded with the batch id (host and device compute it the same way)
+__host__ __device__ inline unsigned long long batch_snapshot_checksum(const HostBatchSnapshot &h)
+{
+    unsigned long long s = 0x9E3779B97F4A7C15ull * (unsigned long long)(unsigned)h.head;
+    s += (unsigned)h.n_chunks + ((unsigned long long)(unsigned)h.n_dirty << 1) + ((unsigned long long)(unsigned)h.error_flags << 2) +
+         ((unsigned long long)(unsigned)h.unit_count << 3) + ((unsigned long long)(unsigned)h.new_count << 4) + ((unsigned long long)(unsigned)h.K << 5);
+    for (int t = 0; t < kMaxBatch; t++)
+        s += (unsigned long long)(unsigned)h.candidates[t] * 3 + (unsigned long long)(unsigned)h.n_new[t] * 5 + (unsigned long long)(unsigned)h.updated_chunks[t] * 7 +
+             (unsigned long long)h.n_upd[t] * 11 + (unsigned long long)h.n_carve[t] * 13 + (unsigned long long)h.n_col[t] * 17;
+    return s + (unsigned long long)h.bricks_span_ns * 19;
+}
 
 struct BatchParams
 {
@@ -93,6 +107,10 @@ struct BatchLaunchInfo
     int W, H, cW, cH;               // depth / colour image size (identical for all frames of a batch)
     long long unionCandidates;      // chunk IDs in the union box
     bool colorPath, perPixel, profiling;
+    int hizFirst, hizCount;         // frames whose Hi-Z pyramid THIS launch builds (distributed batches: the frames this rank ingests; the
+                                    // other ranks' pyramids arrive by all-gather, see afterHiz); hizCount == 0: all K frames
+    int (*afterHiz)(void *);        // called right after the Hi-Z kernel has been enqueued on the prepare stream (or nullptr)
+    void *afterHizCtx;
     bool hizTma;                    // Hi-Z by the TMA bulk-copy kernel (float depth, constant truncator, aligned rows)
     bool fastBricks;                // every frame satisfies the preconditions of batch_bricks_fast_kernel (brick_frames is filled)
     const BrickFrames *brickFrames; // host pointer; copied into the kernel's parameter block
