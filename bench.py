@@ -607,15 +607,19 @@ def run_single_agent(B: Bench, args):
     m.synchronize()
     t_flushed = sum(a.elapsed_time(b) for a, b in ev) / 1000.0
     m.close()
-    # profiling pass (L2 flushed before every step: cold-cache kernel times, like the ncu captures)
+    # profiling pass (L2 flushed before every step: cold-cache kernel times, like the ncu captures). Plain CHS_MEM_DEVICE here: every
+    # kernel of the step then runs on the map's stream, behind the flush, so the per-kernel event times are clean
     m = B.new_map(cfg, sharded=False)
     m.set_profiling(True)
     upd = bytes_alg = 0
     tk = dict(integrate=0.0, prepare=0.0, candidates=0.0, new_chunks=0.0, bricks_span=0.0)
+    prepared_sync = {}
     for t in range(T):
         if t >= warm:
             B.flush_l2(t)
-        step_device(m, t)
+        prepared_sync[t] = m.prepare_batch(integ, None, [frames[i][2] for i in ids(t)], camv,
+                                           device_ptrs=[(d_depth[i].data_ptr(), d_col[i].data_ptr()) for i in ids(t)], channels=ch)
+        m.integrate_prepared(prepared_sync[t])
         sts = m.batch_stats()
         if t >= warm:
             tm = m.timings()

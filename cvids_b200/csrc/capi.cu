@@ -1133,7 +1133,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         size_t bytesPerFrame;
         cudaStream_t st;
     } hizGather{m, bs.hiz, tiles * sizeof(float2), cs};
-    if (dist && m->cfg.world > 1 && !computeTrunc && !anyMm)
+    // (measured: on 2 GPUs the second collective costs more than the Hi-Z kernel it saves; kept for N >= 8 experiments)
+    if (dist && m->cfg.world > 1 && !computeTrunc && !anyMm && std::getenv("CHS_SHARD_HIZ") != nullptr)
     {
         info.hizFirst = locFirst;
         info.hizCount = locEnd - locFirst;
@@ -1146,7 +1147,18 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     // colour packing runs beside the candidates kernel: on the copy stream (host frames: it follows the copies and the Hi-Z kernel
     // there; device frames: forked from the map's stream)
+    // Distributed batches: copies and the NCCL exchange run on the copy stream, beside the kernels of the previous batch (the brick
+    // kernel keeps a few SMs free for the NCCL kernels: BatchParams::reserve_sms); Hi-Z and colour packing then run on the map's
+    // stream, on the whole GPU, once the exchange has landed.
     BatchStreams streams{cs, m->copyStream, st, bs.prepared, bs.packDone, bs.fork};
+    if (dist)
+    {
+        CHS_CUDA(cudaEventRecord(bs.prepared, cs));
+        CHS_CUDA(cudaStreamWaitEvent(st, bs.prepared, 0));
+        streams.prep = st;
+        streams.pack = st;
+    }
+    bp.reserve_sms = (dist && m->cfg.world > 1) ? 1 : 0;
     if (!poolLater)
         CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 3));
     else

@@ -62,10 +62,27 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // All frames of the batch into shared memory: afterwards `sF[f]` is read with warp-uniform shared loads.
 __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &bp)
 {
-    const int nWords = bp.K * (int)(sizeof(FrameParams) / 4);
-    const int *src = reinterpret_cast<const int *>(bp.frames);
-    int *dst = reinterpret_cast<int *>(sF);
-    for (int i = threadIdx.x; i < nWords; i += blockDim.x)
+    static_assert(sizeof(FrameParams) % 16 == 0, "FrameParams is copied as 16-byte words");
+    const int nQuads = bp.K * (int)(sizeof(FrameParams) / 16);
+    const uint4 *src = reinterpret_cast<const uint4 *>(bp.frames);
+    uint4 *dst = reinterpret_cast<uint4 *>(sF);
+    // all loads of a thread in flight at once (the table is a few KB: one round trip instead of one per word)
+    uint4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        const int i = (int)threadIdx.x + r * (int)blockDim.x;
+        if (i < nQuads)
+            v[r] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        const int i = (int)threadIdx.x + r * (int)blockDim.x;
+        if (i < nQuads)
+            dst[i] = v[r];
+    }
+    for (int i = (int)threadIdx.x + 8 * (int)blockDim.x; i < nQuads; i += blockDim.x)
         dst[i] = __ldg(src + i);
     __syncthreads();
 }
@@ -320,10 +337,11 @@ __device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCo
 // A warp per tile of the union candidate box:
 //   0. the chunk indices of the tile that THIS RANK OWNS are compacted by ballot (32 x world indices are looked at), so that at
 //      N ranks a warp still works on full tiles and the kernel's work divides by N;
-//   1. chunk level, a lane per chunk, frames in a loop: is the chunk inside frame f's candidate ID box and does it pass
-//      Frustum::Intersects (ChunkManager.cpp:182-212, exact)? If so, classify the whole chunk against the frame's Hi-Z tiles.
-//      Most (chunk, frame) pairs end here: behind the surface, off the image, or in free space with nothing to carve. One hash
-//      lookup per chunk that is left (all lanes in parallel);
+//   1. chunk level. (a) a lane per chunk, frames in a loop, cheap tests only: is the chunk inside frame f's candidate ID box and
+//      does it pass Frustum::Intersects (ChunkManager.cpp:182-212, exact)? Is it inside the frame's view pyramid at all? The
+//      (chunk, frame) pairs that are go into a queue in shared memory (ballot compaction). (b) a lane per QUEUED PAIR: the
+//      chunk against the frame's Hi-Z tiles. Most pairs end here: behind the surface or in free space with nothing to carve.
+//      One hash lookup per chunk that is left (all lanes in parallel);
 //   2. brick level, the whole warp per surviving chunk: lanes = (brick, one of four frames) -> per-brick frame masks
 //        band   frames in which some voxel of the brick may fall inside the truncation band
 //        free   frames in which the brick lies in free space (only carving of observed voxels can act)
@@ -332,15 +350,17 @@ __device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCo
 //   3. warp-ballot compaction into the unit lists (four cost buckets).
 // Chunk indices go through a multiplicative permutation so that the surviving chunks spread over all warps.
 constexpr int kCandWarps = 4;                       // warps per CTA
-constexpr int kCandList = 16 * 16;                  // owned chunk indices of one tile (16 x min(world, 16) indices are looked at)
+constexpr int kCandList = 32 * 8;                   // owned chunk indices of one tile (32 x min(world, 8) indices are looked at)
 
 template <int CS>
 __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(BatchParams bp, DeviceMap map)
 {
     constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
-    __shared__ FrameParams sF[kMaxBatch];
+    __shared__ __align__(16) FrameParams sF[kMaxBatch];
     __shared__ float2 sCoarse[kMaxBatch][kCoarseTiles];
     __shared__ int sList[kCandWarps][kCandList];
+    __shared__ unsigned short sPairs[kCandWarps][32 * kMaxBatch];     // (chunk of the pass << 8) | frame: pairs that need the depth test
+    __shared__ unsigned sBandC[kCandWarps][32], sFreeC[kCandWarps][32];
     pdl_launch_dependents();                       // the brick kernel may start launching: it waits (pdl_wait) before it reads the unit lists
     load_frames(sF, bp);                           // the frame table was uploaded before the Hi-Z kernel: complete
     pdl_wait();                                    // the Hi-Z kernel's output is read from here on
@@ -397,8 +417,8 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
     const int warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
     const int world = map.world > 1 ? map.world : 1;
-    const int tileSize = 16 * (world < 16 ? world : 16);              // indices per tile: about 16 of them are owned
-    const int rounds = (tileSize + 31) / 32;
+    const int tileSize = 32 * (world < 8 ? world : 8);                // indices per tile: about 32 of them are owned
+    const int rounds = tileSize / 32;
     const int nTiles = (total + tileSize - 1) / tileSize;
     const bool carve = sF[0].carve != 0;
     const float ext = __fmul_rn((float)CS, map.res);
@@ -412,7 +432,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             const int slotIdx = tile * tileSize + r * 32 + (int)lane;
             bool own = false;
             int i = 0;
-            if (r * 32 + (int)lane < tileSize && slotIdx < total)
+            if (slotIdx < total)
             {
                 i = (int)(((long long)slotIdx * bp.cand_stride) % total);
                 own = true;
@@ -428,16 +448,15 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             nList += __popc(m);
         }
         __syncwarp();
-        // 16 chunks per pass: lanes c and c + 16 share chunk c and take the even / odd frames (half the dependent chain)
-        for (int base = 0; base < nList; base += 16)
+        for (int base = 0; base < nList; base += 32)
         {
-            const bool have = base + (int)(lane & 15) < nList;
+            const bool have = base + (int)lane < nList;
             int x = 0, y = 0, z = 0;
             float bx = 0.0f, by = 0.0f, bz = 0.0f;
-            unsigned candM = 0u, chunkBand = 0u, chunkFree = 0u;
+            unsigned candM = 0u;
             if (have)
             {
-                const int i = sList[warp][base + (lane & 15)];
+                const int i = sList[warp][base + lane];
                 x = bp.lo[0] + i / nyz;
                 const int r = i - (i / nyz) * nyz;
                 y = bp.lo[1] + r / bp.n[2];
@@ -446,28 +465,55 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
                 bx = __fmul_rn((float)(x * CS), map.res);
                 by = __fmul_rn((float)(y * CS), map.res);
                 bz = __fmul_rn((float)(z * CS), map.res);
+            }
+            sBandC[warp][lane] = 0u;
+            sFreeC[warp][lane] = 0u;
+            // 1a. chunk level, cheap part, a lane per chunk and all frames: candidate of the frame (exact)? inside its view pyramid?
+            // The (chunk, frame) pairs that are go into the warp's queue.
+            int qn = 0;
+            {
                 const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
-                // 1. chunk level
-                for (int f = (int)(lane >> 4); f < K; f += 2)
+                for (int f = 0; f < K; f++)
                 {
                     const FrameParams &fp = sF[f];
-                    if ((unsigned)(x - fp.lo[0]) >= (unsigned)fp.n[0] || (unsigned)(y - fp.lo[1]) >= (unsigned)fp.n[1] || (unsigned)(z - fp.lo[2]) >= (unsigned)fp.n[2])
-                        continue;
-                    if (!frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
-                        continue;
-                    candM |= 1u << f;
-                    const int code = classify_box<true>(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
-                    chunkBand |= (code == 2 ? 1u : 0u) << f;
-                    chunkFree |= (code == 1 ? 1u : 0u) << f;
+                    bool vis = false;
+                    if (have && (unsigned)(x - fp.lo[0]) < (unsigned)fp.n[0] && (unsigned)(y - fp.lo[1]) < (unsigned)fp.n[1] && (unsigned)(z - fp.lo[2]) < (unsigned)fp.n[2] &&
+                        frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
+                    {
+                        candM |= 1u << f;
+                        vis = !box_outside_view(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, vis);
+                    if (vis)
+                        sPairs[warp][qn + __popc(m & below)] = (unsigned short)((lane << 8) | (unsigned)f);
+                    qn += __popc(m);
                 }
             }
-            candM |= __shfl_xor_sync(0xffffffffu, candM, 16);
-            chunkBand |= __shfl_xor_sync(0xffffffffu, chunkBand, 16);
-            chunkFree |= __shfl_xor_sync(0xffffffffu, chunkFree, 16);
+            __syncwarp();
+            // 1b. the depth test of the queued pairs, a lane per pair (dense)
+            for (int q0 = 0; q0 < qn; q0 += 32)
+            {
+                if (q0 + (int)lane < qn)
+                {
+                    const unsigned pr = sPairs[warp][q0 + lane];
+                    const int cl = (int)(pr >> 8), f = (int)(pr & 255u);
+                    const int i = sList[warp][base + cl];
+                    const int px = bp.lo[0] + i / nyz, r = i - (i / nyz) * nyz, py = bp.lo[1] + r / bp.n[2], pz = bp.lo[2] + r % bp.n[2];
+                    const int code = classify_box_depth<true>(sF[f], __fmul_rn((float)(px * CS), map.res) + map.half, __fmul_rn((float)(py * CS), map.res) + map.half,
+                                                              __fmul_rn((float)(pz * CS), map.res) + map.half, (float)(CS - 1) * map.res);
+                    if (code == 2)
+                        atomicOr(&sBandC[warp][cl], 1u << f);
+                    else if (code == 1)
+                        atomicOr(&sFreeC[warp][cl], 1u << f);
+                }
+            }
+            __syncwarp();
+            const unsigned chunkBand = sBandC[warp][lane], chunkFree = sFreeC[warp][lane];
+            __syncwarp();
             // per-frame candidate counts: lane f of the warp accumulates frame f
             for (int f = 0; f < K; f++)
             {
-                const unsigned m = __ballot_sync(0xffffffffu, lane < 16 && ((candM >> f) & 1u));
+                const unsigned m = __ballot_sync(0xffffffffu, (candM >> f) & 1u);
                 if ((int)lane == f)
                     myCount += __popc(m);
             }
@@ -475,7 +521,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             // without chunks, and a chunk that does not exist only matters if some frame may hit it.
             int slot = -1;
             unsigned long long flags = 0ull;
-            if (lane < 16 && (chunkBand || (chunkFree && carve)))
+            if (chunkBand || (chunkFree && carve))
             {
                 slot = hash_lookup(map, pack_id(x, y, z));
                 if (slot >= 0 && chunkFree && carve)
@@ -485,7 +531,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             // after a band frame of this batch (which may create one)
             const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
             // 2. brick level: the warp takes the surviving chunks one at a time
-            unsigned surv = __ballot_sync(0xffffffffu, lane < 16 && (chunkBand | freeTodo) != 0u);
+            unsigned surv = __ballot_sync(0xffffffffu, (chunkBand | freeTodo) != 0u);
             while (surv)
             {
                 const int src = __ffs(surv) - 1;
@@ -606,6 +652,15 @@ __device__ __forceinline__ void batch_count_frame(BatchShared *s, int f, int nUp
         if (b) atomicAdd(&s->carve[f], b);
         if (c) atomicAdd(&s->col[f], c);
     }
+}
+
+// Distributed batches: the CTAs that land on every 16th SM take no tasks, so that those SMs stay free for the NCCL kernels of the
+// NEXT batch's frame exchange (a persistent grid that fills every SM would keep them queued until it drains).
+__device__ __forceinline__ bool on_reserved_sm(const BatchParams &bp)
+{
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    return bp.reserve_sms && (smid & 15u) == 0u;
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -935,7 +990,7 @@ template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_bricks_kernel(BatchParams bp, DeviceMap map)
 {
     constexpr int BPA = CS / 8;
-    __shared__ FrameParams sF[kMaxBatch];
+    __shared__ __align__(16) FrameParams sF[kMaxBatch];
     __shared__ BatchShared sB;
     batch_shared_zero(&sB);
     load_frames(sF, bp);
@@ -947,7 +1002,7 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
     const int nTasks = uc.total * kParts;
     const bool hasCol = COLOR_PATH && map.use_color;
     const float carveMax = sF[0].sdf_carve_max;
-    while (true)
+    while (!on_reserved_sm(bp))
     {
         int g = 0;
         if (lane == 0)
@@ -1323,12 +1378,14 @@ batch_bricks_fast_kernel(const __grid_constant__ BatchParams bp, const __grid_co
     const int lane = threadIdx.x & 31;
     const UnitCounts uc = unit_counts(bp);
     const int nTasks = uc.total * kParts;
+    const bool idle = on_reserved_sm(bp);          // this CTA takes no tasks (and must not draw any from the queue)
     const float carveMax = bf.f[0].carve_max;
     // Task queue, two entries deep, kept in lanes 0 and 1: entry p is requested (atomicAdd) at a task boundary, its unit record is
     // loaded at the next boundary and it is consumed at the one after, so neither round trip is ever waited for. Tasks are handed
     // out in cost order (bucket 0 first).
     int qg = 0x7fffffff;
     int4 qu = make_int4(0, 0, 0, 0);
+    if (!idle)
     {
         int base = 0;
         if (lane == 0)
@@ -1612,8 +1669,8 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     if (!residentBricks)
         residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, CHS_BRICK_THREADS);
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
-    // a warp per tile of 16 chunk indices (at N ranks: 16 x N indices, about 16 of them owned)
-    const long long candTiles = (info.unionCandidates + 15) / 16;
+    // a warp per tile of 32 chunk indices (at N ranks: 32 x N indices, about 32 of them owned)
+    const long long candTiles = (info.unionCandidates + 31) / 32;
     const unsigned gCand = (unsigned)std::max(1ll, std::min<long long>((candTiles + kCandWarps - 1) / kCandWarps, 148 * 8));
     const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");

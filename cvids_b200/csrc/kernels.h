@@ -73,6 +73,7 @@ struct BatchParams
     BatchCounters *bctr;
     HostBatchSnapshot *host_slot;   // pinned, device-mapped
     unsigned long long *slot_batch; // [capacity] (batch id << 32) | mask of the batch's frames that updated the chunk
+    int reserve_sms;                // the brick kernel leaves every 16th SM idle: room for the NCCL kernels of the next batch's exchange
     int coarse_in_shared;           // the candidates kernel builds the Hi-Z levels >= 4 in shared memory (they fit: <= 48 tiles per frame)
 };
 
