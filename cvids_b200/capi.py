@@ -77,6 +77,7 @@ EXPORTS = (
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic", "chs_host_alloc", "chs_host_free",
+    "chs_device_alloc", "chs_device_free", "chs_upload",
     "chs_comm_unique_id", "chs_comm_init", "chs_comm_attach", "chs_comm_destroy", "chs_integrate_batch_distributed",
     "chs_comm_sync_dirty", "chs_update_meshes_distributed",
 )
@@ -125,6 +126,11 @@ def load_library(build_if_missing: bool = True):
     lib.chs_set_dirty.argtypes = [vp, i64, vp]
     lib.chs_num_dirty.argtypes = [vp, C.POINTER(i64)]
     lib.chs_dirty_ids.argtypes = [vp, vp, i64]
+    lib.chs_device_alloc.restype = vp
+    lib.chs_device_alloc.argtypes = [vp, C.c_size_t]
+    lib.chs_device_free.restype = None
+    lib.chs_device_free.argtypes = [vp, vp]
+    lib.chs_upload.argtypes = [vp, vp, vp, C.c_size_t]
     lib.chs_comm_unique_id.argtypes = [vp]
     lib.chs_comm_init.argtypes = [vp, vp]
     lib.chs_comm_attach.argtypes = [vp, vp]

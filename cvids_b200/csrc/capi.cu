@@ -176,6 +176,7 @@ struct chs_map
         bool used = false;
     } bset[2];
     cudaStream_t copyStream = nullptr;
+    cudaStream_t uploadStream = nullptr;          // chs_upload
     cudaEvent_t callEvent = nullptr;
     int *dHizTickets = nullptr;                // [2 * kMaxBatch + 1] self-resetting block counters of frame_prepare
     HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
@@ -1367,6 +1368,8 @@ int chs_destroy(chs_map *m)
         cudaEventDestroy(m->callEvent);
     if (m->copyStream)
         cudaStreamDestroy(m->copyStream);
+    if (m->uploadStream)
+        cudaStreamDestroy(m->uploadStream);
     cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
@@ -2208,6 +2211,41 @@ void chs_host_free(void *p)
 {
     if (p)
         cudaFreeHost(p);
+}
+
+void *chs_device_alloc(chs_map *m, size_t bytes)
+{
+    if (!m || cudaSetDevice(m->device) != cudaSuccess)
+        return nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void chs_device_free(chs_map *m, void *p)
+{
+    if (m && p && cudaSetDevice(m->device) == cudaSuccess)
+    {
+        cudaStreamSynchronize(m->stream);
+        cudaStreamSynchronize(m->copyStream);
+        cudaFree(p);
+    }
+}
+
+int chs_upload(chs_map *m, void *dst, const void *src, size_t bytes)
+{
+    if (!m || !dst || !src)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    if (!m->uploadStream)
+        CHS_CUDA(cudaStreamCreateWithFlags(&m->uploadStream, cudaStreamNonBlocking));
+    CHS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->uploadStream));
+    CHS_CUDA(cudaStreamSynchronize(m->uploadStream));       // the caller reuses its buffer right away (CR ChiselServer.cpp:285-295)
+    return CHS_OK;
 }
 
 int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4])

@@ -275,14 +275,23 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
 // the brick kernels hand tasks out bucket by bucket, so the long tasks start first and the shortest ones fill the tail.
 __device__ __forceinline__ int unit_bucket(int frames, int K) { return 4 * frames > 3 * K ? 0 : (2 * frames > K ? 1 : (4 * frames > K ? 2 : 3)); }
 
-__device__ __forceinline__ void emit_brick_unit(const BatchParams &bp, bool active, unsigned long long key, int slot, bool exists, bool virt, bool carve,
-                                                unsigned long long flags, int b, unsigned band, unsigned freeFrames, int K, unsigned lane)
+// The free-space frames of a brick that are worth a visit, and whether the brick becomes a unit at all.
+__device__ __forceinline__ bool brick_unit_masks(bool active, bool exists, bool virt, bool carve, unsigned long long flags, int b, unsigned band, unsigned freeFrames,
+                                                 unsigned *fmOut)
 {
     const unsigned afterBand = band ? ~((band & (0u - band)) | ((band & (0u - band)) - 1u)) : 0u;
     unsigned fm = carve ? freeFrames : 0u;
     if (!(exists && ((flags >> b) & 1ull)))
         fm &= afterBand;
-    const bool keepB = active && ((exists && (band | fm) != 0u) || (virt && band != 0u));
+    *fmOut = fm;
+    return active && ((exists && (band | fm) != 0u) || (virt && band != 0u));
+}
+
+__device__ __forceinline__ void emit_brick_unit(const BatchParams &bp, bool active, unsigned long long key, int slot, bool exists, bool virt, bool carve,
+                                                unsigned long long flags, int b, unsigned band, unsigned freeFrames, int K, unsigned lane)
+{
+    unsigned fm;
+    const bool keepB = brick_unit_masks(active, exists, virt, carve, flags, b, band, freeFrames, &fm);
     const int bucket = keepB ? unit_bucket(__popc(band | fm), K) : -1;
     unsigned bm[4];
 #pragma unroll
@@ -361,6 +370,9 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
     __shared__ int sList[kCandWarps][kCandList];
     __shared__ unsigned short sPairs[kCandWarps][32 * kMaxBatch];     // (chunk of the pass << 8) | frame: pairs that need the depth test
     __shared__ unsigned sBandC[kCandWarps][32], sFreeC[kCandWarps][32];
+    // units of a pass (32 chunks x 8 bricks at most), written to the global lists in ONE go: four atomics per pass instead of four
+    // per surviving chunk (the warp waits for their round trip)
+    __shared__ int4 sUnits[kCandWarps][NB == 8 ? 256 : 1];
     pdl_launch_dependents();                       // the brick kernel may start launching: it waits (pdl_wait) before it reads the unit lists
     load_frames(sF, bp);                           // the frame table was uploaded before the Hi-Z kernel: complete
     pdl_wait();                                    // the Hi-Z kernel's output is read from here on
@@ -532,6 +544,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
             // 2. brick level: the warp takes the surviving chunks one at a time
             unsigned surv = __ballot_sync(0xffffffffu, (chunkBand | freeTodo) != 0u);
+            int nUnits = 0;
             while (surv)
             {
                 const int src = __ffs(surv) - 1;
@@ -590,7 +603,13 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
                     const bool virt = !exists && u != 0u;
                     if (lane == 0 && virt)
                         atomicAdd(&bp.bctr->new_count, 1);
-                    emit_brick_unit(bp, lane < 8, key, sSlot, exists, virt, carve, sFlags, b, bandB, freeB, K, lane);
+                    unsigned fm;
+                    const bool keepB = brick_unit_masks(lane < 8, exists, virt, carve, sFlags, b, bandB, freeB, &fm);
+                    const unsigned km = __ballot_sync(0xffffffffu, keepB);
+                    if (keepB)
+                        sUnits[warp][nUnits + __popc(km & below)] = make_int4((int)(unsigned)(key & 0xffffffffull), (int)(unsigned)(key >> 32),
+                                                                              (exists ? sSlot : kVirtualSlot) | (b << 24), (int)(bandB | (fm << 16)));
+                    nUnits += __popc(km);
                 }
                 else
                 {
@@ -620,6 +639,51 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
                     for (int hb = 0; hb < 2; hb++)
                         emit_brick_unit(bp, true, key, sSlot, exists, virt, carve, sFlags, (int)lane + 32 * hb, bandB[hb], freeB[hb], K, lane);
                 }
+            }
+            if (NB == 8 && nUnits > 0)
+            {
+                // one reservation per cost bucket for the whole pass, then every unit goes to its place
+                __syncwarp();
+                int cnt[4] = {0, 0, 0, 0};
+                for (int q = 0; q < nUnits; q += 32)
+                {
+                    const bool in = q + (int)lane < nUnits;
+                    const int w = in ? sUnits[warp][q + lane].w : 0;
+                    const int bucket = in ? unit_bucket(__popc((unsigned)w & 0xFFFFu | ((unsigned)w >> 16)), K) : -1;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        cnt[k] += __popc(__ballot_sync(0xffffffffu, bucket == k));
+                }
+                int base = 0;
+                const int mineCnt = lane == 0 ? cnt[0] : (lane == 1 ? cnt[1] : (lane == 2 ? cnt[2] : cnt[3]));
+                if (lane < 4 && mineCnt)
+                {
+                    int *ctr = lane == 0 ? &bp.bctr->unit_count : (lane == 1 ? &bp.bctr->bucket1 : (lane == 2 ? &bp.bctr->bucket2 : &bp.bctr->light_count));
+                    base = atomicAdd(ctr, mineCnt);
+                }
+                int run[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    run[k] = __shfl_sync(0xffffffffu, base, k);
+                for (int q = 0; q < nUnits; q += 32)
+                {
+                    const bool in = q + (int)lane < nUnits;
+                    const int4 un = in ? sUnits[warp][q + lane] : make_int4(0, 0, 0, 0);
+                    const int bucket = in ? unit_bucket(__popc((unsigned)un.w & 0xFFFFu | ((unsigned)un.w >> 16)), K) : -1;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const unsigned bmk = __ballot_sync(0xffffffffu, bucket == k);
+                        if (bucket == k)
+                        {
+                            const int rank = run[k] + __popc(bmk & below);
+                            // buckets 0 / 2 grow from the front of their buffer, 1 / 3 from the back
+                            bp.units[((k & 1) ? bp.units_cap - 1 - rank : rank) + (k >> 1) * bp.units_cap] = un;
+                        }
+                        run[k] += __popc(bmk);
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncwarp();

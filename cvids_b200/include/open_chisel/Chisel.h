@@ -7,11 +7,17 @@
 // Not kept: the reference's printf chatter and its per-frame PrintMemoryStatistics scan (Chisel.h:62,109-111).
 //
 // Frame batching (extension, off by default; SetFrameBatching(n) or the environment variable CHISEL_B200_BATCH=n, n <= 16):
-// IntegrateDepthScan[Color] copies the frame into a queue and returns; the queue goes to the device as ONE
-// chs_integrate_batch call (fused multi-frame kernels, bit-identical to frame-by-frame integration) when it holds n frames,
-// when the integrator / camera settings change, or when anything reads the device map -- UpdateMeshes on a call that actually
-// re-meshes (every 10th), GetMeshesToUpdate, HasChunk / GetChunk / GetChunks, Reset. chisel_ros calls UpdateMeshes after
-// every frame but re-meshes on every 10th call only, so with n = 10 a live stream runs entirely through the fused path.
+// IntegrateDepthScan[Color] uploads the frame into a device-side queue (one PCIe copy straight from the caller's image -- the
+// facade's DepthImage / ColorImage live in page-locked memory -- and the caller may reuse its buffers at once, as chisel_ros does,
+// CR ChiselServer.cpp:285-295) and returns; the queue is integrated as ONE chs_integrate_batch call (fused multi-frame kernels,
+// bit-identical to frame-by-frame integration) when it holds n frames, when the integrator / camera settings change, or when
+// something needs the device map up to date: UpdateMeshes on a call that actually re-meshes (every 10th), GetChunks, Reset,
+// SaveAllMeshesToPLY.
+// Reads between flushes. chisel_ros looks at the map after EVERY frame (PublishLatestChunkBoxes: GetMeshesToUpdate, then HasChunk /
+// GetChunk()->ComputeBoundingBox() per dirty ID, CR ChiselServer.cpp:533-567). By default those reads flush the queue first --
+// exactly the reference's view at every instant, but then every frame travels alone. With SetRelaxedReads(true) (or
+// CHISEL_B200_RELAXED_READS=1) they are served from host mirrors of the map AS OF THE LAST FLUSH: the marker boxes lag by at most
+// n - 1 frames, the map, its meshes and everything read after a flush are unchanged, and a live stream runs on the fused path.
 #ifndef CHISEL_B200_CHISEL_H_
 #define CHISEL_B200_CHISEL_H_
 #include <cstdio>
@@ -53,7 +59,7 @@ class Chisel
     virtual ~Chisel()
     {
         chunkManager.SetBeforeDeviceRead(std::function<void()>());
-        chs_host_free(ring);
+        FreeRings();
     }
 
     const ChunkManager &GetChunkManager() const { return chunkManager; }
@@ -62,7 +68,7 @@ class Chisel
     {
         Flush();
         chunkManager = manager;
-        chunkManager.SetBeforeDeviceRead([this]() { Flush(); });
+        InstallReadHook();
     }
 
     // Queue up to n frames (1 = off: every frame goes to the device at once). See the header comment.
@@ -72,7 +78,14 @@ class Chisel
         batchFrames = n < 1 ? 1 : (n > 16 ? 16 : n);
     }
     int GetFrameBatching() const { return batchFrames; }
-    // Send the queued frames to the device now.
+    // Reads between flushes are served from the host mirrors of the last flushed state (see the header comment).
+    void SetRelaxedReads(bool on)
+    {
+        relaxedReads = on;
+        InstallReadHook();
+    }
+    bool GetRelaxedReads() const { return relaxedReads; }
+    // Integrate the queued frames now.
     void Flush() const
     {
         if (queued == 0)
@@ -80,9 +93,10 @@ class Chisel
         const int n = queued;
         queued = 0;                                   // re-entrancy: the queue is empty while the call below runs
         std::vector<chs_frame> fr(n);
+        const unsigned char *base = ringDev[curRing];
         for (int i = 0; i < n; i++)
         {
-            const unsigned char *slot = ring + slotBytes * i;
+            const unsigned char *slot = base + slotBytes * i;
             std::memset(&fr[i], 0, sizeof(chs_frame));
             fr[i].depth = reinterpret_cast<const float *>(slot);
             fr[i].color = qColorPath ? slot + colorOff : nullptr;
@@ -92,9 +106,13 @@ class Chisel
         }
         chs_integrator integ = qInteg;
         integ.trunc_per_pixel = nullptr;              // per frame, in chs_frame
-        // the slots are page-locked and equally spaced: the whole queue crosses PCIe as one strided copy per image kind
-        b200::Check(chs_integrate_batch(chunkManager.Handle(), &integ, n, fr.data(), CHS_MEM_HOST, &qCam, qChannels, qColorPath ? &qCcam : nullptr),
+        // the frames are complete in device memory (chs_upload returned): Hi-Z and colour packing of this batch run on the
+        // library's copy stream beside the kernels of the previous one
+        b200::Check(chs_integrate_batch(chunkManager.Handle(), &integ, n, fr.data(), CHS_MEM_DEVICE_ASYNC, &qCam, qChannels, qColorPath ? &qCcam : nullptr),
                     "chs_integrate_batch");
+        b200::Check(chs_last_batch_ticket(chunkManager.Handle(), &ringTicket[curRing]), "chs_last_batch_ticket");
+        curRing ^= 1;                                 // the other ring is refilled while this batch is in flight
+        const_cast<ChunkManager &>(chunkManager).Touch();
     }
 
     template <class DataType>
@@ -105,12 +123,12 @@ class Chisel
         const chs_camera cam = camera.ToC();
         float pose[12];
         b200::PoseToArray(extrinsic, pose);
-        chunkManager.Touch();
         if (batchFrames > 1)
         {
             Enqueue(integ, cam, cam, false, 0, DepthAsFloat(*depthImage), nullptr, pose, pose);
             return;
         }
+        chunkManager.Touch();
         b200::Check(chs_integrate_depth(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam), "chs_integrate_depth");
     }
 
@@ -125,13 +143,13 @@ class Chisel
         float pose[12], cpose[12];
         b200::PoseToArray(depthExtrinsic, pose);
         b200::PoseToArray(colorExtrinsic, cpose);
-        chunkManager.Touch();
         if (batchFrames > 1)
         {
             Enqueue(integ, cam, ccam, true, static_cast<int>(colorImage->GetNumChannels()), DepthAsFloat(*depthImage),
                     reinterpret_cast<const uint8_t *>(colorImage->GetData()), pose, cpose);
             return;
         }
+        chunkManager.Touch();
         b200::Check(chs_integrate_depth_color(chunkManager.Handle(), &integ, DepthAsFloat(*depthImage), CHS_MEM_HOST, pose, &cam,
                                               reinterpret_cast<const uint8_t *>(colorImage->GetData()), static_cast<int>(colorImage->GetNumChannels()), cpose, &ccam),
                     "chs_integrate_depth_color");
@@ -150,9 +168,11 @@ class Chisel
     {
         if (updateCalls++ % 10 == 0)
         {
+            Flush();
             chunkManager.RecomputeDirtyMeshes();
             meshesToUpdate.clear();
             dirtyVersion = -1;
+            dirtyMapVersion = -1;
         }
     }
 
@@ -163,6 +183,7 @@ class Chisel
   protected:
     bool SaveAllMeshes(const std::string &filename, bool binary)
     {
+        Flush();
         // Chisel.cpp:69-105: concatenate every chunk mesh, indices 0..n-1
         MeshPtr full = std::make_shared<Mesh>();
         size_t v = 0;
@@ -189,12 +210,17 @@ class Chisel
         chunkManager.Reset();
         meshesToUpdate.clear();
         dirtyVersion = -1;
+        dirtyMapVersion = -1;
     }
 
     // Host mirror of the device dirty set (Chisel.h:221-224), refreshed when a frame was integrated since the last call.
     const ChunkSet &GetMeshesToUpdate() const
     {
-        Flush();
+        if (!relaxedReads)
+            Flush();
+        if (dirtyMapVersion == chunkManager.Version())
+            return meshesToUpdate;                   // nothing reached the device since the mirror was read
+        dirtyMapVersion = chunkManager.Version();
         int64_t n = 0;
         b200::Check(chs_num_dirty(chunkManager.Handle(), &n), "chs_num_dirty");
         if (dirtyVersion != n || n == 0)
@@ -226,11 +252,32 @@ class Chisel
         return depthScratch.data();
     }
 
+    void InstallReadHook()
+    {
+        // what ChunkManager runs before HasChunk / GetChunk / RecomputeDirtyMeshes; GetChunks (whole-map export) always flushes
+        if (relaxedReads)
+            chunkManager.SetBeforeDeviceRead(std::function<void()>());
+        else
+            chunkManager.SetBeforeDeviceRead([this]() { Flush(); });
+        chunkManager.SetBeforeBulkRead([this]() { Flush(); });
+    }
     void InitBatching()
     {
-        chunkManager.SetBeforeDeviceRead([this]() { Flush(); });
+        if (const char *e = std::getenv("CHISEL_B200_RELAXED_READS"))
+            relaxedReads = std::atoi(e) != 0;
+        InstallReadHook();
         if (const char *e = std::getenv("CHISEL_B200_BATCH"))
             SetFrameBatching(std::atoi(e));
+    }
+    void FreeRings()
+    {
+        for (int r = 0; r < 2; r++)
+        {
+            if (ringDev[r])
+                chs_device_free(chunkManager.Handle(), ringDev[r]);
+            ringDev[r] = nullptr;
+            ringTicket[r] = 0;
+        }
     }
 
     static bool SameCamera(const chs_camera &a, const chs_camera &b) { return std::memcmp(&a, &b, sizeof(chs_camera)) == 0; }
@@ -255,24 +302,35 @@ class Chisel
         const size_t colorBytes = colorPath ? ((static_cast<size_t>(ccam.width) * ccam.height * channels + 255) & ~static_cast<size_t>(255)) : 0;
         const size_t truncBytes = integ.trunc_kind == CHS_TRUNC_PER_PIXEL ? depthBytes : 0;
         const size_t need = depthBytes + colorBytes + truncBytes;
-        if (need != slotBytes || !ring)
+        if (need != slotBytes || !ringDev[0])
         {
             Flush();                                  // nothing is queued with another layout
-            chs_host_free(ring);
+            FreeRings();
             slotBytes = need;
             colorOff = depthBytes;
             truncOff = depthBytes + colorBytes;
-            ring = static_cast<unsigned char *>(chs_host_alloc(slotBytes * 16));
-            if (!ring)
-                throw std::runtime_error("chisel_b200: cannot allocate the page-locked frame queue");
+            for (int r = 0; r < 2; r++)
+            {
+                ringDev[r] = static_cast<unsigned char *>(chs_device_alloc(chunkManager.Handle(), slotBytes * 16));
+                if (!ringDev[r])
+                    throw std::runtime_error("chisel_b200: cannot allocate the device frame queue");
+            }
+            curRing = 0;
             poses.resize(24 * 16);
         }
-        unsigned char *slot = ring + slotBytes * queued;
-        std::memcpy(slot, depth, npx * sizeof(float));
+        if (queued == 0 && ringTicket[curRing])
+        {
+            // the batch that read this ring last (two flushes ago) must be done before its slots are overwritten
+            int n = 0;
+            b200::Check(chs_wait_batch(chunkManager.Handle(), ringTicket[curRing], nullptr, 0, &n), "chs_wait_batch");
+            ringTicket[curRing] = 0;
+        }
+        unsigned char *slot = ringDev[curRing] + slotBytes * queued;
+        b200::Check(chs_upload(chunkManager.Handle(), slot, depth, npx * sizeof(float)), "chs_upload");
         if (colorPath)
-            std::memcpy(slot + colorOff, color, static_cast<size_t>(ccam.width) * ccam.height * channels);
+            b200::Check(chs_upload(chunkManager.Handle(), slot + colorOff, color, static_cast<size_t>(ccam.width) * ccam.height * channels), "chs_upload");
         if (truncBytes)
-            std::memcpy(slot + truncOff, integ.trunc_per_pixel, npx * sizeof(float));
+            b200::Check(chs_upload(chunkManager.Handle(), slot + truncOff, integ.trunc_per_pixel, npx * sizeof(float)), "chs_upload");
         std::memcpy(&poses[24 * queued], pose, 12 * sizeof(float));
         std::memcpy(&poses[24 * queued + 12], cpose, 12 * sizeof(float));
         if (++queued >= batchFrames)
@@ -286,7 +344,11 @@ class Chisel
     std::vector<float> truncScratch, depthScratch;
     int batchFrames;
     mutable int queued = 0;
-    unsigned char *ring = nullptr;                   // 16 page-locked slots [depth | colour | per-pixel truncation]
+    unsigned char *ringDev[2] = {nullptr, nullptr};  // two device rings of 16 slots [depth | colour | per-pixel truncation], used alternately
+    mutable int64_t ringTicket[2] = {0, 0};          // the batch that read the ring last
+    mutable int curRing = 0;
+    bool relaxedReads = false;
+    mutable long dirtyMapVersion = -1;
     size_t slotBytes = 0, colorOff = 0, truncOff = 0;
     std::vector<float> poses;
     chs_integrator qInteg;

@@ -15,6 +15,7 @@
 #include <vector>
 #include <chisel_b200.h>
 #include <open_chisel/Chunk.h>
+#include <open_chisel/b200/PinnedBuffer.h>
 #include <open_chisel/geometry/Geometry.h>
 #include <open_chisel/mesh/Mesh.h>
 
@@ -44,9 +45,9 @@ inline void Check(int rc, const char *what)
 class ChunkManager
 {
   public:
-    ChunkManager() : chunkSize(16, 16, 16), voxelResolutionMeters(0.03f), useColor(false), version(0), chunksVersion(-1) {}   // Q15: useColor initialised
+    ChunkManager() : chunkSize(16, 16, 16), voxelResolutionMeters(0.03f), useColor(false), version(0), chunksVersion(-1), indexVersion(-1), indexCount(0) {}   // Q15: useColor initialised
     ChunkManager(const Eigen::Vector3i &size, float res, bool color, int device = -1, int rank = 0, int world = 1, void *stream = nullptr)
-        : chunkSize(size), voxelResolutionMeters(res), useColor(color), version(0), chunksVersion(-1)
+        : chunkSize(size), voxelResolutionMeters(res), useColor(color), version(0), chunksVersion(-1), indexVersion(-1), indexCount(0)
     {
         if (size(0) != size(1) || size(0) != size(2))
             throw std::invalid_argument("chisel_b200: cubic chunks only (Chunk::GetVoxelID is only correct for them, quirk Q12)");
@@ -69,6 +70,8 @@ class ChunkManager
     void Touch() { version++; }                                  // the device map changed: host mirrors are stale
     // Frame batching (Chisel::SetFrameBatching): frames queued in the facade must reach the device before anything reads it.
     void SetBeforeDeviceRead(const std::function<void()> &f) { beforeDeviceRead = f; }
+    void SetBeforeBulkRead(const std::function<void()> &f) { beforeBulkRead = f; }
+    long Version() const { return version; }
     void Sync() const
     {
         if (beforeDeviceRead)
@@ -80,30 +83,63 @@ class ChunkManager
     bool GetUseColor() const { return useColor; }
     const Vec3List &GetCentroids() const { return centroids; }
 
+    // Host index of the chunk IDs of the device map, extended lazily (pool slots are append-only between resets): HasChunk is a
+    // hash lookup, not a device round trip -- chisel_ros asks it for every dirty ID after every frame (CR ChiselServer.cpp:554-559).
+    void RefreshIndex() const
+    {
+        if (indexVersion == version)
+            return;
+        int64_t n = 0;
+        b200::Check(chs_num_chunks(handle.get(), &n), "chs_num_chunks");
+        if (n < indexCount)
+        {
+            idIndex.clear();
+            indexCount = 0;
+        }
+        if (n > indexCount)
+        {
+            std::vector<int32_t> ids(3 * n);
+            b200::Check(chs_chunk_ids(handle.get(), ids.data(), n), "chs_chunk_ids");
+            for (int64_t i = indexCount; i < n; i++)
+                idIndex[ChunkID(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2])] = true;
+            indexCount = n;
+        }
+        indexVersion = version;
+    }
+
     bool HasChunk(const ChunkID &id) const
     {
         Sync();
-        int found = 0;
-        const int32_t cid[3] = {id(0), id(1), id(2)};
-        b200::Check(chs_has_chunk(handle.get(), cid, &found), "chs_has_chunk");
-        return found != 0;
+        RefreshIndex();
+        return idIndex.find(id) != idIndex.end();
     }
     bool HasChunk(int x, int y, int z) const { return HasChunk(ChunkID(x, y, z)); }
 
-    // unordered_map::at semantics: throws std::out_of_range for a missing chunk (ChunkManager.h:84-87)
+    // unordered_map::at semantics: throws std::out_of_range for a missing chunk (ChunkManager.h:84-87). The mirror object is
+    // cached; its voxels are downloaded on first access and again after the device map has changed (Chunk::Invalidate).
     ChunkPtr GetChunk(const ChunkID &id) const
     {
         Sync();
-        ChunkPtr c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor);
-        const size_t V = c->GetTotalNumVoxels();
-        std::vector<float> sdf(V), w(V);
-        std::vector<uint8_t> rgbw(useColor ? 4 * V : 0);
-        const int32_t cid[3] = {id(0), id(1), id(2)};
-        const int rc = chs_download_chunk(handle.get(), cid, sdf.data(), w.data(), useColor ? rgbw.data() : nullptr);
-        if (rc == CHS_ERR_NOT_FOUND)
+        RefreshIndex();
+        if (idIndex.find(id) == idIndex.end())
             throw std::out_of_range("ChunkManager::GetChunk: no such chunk");
-        b200::Check(rc, "chs_download_chunk");
-        Fill(c.get(), sdf.data(), w.data(), useColor ? rgbw.data() : nullptr);
+        ChunkPtr &c = chunks[id];
+        if (!c)
+        {
+            c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor, true);
+            std::shared_ptr<chs_map> h = handle;                 // not `this`: the manager may be copied (Chisel::SetChunkManager)
+            const bool color = useColor;
+            c->SetLoader([h, color](Chunk *ch)
+                         {
+                             const size_t V = ch->GetTotalNumVoxels();
+                             std::vector<float> sdf(V), w(V);
+                             std::vector<uint8_t> rgbw(color ? 4 * V : 0);
+                             const int32_t cid[3] = {ch->GetID()(0), ch->GetID()(1), ch->GetID()(2)};
+                             b200::Check(chs_download_chunk(h.get(), cid, sdf.data(), w.data(), color ? rgbw.data() : nullptr), "chs_download_chunk");
+                             FillChunk(ch, sdf.data(), w.data(), color ? rgbw.data() : nullptr);
+                         });
+        }
+        c->Invalidate(version);
         return c;
     }
     ChunkPtr GetChunk(int x, int y, int z) const { return GetChunk(ChunkID(x, y, z)); }
@@ -117,6 +153,8 @@ class ChunkManager
     // Whole-map host mirror (one bulk transfer), refreshed only if the device map changed since the last call.
     const ChunkMap &GetChunks() const
     {
+        if (beforeBulkRead)
+            beforeBulkRead();
         Sync();
         if (chunksVersion != version)
         {
@@ -133,7 +171,7 @@ class ChunkManager
             {
                 const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
                 ChunkPtr c = std::make_shared<Chunk>(id, chunkSize, voxelResolutionMeters, useColor);
-                Fill(c.get(), sdf.data() + i * V, w.data() + i * V, useColor ? rgbw.data() + i * V * 4 : nullptr);
+                FillChunk(c.get(), sdf.data() + i * V, w.data() + i * V, useColor ? rgbw.data() + i * V * 4 : nullptr);
                 chunks[id] = c;
             }
             chunksVersion = version;
@@ -158,9 +196,13 @@ class ChunkManager
         b200::Check(chs_mesh_counts_last(handle.get(), &mc), "chs_mesh_counts_last");
         std::vector<int32_t> ids(3 * mc.n_chunks);
         std::vector<int64_t> voff(mc.n_chunks + 1), goff(mc.n_chunks + 1);
-        std::vector<float> v(3 * mc.n_vertices), nr(3 * mc.n_vertices), col(mc.has_colors ? 3 * mc.n_vertices : 0), g(3 * mc.n_grids);
-        b200::Check(chs_download_meshes(handle.get(), ids.data(), voff.data(), goff.data(), v.data(), nr.data(), mc.has_colors ? col.data() : nullptr, g.data()),
-                    "chs_download_meshes");
+        // vertex arrays land in page-locked staging (kept between re-meshes): the download runs at full PCIe speed
+        const size_t nvf = 3 * static_cast<size_t>(mc.n_vertices), ngf = 3 * static_cast<size_t>(mc.n_grids);
+        const size_t need = nvf * (mc.has_colors ? 3 : 2) + ngf + 16;
+        if (!meshStage || meshStage->size() < need)
+            meshStage.reset(new b200::PinnedBuffer<float>(need + need / 4));
+        float *v = meshStage->data(), *nr = v + nvf, *col = nr + nvf, *g = col + (mc.has_colors ? nvf : 0);
+        b200::Check(chs_download_meshes(handle.get(), ids.data(), voff.data(), goff.data(), v, nr, mc.has_colors ? col : nullptr, g), "chs_download_meshes");
         for (int64_t i = 0; i < mc.n_chunks; i++)
         {
             const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
@@ -206,6 +248,8 @@ class ChunkManager
         b200::Check(chs_reset(handle.get()), "chs_reset");
         allMeshes.clear();
         chunks.clear();
+        idIndex.clear();
+        indexCount = 0;
         Touch();
     }
 
@@ -222,7 +266,7 @@ class ChunkManager
     }
 
   protected:
-    void Fill(Chunk *c, const float *sdf, const float *w, const uint8_t *rgbw) const
+    static void FillChunk(Chunk *c, const float *sdf, const float *w, const uint8_t *rgbw)
     {
         std::vector<DistVoxel> &dv = c->GetMutableVoxels();
         for (size_t i = 0; i < dv.size(); i++)
@@ -244,7 +288,11 @@ class ChunkManager
     long version;
     mutable ChunkMap chunks;
     mutable long chunksVersion;
-    std::function<void()> beforeDeviceRead;
+    mutable ChunkSet idIndex;                 // IDs of the chunks of the device map (RefreshIndex)
+    mutable long indexVersion;
+    mutable int64_t indexCount;
+    std::function<void()> beforeDeviceRead, beforeBulkRead;
+    std::shared_ptr<b200::PinnedBuffer<float>> meshStage;
 };
 typedef std::shared_ptr<ChunkManager> ChunkManagerPtr;
 typedef std::shared_ptr<const ChunkManager> ChunkManagerConstPtr;

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <memory>
 #include <vector>
+#include <open_chisel/b200/PinnedBuffer.h>
 
 namespace chisel
 {
@@ -31,7 +32,7 @@ class ColorImage
     size_t GetNumChannels() const { return numChannels; }
 
   protected:
-    std::vector<DataType> store;
+    b200::PinnedBuffer<DataType> store;
     int width, height;
     size_t numChannels;
 };

@@ -1,8 +1,10 @@
-// open_chisel/camera/DepthImage.h -- facade; cf. OC/include/open_chisel/camera/DepthImage.h:33-103. Caller-owned host image.
+// open_chisel/camera/DepthImage.h -- facade; cf. OC/include/open_chisel/camera/DepthImage.h:33-103. Caller-owned host image, in
+// page-locked memory (b200/PinnedBuffer.h) so that it uploads at full PCIe speed.
 #ifndef CHISEL_B200_DEPTHIMAGE_H_
 #define CHISEL_B200_DEPTHIMAGE_H_
 #include <memory>
 #include <vector>
+#include <open_chisel/b200/PinnedBuffer.h>
 
 namespace chisel
 {
@@ -22,7 +24,7 @@ class DepthImage
     int GetHeight() const { return height; }
 
   protected:
-    std::vector<DataType> store;
+    b200::PinnedBuffer<DataType> store;
     int width, height;
 };
 } // namespace chisel

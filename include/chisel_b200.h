@@ -228,6 +228,14 @@ int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4]);
 void *chs_host_alloc(size_t bytes);
 void chs_host_free(void *p);
 
+/* Device-side frame queue for callers that receive frames one at a time and reuse their image buffers (the facade's
+ * Chisel::IntegrateDepthScan[Color] with frame batching, CR/src/ChiselServer.cpp:285-295): device memory on the map's device,
+ * and an upload that returns as soon as the HOST buffer may be reused (one PCIe copy on a dedicated stream -- no staging memcpy
+ * on the host). Frames uploaded this way are handed to chs_integrate_batch with CHS_MEM_DEVICE_ASYNC. */
+void *chs_device_alloc(chs_map *map, size_t bytes);
+void chs_device_free(chs_map *map, void *p);
+int chs_upload(chs_map *map, void *dst_device, const void *src_host, size_t bytes);
+
 /* Host-side exact restatements the facade needs (no device work). */
 int chs_frustum(const float pose[12], const chs_camera *cam, float corners[24], float lines[72], float planes[24]);
 int chs_candidate_ids(int chunk_size, float resolution, const float pose[12], const chs_camera *cam,

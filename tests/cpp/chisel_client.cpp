@@ -5,7 +5,8 @@
 //
 //   chisel_client <stream.bin> <dump.bin> [time]
 // With "time" the frames are read into memory first, the per-frame loop is exactly ChiselServer::IntegrateLastDepthImage
-// (integrate, then UpdateMeshes -- the every-10th gate decides) and its wall time is printed (tools/dropin_demo.py).
+// (integrate, PublishLatestChunkBoxes, PublishDepthFrustum, then UpdateMeshes -- the every-10th gate decides) and its wall time
+// is printed (tools/dropin_demo.py, tests/test_facade.py::test_dropin_full_size).
 #include <open_chisel/Chisel.h>
 #include <open_chisel/truncation/ConstantTruncator.h>
 #include <open_chisel/truncation/InverseTruncator.h>
@@ -99,6 +100,8 @@ int main(int argc, char **argv)
             if (h.channels > 0 && fread(&allColor[(size_t)f * npx * h.channels], 1, npx * h.channels, in) != npx * h.channels) return 5;
         }
     }
+    double boxSum = 0.0;
+    long boxes = 0;
     const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < h.frames; f++)
     {
@@ -130,6 +133,20 @@ int main(int argc, char **argv)
             chiselMap->IntegrateDepthScanColor<float, uint8_t>(projectionIntegrator, depth, lastPose, cameraModel, color, lastPose, cameraModel);
         else
             chiselMap->IntegrateDepthScan<float>(projectionIntegrator, depth, lastPose, cameraModel);
+        // ChiselServer::PublishLatestChunkBoxes (CR/src/ChiselServer.cpp:533-567), run after EVERY frame: the centre of every dirty
+        // chunk that exists goes into a marker message
+        {
+            const chisel::ChunkManager &chunkManager = chiselMap->GetChunkManager();
+            const chisel::ChunkSet &latest = chiselMap->GetMeshesToUpdate();
+            for (const std::pair<const chisel::ChunkID, bool> &id : latest)
+                if (chunkManager.HasChunk(id.first))
+                {
+                    const chisel::Vec3 center = chunkManager.GetChunk(id.first)->ComputeBoundingBox().GetCenter();
+                    boxSum += center.x() + center.y() + center.z();
+                    boxes++;
+                }
+        }
+        // ChiselServer::PublishDepthFrustum
         cameraModel.SetupFrustum(lastPose, &frustum);
         // the reference gates re-meshing on a process-global call counter (Chisel.cpp:50-59): call it every frame like
         // ChiselServer::IntegrateLastDepthImage does and let the gate decide
@@ -147,7 +164,7 @@ int main(int argc, char **argv)
     {
         (void)chiselMap->GetMeshesToUpdate().size();             // everything the loop queued has reached the map
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "TIMING frames %d seconds %.6f fps %.3f\n", h.frames, sec, h.frames / sec);
+        fprintf(stderr, "TIMING frames %d seconds %.6f fps %.3f boxes %ld (%.3f)\n", h.frames, sec, h.frames / sec, boxes, boxSum);
     }
     fclose(in);
 

@@ -94,6 +94,58 @@ def test_facade_client_on_device(tmp_path, case, batch):
     assert ply[0] == "ply" and ("element vertex %d" % nverts) in ply[2]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_facade_relaxed_reads_same_final_state(tmp_path, case):
+    """CHISEL_B200_RELAXED_READS: the per-frame reads of chisel_ros (dirty set, HasChunk, GetChunk) are served from the mirrors of
+    the last flushed state, so a batching facade stays on the fused path. Everything observable after a flush -- the map, the
+    dirty set, every mesh -- is unchanged; only the client's own per-frame `remeshes` bookkeeping (it compares dirty-set sizes
+    around UpdateMeshes) sees the lag."""
+    exe = facade_util.build_facade_client()
+    stream, frames = _stream(tmp_path, case)
+    dump = str(tmp_path / "relaxed.dump")
+    subprocess.run([exe, stream, dump], check=True, env=dict(os.environ, CHISEL_B200_BATCH="10", CHISEL_B200_RELAXED_READS="1"))
+    d = facade_util.read_dump(dump)
+    _compare(d, _oracle_expectation(case, frames), CASES[case]["color"])
+
+
+@pytest.mark.gpu
+def test_dropin_full_size(tmp_path):
+    """The drop-in claim at full size (configs[1] shape: 752x480 depth + colour, 2 cm, 41 frames), through the reference's C++ API
+    with chisel_ros's per-frame call sequence (integrate, PublishLatestChunkBoxes, frustum, UpdateMeshes): the facade's dump -- every
+    voxel, the dirty set, every mesh array -- equals the oracle's, in all three modes, and the batching mode is the fast one."""
+    import re
+    cfg = scenes.CONFIG2
+    setup = Setup(cfg.chunk, cfg.resolution, True)
+    n = 41
+    frames = [scenes.stream_frame(cfg, f) for f in range(n)]
+    stream = str(tmp_path / "c2.stream")
+    facade_util.write_stream(stream, setup, cfg.cam, frames, 3)
+    exe = facade_util.build_facade_client()
+    drv = common.Driver(setup, "oracle")
+    for i, (depth, col, pose) in enumerate(frames):
+        drv.integrate(depth, pose, cfg.cam.as_array(), col)
+        if i % 10 == 0:
+            drv.remesh()
+    fps = {}
+    for name, env in (("one_frame_per_call", {"CHISEL_B200_BATCH": "1"}), ("batch10_exact_reads", {"CHISEL_B200_BATCH": "10"}),
+                      ("batch10_relaxed_reads", {"CHISEL_B200_BATCH": "10", "CHISEL_B200_RELAXED_READS": "1"})):
+        dump = str(tmp_path / (name + ".dump"))
+        best = 0.0
+        for _ in range(2):
+            p = subprocess.run([exe, stream, dump, "time"], capture_output=True, text=True, env=dict(os.environ, **env))
+            assert p.returncode == 0, p.stderr[-2000:]
+            best = max(best, float(re.search(r"fps ([0-9.]+)", p.stderr).group(1)))
+        fps[name] = best
+        d = facade_util.read_dump(dump)
+        common.assert_state_equal(d["state"], drv.state(), name)
+        assert np.array_equal(d["dirty"], drv.dirty()), name
+        common.assert_meshes_equal(d["meshes"], drv.meshes())
+    print("drop-in fps:", fps)
+    assert fps["batch10_relaxed_reads"] > fps["one_frame_per_call"], fps
+    assert fps["batch10_relaxed_reads"] > 1500.0, fps
+
+
 def test_ply_writers_ascii_and_binary_agree(tmp_path):
     """Host-only: SaveMeshPLYASCII (the reference's layout, OC/src/io/PLY.cpp:29-88) and the binary_little_endian variant hold
     the same vertices, colours and faces."""
