@@ -340,7 +340,7 @@ def run_multi_agent(B: Bench, args):
     # ---------------- value: K steps back to back, CUDA events on the map's stream, median of several passes --------------
     sampler = ClockSampler(range(world), enabled=(rank == 0))
     sampler.start()
-    pass_ms = []
+    pass_ms, host_us = [], []
     for _ in range(max(1, args.passes)):
         m = B.new_map(cfg)
         for t in range(warm):
@@ -349,8 +349,10 @@ def run_multi_agent(B: Bench, args):
         B.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(B.stream)
+        h0 = time.perf_counter()
         for t in range(warm, T):
             step_device(m, t)
+        host_us.append(1e6 * (time.perf_counter() - h0) / steps)
         e1.record(B.stream)
         m.synchronize()
         B.barrier()
@@ -518,6 +520,7 @@ def run_multi_agent(B: Bench, args):
                          % ((frame_bytes * F * steps) >> 20, (126 << 20) // (frame_bytes * F) + 1),
                    "timing": "CUDA events on the map's stream around the %d timed steps, barrier + synchronize on both sides, max over ranks; median of %d passes %s ms"
                              % (steps, len(pass_ms), [round(x, 3) for x in pass_ms]),
+                   "host_enqueue_us_per_step": float(np.median(host_us)),
                    "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
                    "rank0_kernels_us_per_step": {"hiz": 1e6 * tk["prepare"] / steps, "candidates": 1e6 * tk["candidates"] / steps,
                                                  "wait_for_colour_pack": 1e6 * tk["new_chunks"] / steps, "bricks": 1e6 * tk["integrate"] / steps,

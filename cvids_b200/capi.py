@@ -77,7 +77,7 @@ EXPORTS = (
     "chs_get_timings", "chs_update_meshes", "chs_mesh_counts_last", "chs_download_meshes", "chs_num_chunks",
     "chs_chunk_ids", "chs_has_chunk", "chs_download_chunk", "chs_download_all", "chs_export_chunks", "chs_import_chunks", "chs_set_dirty", "chs_num_dirty", "chs_dirty_ids", "chs_frustum",
     "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic", "chs_host_alloc", "chs_host_free",
-    "chs_device_alloc", "chs_device_free", "chs_upload",
+    "chs_device_alloc", "chs_device_free", "chs_upload", "chs_save_map", "chs_load_map", "chs_ingest_depth",
     "chs_comm_unique_id", "chs_comm_init", "chs_comm_attach", "chs_comm_destroy", "chs_integrate_batch_distributed",
     "chs_comm_sync_dirty", "chs_update_meshes_distributed",
 )
@@ -126,6 +126,9 @@ def load_library(build_if_missing: bool = True):
     lib.chs_set_dirty.argtypes = [vp, i64, vp]
     lib.chs_num_dirty.argtypes = [vp, C.POINTER(i64)]
     lib.chs_dirty_ids.argtypes = [vp, vp, i64]
+    lib.chs_ingest_depth.argtypes = [vp, vp, i32, i32, vp, i32, i32, C.c_float, C.c_float, i32]
+    lib.chs_save_map.argtypes = [vp, C.c_char_p]
+    lib.chs_load_map.argtypes = [vp, C.c_char_p]
     lib.chs_device_alloc.restype = vp
     lib.chs_device_alloc.argtypes = [vp, C.c_size_t]
     lib.chs_device_free.restype = None
@@ -578,6 +581,22 @@ class Chisel:
             weight = np.ascontiguousarray(weight, np.float32)
             c = np.ascontiguousarray(rgbw, np.uint8) if (rgbw is not None and self.use_color) else None
             _check(self._lib.chs_import_chunks(self._h, len(ids), _ptr(ids), _ptr(sdf), _ptr(weight), _ptr(c)))
+
+    def ingest_depth(self, depth: np.ndarray, width: int, height: int, valid_min: float = 0.1, valid_max: float = 20.0) -> np.ndarray:
+        """The collaborative server's frame ingestion (chs_ingest_depth): bilinear resize to width x height + NaN outside the valid range."""
+        src = np.ascontiguousarray(depth, np.float32)
+        out = np.empty((height, width), np.float32)
+        _check(self._lib.chs_ingest_depth(self._h, _ptr(src), src.shape[1], src.shape[0], _ptr(out), width, height, valid_min, valid_max, MEM_HOST))
+        return out
+
+    def save_map(self, path: str):
+        """Checkpoint of the whole map (voxels + dirty set) in one file (chs_save_map)."""
+        _check(self._lib.chs_save_map(self._h, path.encode()))
+
+    def load_map(self, path: str):
+        """Replace the map's contents by a checkpoint; the host MeshMap mirror is emptied (meshes are not part of the checkpoint)."""
+        _check(self._lib.chs_load_map(self._h, path.encode()))
+        self.chunk_manager.all_meshes.clear()
 
     def set_dirty(self, ids):
         ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1, 3))

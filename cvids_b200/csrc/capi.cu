@@ -229,9 +229,40 @@ struct chs_map
 namespace chs
 {
 
+// The library's stream-ordered allocations come from its OWN memory pool (one per device, shared by the maps on it), which keeps
+// freed memory cached instead of returning it to the OS at every synchronisation. The device's default pool -- which the rest of
+// the process (PyTorch, the caller) may use -- is left alone.
+static cudaMemPool_t g_pools[64] = {};
+static int library_pool(cudaMemPool_t *out)
+{
+    int dev = 0;
+    CHS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64)
+        return fail(CHS_ERR_INVALID, "device ordinal out of range");
+    if (!g_pools[dev])
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        CHS_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long thr = ~0ull;
+        CHS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        g_pools[dev] = pool;
+    }
+    *out = g_pools[dev];
+    return CHS_OK;
+}
+
 static int alloc_async(void **p, size_t bytes, cudaStream_t st)
 {
-    CHS_CUDA(cudaMallocAsync(p, std::max<size_t>(bytes, 256), st));
+    cudaMemPool_t pool = nullptr;
+    int rc = library_pool(&pool);
+    if (rc)
+        return rc;
+    CHS_CUDA(cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 256), pool, st));
     return CHS_OK;
 }
 
@@ -269,19 +300,41 @@ static int ensure_pool(chs_map *m, long long chunks)
     const size_t needSlabs = (size_t)((chunks + kSlabChunks - 1) / kSlabChunks);
     if (needSlabs > (size_t)kMaxSlabs)
         return fail(CHS_ERR_CAPACITY, "chunk pool would exceed kMaxSlabs");
-    const size_t oldSlabs = m->distSlabs.size();
+    // failure-atomic: the slab vectors always describe exactly dm.capacity chunks; slabs allocated by a call that fails later are
+    // given back, so a retry starts from a consistent state
+    const size_t oldSlabs = (size_t)m->dm.capacity / kSlabChunks;
+    auto roll_back = [&]()
+    {
+        while (m->distSlabs.size() > oldSlabs)
+        {
+            cudaFreeAsync(m->distSlabs.back(), m->stream);
+            m->distSlabs.pop_back();
+        }
+        while (m->colorSlabs.size() > (m->cfg.use_color ? oldSlabs : 0))
+        {
+            cudaFreeAsync(m->colorSlabs.back(), m->stream);
+            m->colorSlabs.pop_back();
+        }
+    };
+    roll_back();                                                     // leftovers of an earlier failed call
     for (size_t s = oldSlabs; s < needSlabs; s++)
     {
         void *p = nullptr;
         int rc = alloc_async(&p, sizeof(float2) * (size_t)kSlabChunks * V, m->stream);
         if (rc)
+        {
+            roll_back();
             return rc;
+        }
         m->distSlabs.push_back((float2 *)p);
         if (m->cfg.use_color)
         {
             rc = alloc_async(&p, sizeof(uchar4) * (size_t)kSlabChunks * V, m->stream);
             if (rc)
+            {
+                roll_back();
                 return rc;
+            }
             m->colorSlabs.push_back((uchar4 *)p);
         }
     }
@@ -1234,6 +1287,8 @@ static int sync_counts(chs_map *m)
 // ---------------------------------------------------------------------------------------------------------
 // C ABI
 
+static int create_body(chs_map *m, const chs_config *cfg);
+
 extern "C"
 {
 
@@ -1261,6 +1316,23 @@ int chs_create(const chs_config *cfg, chs_map **out)
         delete m;
         return fail(CHS_ERR_INVALID, "rank outside [0, world)");
     }
+    // everything that can fail runs in create_body: a failure there must not leak the half-built map
+    const int rc = create_body(m, cfg);
+    if (rc)
+    {
+        const std::string why = g_last_error;
+        chs_destroy(m);
+        g_last_error = why;
+        return rc;
+    }
+    *out = m;
+    return CHS_OK;
+}
+
+} // extern "C"
+
+static int create_body(chs_map *m, const chs_config *cfg)
+{
     if (cfg->device >= 0)
         m->device = cfg->device;
     else
@@ -1272,13 +1344,6 @@ int chs_create(const chs_config *cfg, chs_map **out)
     {
         CHS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         m->ownStream = true;
-    }
-    // keep freed stream-ordered memory cached in the pool instead of returning it to the OS at every sync
-    {
-        cudaMemPool_t pool;
-        CHS_CUDA(cudaDeviceGetDefaultMemPool(&pool, m->device));
-        unsigned long long thr = ~0ull;
-        CHS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     DeviceMap &d = m->dm;
     d.cs = cfg->chunk_size;
@@ -1321,14 +1386,13 @@ int chs_create(const chs_config *cfg, chs_map **out)
     const long long initial = cfg->initial_chunks > 0 ? cfg->initial_chunks : 4096;
     int rc;
     if ((rc = ensure_pool(m, initial)) || (rc = ensure_hash(m, initial)) || (rc = ensure_dirty(m, initial * 2)))
-    {
-        chs_destroy(m);
         return rc;
-    }
     CHS_CUDA(cudaStreamSynchronize(m->stream));
-    *out = m;
     return CHS_OK;
 }
+
+extern "C"
+{
 
 int chs_destroy(chs_map *m)
 {
@@ -1819,7 +1883,32 @@ int chs_export_chunks(chs_map *m, int64_t n, const int32_t *ids, uint8_t *found,
     return CHS_OK;
 }
 
-// Insert or overwrite chunks from host buffers (n*V each; rgbw may be NULL). Existing chunks keep their slot.
+// One CTA per imported chunk: voxels from the staging buffers into the chunk's pool slot. Every imported chunk -- new or
+// overwritten -- gets all brick flags set: its history is unknown, so every brick may hold a carvable voxel (conservative; an
+// overwritten chunk that kept its old flags could make later free-space frames skip a brick that needs carving).
+__global__ void import_scatter_kernel(DeviceMap map, int n, const int *slots, const float *sdf, const float *weight, const unsigned *rgbw)
+{
+    const int i = blockIdx.x;
+    if (i >= n)
+        return;
+    const int s = slots[i];
+    float2 *dst = dist_ptr(map, s);
+    const float *ps = sdf + (size_t)i * map.V, *pw = weight + (size_t)i * map.V;
+    for (int v = threadIdx.x; v < map.V; v += blockDim.x)
+        dst[v] = make_float2(ps[v], pw[v]);
+    if (map.use_color)
+    {
+        unsigned *cd = reinterpret_cast<unsigned *>(color_ptr(map, s));
+        for (int v = threadIdx.x; v < map.V; v += blockDim.x)
+            cd[v] = rgbw ? rgbw[(size_t)i * map.V + v] : 0u;
+    }
+    if (threadIdx.x == 0)
+        map.brick_flags[s] = ~0ull;
+}
+
+// Insert or overwrite chunks from host buffers (n*V each; rgbw may be NULL). Existing chunks keep their slot. The voxels travel
+// in slices of a few thousand chunks: three bulk copies and one scatter kernel per slice, one synchronisation per slice (the
+// host staging of the slice is reused) -- not one per chunk.
 int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sdf, const float *weight, const uint8_t *rgbw)
 {
     if (!m || !ids || !sdf || !weight)
@@ -1832,6 +1921,7 @@ int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sd
     const int V = m->dm.V;
     std::vector<int> slots((size_t)n);
     std::vector<int32_t> newIds;
+    std::unordered_map<unsigned long long, int> fresh;      // IDs this call adds (committed to the host mirror only after the device insert)
     long long next = m->knownChunks;
     for (int64_t i = 0; i < n; i++)
     {
@@ -1843,12 +1933,15 @@ int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sd
             slots[(size_t)i] = it->second;
         else
         {
-            slots[(size_t)i] = (int)next;
-            m->hostIndex[key] = (int)next++;
-            for (int k = 0; k < 3; k++)
+            auto jt = fresh.find(key);
+            if (jt != fresh.end())
+                slots[(size_t)i] = jt->second;               // the same new ID twice in one call: the later entry wins
+            else
             {
-                newIds.push_back(ids[3 * i + k]);
-                m->hostIds.push_back(ids[3 * i + k]);
+                slots[(size_t)i] = (int)next;
+                fresh[key] = (int)next++;
+                for (int k = 0; k < 3; k++)
+                    newIds.push_back(ids[3 * i + k]);
             }
         }
     }
@@ -1856,24 +1949,6 @@ int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sd
     if ((rc = ensure_pool(m, next + 1)) || (rc = ensure_hash(m, next + 1)))
         return rc;
     cudaStream_t st = m->stream;
-    std::vector<float2> tmp((size_t)V);
-    for (int64_t i = 0; i < n; i++)
-    {
-        const int slot = slots[(size_t)i];
-        for (int v = 0; v < V; v++)
-            tmp[(size_t)v] = make_float2(sdf[(size_t)i * V + v], weight[(size_t)i * V + v]);
-        float2 *dst = m->distSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
-        CHS_CUDA(cudaMemcpyAsync(dst, tmp.data(), sizeof(float2) * V, cudaMemcpyHostToDevice, st));
-        if (m->cfg.use_color)
-        {
-            uchar4 *cd = m->colorSlabs[slot >> kSlabChunksLog2] + (size_t)(slot & (kSlabChunks - 1)) * V;
-            if (rgbw)
-                CHS_CUDA(cudaMemcpyAsync(cd, rgbw + (size_t)i * V * 4, 4 * (size_t)V, cudaMemcpyHostToDevice, st));
-            else
-                CHS_CUDA(cudaMemsetAsync(cd, 0, 4 * (size_t)V, st));
-        }
-        CHS_CUDA(cudaStreamSynchronize(st));             // tmp is reused
-    }
     if (nNew > 0)
     {
         int *dIds = nullptr;
@@ -1882,10 +1957,136 @@ int chs_import_chunks(chs_map *m, int64_t n, const int32_t *ids, const float *sd
         import_insert_kernel<<<(int)std::min<long long>((nNew + 255) / 256, 148), 256, 0, st>>>(m->dm, dIds, (int)m->knownChunks, (int)nNew);
         CHS_CUDA(cudaGetLastError());
         CHS_CUDA(cudaFreeAsync(dIds, st));
-        CHS_CUDA(cudaStreamSynchronize(st));
-        m->knownChunks = next;
     }
+    const int64_t slice = 2048;
+    int *dSlots = nullptr;
+    float *dSdf = nullptr, *dW = nullptr;
+    unsigned *dCol = nullptr;
+    const size_t sliceVox = (size_t)std::min<int64_t>(slice, std::max<int64_t>(n, 1)) * V;
+    CHS_CUDA(cudaMallocAsync((void **)&dSlots, sizeof(int) * (size_t)std::min<int64_t>(slice, std::max<int64_t>(n, 1)), st));
+    CHS_CUDA(cudaMallocAsync((void **)&dSdf, sizeof(float) * sliceVox, st));
+    CHS_CUDA(cudaMallocAsync((void **)&dW, sizeof(float) * sliceVox, st));
+    if (m->cfg.use_color && rgbw)
+        CHS_CUDA(cudaMallocAsync((void **)&dCol, sizeof(unsigned) * sliceVox, st));
+    for (int64_t i0 = 0; i0 < n; i0 += slice)
+    {
+        const int64_t cnt = std::min<int64_t>(slice, n - i0);
+        CHS_CUDA(cudaMemcpyAsync(dSlots, slots.data() + i0, sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, st));
+        CHS_CUDA(cudaMemcpyAsync(dSdf, sdf + (size_t)i0 * V, sizeof(float) * (size_t)cnt * V, cudaMemcpyHostToDevice, st));
+        CHS_CUDA(cudaMemcpyAsync(dW, weight + (size_t)i0 * V, sizeof(float) * (size_t)cnt * V, cudaMemcpyHostToDevice, st));
+        if (dCol)
+            CHS_CUDA(cudaMemcpyAsync(dCol, rgbw + (size_t)i0 * V * 4, 4 * (size_t)cnt * V, cudaMemcpyHostToDevice, st));
+        import_scatter_kernel<<<(int)cnt, 256, 0, st>>>(m->dm, (int)cnt, dSlots, dSdf, dW, dCol);
+        CHS_CUDA(cudaGetLastError());
+        CHS_CUDA(cudaStreamSynchronize(st));                         // the staging buffers are reused by the next slice
+    }
+    for (void *p : {(void *)dSlots, (void *)dSdf, (void *)dW, (void *)dCol})
+        if (p)
+            CHS_CUDA(cudaFreeAsync(p, st));
+    CHS_CUDA(cudaStreamSynchronize(st));
+    // the device insert has succeeded: now the host mirror may know the new chunks
+    for (const auto &kv : fresh)
+        m->hostIndex[kv.first] = kv.second;
+    m->hostIds.insert(m->hostIds.end(), newIds.begin(), newIds.end());
+    m->knownChunks = next;
     return CHS_OK;
+}
+
+// ---- map checkpoint on disk (replaces the reference's broken chunk wire format, CR Serialization.h:31-84) ----
+// Layout (little endian): header {magic "CHSMAP01", int32 version = 1, chunk_size, use_color, float resolution, int64 n_chunks, int64
+// n_dirty, int32 voxels per chunk, int32 reserved}, then SoA payload: ids int32[3 n], sdf float[n V], weight float[n V],
+// rgbw uint8[4 n V] (colour maps only), dirty ids int32[3 n_dirty]. Chunks in pool order; everything a resumed run needs to
+// continue bit-identically (brick flags are a conservative cache and are rebuilt as "all set").
+namespace
+{
+struct CheckpointHeader
+{
+    char magic[8];
+    int32_t version, chunk_size, use_color;
+    float resolution;
+    int64_t n_chunks, n_dirty;
+    int32_t voxels, reserved;
+};
+} // namespace
+
+int chs_save_map(chs_map *m, const char *path)
+{
+    if (!m || !path)
+        return fail(CHS_ERR_INVALID, "null argument");
+    int rc = sync_counts(m);
+    if (rc)
+        return rc;
+    const int64_t n = m->knownChunks, nd = m->knownDirty;
+    const size_t V = (size_t)m->dm.V;
+    std::vector<int32_t> ids((size_t)n * 3), dirty((size_t)nd * 3);
+    std::vector<float> sdf((size_t)n * V), w((size_t)n * V);
+    std::vector<uint8_t> rgbw(m->cfg.use_color ? (size_t)n * V * 4 : 0);
+    if (n && (rc = chs_download_all(m, n, ids.data(), sdf.data(), w.data(), m->cfg.use_color ? rgbw.data() : nullptr)))
+        return rc;
+    if (nd && (rc = chs_dirty_ids(m, dirty.data(), nd)))
+        return rc;
+    CheckpointHeader h{};
+    std::memcpy(h.magic, "CHSMAP01", 8);
+    h.version = 1;
+    h.chunk_size = m->cfg.chunk_size;
+    h.use_color = m->cfg.use_color ? 1 : 0;
+    h.resolution = m->cfg.resolution;
+    h.n_chunks = n;
+    h.n_dirty = nd;
+    h.voxels = (int32_t)V;
+    FILE *f = std::fopen(path, "wb");
+    if (!f)
+        return fail(CHS_ERR_INVALID, std::string("cannot open ") + path + " for writing");
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
+    auto put = [&](const void *p, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes); };
+    put(ids.data(), ids.size() * 4);
+    put(sdf.data(), sdf.size() * 4);
+    put(w.data(), w.size() * 4);
+    put(rgbw.data(), rgbw.size());
+    put(dirty.data(), dirty.size() * 4);
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? CHS_OK : fail(CHS_ERR_INVALID, std::string("short write to ") + path);
+}
+
+int chs_load_map(chs_map *m, const char *path)
+{
+    if (!m || !path)
+        return fail(CHS_ERR_INVALID, "null argument");
+    FILE *f = std::fopen(path, "rb");
+    if (!f)
+        return fail(CHS_ERR_NOT_FOUND, std::string("cannot open ") + path);
+    CheckpointHeader h{};
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "CHSMAP01", 8) != 0 || h.version != 1)
+    {
+        std::fclose(f);
+        return fail(CHS_ERR_INVALID, "not a chisel_b200 map checkpoint (version 1)");
+    }
+    if (h.chunk_size != m->cfg.chunk_size || h.resolution != m->cfg.resolution || (h.use_color != 0) != (m->cfg.use_color != 0) || h.voxels != m->dm.V ||
+        h.n_chunks < 0 || h.n_dirty < 0)
+    {
+        std::fclose(f);
+        return fail(CHS_ERR_INVALID, "the checkpoint was written by a map with another chunk size, resolution or colour setting");
+    }
+    const size_t n = (size_t)h.n_chunks, nd = (size_t)h.n_dirty, V = (size_t)h.voxels;
+    std::vector<int32_t> ids(n * 3), dirty(nd * 3);
+    std::vector<float> sdf(n * V), w(n * V);
+    std::vector<uint8_t> rgbw(h.use_color ? n * V * 4 : 0);
+    bool ok = true;
+    auto get = [&](void *p, size_t bytes) { ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes); };
+    get(ids.data(), ids.size() * 4);
+    get(sdf.data(), sdf.size() * 4);
+    get(w.data(), w.size() * 4);
+    get(rgbw.data(), rgbw.size());
+    get(dirty.data(), dirty.size() * 4);
+    std::fclose(f);
+    if (!ok)
+        return fail(CHS_ERR_INVALID, "truncated checkpoint");
+    int rc = chs_reset(m);
+    if (rc)
+        return rc;
+    if (n && (rc = chs_import_chunks(m, (int64_t)n, ids.data(), sdf.data(), w.data(), h.use_color ? rgbw.data() : nullptr)))
+        return rc;
+    return chs_set_dirty(m, (int64_t)nd, dirty.data());
 }
 
 // Replace the dirty set by the given IDs (Chisel::meshesToUpdate assigned from outside).
@@ -2211,6 +2412,75 @@ void chs_host_free(void *p)
 {
     if (p)
         cudaFreeHost(p);
+}
+
+// ---- frame ingestion of the collaborative server (SPG/src/collaborative_server_system.cpp:213-276): cv::resize + validity mask ----
+// cv::resize, INTER_LINEAR, float images: per destination column x = (dx + 0.5) * scale - 0.5 with scale = 1 / (double(dst) / src),
+// sx = floor(x), fx = x - sx, clamped at the borders (weight 0 on the missing neighbour); rows alike. Horizontal pass first
+// (S[sx] * (1 - fx) + S[sx + 1] * fx), then vertical. OpenCV's own SIMD and scalar paths differ in the last bit (fused vs. separate
+// multiply-add), so this agrees with cv2 to 1 ulp, not bit for bit (tests/test_parity_gpu.py::test_ingest_depth_resize_and_mask).
+// Then NaN outside [vmin, vmax] (exact).
+__global__ void ingest_depth_kernel(const float *src, int sw, int sh, float *dst, int dw, int dh, double scaleX, double scaleY, float vmin, float vmax)
+{
+    const float nanv = __int_as_float(0x7fc00000);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dw * dh; i += gridDim.x * blockDim.x)
+    {
+        const int dx = i % dw, dy = i / dw;
+        float v;
+        if (sw == dw && sh == dh)
+            v = src[i];
+        else
+        {
+            // source position and its fraction in double (OpenCV 4 keeps the fraction's precision: rounding the position to float
+            // first costs up to 1e-5 of relative weight at x ~ 100), the weights themselves in float
+            const double px = (dx + 0.5) * scaleX - 0.5, py = (dy + 0.5) * scaleY - 0.5;
+            int sx = (int)floor(px), sy = (int)floor(py);
+            float fx = (float)(px - (double)sx), fy = (float)(py - (double)sy);
+            if (sx < 0) { sx = 0; fx = 0.0f; }
+            if (sx >= sw - 1) { sx = sw - 1; fx = 0.0f; }
+            if (sy < 0) { sy = 0; fy = 0.0f; }
+            if (sy >= sh - 1) { sy = sh - 1; fy = 0.0f; }
+            const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+            const float a0 = 1.0f - fx, a1 = fx, b0 = 1.0f - fy, b1 = fy;
+            const float r0 = __fadd_rn(__fmul_rn(src[(size_t)sy * sw + sx], a0), __fmul_rn(src[(size_t)sy * sw + sx1], a1));
+            const float r1 = __fadd_rn(__fmul_rn(src[(size_t)sy1 * sw + sx], a0), __fmul_rn(src[(size_t)sy1 * sw + sx1], a1));
+            v = __fmaf_rn(r0, b0, __fmul_rn(r1, b1));
+        }
+        dst[i] = (v < vmin || v > vmax) ? nanv : v;            // a NaN input stays NaN (both comparisons are false, the value is kept)
+    }
+}
+
+int chs_ingest_depth(chs_map *m, const float *src, int src_w, int src_h, float *dst, int dst_w, int dst_h, float valid_min, float valid_max, int mem)
+{
+    if (!m || !src || !dst || src_w <= 0 || src_h <= 0 || dst_w <= 0 || dst_h <= 0)
+        return fail(CHS_ERR_INVALID, "bad argument");
+    if (mem != CHS_MEM_HOST && mem != CHS_MEM_DEVICE)
+        return fail(CHS_ERR_INVALID, "chs_ingest_depth takes CHS_MEM_HOST or CHS_MEM_DEVICE");
+    CHS_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const double scaleX = 1.0 / ((double)dst_w / src_w), scaleY = 1.0 / ((double)dst_h / src_h);
+    const size_t ns = (size_t)src_w * src_h, nd = (size_t)dst_w * dst_h;
+    const float *dSrc = src;
+    float *dDst = dst;
+    float *tmpS = nullptr, *tmpD = nullptr;
+    if (mem == CHS_MEM_HOST)
+    {
+        CHS_CUDA(cudaMallocAsync((void **)&tmpS, ns * sizeof(float), st));
+        CHS_CUDA(cudaMallocAsync((void **)&tmpD, nd * sizeof(float), st));
+        CHS_CUDA(cudaMemcpyAsync(tmpS, src, ns * sizeof(float), cudaMemcpyHostToDevice, st));
+        dSrc = tmpS;
+        dDst = tmpD;
+    }
+    ingest_depth_kernel<<<(int)std::min<size_t>((nd + 255) / 256, 148 * 8), 256, 0, st>>>(dSrc, src_w, src_h, dDst, dst_w, dst_h, scaleX, scaleY, valid_min, valid_max);
+    CHS_CUDA(cudaGetLastError());
+    if (mem == CHS_MEM_HOST)
+    {
+        CHS_CUDA(cudaMemcpyAsync(dst, tmpD, nd * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CHS_CUDA(cudaFreeAsync(tmpS, st));
+        CHS_CUDA(cudaFreeAsync(tmpD, st));
+        CHS_CUDA(cudaStreamSynchronize(st));
+    }
+    return CHS_OK;
 }
 
 void *chs_device_alloc(chs_map *m, size_t bytes)

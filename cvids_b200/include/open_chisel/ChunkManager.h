@@ -11,6 +11,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include <chisel_b200.h>
@@ -203,43 +204,74 @@ class ChunkManager
             meshStage.reset(new b200::PinnedBuffer<float>(need + need / 4));
         float *v = meshStage->data(), *nr = v + nvf, *col = nr + nvf, *g = col + (mc.has_colors ? nvf : 0);
         b200::Check(chs_download_meshes(handle.get(), ids.data(), voff.data(), goff.data(), v, nr, mc.has_colors ? col : nullptr, g), "chs_download_meshes");
+        // publication rule first (serial: it touches the MeshMap), then the vertex arrays are copied by a few threads -- a re-mesh of a
+        // room-sized dirty set is tens of MB of host copies, the largest host cost of the facade
+        std::vector<std::pair<int64_t, Mesh *>> jobs;
+        jobs.reserve(static_cast<size_t>(mc.n_chunks));
         for (int64_t i = 0; i < mc.n_chunks; i++)
         {
             const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
-            const bool had = HasMesh(id);
+            MeshMap::iterator it = allMeshes.find(id);
+            const bool had = it != allMeshes.end();
             if (!had && goff[i + 1] == goff[i])
                 continue;
-            MeshPtr m = had ? allMeshes[id] : std::make_shared<Mesh>();
-            m->Clear();
-            const size_t nv = static_cast<size_t>(voff[i + 1] - voff[i]), ng = static_cast<size_t>(goff[i + 1] - goff[i]);
-            m->Resize(nv, ng, mc.has_colors != 0);
-            if (sizeof(Vec3) == 3 * sizeof(float))
+            MeshPtr m = had ? it->second : std::make_shared<Mesh>();
+            if (!had)
+                allMeshes[id] = m;
+            jobs.push_back(std::make_pair(i, m.get()));
+        }
+        const bool colors = mc.has_colors != 0;
+        auto fill = [&](size_t lo, size_t hi)
+        {
+            for (size_t j = lo; j < hi; j++)
             {
-                // Vec3 is three packed floats: whole arrays at once
-                if (nv)
+                const int64_t i = jobs[j].first;
+                Mesh *m = jobs[j].second;
+                const size_t nv = static_cast<size_t>(voff[i + 1] - voff[i]), ng = static_cast<size_t>(goff[i + 1] - goff[i]);
+                m->Clear();
+                if (sizeof(Vec3) == 3 * sizeof(float))
                 {
-                    std::memcpy(static_cast<void *>(m->vertices.data()), &v[3 * voff[i]], nv * sizeof(Vec3));
-                    std::memcpy(static_cast<void *>(m->normals.data()), &nr[3 * voff[i]], nv * sizeof(Vec3));
-                    if (mc.has_colors)
-                        std::memcpy(static_cast<void *>(m->colors.data()), &col[3 * voff[i]], nv * sizeof(Vec3));
+                    // Vec3 is three packed floats: whole arrays at once, one pass over the memory
+                    const Vec3 *pv = reinterpret_cast<const Vec3 *>(v + 3 * voff[i]), *pn = reinterpret_cast<const Vec3 *>(nr + 3 * voff[i]);
+                    m->vertices.assign(pv, pv + nv);
+                    m->normals.assign(pn, pn + nv);
+                    if (colors)
+                    {
+                        const Vec3 *pc = reinterpret_cast<const Vec3 *>(col + 3 * voff[i]);
+                        m->colors.assign(pc, pc + nv);
+                    }
+                    const Vec3 *pg = reinterpret_cast<const Vec3 *>(g + 3 * goff[i]);
+                    m->grids.assign(pg, pg + ng);
+                    m->indices.resize(nv);
+                    for (size_t k = 0; k < nv; k++)
+                        m->indices[k] = k;
                 }
-                if (ng)
-                    std::memcpy(static_cast<void *>(m->grids.data()), &g[3 * goff[i]], ng * sizeof(Vec3));
-            }
-            else
-            {
-                for (size_t k = 0; k < nv; k++)
+                else
                 {
-                    const int64_t q = voff[i] + static_cast<int64_t>(k);
-                    m->vertices[k] = Vec3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
-                    m->normals[k] = Vec3(nr[3 * q], nr[3 * q + 1], nr[3 * q + 2]);
-                    if (mc.has_colors)
-                        m->colors[k] = Vec3(col[3 * q], col[3 * q + 1], col[3 * q + 2]);
+                    m->Resize(nv, ng, colors);
+                    for (size_t k = 0; k < nv; k++)
+                    {
+                        const int64_t q = voff[i] + static_cast<int64_t>(k);
+                        m->vertices[k] = Vec3(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+                        m->normals[k] = Vec3(nr[3 * q], nr[3 * q + 1], nr[3 * q + 2]);
+                        if (colors)
+                            m->colors[k] = Vec3(col[3 * q], col[3 * q + 1], col[3 * q + 2]);
+                    }
+                    for (size_t k = 0; k < ng; k++)
+                        m->grids[k] = Vec3(g[3 * (goff[i] + k)], g[3 * (goff[i] + k) + 1], g[3 * (goff[i] + k) + 2]);
                 }
-                for (size_t k = 0; k < ng; k++)
-                    m->grids[k] = Vec3(g[3 * (goff[i] + k)], g[3 * (goff[i] + k) + 1], g[3 * (goff[i] + k) + 2]);
             }
-            allMeshes[id] = m;
+        };
+        const size_t nThreads = mc.n_vertices > 200000 ? 4 : 1;
+        if (nThreads == 1)
+            fill(0, jobs.size());
+        else
+        {
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < nThreads; t++)
+                pool.emplace_back(fill, jobs.size() * t / nThreads, jobs.size() * (t + 1) / nThreads);
+            for (std::thread &th : pool)
+                th.join();
         }
     }
 

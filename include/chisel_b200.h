@@ -188,6 +188,12 @@ int chs_download_all(chs_map *map, int64_t cap_chunks, int32_t *ids, float *sdf,
 int chs_export_chunks(chs_map *map, int64_t n, const int32_t *ids, uint8_t *found, float *sdf, float *weight, uint8_t *rgbw);
 int chs_import_chunks(chs_map *map, int64_t n, const int32_t *ids, const float *sdf, const float *weight, const uint8_t *rgbw);
 int chs_set_dirty(chs_map *map, int64_t n, const int32_t *ids);
+/* Map checkpoint on disk and resume (stands in for the reference's chunk wire format, CR/include/chisel_ros/
+ * Serialization.h:31-84 + CR/msg/ChunkMessage.msg, whose bit packing is broken). One file: header (magic "CHSMAP01", version, chunk
+ * size, resolution, colour flag, counts), then ids, sdf, weight, rgbw and the dirty set as flat little-endian arrays. A map that
+ * loads it continues exactly like the map that wrote it (same voxels, same dirty set); chs_load_map replaces the map's contents. */
+int chs_save_map(chs_map *map, const char *path);
+int chs_load_map(chs_map *map, const char *path);
 int chs_num_dirty(chs_map *map, int64_t *n);                   /* synchronises */
 int chs_dirty_ids(chs_map *map, int32_t *ids, int64_t cap);
 
@@ -227,6 +233,14 @@ int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4]);
  * speed and asynchronously. NULL on failure. */
 void *chs_host_alloc(size_t bytes);
 void chs_host_free(void *p);
+
+/* Frame ingestion of the collaborative server, the step right before the path (SURVEY.md 8(f) item 2;
+ * server_pose_graph/src/collaborative_server_system.cpp:213-276): cv::resize (INTER_LINEAR, half-pixel centres, OpenCV's float path) of
+ * the float depth map to dst_w x dst_h, then NaN for every depth outside [valid_min, valid_max] (0.1 m / 20 m there). Equal sizes:
+ * masking only. CHS_MEM_HOST (copied through the device, synchronous) or CHS_MEM_DEVICE (in place on the map's stream: the result
+ * can go straight into chs_integrate_*, no host hop). The 16UC1 millimetre conversion of chisel_ros (CR Conversions.h:141-152) is
+ * chs_frame.depth_mm. */
+int chs_ingest_depth(chs_map *map, const float *src, int src_w, int src_h, float *dst, int dst_w, int dst_h, float valid_min, float valid_max, int mem);
 
 /* Device-side frame queue for callers that receive frames one at a time and reuse their image buffers (the facade's
  * Chisel::IntegrateDepthScan[Color] with frame batching, CR/src/ChiselServer.cpp:285-295): device memory on the map's device,

@@ -25,7 +25,7 @@ def build_facade_client() -> str:
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     lib = os.path.join(ROOT, "cvids_b200")
-    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wno-unused-parameter", "-I", os.path.join(ROOT, "oracle", "eigen_shim"),
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-pthread", "-Wall", "-Wno-unused-parameter", "-I", os.path.join(ROOT, "oracle", "eigen_shim"),
                            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "cvids_b200", "include"), SRC, "-o", out,
                            "-L", lib, "-lchisel_b200", "-Wl,-rpath," + lib])
     return out

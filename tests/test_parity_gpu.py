@@ -376,3 +376,123 @@ def test_full_size_properties_config2():
     nrm = np.concatenate([m["normals"] for m in m1.values() if len(m["normals"])])
     ln = np.linalg.norm(nrm, axis=1)
     assert np.all((np.abs(ln - 1) < 1e-3) | (ln == 0))
+
+
+def test_checkpoint_file_save_resume_equals_uninterrupted_run_and_oracle(tmp_path):
+    """chs_save_map at frame 5, chs_load_map into a FRESH map, continue to frame 10 == the uninterrupted CUDA
+    run == the oracle: voxel state, dirty set and the meshes of the final re-mesh. The file is the documented flat SoA layout."""
+    import struct
+    setup = Setup(16, 0.05, True)
+    cam = common.SMALL_CAM
+    camv = cam.as_array()
+    frames = list(common.orbit_stream(cam, 10, total=30, color=True, nan_frac=0.02, seed=9))
+    a, b, o = common.Driver(setup, "cuda"), common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    for depth, col, pose in frames:
+        o.integrate(depth, pose, camv, col)
+    first, rest = frames[:5], frames[5:]
+    a.m.integrate_batch(a.integ, [f[0] for f in first], [f[2] for f in first], camv, [f[1] for f in first])
+    path = str(tmp_path / "map.chs")
+    a.m.save_map(path)
+    raw = open(path, "rb").read()
+    magic, version, cs, color, res, n, nd, V, _ = struct.unpack_from("<8s3if2q2i", raw, 0)
+    assert magic == b"CHSMAP01" and version == 1 and cs == 16 and color == 1 and V == 4096 and abs(res - 0.05) < 1e-7
+    assert n == len(a.state()[0]) and nd == len(a.dirty())
+    assert len(raw) == struct.calcsize("<8s3if2q2i") + n * 12 + 2 * n * V * 4 + n * V * 4 + nd * 12
+    b.m.load_map(path)
+    common.assert_state_equal(b.state(), a.state(), "loaded map")
+    assert np.array_equal(b.dirty(), a.dirty())
+    for drv in (a, b):
+        drv.m.integrate_batch(drv.integ, [f[0] for f in rest], [f[2] for f in rest], camv, [f[1] for f in rest])
+    common.assert_state_equal(b.state(), a.state(), "resumed vs uninterrupted")
+    common.assert_state_equal(b.state(), o.state(), "resumed vs oracle")
+    assert np.array_equal(b.dirty(), o.dirty())
+    b.remesh()
+    o.remesh()
+    common.assert_meshes_equal(b.meshes(), o.meshes(), "meshes after resume")
+    # a checkpoint of another configuration is refused
+    c = common.Driver(Setup(16, 0.04, True), "cuda")
+    with pytest.raises(Exception):
+        c.m.load_map(path)
+
+
+def test_import_overwrite_resets_brick_flags_for_carving():
+    """An existing chunk overwritten through chs_import_chunks may now hold carvable voxels (weight > 0, sdf < 1e-5) in bricks
+    whose carving flag was clear; the following free-space frames must carve them, as the oracle does."""
+    setup = Setup(16, 0.05, False)
+    cam = common.SMALL_CAM
+    camv = cam.as_array()
+    frames = list(common.carve_stream(cam, 3, 5))
+    a, o = common.Driver(setup, "cuda"), common.Driver(setup, "oracle")
+    # a map of the EMPTY room (no obstacle): its chunks in front of the wall hold no carvable voxel, flags clear
+    for depth, _, pose in frames[3:5]:
+        a.integrate(depth, pose, camv)
+        o.integrate(depth, pose, camv)
+    ids, sdf, w, rgbw = o.state()
+    sdf, w = sdf.copy(), w.copy()
+    rng = np.random.RandomState(3)
+    # plant observed, negative-sdf voxels all over a third of the chunks (what the removed obstacle would have left)
+    for c in range(0, len(ids), 3):
+        v = rng.choice(sdf.shape[1], 400, replace=False)
+        sdf[c, v] = np.float32(-0.02)
+        w[c, v] = np.float32(3.0)
+    a.m.import_chunks(ids, sdf, w)
+    o.m.import_chunks(ids, sdf, w)
+    grp = frames[5:]
+    a.m.integrate_batch(a.integ, [f[0] for f in grp], [f[2] for f in grp], camv)
+    n_carve = 0
+    for depth, _, pose in grp:
+        o.integrate(depth, pose, camv)
+        n_carve += o.counters()["n_carve"]
+    assert n_carve > 0
+    common.assert_state_equal(a.state(), o.state())
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_per_pixel_truncation_supplied_by_the_caller(batch):
+    """CHS_TRUNC_PER_PIXEL: the caller evaluates its own Truncator per pixel (any subclass; here the reference's QuadraticTruncator
+    through chs_truncation) and hands over the image; the result must equal the oracle running that truncator itself."""
+    from cvids_b200 import capi
+    setup = Setup(16, 0.05, True, trunc_kind=common.TRUNC_QUADRATIC, trunc_param=4.0, carve_dist=0.0)
+    cam = common.SMALL_CAM
+    camv = cam.as_array()
+    frames = list(common.orbit_stream(cam, 5, total=30, color=True, nan_frac=0.02, seed=4))
+    o = common.Driver(setup, "oracle")
+    m = capi.Chisel(setup.chunk, setup.resolution, True)
+    for depth, col, pose in frames:
+        o.integrate(depth, pose, camv, col)
+    truncs = [np.array([capi.truncation(capi.TRUNC_QUADRATIC, 4.0, float(d)) for d in f[0].ravel()], np.float32).reshape(f[0].shape) for f in frames]
+    if batch == 1:
+        for (depth, col, pose), tr in zip(frames, truncs):
+            integ = capi.ProjectionIntegrator(capi.TRUNC_PER_PIXEL, 0.0, setup.weight, setup.carve, setup.carve_dist, trunc_per_pixel=tr)
+            m.integrate_depth_scan_color(integ, depth, pose, camv, col)
+    else:
+        integ = capi.ProjectionIntegrator(capi.TRUNC_PER_PIXEL, 0.0, setup.weight, setup.carve, setup.carve_dist)
+        m.integrate_batch(integ, [f[0] for f in frames], [f[2] for f in frames], camv, [f[1] for f in frames], truncs=truncs)
+    common.assert_state_equal(m.state(), o.state(), "caller-evaluated truncator")
+    assert np.array_equal(m.dirty_ids(), o.dirty())
+
+
+def test_ingest_depth_resize_and_mask():
+    """SURVEY 8(f) item 2, the step before the path (SPG/src/collaborative_server_system.cpp:213-276): cv::resize of the depth map +
+    NaN outside [0.1, 20] m, on the device. The resize agrees with OpenCV (golden vectors from cv2, tests/golden/make_ingest_golden.py)
+    to a few ulp -- OpenCV's own scalar and SIMD paths differ in the last bit --, NaN propagation and the mask are exact."""
+    from cvids_b200 import capi
+    g = np.load(os.path.join(GOLDEN, "ingest_golden.npz"))
+    m = capi.Chisel(16, 0.05, False)
+    for name in ("euroc_quarter", "both_axes", "upscale"):
+        src, want = g[name + "_src"], g[name + "_resized"]
+        got = m.ingest_depth(src, want.shape[1], want.shape[0], valid_min=-1e30, valid_max=1e30)      # resize only
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        ok = ~np.isnan(want)
+        assert np.allclose(got[ok], want[ok], rtol=3e-6, atol=0.0), (name, float(np.abs(got[ok] - want[ok]).max()))
+        assert np.mean(got[ok] == want[ok]) > 0.6, name
+        masked = m.ingest_depth(src, want.shape[1], want.shape[0])                                     # 0.1 m .. 20 m
+        keep = ok & (got >= 0.1) & (got <= 20.0)
+        assert np.array_equal(np.isnan(masked), ~keep), name
+        assert np.array_equal(masked[keep].view(np.uint32), got[keep].view(np.uint32)), name
+    # equal sizes: the mask alone, bit-exact passthrough
+    d = np.linspace(-1.0, 30.0, 160 * 120, dtype=np.float32).reshape(120, 160)
+    d[5, 5] = np.nan
+    out = m.ingest_depth(d, 160, 120)
+    keep = (d >= 0.1) & (d <= 20.0)
+    assert np.array_equal(np.isnan(out), ~keep) and np.array_equal(out[keep].view(np.uint32), d[keep].view(np.uint32))
