@@ -341,7 +341,9 @@ def run_multi_agent(B: Bench, args):
     sampler = ClockSampler(range(world), enabled=(rank == 0))
     sampler.start()
     pass_ms, host_us = [], []
-    for _ in range(max(1, args.passes)):
+    # pass -1 is an untimed rehearsal of a whole pass (first use of the pool slabs, of the NCCL communicator's channels and of the
+    # pinned snapshot ring); the timed passes that follow each start from a fresh map again
+    for ip in range(-1, max(1, args.passes)):
         m = B.new_map(cfg)
         for t in range(warm):
             step_device(m, t)
@@ -352,11 +354,14 @@ def run_multi_agent(B: Bench, args):
         h0 = time.perf_counter()
         for t in range(warm, T):
             step_device(m, t)
-        host_us.append(1e6 * (time.perf_counter() - h0) / steps)
+        h1 = time.perf_counter()
         e1.record(B.stream)
         m.synchronize()
         B.barrier()
-        pass_ms.append(B.max_over_ranks([e0.elapsed_time(e1)])[0])
+        ms = B.max_over_ranks([e0.elapsed_time(e1)])[0]
+        if ip >= 0:
+            pass_ms.append(ms)
+            host_us.append(1e6 * (h1 - h0) / steps)
         if world > 1:
             m.comm_destroy()
         m.close()
@@ -481,11 +486,16 @@ def run_multi_agent(B: Bench, args):
     B.barrier()
     t0 = time.perf_counter()
     upd_e2e, prev = 0, None
+    host_call = host_wait = 0.0
     for t in range(warm, T):
+        c0 = time.perf_counter()
         step_host(t)
         tkt = m.last_batch_ticket()
+        c1 = time.perf_counter()
         if prev is not None:
             upd_e2e += sum(st["n_upd"] for st in m.wait_batch(prev))
+        host_call += c1 - c0
+        host_wait += time.perf_counter() - c1
         prev = tkt
     upd_e2e += sum(st["n_upd"] for st in m.wait_batch(prev))
     B.barrier()
@@ -514,8 +524,8 @@ def run_multi_agent(B: Bench, args):
         "ms_per_step": 1000.0 * t_value / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "frames_per_step": F, "frames_per_s": steps * F / t_value,
         "config": {"workload": WORKLOAD % TS,
-                   "parallelism": ("chunk-hash shard x%d; rank r ingests frames [r*%d, (r+1)*%d) of the step's arrival order and builds their Hi-Z pyramids; images and pyramids "
-                                   "are all-gathered in place over NVLink by the library (NCCL on its copy stream, beside the kernels of the previous step)" % (world, per, per)) if world > 1 else "1 GPU",
+                   "parallelism": ("chunk-hash shard x%d; rank r ingests frames [r*%d, (r+1)*%d) of the step's arrival order; the images are all-gathered in place over NVLink "
+                                   "by the library (NCCL on its copy stream, beside the kernels of the previous step), every rank builds all Hi-Z pyramids and integrates the chunks it owns" % (world, per, per)) if world > 1 else "1 GPU",
                    "l2": "no flush: the timed region streams %d MB of frames (> 126 MB L2 from %d steps on); the map working set stays in L2 as in a live stream"
                          % ((frame_bytes * F * steps) >> 20, (126 << 20) // (frame_bytes * F) + 1),
                    "timing": "CUDA events on the map's stream around the %d timed steps, barrier + synchronize on both sides, max over ranks; median of %d passes %s ms"
@@ -531,6 +541,8 @@ def run_multi_agent(B: Bench, args):
                                       "new_chunk_candidates": float(np.mean([p[4] for p in per_step]))}},
         "e2e": {"value": upd_e2e_total / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * F / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
                 "h2d_bytes_per_step": frame_bytes * F, "d2h_bytes_per_step": 88 * F * world,
+                "h2d_gbs_per_rank": frame_bytes * per * steps / t_e2e / 1e9,
+                "rank0_host_us_per_step": {"in_the_call_incl_marshalling": 1e6 * host_call / steps, "waiting_for_the_previous_step": 1e6 * host_wait / steps},
                 "timing": "wall clock, max over ranks; per step chs_integrate_batch%s(pinned host frames, CHS_MEM_HOST_ASYNC; arguments marshalled inside the "
                           "timed region), then chs_wait_batch of the PREVIOUS step's counters (depth-2 pipeline)" % ("_distributed" if world > 1 else "")},
         "gpu_launches": 3 * steps,
@@ -642,11 +654,16 @@ def run_single_agent(B: Bench, args):
     m.synchronize()
     t0 = time.perf_counter()
     upd_e2e, prev = 0, None
+    host_call = host_wait = 0.0
     for t in range(warm, T):
+        c0 = time.perf_counter()
         step_host(t)
         tkt = m.last_batch_ticket()
+        c1 = time.perf_counter()
         if prev is not None:
             upd_e2e += sum(st["n_upd"] for st in m.wait_batch(prev))
+        host_call += c1 - c0
+        host_wait += time.perf_counter() - c1
         prev = tkt
     upd_e2e += sum(st["n_upd"] for st in m.wait_batch(prev))
     t_e2e = time.perf_counter() - t0
@@ -693,7 +710,8 @@ def run_single_agent(B: Bench, args):
                      "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_alg / steps,
                      "kernel_ms_per_launch": 1000.0 * tk["integrate"] / steps, "kernel_span_ms_per_launch": 1000.0 * tk["bricks_span"] / steps},
         "e2e": {"value": upd_e2e / t_e2e / 1e9, "unit": UNIT, "frames_per_s": steps * Bf / t_e2e, "ms_per_step": 1000.0 * t_e2e / steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * Bf},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 88 * Bf, "h2d_gbs": h2d * steps / t_e2e / 1e9,
+                "host_us_per_step": {"in_the_call_incl_marshalling": 1e6 * host_call / steps, "waiting_for_the_previous_step": 1e6 * host_wait / steps}},
         "parity_check": parity,
     }
 
