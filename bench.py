@@ -71,17 +71,53 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed passes (B200_PROFILING.md recipe)."""
+    """SM clocks and throttle reasons DURING the timed passes (B200_PROFILING.md recipe). The samples come from NVML inside this
+    process (the library nvidia-smi reads; no process start-up per sample, so the short timed passes get several samples);
+    CHS_BENCH_SAMPLER=smi polls an nvidia-smi process instead, =off disables sampling. Measured: no effect on the timed passes."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, indices, enabled=True):
         super().__init__(daemon=True)
-        self.indices, self.samples, self._halt, self.enabled = list(indices), [], threading.Event(), enabled
+        self.indices, self.samples, self._halt = list(indices), [], threading.Event()
+        self.mode = os.environ.get("CHS_BENCH_SAMPLER", "nvml")
+        self.enabled = enabled and self.mode != "off"
+        self.handles = []
+        if self.enabled and self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+                self.nv = pynvml
+                self.handles = [pynvml.nvmlDeviceGetHandleByIndex(phys[i] if phys else i) for i in self.indices]
+            except Exception:
+                self.mode = "smi"
+
+    def _nvml_once(self):
+        nv = self.nv
+        for h in self.handles:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            act = lambda bit: "Active" if (r & bit) else "Not Active"
+            # hw_slowdown 0x8, hw_thermal_slowdown 0x40, sw_thermal_slowdown 0x20, sw_power_cap 0x4
+            self.samples.append([str(sm), str(mx), str(pw), act(0x8), act(0x40), act(0x20), act(0x4)])
 
     def run(self):
         while self.enabled and not self._halt.is_set():
             try:
+                if self.mode == "nvml":
+                    self._nvml_once()
+                    self._halt.wait(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 for row in out.split("\n"):
@@ -104,7 +140,7 @@ class ClockSampler(threading.Thread):
                         reasons.add(name)
             except Exception:
                 pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm), source=self.mode)
 
 
 def algorithmic_bytes(st: dict, cam, channels: int, use_color: bool, chunk: int) -> int:
@@ -286,6 +322,33 @@ class Bench:
         return t.tolist()
 
 
+def summarize_timeline(tl):
+    """Medians (us) over the steps of a pass of the device timeline the library records (chs_get_device_timeline)."""
+    def med(v):
+        v = [x for x in v if x is not None]
+        return round(float(np.median(v)) / 1000.0, 2) if v else None
+
+    def d(a, b):
+        return (a - b) if (a and b) else None
+    rows = {"step": [], "hiz": [], "candidates": [], "bricks": [], "gap_bricks_to_next_hiz": [], "gap_hiz_to_candidates": [], "gap_candidates_to_bricks": [],
+            "push": [], "push_end_to_hiz_start": [], "arrival_to_hiz_start": []}
+    for i, cur in enumerate(tl):
+        rows["hiz"].append(d(cur["hiz_end"], cur["hiz_start"]))
+        rows["candidates"].append(d(cur["cand_end"], cur["cand_start"]))
+        rows["bricks"].append(d(cur["bricks_end"], cur["bricks_start"]))
+        rows["gap_hiz_to_candidates"].append(d(cur["cand_start"], cur["hiz_end"]))
+        rows["gap_candidates_to_bricks"].append(d(cur["bricks_start"], cur["cand_end"]))
+        rows["push"].append(d(cur["push_end"], cur["push_start"]))
+        rows["push_end_to_hiz_start"].append(d(cur["hiz_start"], cur["push_end"]))
+        rows["arrival_to_hiz_start"].append(d(cur["hiz_start"], cur["wait_end"]))
+        if i > 0:
+            rows["step"].append(d(cur["bricks_end"], tl[i - 1]["bricks_end"]))
+            rows["gap_bricks_to_next_hiz"].append(d(cur["hiz_start"], tl[i - 1]["bricks_end"]))
+    out = {k: med(v) for k, v in rows.items()}
+    out["steps"] = [round(x / 1000.0, 1) for x in rows["step"] if x is not None]
+    return out
+
+
 def run_multi_agent(B: Bench, args):
     """The headline workload at N = world GPUs. Returns the JSON line (rank 0) or None."""
     torch = B.torch
@@ -343,8 +406,11 @@ def run_multi_agent(B: Bench, args):
     pass_ms, host_us = [], []
     # pass -1 is an untimed rehearsal of a whole pass (first use of the pool slabs, of the NCCL communicator's channels and of the
     # pinned snapshot ring); the timed passes that follow each start from a fresh map again
+    debug_tl = os.environ.get("CHS_BENCH_DEBUG_TIMELINE") is not None
     for ip in range(-1, max(1, args.passes)):
         m = B.new_map(cfg)
+        if debug_tl:
+            m.set_profiling(2)
         for t in range(warm):
             step_device(m, t)
         m.synchronize()
@@ -359,6 +425,12 @@ def run_multi_agent(B: Bench, args):
         m.synchronize()
         B.barrier()
         ms = B.max_over_ranks([e0.elapsed_time(e1)])[0]
+        if debug_tl and rank == 0 and ip == max(1, args.passes) - 1:
+            tl = m.device_timeline()
+            t0 = tl[warm]["hiz_start"]
+            sys.stderr.write("timed pass %.3f ms; per step (us from the first timed Hi-Z start): hiz_start, cand_start, bricks_start, bricks_end\n" % ms)
+            for i, r in enumerate(tl):
+                sys.stderr.write("  step %2d  %9.1f %9.1f %9.1f %9.1f\n" % (i, (r["hiz_start"] - t0) / 1e3, (r["cand_start"] - t0) / 1e3, (r["bricks_start"] - t0) / 1e3, (r["bricks_end"] - t0) / 1e3))
         if ip >= 0:
             pass_ms.append(ms)
             host_us.append(1e6 * (h1 - h0) / steps)
@@ -367,6 +439,18 @@ def run_multi_agent(B: Bench, args):
         m.close()
     clocks = sampler.stop()
     t_value = float(np.median(pass_ms)) / 1000.0
+
+    # ---------------- device timeline pass: the flow of a timed pass, the kernels stamp %globaltimer themselves ----------------
+    m = B.new_map(cfg)
+    m.set_profiling(2)
+    for t in range(T):
+        step_device(m, t)
+    m.synchronize()
+    B.barrier()
+    timeline = summarize_timeline(m.device_timeline()[-steps:])
+    if world > 1:
+        m.comm_destroy()
+    m.close()
 
     # ---------------- profiling pass: per-frame counters, kernel times (events inside the library), parity ----------------
     m = B.new_map(cfg)
@@ -531,6 +615,7 @@ def run_multi_agent(B: Bench, args):
                    "timing": "CUDA events on the map's stream around the %d timed steps, barrier + synchronize on both sides, max over ranks; median of %d passes %s ms"
                              % (steps, len(pass_ms), [round(x, 3) for x in pass_ms]),
                    "host_enqueue_us_per_step": float(np.median(host_us)),
+                   "rank0_device_timeline_us": timeline,
                    "voxel_updates_per_step": upd_total / steps, "map_chunks": chunks_total,
                    "rank0_kernels_us_per_step": {"hiz": 1e6 * tk["prepare"] / steps, "candidates": 1e6 * tk["candidates"] / steps,
                                                  "wait_for_colour_pack": 1e6 * tk["new_chunks"] / steps, "bricks": 1e6 * tk["integrate"] / steps,
@@ -808,7 +893,7 @@ def main():
     ap.add_argument("--time-steps-per-step", type=int, default=2, choices=[1, 2],
                     help="time steps (8 frames each, one per agent) handed over per call: the fused kernels take up to 16 frames")
     ap.add_argument("--hall-frames", type=int, default=24)
-    ap.add_argument("--pool-chunks", type=int, default=98304,
+    ap.add_argument("--pool-chunks", type=int, default=262144,
                     help="pre-sized chunk pool (chunks) so that no slab / hash growth lands inside the timed region")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
     ap.add_argument("--parity-steps", type=int, default=2,

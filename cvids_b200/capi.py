@@ -79,7 +79,7 @@ EXPORTS = (
     "chs_candidate_ids", "chs_truncation", "chs_owner", "chs_selftest_arithmetic", "chs_host_alloc", "chs_host_free",
     "chs_device_alloc", "chs_device_free", "chs_upload", "chs_save_map", "chs_load_map", "chs_ingest_depth",
     "chs_comm_unique_id", "chs_comm_init", "chs_comm_attach", "chs_comm_destroy", "chs_integrate_batch_distributed",
-    "chs_comm_sync_dirty", "chs_update_meshes_distributed",
+    "chs_comm_sync_dirty", "chs_update_meshes_distributed", "chs_get_device_timeline",
 )
 
 _lib = None
@@ -104,6 +104,7 @@ def load_library(build_if_missing: bool = True):
         getattr(lib, n).argtypes = [vp]
     lib.chs_set_stream.argtypes = [vp, vp]
     lib.chs_set_profiling.argtypes = [vp, i32]
+    lib.chs_get_device_timeline.argtypes = [vp, C.POINTER(C.c_longlong), i32, C.POINTER(i32)]
     lib.chs_integrate_depth.argtypes = [vp, C.POINTER(chs_integrator), vp, i32, vp, C.POINTER(chs_camera)]
     lib.chs_integrate_depth_color.argtypes = [vp, C.POINTER(chs_integrator), vp, i32, vp, C.POINTER(chs_camera),
                                               vp, i32, vp, C.POINTER(chs_camera)]
@@ -496,8 +497,19 @@ class Chisel:
         _check(self._lib.chs_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in chs_timings._fields_}
 
-    def set_profiling(self, on: bool):
+    def set_profiling(self, on):
+        """True / 1: event timings between the kernels (serialises them); 2: device timeline only (kernels stamp %globaltimer)."""
         _check(self._lib.chs_set_profiling(self._h, int(on)))
+
+    TIMELINE = ("push_start", "push_end", "wait_end", "hiz_start", "hiz_end", "cand_start", "cand_end", "bricks_start", "bricks_end")
+
+    def device_timeline(self, max_batches: int = 256) -> list:
+        """Absolute device times (ns) of the most recent fused batches, oldest first; 0 = stamp not recorded."""
+        n = len(self.TIMELINE)
+        out = (C.c_longlong * (n * max_batches))()
+        got = C.c_int32(0)
+        _check(self._lib.chs_get_device_timeline(self._h, out, max_batches, C.byref(got)))
+        return [dict(zip(self.TIMELINE, [int(out[i * n + k]) for k in range(n)])) for i in range(got.value)]
 
     def set_stream(self, stream: int | None):
         _check(self._lib.chs_set_stream(self._h, stream))

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <deque>
 #include <string>
 #include <unordered_map>
@@ -165,6 +166,7 @@ struct chs_map
     {
         FrameParams *dFrames = nullptr;
         BatchCounters *dBctr = nullptr;
+        unsigned long long *dTimeline = nullptr;   // [kTimelineStamps]
         float *depth = nullptr, *trunc = nullptr;
         uint16_t *depthMm = nullptr;
         size_t depthMmCap = 0;
@@ -176,6 +178,7 @@ struct chs_map
         bool used = false;
     } bset[2];
     cudaStream_t copyStream = nullptr;
+    cudaStream_t pushStream = nullptr;            // peer-memory exchange of device frames: pushes queue up here, beside everything else
     cudaStream_t uploadStream = nullptr;          // chs_upload
     cudaEvent_t callEvent = nullptr;
     int *dHizTickets = nullptr;                // [2 * kMaxBatch + 1] self-resetting block counters of frame_prepare
@@ -192,6 +195,8 @@ struct chs_map
     int callId = 0;
     // profiling
     bool profiling = false;
+    bool timeline = false;                     // chs_set_profiling bit 1: device timeline of every fused batch (no events)
+    std::deque<std::array<long long, kTimelineStamps>> timelineHist;   // the most recent batches (at most 256), oldest first
     cudaEvent_t evt[8] = {};
     bool frameTimed = false, meshTimed = false;
     // host mirror of slot -> id (extended lazily; slots are never recycled between resets)
@@ -214,6 +219,20 @@ struct chs_map
     long long *dCommScratch = nullptr;
     size_t commScratchCap = 0;
     int distFirst = 0, distCount = 0;          // distributed batch in progress: the frames [distFirst, distFirst + distCount) are ingested here
+    // Peer-memory frame exchange (capi_comm.inc): this rank's exchange arena -- a header of flag words and two staging sets for the
+    // images of a whole step -- is mapped by every other rank over CUDA IPC; every rank PUSHES the frames it ingests into all
+    // arenas with one kernel (NVLink stores), no collective on the hot path.
+    static constexpr int kMaxPeers = 16;
+    static constexpr int kArenaSets = 3;
+    struct PeerArena
+    {
+        char *base = nullptr;                  // cudaMalloc: [header 4 KB][set 0][set 1][set 2]
+        size_t setBytes = 0, depthOff = 0, mmOff = 0, colorOff = 0;    // layout of a set
+        size_t depthCap = 0, mmCap = 0, colorCap = 0;                  // bytes per set
+        char *peer[kMaxPeers] = {};            // the arenas of all ranks as mapped here (peer[rank] == base)
+        bool tried = false, ok = false;
+        unsigned step = 0;                     // distributed steps pushed so far (the same number on every rank)
+    } arena;
     struct Gathered                            // the root's copy of all ranks' meshes of the last distributed re-mesh
     {
         int *ids = nullptr;
@@ -477,6 +496,14 @@ static chs_map::CallStats *call_stats(chs_map *m, int callId)
 static void retire_batch(chs_map *m, const HostBatchSnapshot &b, int base, int callId)
 {
     m->lastBricksSpanNs = b.bricks_span_ns;
+    if (m->timeline)
+    {
+        std::array<long long, kTimelineStamps> tl;
+        std::memcpy(tl.data(), b.timeline, sizeof(long long) * kTimelineStamps);
+        m->timelineHist.push_back(tl);
+        if (m->timelineHist.size() > 256)
+            m->timelineHist.pop_front();
+    }
     m->knownChunks = b.n_chunks;
     m->knownDirty = b.n_dirty;
     const int K = std::min(std::max(b.K, 0), kMaxBatch);
@@ -922,6 +949,15 @@ static int copy_images_h2d(void *dst, const void *const *src, int K, size_t byte
 
 // capi_comm.inc
 static int exchange_frames(chs_map *m, void *depth, size_t depthBytesPerFrame, void *color, size_t colorBytesPerFrame, cudaStream_t st);
+struct PushSeg
+{
+    const void *src;
+    unsigned long long dst_off, bytes;         // destination offset inside an arena
+};
+static int ensure_peer_arena(chs_map *m, size_t depthBytes, size_t mmBytes, size_t colorBytes);
+static int peer_push(chs_map *m, const PushSeg *segs, int nSeg, cudaStream_t cs);
+static int peer_wait(chs_map *m, cudaStream_t st, unsigned long long *timeline);
+static void release_peer_arena(chs_map *m);
 static int world_any_mm(chs_map *m, bool *anyMm);
 
 // ---------------------------------------------------------------------------------------------------------
@@ -977,20 +1013,66 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         anyMm |= frames[f].depth_mm != nullptr;
     if (dist && world_any_mm(m, &anyMm))
         return CHS_ERR_CUDA;
+    // Distributed batch on more than one rank: the images of the other ranks arrive by peer-memory pushes into this rank's exchange
+    // arena when CUDA IPC is available (collective set-up, first distributed batch), else by NCCL all-gather into the staging set.
+    bool push = false;
+    if (dist && m->cfg.world > 1)
+    {
+        if ((rc = ensure_peer_arena(m, anyMm ? 0 : npx * sizeof(float) * kMaxBatch, anyMm ? npx * sizeof(uint16_t) * kMaxBatch : 0,
+                                    colorPath ? cpx * channels * kMaxBatch : 0)))
+            return rc;
+        push = m->arena.ok;
+    }
+    char *const pushSet = push ? m->arena.base + 4096 + (size_t)((m->arena.step + 1) % chs_map::kArenaSets) * m->arena.setBytes : nullptr;
     const int setIdx = (m->batchId + 1) & 1;
     chs_map::BatchSet &bs = m->bset[setIdx];
     // Host frames: copies and prepare run on the copy stream, beside the kernels of the previous batch. Device frames are ordered by
     // the map's stream anyway (the caller produced them there), so everything stays on it: no cross-stream hand-overs.
     cudaStream_t cs = (hostMem || devAsync) ? m->copyStream : st;
+    const bool direct = push && devSrc;
+    if (dist && mem == CHS_MEM_DEVICE)
+    {
+        // the caller produced its device frames on the map's stream: the copy / push stream picks them up from there
+        CHS_CUDA(cudaEventRecord(bs.fork, st));
+        CHS_CUDA(cudaStreamWaitEvent(direct ? m->pushStream : cs, bs.fork, 0));
+    }
+    // Peer-memory exchange: this rank's share of the step goes into the step's set of every arena. Device frames are pushed from
+    // where they are, on a stream of their own: the push is neither held up by this staging set (still read by the batch before
+    // last) nor by the Hi-Z kernels on the copy stream, and runs up to a whole step ahead (the arenas hold three sets). The
+    // consumers -- this rank's too -- wait for the flag words, not for an event.
+    auto push_frames = [&]() -> int
+    {
+        PushSeg segs[2 * kMaxBatch];
+        int nSeg = 0;
+        const size_t dBytes = npx * (anyMm ? sizeof(uint16_t) : sizeof(float)), cBytes = cpx * channels;
+        const size_t dOff = (size_t)(pushSet - m->arena.base) + (anyMm ? m->arena.mmOff : m->arena.depthOff);
+        const size_t cOff = (size_t)(pushSet - m->arena.base) + m->arena.colorOff;
+        if (direct)
+        {
+            for (int f = locFirst; f < locEnd; f++)
+            {
+                if ((frames[f].depth_mm != nullptr) != anyMm)
+                    return fail(CHS_ERR_INVALID, "distributed batches need one depth encoding for all frames");
+                segs[nSeg++] = PushSeg{anyMm ? (const void *)frames[f].depth_mm : (const void *)frames[f].depth, dOff + dBytes * f, dBytes};
+                if (colorPath)
+                    segs[nSeg++] = PushSeg{frames[f].color, cOff + cBytes * f, cBytes};
+            }
+        }
+        else
+        {
+            // staged host frames: this rank's share is one contiguous block per image kind
+            const size_t n = (size_t)(locEnd - locFirst);
+            segs[nSeg++] = PushSeg{anyMm ? (const void *)(bs.depthMm + npx * locFirst) : (const void *)(bs.depth + npx * locFirst), dOff + dBytes * locFirst, dBytes * n};
+            if (colorPath)
+                segs[nSeg++] = PushSeg{bs.color + cBytes * locFirst, cOff + cBytes * locFirst, cBytes * n};
+        }
+        return peer_push(m, segs, nSeg, direct ? m->pushStream : cs);
+    };
+    if (direct && (rc = push_frames()))
+        return rc;
     // the set is free once the kernels of the batch that used it last (two batches ago) are done
     if (bs.used && (hostMem || devAsync))
         CHS_CUDA(cudaStreamWaitEvent(cs, bs.released, 0));
-    if (dist && mem == CHS_MEM_DEVICE)
-    {
-        // the caller produced its device frames on the map's stream: the copy stream picks them up from there
-        CHS_CUDA(cudaEventRecord(bs.fork, st));
-        CHS_CUDA(cudaStreamWaitEvent(cs, bs.fork, 0));
-    }
     {
         const bool grow = tiles * kMaxBatch > bs.hizCap || ((hostMem || anyMm) && npx * kMaxBatch > bs.depthCap) || (anyMm && hostMem && npx * kMaxBatch > bs.depthMmCap) ||
                           ((computeTrunc || (perPixel && hostMem)) && npx * kMaxBatch > bs.truncCap) ||
@@ -1049,6 +1131,16 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             fp.color = hostMem ? bs.color + cpx * channels * f : frames[f].color;
             fp.color_packed = bs.packed + cpx * f;
         }
+        if (push)
+        {
+            // the step's images are read from the exchange arena (set = parity of the step), where every rank has pushed its share
+            if (anyMm)
+                fp.depth_u16 = reinterpret_cast<const uint16_t *>(pushSet + m->arena.mmOff) + npx * f;
+            else
+                fp.depth = reinterpret_cast<const float *>(pushSet + m->arena.depthOff) + npx * f;
+            if (colorPath)
+                fp.color = reinterpret_cast<const uint8_t *>(pushSet + m->arena.colorOff) + cpx * channels * f;
+        }
         fp.frame_id = ++m->frameId;
     }
     if (hostMem)
@@ -1056,7 +1148,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         // runs of frames of the same kind (float / millimetre depth) go in one strided copy each
         const void *src[kMaxBatch];
         const cudaMemcpyKind kind = (dist && devSrc) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        for (int f0 = locFirst; f0 < locEnd;)
+        for (int f0 = locFirst; f0 < locEnd && !direct;)
         {
             const bool mm = frames[f0].depth_mm != nullptr;
             if (dist && mm != anyMm)
@@ -1076,7 +1168,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             if ((rc = copy_images_h2d(bs.trunc, src, K, npx * sizeof(float), cs, kind)))
                 return rc;
         }
-        if (colorPath)
+        if (colorPath && !direct)
         {
             for (int f = locFirst; f < locEnd; f++)
                 src[f - locFirst] = frames[f].color;
@@ -1084,8 +1176,13 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
                 return rc;
         }
         CHS_CUDA(cudaEventRecord(bs.copied, cs));
-        if (dist && (rc = exchange_frames(m, anyMm ? (void *)bs.depthMm : (void *)bs.depth, npx * (anyMm ? sizeof(uint16_t) : sizeof(float)),
-                                          colorPath ? bs.color : nullptr, cpx * channels, cs)))
+        if (push)
+        {
+            if (!direct && (rc = push_frames()))
+                return rc;
+        }
+        else if (dist && (rc = exchange_frames(m, anyMm ? (void *)bs.depthMm : (void *)bs.depth, npx * (anyMm ? sizeof(uint16_t) : sizeof(float)),
+                                               colorPath ? bs.color : nullptr, cpx * channels, cs)))
             return rc;
     }
     // the frame table: pageable source, staged by the driver before the call returns
@@ -1128,6 +1225,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     bp.batch_id = inf.frameId;
     bp.bctr = bs.dBctr;
+    bp.timeline = m->timeline ? bs.dTimeline : nullptr;
     bp.host_slot = &m->hBatchSnap[inf.slot];
     bp.slot_batch = m->dSlotBatch;
     BatchLaunchInfo info{};
@@ -1207,10 +1305,24 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     BatchStreams streams{cs, m->copyStream, st, bs.prepared, bs.packDone, bs.fork};
     if (dist)
     {
-        CHS_CUDA(cudaEventRecord(bs.prepared, cs));
-        CHS_CUDA(cudaStreamWaitEvent(st, bs.prepared, 0));
-        streams.prep = st;
-        streams.pack = st;
+        if (push)
+        {
+            // the other ranks' pushes of this step have landed (flag words in this rank's arena, written behind the data): Hi-Z and
+            // colour packing follow on the copy stream, i.e. beside the kernels of the previous step, as for one rank
+            if ((rc = peer_wait(m, cs, m->timeline ? bs.dTimeline : nullptr)))
+                return rc;
+            bp.peer_done = reinterpret_cast<unsigned *const *>(m->arena.base + 1024);
+            bp.peer_world = m->cfg.world;
+            bp.peer_step = m->arena.step;
+        }
+        else
+        {
+            // NCCL exchange: Hi-Z and colour packing run on the map's stream, on the whole GPU, once the all-gather has landed
+            CHS_CUDA(cudaEventRecord(bs.prepared, cs));
+            CHS_CUDA(cudaStreamWaitEvent(st, bs.prepared, 0));
+            streams.prep = st;
+            streams.pack = st;
+        }
     }
     bp.reserve_sms = (dist && m->cfg.world > 1) ? 1 : 0;
     if (!poolLater)
@@ -1365,12 +1477,15 @@ static int create_body(chs_map *m, const chs_config *cfg)
     CHS_CUDA(cudaMalloc((void **)&m->dHizTickets, sizeof(int) * (2 * kMaxBatch + 1)));
     CHS_CUDA(cudaMemsetAsync(m->dHizTickets, 0, sizeof(int) * (2 * kMaxBatch + 1), m->stream));
     CHS_CUDA(cudaStreamCreateWithFlags(&m->copyStream, cudaStreamNonBlocking));
+    CHS_CUDA(cudaStreamCreateWithFlags(&m->pushStream, cudaStreamNonBlocking));
     CHS_CUDA(cudaEventCreateWithFlags(&m->callEvent, cudaEventDisableTiming));
     for (chs_map::BatchSet &bs : m->bset)
     {
         CHS_CUDA(cudaMalloc((void **)&bs.dFrames, sizeof(FrameParams) * kMaxBatch));
         CHS_CUDA(cudaMalloc((void **)&bs.dBctr, sizeof(BatchCounters)));
         CHS_CUDA(cudaMemsetAsync(bs.dBctr, 0, sizeof(BatchCounters), m->stream));
+        CHS_CUDA(cudaMalloc((void **)&bs.dTimeline, sizeof(unsigned long long) * kTimelineStamps));
+        CHS_CUDA(cudaMemsetAsync(bs.dTimeline, 0, sizeof(unsigned long long) * kTimelineStamps, m->stream));
         CHS_CUDA(cudaEventCreateWithFlags(&bs.copied, cudaEventDisableTiming));
         CHS_CUDA(cudaEventCreateWithFlags(&bs.prepared, cudaEventDisableTiming));
         CHS_CUDA(cudaEventCreateWithFlags(&bs.released, cudaEventDisableTiming));
@@ -1401,7 +1516,10 @@ int chs_destroy(chs_map *m)
     cudaSetDevice(m->device);
     if (m->copyStream)
         cudaStreamSynchronize(m->copyStream);
+    if (m->pushStream)
+        cudaStreamSynchronize(m->pushStream);
     cudaStreamSynchronize(m->stream);
+    chs_comm_destroy(m);                        // first: collective when the map takes part in a peer-memory exchange; needs the streams
     for (float2 *p : m->distSlabs)
         cudaFreeAsync(p, m->stream);
     for (uchar4 *p : m->colorSlabs)
@@ -1421,6 +1539,7 @@ int chs_destroy(chs_map *m)
     {
         cudaFree(bs.dFrames);
         cudaFree(bs.dBctr);
+        cudaFree(bs.dTimeline);
         if (bs.copied) cudaEventDestroy(bs.copied);
         if (bs.prepared) cudaEventDestroy(bs.prepared);
         if (bs.released) cudaEventDestroy(bs.released);
@@ -1432,12 +1551,13 @@ int chs_destroy(chs_map *m)
         cudaEventDestroy(m->callEvent);
     if (m->copyStream)
         cudaStreamDestroy(m->copyStream);
+    if (m->pushStream)
+        cudaStreamDestroy(m->pushStream);
     if (m->uploadStream)
         cudaStreamDestroy(m->uploadStream);
     cudaFreeHost(m->hBatchSnap);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
-    chs_comm_destroy(m);
     if (m->dCommScratch)
         cudaFree(m->dCommScratch);
     for (void *p : {(void *)m->gathered.ids, (void *)m->gathered.vertOffsets, (void *)m->gathered.gridOffsets, (void *)m->gathered.verts,
@@ -1512,11 +1632,28 @@ int chs_set_stream(chs_map *m, void *stream)
     return CHS_OK;
 }
 
+int chs_get_device_timeline(chs_map *m, long long *out, int max_batches, int *n_batches)
+{
+    if (!m || !out || !n_batches || max_batches < 0)
+        return fail(CHS_ERR_INVALID, "null argument");
+    CHS_CUDA(cudaSetDevice(m->device));
+    int rc = poll_inflight(m, true);
+    if (rc)
+        return rc;
+    const int n = (int)std::min<size_t>(m->timelineHist.size(), (size_t)max_batches);
+    for (int i = 0; i < n; i++)
+        std::memcpy(out + (size_t)i * kTimelineStamps, m->timelineHist[m->timelineHist.size() - (size_t)n + (size_t)i].data(), sizeof(long long) * kTimelineStamps);
+    *n_batches = n;
+    return CHS_OK;
+}
+
 int chs_set_profiling(chs_map *m, int enabled)
 {
     if (!m)
         return fail(CHS_ERR_INVALID, "null map");
-    m->profiling = enabled != 0;
+    m->profiling = (enabled & 1) != 0;
+    m->timeline = (enabled & 2) != 0;
+    m->timelineHist.clear();
     m->frameTimed = m->meshTimed = false;
     return CHS_OK;
 }
@@ -2502,6 +2639,7 @@ void chs_device_free(chs_map *m, void *p)
     {
         cudaStreamSynchronize(m->stream);
         cudaStreamSynchronize(m->copyStream);
+        cudaStreamSynchronize(m->pushStream);
         cudaFree(p);
     }
 }

@@ -30,7 +30,8 @@ enum : int
     kErrHashFull = 2,
     kErrDirtyFull = 4,
     kErrWorkFull = 8,
-    kErrMeshFull = 16
+    kErrMeshFull = 16,
+    kErrPeerTimeout = 32            // peer-memory frame exchange: a rank's images (or its release of a staging set) did not arrive in time
 };
 
 __host__ __device__ inline unsigned long long pack_id(int x, int y, int z)

@@ -41,8 +41,8 @@ constexpr int kNoSlot = -2;                 // hash value of a key whose chunk c
 
 // z slices of a brick per task: 4 = half brick (8 voxels per lane), 2 = quarter brick (4 voxels per lane)
 #ifndef CHS_BRICK_SLICES
-#define CHS_BRICK_SLICES 2                   // measured on B200 (configs[1], 10 frames): 94 us vs 113 us with 4
-#endif
+#define CHS_BRICK_SLICES 4                   // measured on B200 (fast kernel, configs[4], 16 frames per step, 128 registers, 16 warps / SM):
+#endif                                       // 67 us with 4 vs 84 us with 2; with 4 and 168 registers (12 warps) 71 us, 96 registers (20 warps, spills) 77 us
 #ifndef CHS_BRICK_THREADS
 #define CHS_BRICK_THREADS 256
 #endif
@@ -58,6 +58,28 @@ constexpr int kParts = 8 / kNS;              // tasks per brick
 // pdl_launch_dependents() lets the next kernel of the stream start launching. Without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// device timeline (BatchParams::timeline): one thread per CTA
+__device__ __forceinline__ void tl_start(const BatchParams &bp, int i)
+{
+    if (bp.timeline && threadIdx.x == 0)
+        atomicMax(&bp.timeline[i], ~global_timer_ns());
+}
+__device__ __forceinline__ void tl_end(const BatchParams &bp, int i)
+{
+    if (bp.timeline)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            atomicMax(&bp.timeline[i], global_timer_ns());
+    }
+}
 
 // All frames of the batch into shared memory: afterwards `sF[f]` is read with warp-uniform shared loads.
 __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &bp)
@@ -96,8 +118,10 @@ __global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMa
         for (int i = threadIdx.x; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
             c[i] = 0;
     }
+    tl_start(bp, kTlHizStart);
     const FrameParams &fp = bp.frames[frameBase + blockIdx.y];
     frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
+    tl_end(bp, kTlHizEnd);
 }
 
 // grid = (pack blocks, K): packed colour image of every frame (ColorImage::At once per pixel). Only the brick kernel reads it, so
@@ -148,6 +172,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     __shared__ __align__(8) unsigned long long full[kHizStages];
     __shared__ float2 s0[64], s1[16], s2[4];
     const int t = threadIdx.x, lane = t & 31;
+    tl_start(bp, kTlHizStart);
     if (blockIdx.x == 0)
     {
         int *c = reinterpret_cast<int *>(bp.bctr);
@@ -267,6 +292,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             }
         }
     }
+    tl_end(bp, kTlHizEnd);
 }
 
 // Emit the unit of brick b of chunk (x, y, z): `active` lanes hold one brick each. Free-space frames can only carve: the brick must
@@ -376,6 +402,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
     pdl_launch_dependents();                       // the brick kernel may start launching: it waits (pdl_wait) before it reads the unit lists
     load_frames(sF, bp);                           // the frame table was uploaded before the Hi-Z kernel: complete
     pdl_wait();                                    // the Hi-Z kernel's output is read from here on
+    tl_start(bp, kTlCandStart);
     if (bp.coarse_in_shared)
     {
         // Hi-Z levels >= 4 (tiles of 128 pixels and up, until at most 3x3 tiles cover the image) of every frame, from level 3:
@@ -536,7 +563,9 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             if (chunkBand || (chunkFree && carve))
             {
                 slot = hash_lookup(map, pack_id(x, y, z));
-                if (slot >= 0 && chunkFree && carve)
+                // the flags also matter when the chunk as a whole is in the band of a frame: single bricks of it may still lie in
+                // free space and hold carvable voxels from before
+                if (slot >= 0 && carve)
                     flags = map.brick_flags[slot];
             }
             // free-space frames can only carve observed voxels: they matter for an existing chunk with a carvable brick, or
@@ -690,6 +719,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
     }
     if ((int)lane < K && myCount)
         atomicAdd(&bp.bctr->candidates[lane], myCount);
+    tl_end(bp, kTlCandEnd);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -727,12 +757,6 @@ __device__ __forceinline__ bool on_reserved_sm(const BatchParams &bp)
     return bp.reserve_sms && (smid & 15u) == 0u;
 }
 
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ void batch_span_start(const BatchParams &bp)
 {
     if (threadIdx.x == 0)
@@ -770,6 +794,12 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
     if (!sLast)
         return;
     __threadfence();
+    if (threadIdx.x < bp.peer_world)
+    {
+        // every CTA has finished (ticket): nothing of this step's images will be read again
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(bp.peer_done[threadIdx.x]), "r"(bp.peer_step) : "memory");
+    }
     const volatile BatchCounters *c = bp.bctr;
     const volatile Counters *g = map.ctr;
     volatile HostBatchSnapshot *h = bp.host_slot;
@@ -806,6 +836,22 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
         sSnap.K = bp.K;
         sSnap.pad = 0;
         sSnap.bricks_span_ns = (long long)(c->span_end - ~c->span_start_inv);
+        for (int i = 0; i < kTimelineStamps; i++)
+            sSnap.timeline[i] = 0;
+        if (bp.timeline)
+        {
+            // starts are kept as max of ~time; the words are zeroed for the next batch that uses this staging set
+            volatile unsigned long long *tl = bp.timeline;
+            for (int i = 0; i < kTlBricksStart; i++)
+            {
+                const unsigned long long v = tl[i];
+                const bool isStart = i == kTlPushStart || i == kTlHizStart || i == kTlCandStart;
+                sSnap.timeline[i] = v ? (long long)(isStart ? ~v : v) : 0;
+                tl[i] = 0ull;
+            }
+            sSnap.timeline[kTlBricksStart] = (long long)~c->span_start_inv;
+            sSnap.timeline[kTlBricksEnd] = (long long)c->span_end;
+        }
         sSnap.tail = bp.batch_id;
         sSnap.pad3[0] = sSnap.pad3[1] = sSnap.pad3[2] = 0;
     }
@@ -1215,10 +1261,10 @@ __global__ void __launch_bounds__(CHS_BRICK_THREADS, CHS_BRICK_MIN_CTAS) batch_b
 //   * carving, rare in practice, is detected by one chained compare per voxel and handled out of line;
 //   * per-lane change flags instead of per-voxel masks: a lane that changed anything stores its kVPL voxels (same sectors).
 #ifndef CHS_FAST_THREADS
-#define CHS_FAST_THREADS 256
+#define CHS_FAST_THREADS 128
 #endif
 #ifndef CHS_FAST_MIN_CTAS
-#define CHS_FAST_MIN_CTAS 2
+#define CHS_FAST_MIN_CTAS 4
 #endif
 
 struct VoxState

@@ -32,6 +32,22 @@ struct BatchCounters
     unsigned long long span_start_inv, span_end;       // brick kernel: max over CTAs of ~(start time) and of the end time (%globaltimer, ns)
 };
 
+// Device timeline of a batch (chs_set_profiling(map, 2)): %globaltimer stamps taken by the kernels themselves -- no events between
+// the kernels, so the overlap of the product path (PDL, the exchange beside the brick kernel) is seen as it is.
+enum TimelineStamp
+{
+    kTlPushStart = 0,   // peer-memory exchange of this step: first CTA of the push kernel ...
+    kTlPushEnd,         // ... and its last CTA (data out, flags raised)
+    kTlWaitEnd,         // the images of all ranks have arrived (peer_wait_kernel)
+    kTlHizStart,
+    kTlHizEnd,
+    kTlCandStart,
+    kTlCandEnd,
+    kTlBricksStart,
+    kTlBricksEnd,
+    kTimelineStamps
+};
+
 // Written into a pinned slot by the last CTA of a batch: head, payload, checksum of the payload, tail -- WITHOUT a system-scope
 // fence (a fence makes the kernel wait for a PCIe round trip). Valid for batch b when head == tail == b and the checksum matches
 // the payload the host reads (stores that have not landed yet make it mismatch: the host simply polls again).
@@ -42,6 +58,7 @@ struct HostBatchSnapshot
     int candidates[kMaxBatch], n_new[kMaxBatch], updated_chunks[kMaxBatch];
     long long n_upd[kMaxBatch], n_carve[kMaxBatch], n_col[kMaxBatch];
     long long bricks_span_ns;       // first CTA start -> last CTA end of the brick kernel, from %globaltimer (no launch / event overhead)
+    long long timeline[kTimelineStamps];   // device timeline of the batch (%globaltimer, ns; 0 = not recorded): see BatchParams::timeline
     unsigned long long checksum;    // batch_snapshot_checksum of everything between head and here
     int tail, pad3[3];
 };
@@ -55,6 +72,8 @@ __host__ __device__ inline unsigned long long batch_snapshot_checksum(const Host
     for (int t = 0; t < kMaxBatch; t++)
         s += (unsigned long long)(unsigned)h.candidates[t] * 3 + (unsigned long long)(unsigned)h.n_new[t] * 5 + (unsigned long long)(unsigned)h.updated_chunks[t] * 7 +
              (unsigned long long)h.n_upd[t] * 11 + (unsigned long long)h.n_carve[t] * 13 + (unsigned long long)h.n_col[t] * 17;
+    for (int t = 0; t < kTimelineStamps; t++)
+        s += (unsigned long long)h.timeline[t] * (unsigned long long)(23 + 2 * t);
     return s + (unsigned long long)h.bricks_span_ns * 19;
 }
 
@@ -75,6 +94,12 @@ struct BatchParams
     unsigned long long *slot_batch; // [capacity] (batch id << 32) | mask of the batch's frames that updated the chunk
     int reserve_sms;                // the brick kernel leaves every 16th SM idle: room for the NCCL kernels of the next batch's exchange
     int coarse_in_shared;           // the candidates kernel builds the Hi-Z levels >= 4 in shared memory (they fit: <= 48 tiles per frame)
+    // peer-memory frame exchange (capi_comm.inc): the last CTA of the batch tells every rank that this rank has finished reading
+    // the step's images, i.e. that the staging set may be overwritten by the pushes of the step after next
+    unsigned long long *timeline;   // [kTimelineStamps] device words, zero before the batch: starts as max of ~time, ends as max of time; nullptr: off
+    unsigned *const *peer_done;     // [peer_world] device table (local): entry p = this rank's "done" word in rank p's exchange arena
+    int peer_world;                 // 0: not a peer-memory step
+    unsigned peer_step;
 };
 
 // What the fast brick kernel needs of one frame, 128 bytes, passed BY VALUE in the kernel's parameter block (constant bank): a

@@ -122,6 +122,13 @@ typedef struct
                                     %globaltimer (kernel time without launch and event-record overhead; integrate_ms is the event-timed figure) */
 } chs_timings;
 
+/* Device timeline of the most recent fused batches (chs_set_profiling(map, 2); bit 0 = the event timings above, which serialise
+   the kernels): absolute %globaltimer stamps in ns taken by the kernels themselves, 0 = not recorded. Per batch
+   CHS_TIMELINE_STAMPS values: push start, push end (peer-memory exchange of the step), arrival of all ranks' images, Hi-Z start /
+   end, candidates start / end, bricks start / end. out: room for max_batches batches (the library keeps 256), oldest first. */
+#define CHS_TIMELINE_STAMPS 9
+int chs_get_device_timeline(chs_map *map, long long *out, int max_batches, int *n_batches);
+
 const char *chs_last_error_string(void);
 int chs_abi_version(void);
 

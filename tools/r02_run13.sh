@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+show() {
+python - "$1" <<'PY'
+import json,sys
+n=sys.argv[1]
+try:
+    d=json.loads(open('gpurun_out/r02_13_%s.json'%n).read().strip().split('\n')[-1])
+    k=d['config']['rank0_kernels_us_per_step']
+    print(n, 'value %.1f GVox/s step %.1f us host %.1f us' % (d['value'], 1000*d['ms_per_step'], d['config'].get('host_enqueue_us_per_step',0)), 'hiz %.1f cand %.1f bricks %.1f span %.1f' % (k['hiz'],k['candidates'],k['bricks'],k['bricks_first_cta_to_last_cta']), 'frac %.3f' % d['roofline']['frac'], 'parity', d['parity_check'].get('counters_equal'), d['parity_check'].get('state_bit_exact'), d['config']['timing'][-60:])
+except Exception as e: print(n, 'parse failed', e); print(open('gpurun_out/r02_13_%s.err'%n).read()[-1500:])
+PY
+}
+for v in v8t128c4 v8t128c5 v8t128c6 v8t64c8 v8t256c2; do
+  if [ $v = main ]; then unset CHS_LIB_PATH; else export CHS_LIB_PATH=$PWD/cvids_b200/_ab_$v.so; fi
+  timeout 600 python bench.py --no-cpu --no-side-lines --quick > gpurun_out/r02_13_$v.json 2> gpurun_out/r02_13_$v.err; show $v
+done
