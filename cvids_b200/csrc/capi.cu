@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <array>
+#include <chrono>
 #include <deque>
 #include <string>
 #include <unordered_map>
@@ -183,6 +184,8 @@ struct chs_map
     cudaEvent_t callEvent = nullptr;
     int *dHizTickets = nullptr;                // [2 * kMaxBatch + 1] self-resetting block counters of frame_prepare
     HostBatchSnapshot *hBatchSnap = nullptr;   // pinned, device-mapped ring [kRing]
+    FrameParams *hFrameTables = nullptr;       // pinned ring [kRing][kMaxBatch]: staging of the per-batch frame table (at most 4 batches are in flight)
+    int frameTableNext = 0;
     unsigned long long *dSlotBatch = nullptr;  // [capacity]
     int batchId = 0, batchRingNext = 0;
     long long lastBricksSpanNs = 0;
@@ -964,11 +967,62 @@ static int world_any_mm(chs_map *m, bool *anyMm);
 // chs_integrate_batch: n consecutive frames of one sensor stream (same image size, intrinsics and integrator). Sub-batches of
 // up to kMaxBatch frames go through the fused kernels (integrate_batch.cu); the map afterwards is bit-identical to n calls of
 // chs_integrate_depth[_color] in order. Frames whose colour camera differs from the depth camera are integrated one by one.
+// CHS_HOST_PROFILE=1: where the host time of a fused batch call goes (printed per process at exit)
+static double g_launchLapNs[12] = {};
+static std::chrono::steady_clock::time_point g_launchLapT;
+struct HostProfile
+{
+    static constexpr int kSections = 9;
+    const char *names[kSections] = {"plan", "capacity+slot", "arena+buffers", "frame params", "copies+push", "frame table upload", "brick frames", "launch", "waiting for a batch in flight"};
+    double ns[kSections] = {};
+    long long calls = 0;
+    bool on = std::getenv("CHS_HOST_PROFILE") != nullptr;
+    ~HostProfile()
+    {
+        if (!on || !calls)
+            return;
+        double tot = 0;
+        for (double v : ns)
+            tot += v;
+        std::fprintf(stderr, "[chs host profile] %lld fused batches, %.1f us per call:", calls, tot / calls / 1e3);
+        for (int i = 0; i < kSections; i++)
+            std::fprintf(stderr, " %s %.1f;", names[i], ns[i] / calls / 1e3);
+        std::fprintf(stderr, "\n[chs host profile] inside launch: in capi %.1f; dispatch %.1f; resident %.1f; grids %.1f; before %.1f; released event %.1f; pack+fork %.1f; hiz %.1f; prepared event+wait %.1f; candidates %.1f; pack wait %.1f; bricks %.1f\n",
+                     g_launchLapNs[8] / calls / 1e3, g_launchLapNs[9] / calls / 1e3, g_launchLapNs[10] / calls / 1e3, g_launchLapNs[11] / calls / 1e3, g_launchLapNs[7] / calls / 1e3, g_launchLapNs[6] / calls / 1e3, g_launchLapNs[0] / calls / 1e3, g_launchLapNs[1] / calls / 1e3, g_launchLapNs[2] / calls / 1e3, g_launchLapNs[3] / calls / 1e3,
+                     g_launchLapNs[4] / calls / 1e3, g_launchLapNs[5] / calls / 1e3);
+    }
+};
+static HostProfile g_hostProfile;
+void host_launch_lap(int i)
+{
+    if (!g_hostProfile.on)
+        return;
+    const auto t1 = std::chrono::steady_clock::now();
+    if (i >= 0)
+        g_launchLapNs[i] += (double)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - g_launchLapT).count();
+    g_launchLapT = t1;
+}
+struct HostSection
+{
+    std::chrono::steady_clock::time_point t0;
+    HostSection() : t0(std::chrono::steady_clock::now()) {}
+    void lap(int i)
+    {
+        if (!g_hostProfile.on)
+            return;
+        const auto t1 = std::chrono::steady_clock::now();
+        g_hostProfile.ns[i] += (double)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        t0 = t1;
+    }
+};
+
 static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K, const chs_frame *frames, int mem, const chs_camera *cam,
                                  int channels, const chs_camera *ccam, bool colorPath, int statsBase)
 {
     cudaStream_t st = m->stream;
     int rc;
+    HostSection hs;
+    g_hostProfile.calls++;
     FramePlan pl[kMaxBatch];
     int ulo[3], uhi[3];
     for (int f = 0; f < K; f++)
@@ -989,12 +1043,15 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     }
     if (unionCand > (1ll << 26))
         return CHS_ERR_NOT_FOUND;                                   // frames too far apart to share a box: the caller falls back to single frames
+    hs.lap(0);
     if ((rc = wait_inflight_below(m, 4)))
         return rc;
+    hs.lap(8);
     bool poolLater = false;
     if ((rc = ensure_capacity(m, unionCand, dirtyBound, &poolLater)))
         return rc;
 
+    hs.lap(1);
     const size_t npx = (size_t)cam->width * cam->height;
     const size_t cpx = colorPath ? (size_t)ccam->width * ccam->height : 0;
     const size_t tiles = hiz_tiles(cam);
@@ -1099,6 +1156,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         if ((rc = grow_buffer(&bs.packed, &bs.packedCap, cpx * kMaxBatch, cs)))
             return rc;
     }
+    hs.lap(2);
     FrameParams fps[kMaxBatch];
     std::memset(fps, 0, sizeof(fps));
     for (int f = 0; f < K; f++)
@@ -1143,6 +1201,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         }
         fp.frame_id = ++m->frameId;
     }
+    hs.lap(3);
     if (hostMem)
     {
         // runs of frames of the same kind (float / millimetre depth) go in one strided copy each
@@ -1185,8 +1244,15 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
                                                colorPath ? bs.color : nullptr, cpx * channels, cs)))
             return rc;
     }
-    // the frame table: pageable source, staged by the driver before the call returns
-    CHS_CUDA(cudaMemcpyAsync(bs.dFrames, fps, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
+    hs.lap(4);
+    // the frame table, through a pinned ring slot (a pageable source costs the driver a staging copy per call)
+    {
+        FrameParams *slot = m->hFrameTables + (size_t)m->frameTableNext * kMaxBatch;
+        m->frameTableNext = (m->frameTableNext + 1) % chs_map::kRing;
+        std::memcpy(slot, fps, sizeof(FrameParams) * K);
+        CHS_CUDA(cudaMemcpyAsync(bs.dFrames, slot, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
+    }
+    hs.lap(5);
 
     // reserve a slot of the batch snapshot ring
     if ((int)m->inflight.size() >= chs_map::kRing && (rc = poll_inflight(m, true)))
@@ -1248,6 +1314,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             tma = (reinterpret_cast<size_t>(fps[f].depth) & 15) == 0;
         info.hizTma = tma;
     }
+    hs.lap(1);
     // the fast brick kernel's per-frame constants and its preconditions (integrate_batch.cu: batch_bricks_fast_kernel)
     BrickFrames brickFrames;
     info.fastBricks = !perPixel && cam->width < (1 << 22) && cam->height < (1 << 22) && std::getenv("CHS_NO_FAST_BRICKS") == nullptr;
@@ -1277,6 +1344,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
                           (b.thr_carve == b.thr_carve);
     }
     info.brickFrames = &brickFrames;
+    hs.lap(6);
+    host_launch_lap(-1);
     // distributed batch: every rank builds the Hi-Z pyramids of the frames it ingests; the others arrive by all-gather right after
     struct HizGather
     {
@@ -1325,6 +1394,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         }
     }
     bp.reserve_sms = (dist && m->cfg.world > 1) ? 1 : 0;
+    host_launch_lap(8);
     if (!poolLater)
         CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 3));
     else
@@ -1350,6 +1420,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         CHS_CUDA(launch_batch(bp, m->dm, info, m->evt, streams, 2));
     }
     CHS_CUDA(cudaEventRecord(bs.released, st));
+    host_launch_lap(6);
+    hs.lap(7);
     bs.used = true;
     if (m->profiling)
         m->frameTimed = true;
@@ -1494,6 +1566,7 @@ static int create_body(chs_map *m, const chs_config *cfg)
     }
     CHS_CUDA(cudaHostAlloc((void **)&m->hBatchSnap, sizeof(HostBatchSnapshot) * chs_map::kRing, cudaHostAllocPortable | cudaHostAllocMapped));
     std::memset(m->hBatchSnap, 0, sizeof(HostBatchSnapshot) * chs_map::kRing);
+    CHS_CUDA(cudaHostAlloc((void **)&m->hFrameTables, sizeof(FrameParams) * kMaxBatch * chs_map::kRing, cudaHostAllocPortable));
     CHS_CUDA(cudaEventCreateWithFlags(&m->h2dDone, cudaEventDisableTiming));
     m->frameGraph = frame_graph_create();
     for (int i = 0; i < 8; i++)
@@ -1556,6 +1629,7 @@ int chs_destroy(chs_map *m)
     if (m->uploadStream)
         cudaStreamDestroy(m->uploadStream);
     cudaFreeHost(m->hBatchSnap);
+    cudaFreeHost(m->hFrameTables);
     cudaFreeHost(m->hCtr);
     cudaFreeHost(m->hSnap);
     if (m->dCommScratch)

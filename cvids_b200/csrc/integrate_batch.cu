@@ -370,9 +370,9 @@ __device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCo
 // ------------------------------------------------------------------------------------------------------
 // batch_candidates_kernel: which bricks of which chunks can change in which frames of the batch.
 // A warp per tile of the union candidate box:
-//   0. the chunk indices of the tile that THIS RANK OWNS are compacted by ballot (32 x world indices are looked at), so that at
+//   0. the chunk indices of the tile that THIS RANK OWNS are compacted by ballot (8 x world indices are looked at), so that at
 //      N ranks a warp still works on full tiles and the kernel's work divides by N;
-//   1. chunk level. (a) a lane per chunk, frames in a loop, cheap tests only: is the chunk inside frame f's candidate ID box and
+//   1. chunk level. (a) four lanes per chunk, a quarter of the frames each, cheap tests only: is the chunk inside frame f's candidate ID box and
 //      does it pass Frustum::Intersects (ChunkManager.cpp:182-212, exact)? Is it inside the frame's view pyramid at all? The
 //      (chunk, frame) pairs that are go into a queue in shared memory (ballot compaction). (b) a lane per QUEUED PAIR: the
 //      chunk against the frame's Hi-Z tiles. Most pairs end here: behind the surface or in free space with nothing to carve.
@@ -384,21 +384,28 @@ __device__ __forceinline__ int unit_position(const BatchParams &bp, const UnitCo
 //      frame of this batch may create one (the brick kernels check the actual register state before spending the frame);
 //   3. warp-ballot compaction into the unit lists (four cost buckets).
 // Chunk indices go through a multiplicative permutation so that the surviving chunks spread over all warps.
+// Lanes of a pass = (chunk lane & 7, frame group lane >> 3): EIGHT chunks per warp pass, each lane walks a quarter of the frames.
+// (32 chunks per pass, a lane per chunk, left 7 warps per SM on a 35 K chunk union box: the kernel ran at the latency of one
+// warp's chain. Four times the warps, a quarter of the chain each.)
 constexpr int kCandWarps = 4;                       // warps per CTA
-constexpr int kCandList = 32 * 8;                   // owned chunk indices of one tile (32 x min(world, 8) indices are looked at)
+constexpr int kCandChunks = 8;                      // chunks per warp pass
+constexpr int kCandList = kCandChunks * 8;          // owned chunk indices of one tile (8 x min(world, 8) indices are looked at)
 
+#ifndef CHS_CAND_MIN_CTAS
+#define CHS_CAND_MIN_CTAS 8                  // 64 registers: 32 warps per SM, so that a 35 K chunk union box is ONE wave of warps
+#endif
 template <int CS>
-__global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(BatchParams bp, DeviceMap map)
+__global__ void __launch_bounds__(32 * kCandWarps, CHS_CAND_MIN_CTAS) batch_candidates_kernel(BatchParams bp, DeviceMap map)
 {
     constexpr int BPA = CS / 8, NB = BPA * BPA * BPA;
     __shared__ __align__(16) FrameParams sF[kMaxBatch];
     __shared__ float2 sCoarse[kMaxBatch][kCoarseTiles];
     __shared__ int sList[kCandWarps][kCandList];
-    __shared__ unsigned short sPairs[kCandWarps][32 * kMaxBatch];     // (chunk of the pass << 8) | frame: pairs that need the depth test
-    __shared__ unsigned sBandC[kCandWarps][32], sFreeC[kCandWarps][32];
-    // units of a pass (32 chunks x 8 bricks at most), written to the global lists in ONE go: four atomics per pass instead of four
+    __shared__ unsigned short sPairs[kCandWarps][kCandChunks * kMaxBatch];     // (chunk of the pass << 8) | frame: pairs that need the depth test
+    __shared__ unsigned sBandC[kCandWarps][kCandChunks], sFreeC[kCandWarps][kCandChunks];
+    // units of a pass (8 chunks x 8 bricks at most), written to the global lists in ONE go: four atomics per pass instead of four
     // per surviving chunk (the warp waits for their round trip)
-    __shared__ int4 sUnits[kCandWarps][NB == 8 ? 256 : 1];
+    __shared__ int4 sUnits[kCandWarps][NB == 8 ? kCandChunks * 8 : 1];
     pdl_launch_dependents();                       // the brick kernel may start launching: it waits (pdl_wait) before it reads the unit lists
     load_frames(sF, bp);                           // the frame table was uploaded before the Hi-Z kernel: complete
     pdl_wait();                                    // the Hi-Z kernel's output is read from here on
@@ -456,8 +463,10 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
     const int warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
     const int world = map.world > 1 ? map.world : 1;
-    const int tileSize = 32 * (world < 8 ? world : 8);                // indices per tile: about 32 of them are owned
-    const int rounds = tileSize / 32;
+    const int tileSize = kCandChunks * (world < 8 ? world : 8);       // indices per tile: about 8 of them are owned
+    const int rounds = (tileSize + 31) / 32;
+    const int cl = (int)lane & (kCandChunks - 1), fg = (int)lane / kCandChunks;      // chunk of the pass, frame group
+    constexpr int kGroups = 32 / kCandChunks;
     const int nTiles = (total + tileSize - 1) / tileSize;
     const bool carve = sF[0].carve != 0;
     const float ext = __fmul_rn((float)CS, map.res);
@@ -468,10 +477,11 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
         int nList = 0;
         for (int r = 0; r < rounds; r++)
         {
-            const int slotIdx = tile * tileSize + r * 32 + (int)lane;
+            const int inTile = r * 32 + (int)lane;
+            const int slotIdx = tile * tileSize + inTile;
             bool own = false;
             int i = 0;
-            if (slotIdx < total)
+            if (inTile < tileSize && slotIdx < total)
             {
                 i = (int)(((long long)slotIdx * bp.cand_stride) % total);
                 own = true;
@@ -487,15 +497,15 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             nList += __popc(m);
         }
         __syncwarp();
-        for (int base = 0; base < nList; base += 32)
+        for (int base = 0; base < nList; base += kCandChunks)
         {
-            const bool have = base + (int)lane < nList;
+            const bool have = base + cl < nList;
             int x = 0, y = 0, z = 0;
             float bx = 0.0f, by = 0.0f, bz = 0.0f;
             unsigned candM = 0u;
             if (have)
             {
-                const int i = sList[warp][base + lane];
+                const int i = sList[warp][base + cl];
                 x = bp.lo[0] + i / nyz;
                 const int r = i - (i / nyz) * nyz;
                 y = bp.lo[1] + r / bp.n[2];
@@ -505,26 +515,30 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
                 by = __fmul_rn((float)(y * CS), map.res);
                 bz = __fmul_rn((float)(z * CS), map.res);
             }
-            sBandC[warp][lane] = 0u;
-            sFreeC[warp][lane] = 0u;
-            // 1a. chunk level, cheap part, a lane per chunk and all frames: candidate of the frame (exact)? inside its view pyramid?
-            // The (chunk, frame) pairs that are go into the warp's queue.
+            if (lane < kCandChunks)
+            {
+                sBandC[warp][lane] = 0u;
+                sFreeC[warp][lane] = 0u;
+            }
+            // 1a. chunk level, cheap part, four lanes per chunk with a quarter of the frames each: candidate of the frame (exact)?
+            // inside its view pyramid? The (chunk, frame) pairs that are go into the warp's queue.
             int qn = 0;
             {
                 const float ex = __fadd_rn(bx, ext), ey = __fadd_rn(by, ext), ez = __fadd_rn(bz, ext);
-                for (int f = 0; f < K; f++)
+                for (int f0 = 0; f0 < K; f0 += kGroups)
                 {
-                    const FrameParams &fp = sF[f];
+                    const int f = f0 + fg;
+                    const FrameParams &fp = sF[f < K ? f : 0];
                     bool vis = false;
-                    if (have && (unsigned)(x - fp.lo[0]) < (unsigned)fp.n[0] && (unsigned)(y - fp.lo[1]) < (unsigned)fp.n[1] && (unsigned)(z - fp.lo[2]) < (unsigned)fp.n[2] &&
-                        frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
+                    if (have && f < K && (unsigned)(x - fp.lo[0]) < (unsigned)fp.n[0] && (unsigned)(y - fp.lo[1]) < (unsigned)fp.n[1] &&
+                        (unsigned)(z - fp.lo[2]) < (unsigned)fp.n[2] && frustum_intersects_exact(fp, bx, by, bz, ex, ey, ez))
                     {
                         candM |= 1u << f;
                         vis = !box_outside_view(fp, bx + map.half, by + map.half, bz + map.half, (float)(CS - 1) * map.res);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, vis);
                     if (vis)
-                        sPairs[warp][qn + __popc(m & below)] = (unsigned short)((lane << 8) | (unsigned)f);
+                        sPairs[warp][qn + __popc(m & below)] = (unsigned short)(((unsigned)cl << 8) | (unsigned)f);
                     qn += __popc(m);
                 }
             }
@@ -535,19 +549,19 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
                 if (q0 + (int)lane < qn)
                 {
                     const unsigned pr = sPairs[warp][q0 + lane];
-                    const int cl = (int)(pr >> 8), f = (int)(pr & 255u);
-                    const int i = sList[warp][base + cl];
+                    const int pc = (int)(pr >> 8), f = (int)(pr & 255u);
+                    const int i = sList[warp][base + pc];
                     const int px = bp.lo[0] + i / nyz, r = i - (i / nyz) * nyz, py = bp.lo[1] + r / bp.n[2], pz = bp.lo[2] + r % bp.n[2];
                     const int code = classify_box_depth<true>(sF[f], __fmul_rn((float)(px * CS), map.res) + map.half, __fmul_rn((float)(py * CS), map.res) + map.half,
                                                               __fmul_rn((float)(pz * CS), map.res) + map.half, (float)(CS - 1) * map.res);
                     if (code == 2)
-                        atomicOr(&sBandC[warp][cl], 1u << f);
+                        atomicOr(&sBandC[warp][pc], 1u << f);
                     else if (code == 1)
-                        atomicOr(&sFreeC[warp][cl], 1u << f);
+                        atomicOr(&sFreeC[warp][pc], 1u << f);
                 }
             }
             __syncwarp();
-            const unsigned chunkBand = sBandC[warp][lane], chunkFree = sFreeC[warp][lane];
+            const unsigned chunkBand = sBandC[warp][cl], chunkFree = sFreeC[warp][cl];
             __syncwarp();
             // per-frame candidate counts: lane f of the warp accumulates frame f
             for (int f = 0; f < K; f++)
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             // without chunks, and a chunk that does not exist only matters if some frame may hit it.
             int slot = -1;
             unsigned long long flags = 0ull;
-            if (chunkBand || (chunkFree && carve))
+            if (fg == 0 && (chunkBand || (chunkFree && carve)))
             {
                 slot = hash_lookup(map, pack_id(x, y, z));
                 // the flags also matter when the chunk as a whole is in the band of a frame: single bricks of it may still lie in
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) batch_candidates_kernel(Batch
             // after a band frame of this batch (which may create one)
             const unsigned freeTodo = (carve && (chunkBand || (slot >= 0 && flags != 0ull))) ? chunkFree : 0u;
             // 2. brick level: the warp takes the surviving chunks one at a time
-            unsigned surv = __ballot_sync(0xffffffffu, (chunkBand | freeTodo) != 0u);
+            unsigned surv = __ballot_sync(0xffffffffu, fg == 0 && (chunkBand | freeTodo) != 0u);
             int nUnits = 0;
             while (surv)
             {
@@ -1775,22 +1789,28 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 template <int CS, bool COLOR_PATH, bool PER_PIXEL>
 static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
 {
-    static int residentBricks = 0;
-    if (!residentBricks)
-        residentBricks = batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, CHS_BRICK_THREADS);
+    host_launch_lap(9);
+    // (the occupancy query costs 15 us of host time: once per kernel variant, whatever it answers)
+    static int residentBricks = -1;
+    if (residentBricks < 0)
+        residentBricks = std::max(1, batch_resident(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, CHS_BRICK_THREADS));
+    host_launch_lap(10);
     constexpr long long NB = (CS / 8) * (CS / 8) * (CS / 8);
-    // a warp per tile of 32 chunk indices (at N ranks: 32 x N indices, about 32 of them owned)
-    const long long candTiles = (info.unionCandidates + 31) / 32;
-    const unsigned gCand = (unsigned)std::max(1ll, std::min<long long>((candTiles + kCandWarps - 1) / kCandWarps, 148 * 8));
+    // a warp per tile of 8 chunk indices (at N ranks: 8 x N indices, about 8 of them owned)
+    const long long tileIdx = kCandChunks * std::min(std::max(map.world, 1), 8);
+    const long long candTiles = (info.unionCandidates + tileIdx - 1) / tileIdx;
+    const unsigned gCand = (unsigned)std::max(1ll, std::min<long long>((candTiles + kCandWarps - 1) / kCandWarps, 148 * 2 * CHS_CAND_MIN_CTAS));
     const unsigned gBricks = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_BRICK_THREADS / 32 - 1) / (CHS_BRICK_THREADS / 32), residentBricks));
     static_assert(CHS_BRICK_THREADS % 32 == 0, "whole warps");
     bp.total_ctas = (int)gBricks;
     cudaStream_t st = bs.main;
     cudaError_t e;
+    host_launch_lap(11);
     if (phases & 1)
     {
     if (info.profiling && (e = cudaEventRecord(evt[0], bs.prep)) != cudaSuccess)
         return e;
+    host_launch_lap(7);
     const int tilesX = (info.W + 63) / 64, tiles = tilesX * ((info.H + 63) / 64);
     const int packBlocks = info.colorPath ? std::max(1, std::min(148, (info.cW * info.cH / 4 + 255) / 256)) : 0;
     if (packBlocks && bs.pack != bs.prep)
@@ -1802,6 +1822,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         if ((e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
             return e;
     }
+    host_launch_lap(0);
     const int hizFirst = info.hizCount > 0 ? info.hizFirst : 0, hizCount = info.hizCount > 0 ? info.hizCount : bp.K;
     if (info.hizTma)
     {
@@ -1817,6 +1838,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     }
     else
         batch_hiz_kernel<<<dim3(tiles, hizCount), 256, 0, bs.prep>>>(bp, map, tilesX, hizFirst);
+    host_launch_lap(1);
     if (info.afterHiz && info.afterHiz(info.afterHizCtx) != 0)
         return cudaErrorUnknown;
     if (info.profiling && (e = cudaEventRecord(evt[1], bs.prep)) != cudaSuccess)
@@ -1829,22 +1851,25 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
         if (bs.pack != st && (e = cudaEventRecord(bs.packed, bs.pack)) != cudaSuccess)
             return e;
     }
+    host_launch_lap(2);
     if ((e = launch_pdl(batch_candidates_kernel<CS>, dim3(gCand), dim3(32 * kCandWarps), 0, st, bp, map)) != cudaSuccess)
         return e;
+    host_launch_lap(3);
     if (info.profiling && (e = cudaEventRecord(evt[2], st)) != cudaSuccess)
         return e;
     if (packBlocks && bs.pack != st && (e = cudaStreamWaitEvent(st, bs.packed, 0)) != cudaSuccess)
         return e;
     }
+    host_launch_lap(4);
     if (!(phases & 2))
         return cudaGetLastError();
     if (info.profiling && (e = cudaEventRecord(evt[7], st)) != cudaSuccess)
         return e;
     if (!PER_PIXEL && info.fastBricks)
     {
-        static int residentFast = 0;
-        if (!residentFast)
-            residentFast = batch_resident(batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH>, CHS_FAST_THREADS);
+        static int residentFast = -1;
+        if (residentFast < 0)
+            residentFast = std::max(1, batch_resident(batch_bricks_fast_kernel<CS, COLOR_PATH, COLOR_PATH>, CHS_FAST_THREADS));
         const unsigned gFast = (unsigned)std::max(1ll, std::min<long long>((info.unionCandidates * NB * kParts + CHS_FAST_THREADS / 32 - 1) / (CHS_FAST_THREADS / 32), residentFast));
         bp.total_ctas = (int)gFast;
         if (COLOR_PATH && map.use_color)
@@ -1854,6 +1879,7 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     }
     else
         e = launch_pdl(batch_bricks_kernel<CS, COLOR_PATH, PER_PIXEL>, dim3(gBricks), dim3(CHS_BRICK_THREADS), 0, st, bp, map);
+    host_launch_lap(5);
     if (e != cudaSuccess)
         return e;
     if (info.profiling && (e = cudaEventRecord(evt[3], st)) != cudaSuccess)

@@ -145,6 +145,9 @@ struct BatchLaunchInfo
 // colour packing kernel (only the brick kernel reads its output) runs on `pack` BESIDE the candidates kernel and records
 // `packed`, which the brick kernel waits for. pack == prep: it simply follows the Hi-Z kernel there (host frames: both follow
 // the copies on the copy stream). pack != prep (device frames, prep == main): forked from `main` with `fork`.
+// CHS_HOST_PROFILE: laps inside launch_batch (capi.cu); i < 0 restarts the clock
+void host_launch_lap(int i);
+
 struct BatchStreams
 {
     cudaStream_t prep, pack, main;
