@@ -27,6 +27,7 @@
 #include "device_map.cuh"
 #include "host_geometry.h"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace chs
 {
@@ -230,8 +231,8 @@ struct chs_map
     struct PeerArena
     {
         char *base = nullptr;                  // cudaMalloc: [header 4 KB][set 0][set 1][set 2]
-        size_t setBytes = 0, depthOff = 0, mmOff = 0, colorOff = 0;    // layout of a set
-        size_t depthCap = 0, mmCap = 0, colorCap = 0;                  // bytes per set
+        size_t setBytes = 0, depthOff = 0, mmOff = 0, colorOff = 0, hizOff = 0;    // layout of a set
+        size_t depthCap = 0, mmCap = 0, colorCap = 0, hizCap = 0;      // bytes per set
         char *peer[kMaxPeers] = {};            // the arenas of all ranks as mapped here (peer[rank] == base)
         bool tried = false, ok = false;
         unsigned step = 0;                     // distributed steps pushed so far (the same number on every rank)
@@ -752,6 +753,24 @@ static size_t hiz_tiles(const chs_camera *cam)
     return total;
 }
 
+// The Hi-Z levels >= 4 of a frame fit the candidates kernel's shared memory (then the TMA Hi-Z kernel, which stops at level 3, can be used).
+static bool hiz_coarse_fits(const chs_camera *cam)
+{
+    int levels = kHizLevels, coarse = 0;
+    for (int l = 0; l < kHizLevels; l++)
+    {
+        const int tile = 8 << l, w = (cam->width + tile - 1) / tile, h = (cam->height + tile - 1) / tile;
+        if (l >= 3 && w <= 3 && h <= 3 && levels == kHizLevels)
+            levels = l + 1;
+    }
+    for (int l = 4; l < levels; l++)
+    {
+        const int tile = 8 << l;
+        coarse += ((cam->width + tile - 1) / tile) * ((cam->height + tile - 1) / tile);
+    }
+    return coarse <= 48;
+}
+
 // Everything of FrameParams except the image pointers, the work lists and the ids.
 static void fill_frame_params(chs_map *m, const chs_integrator *integ, const float pose[12], const chs_camera *cam, const float cpose[12],
                               const chs_camera *ccam, bool colorPath, int channels, const FramePlan &pl, float2 *hizBase, FrameParams *out)
@@ -957,9 +976,9 @@ struct PushSeg
     const void *src;
     unsigned long long dst_off, bytes;         // destination offset inside an arena
 };
-static int ensure_peer_arena(chs_map *m, size_t depthBytes, size_t mmBytes, size_t colorBytes);
-static int peer_push(chs_map *m, const PushSeg *segs, int nSeg, cudaStream_t cs);
-static int peer_wait(chs_map *m, cudaStream_t st, unsigned long long *timeline);
+static int ensure_peer_arena(chs_map *m, size_t depthBytes, size_t mmBytes, size_t colorBytes, size_t hizBytes);
+static int peer_push(chs_map *m, const PushSeg *segs, int nSeg, cudaStream_t cs, bool raiseFlags);
+static int peer_wait(chs_map *m, cudaStream_t st, unsigned long long *timeline, bool hizStamps);
 static void release_peer_arena(chs_map *m);
 static int world_any_mm(chs_map *m, bool *anyMm);
 
@@ -1076,10 +1095,17 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     if (dist && m->cfg.world > 1)
     {
         if ((rc = ensure_peer_arena(m, anyMm ? 0 : npx * sizeof(float) * kMaxBatch, anyMm ? npx * sizeof(uint16_t) * kMaxBatch : 0,
-                                    colorPath ? cpx * channels * kMaxBatch : 0)))
+                                    colorPath ? cpx * channels * kMaxBatch : 0, tiles * kMaxBatch * sizeof(float2))))
             return rc;
         push = m->arena.ok;
     }
+    // Device frames over the peer-memory exchange, opt-in (CHS_SHARD_HIZ_PUSH=1): the Hi-Z pyramids are built rank by rank, each
+    // rank those of the frames it ingests, and stored into every arena behind the frames (conditions of the TMA Hi-Z kernel: float
+    // depth, constant truncator). Measured on 2 B200s: the push stream then carries push + Hi-Z of every
+    // step back to back and becomes the longest chain of the step (127 us vs 79 us) -- off by default until the push is faster.
+    static const bool shardHizOn = std::getenv("CHS_SHARD_HIZ_PUSH") != nullptr;
+    const bool shardHiz = shardHizOn && push && devSrc && !perPixel && !anyMm && (cam->width % 4) == 0 && hiz_coarse_fits(cam) &&
+                          std::getenv("CHS_NO_TMA_HIZ") == nullptr;
     char *const pushSet = push ? m->arena.base + 4096 + (size_t)((m->arena.step + 1) % chs_map::kArenaSets) * m->arena.setBytes : nullptr;
     const int setIdx = (m->batchId + 1) & 1;
     chs_map::BatchSet &bs = m->bset[setIdx];
@@ -1123,7 +1149,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             if (colorPath)
                 segs[nSeg++] = PushSeg{bs.color + cBytes * locFirst, cOff + cBytes * locFirst, cBytes * n};
         }
-        return peer_push(m, segs, nSeg, direct ? m->pushStream : cs);
+        return peer_push(m, segs, nSeg, direct ? m->pushStream : cs, !shardHiz);
     };
     if (direct && (rc = push_frames()))
         return rc;
@@ -1162,7 +1188,8 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
     for (int f = 0; f < K; f++)
     {
         FrameParams &fp = fps[f];
-        fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f], bs.hiz + tiles * f, &fp);
+        fill_frame_params(m, integ, frames[f].pose, cam, frames[f].color_pose, ccam, colorPath, channels, pl[f],
+                          shardHiz ? reinterpret_cast<float2 *>(pushSet + m->arena.hizOff) + tiles * f : bs.hiz + tiles * f, &fp);
         fp.hiz_ticket = m->dHizTickets + setIdx * kMaxBatch + f;
         if (dist ? anyMm : frames[f].depth_mm != nullptr)
         {
@@ -1250,6 +1277,40 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         FrameParams *slot = m->hFrameTables + (size_t)m->frameTableNext * kMaxBatch;
         m->frameTableNext = (m->frameTableNext + 1) % chs_map::kRing;
         std::memcpy(slot, fps, sizeof(FrameParams) * K);
+        if (shardHiz)
+        {
+            // this rank's Hi-Z kernel follows its push at once, on the push stream -- a step ahead of the kernels that consume the
+            // pyramids -- and raises the rank's arrived word everywhere. What it needs of the frames travels in its parameters.
+            HizPeers hp{};
+            for (int d = 0; d < m->cfg.world; d++)
+            {
+                hp.delta[d] = (long long)(m->arena.peer[d] - m->arena.base);
+                hp.flag[d] = reinterpret_cast<unsigned *>(m->arena.peer[d]) + m->cfg.rank;
+            }
+            hp.hdr = reinterpret_cast<unsigned *>(m->arena.base);
+            hp.world = m->cfg.world;
+            hp.rank = m->cfg.rank;
+            hp.step = m->arena.step;
+            hp.stamp_slot = (int)(m->arena.step % chs_map::kArenaSets);
+            hp.depth0 = reinterpret_cast<const float *>(pushSet + m->arena.depthOff);
+            hp.hiz0 = reinterpret_cast<float2 *>(pushSet + m->arena.hizOff);
+            hp.npx = (long long)npx;
+            hp.tiles_per_frame = (long long)tiles;
+            for (int l = 0; l < 4; l++)
+            {
+                hp.level_off[l] = (int)(fps[0].hiz[l] - fps[0].hiz[0]);
+                hp.hizW[l] = fps[0].hizW[l];
+                hp.hizH[l] = fps[0].hizH[l];
+            }
+            hp.W = cam->width;
+            hp.H = cam->height;
+            hp.carve = fps[0].carve;
+            hp.cutoff = fps[0].depth_cutoff;
+            hp.trunc = fps[0].trunc_param;
+            hp.diag = fps[0].diag;
+            hp.carve_dist = fps[0].carve_dist;
+            CHS_CUDA(launch_hiz_sharded(locFirst, locEnd - locFirst, hp, m->pushStream));
+        }
         CHS_CUDA(cudaMemcpyAsync(bs.dFrames, slot, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
     }
     hs.lap(5);
@@ -1378,7 +1439,16 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         {
             // the other ranks' pushes of this step have landed (flag words in this rank's arena, written behind the data): Hi-Z and
             // colour packing follow on the copy stream, i.e. beside the kernels of the previous step, as for one rank
-            if ((rc = peer_wait(m, cs, m->timeline ? bs.dTimeline : nullptr)))
+            if (shardHiz)
+            {
+                // ... and so have the pyramids: only the frame table went over the copy stream
+                CHS_CUDA(cudaEventRecord(bs.prepared, cs));
+                CHS_CUDA(cudaStreamWaitEvent(st, bs.prepared, 0));
+                streams.prep = st;
+                streams.pack = st;
+                info.skipHiz = true;
+            }
+            if ((rc = peer_wait(m, shardHiz ? st : cs, m->timeline ? bs.dTimeline : nullptr, shardHiz)))
                 return rc;
             bp.peer_done = reinterpret_cast<unsigned *const *>(m->arena.base + 1024);
             bp.peer_world = m->cfg.world;

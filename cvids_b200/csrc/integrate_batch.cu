@@ -30,6 +30,7 @@
 #include "device_map.cuh"
 #include "integrate_device.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace chs
 {
@@ -112,12 +113,6 @@ __device__ __forceinline__ void load_frames(FrameParams *sF, const BatchParams &
 // grid = (64x64 pixel tiles, K): Hi-Z levels (+ per-pixel truncation, millimetre conversion) of every frame of the batch
 __global__ void __launch_bounds__(256) batch_hiz_kernel(BatchParams bp, DeviceMap map, int tilesX, int frameBase)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0)
-    {
-        int *c = reinterpret_cast<int *>(bp.bctr);
-        for (int i = threadIdx.x; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
-            c[i] = 0;
-    }
     tl_start(bp, kTlHizStart);
     const FrameParams &fp = bp.frames[frameBase + blockIdx.y];
     frame_prepare_tile(fp, blockIdx.x % tilesX, blockIdx.x / tilesX);
@@ -143,42 +138,31 @@ constexpr int kHizPitch = 68;                          // floats per shared row:
 constexpr int kHizThreads = 256;
 constexpr size_t kHizSmem = (size_t)kHizStages * 64 * kHizPitch * sizeof(float);
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+// PEERS: sharded Hi-Z of a distributed step -- every tile is stored into the arena of every rank (HizPeers), the last CTA raises
+// this rank's arrived word everywhere. The kernel then runs on the push stream, possibly a whole step ahead: it touches neither
+// the batch counters nor the timeline words of a staging set.
+template <bool PEERS>
+__device__ __forceinline__ void hiz_store(float2 *p, float2 v, const HizPeers &hp)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)), "l"(srcGlobal),
-                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    if (!PEERS)
+        *p = v;
+    else
+        for (int d = 0; d < hp.world; d++)
+            *reinterpret_cast<float2 *>(reinterpret_cast<char *>(p) + hp.delta[d]) = v;
 }
 
-__global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams bp, int tilesX, int tilesPerFrame, int nItems, int frameBase)
+template <bool PEERS>
+__global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams bp, int tilesX, int tilesPerFrame, int nItems, int frameBase, const __grid_constant__ HizPeers hp)
 {
     extern __shared__ __align__(128) unsigned char hizSmem[];
     float *stage = reinterpret_cast<float *>(hizSmem);
     __shared__ __align__(8) unsigned long long full[kHizStages];
     __shared__ float2 s0[64], s1[16], s2[4];
     const int t = threadIdx.x, lane = t & 31;
-    tl_start(bp, kTlHizStart);
-    if (blockIdx.x == 0)
-    {
-        int *c = reinterpret_cast<int *>(bp.bctr);
-        for (int i = t; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
-            c[i] = 0;
-    }
+    if (!PEERS)
+        tl_start(bp, kTlHizStart);
+    else if (blockIdx.x == 0 && t == 0)
+        reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(hp.hdr) + 2048)[8 + 2 * hp.stamp_slot] = global_timer_ns();
     if (t == 0)
     {
         for (int s = 0; s < kHizStages; s++)
@@ -188,16 +172,25 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     __syncthreads();
     const int nMine = ((int)blockIdx.x < nItems) ? (nItems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     // what the arithmetic needs of a frame is the same for all frames of a batch (one integrator, one camera)
-    const FrameParams &f0 = bp.frames[0];
-    const int W = f0.cam.W, H = f0.cam.H;
-    const float cutoff = f0.depth_cutoff, tr = f0.trunc_param, diag = f0.diag, carveDist = f0.carve_dist;
-    const int carve = f0.carve;
-    const int hw0 = f0.hizW[0], hh0 = f0.hizH[0], hw1 = f0.hizW[1], hh1 = f0.hizH[1], hw2 = f0.hizW[2], hh2 = f0.hizH[2], hw3 = f0.hizW[3];
+    int W, H, carve, hw0, hh0, hw1, hh1, hw2, hh2, hw3;
+    float cutoff, tr, diag, carveDist;
+    if (PEERS)
+    {
+        W = hp.W; H = hp.H; carve = hp.carve; cutoff = hp.cutoff; tr = hp.trunc; diag = hp.diag; carveDist = hp.carve_dist;
+        hw0 = hp.hizW[0]; hh0 = hp.hizH[0]; hw1 = hp.hizW[1]; hh1 = hp.hizH[1]; hw2 = hp.hizW[2]; hh2 = hp.hizH[2]; hw3 = hp.hizW[3];
+    }
+    else
+    {
+        const FrameParams &f0 = bp.frames[0];
+        W = f0.cam.W; H = f0.cam.H; carve = f0.carve; cutoff = f0.depth_cutoff; tr = f0.trunc_param; diag = f0.diag; carveDist = f0.carve_dist;
+        hw0 = f0.hizW[0]; hh0 = f0.hizH[0]; hw1 = f0.hizW[1]; hh1 = f0.hizH[1]; hw2 = f0.hizW[2]; hh2 = f0.hizH[2]; hw3 = f0.hizW[3];
+    }
     // warp 0 issues the row copies of item j into stage s: lane r rows r and r + 32
     auto issue = [&](int j, int s)
     {
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
-        const float *depth = bp.frames[frameBase + item / tilesPerFrame].depth;
+        const int fr = frameBase + item / tilesPerFrame;
+        const float *depth = PEERS ? hp.depth0 + (size_t)fr * hp.npx : bp.frames[fr].depth;
         const int tile = item % tilesPerFrame, x0 = (tile % tilesX) * 64, y0 = (tile / tilesX) * 64;
         const unsigned rowBytes = (unsigned)min(64, W - x0) * 4u;
         const int nRows = min(64, H - y0);
@@ -216,8 +209,18 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
     {
         const int s = j % kHizStages;
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
-        const FrameParams &fp = bp.frames[frameBase + item / tilesPerFrame];
-        float2 *const h0 = fp.hiz[0], *const h1 = fp.hiz[1], *const h2 = fp.hiz[2], *const h3 = fp.hiz[3];
+        const int fr = frameBase + item / tilesPerFrame;
+        float2 *h0, *h1, *h2, *h3;
+        if (PEERS)
+        {
+            float2 *base = hp.hiz0 + (size_t)fr * hp.tiles_per_frame;
+            h0 = base + hp.level_off[0]; h1 = base + hp.level_off[1]; h2 = base + hp.level_off[2]; h3 = base + hp.level_off[3];
+        }
+        else
+        {
+            const FrameParams &fp = bp.frames[fr];
+            h0 = fp.hiz[0]; h1 = fp.hiz[1]; h2 = fp.hiz[2]; h3 = fp.hiz[3];
+        }
         const int tile = item % tilesPerFrame, bx = tile % tilesX, by = tile / tilesX;
         mbar_wait(&full[s], (unsigned)(j / kHizStages) & 1u);
         const float *src = stage + (size_t)s * 64 * kHizPitch;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             const float2 v = hiz_apply_band(lo, hi, tr, diag, carve, carveDist);
             s0[tile8] = v;
             if (tx < hw0 && ty < hh0)
-                h0[ty * hw0 + tx] = v;
+                hiz_store<PEERS>(h0 + ty * hw0 + tx, v, hp);
         }
         __syncthreads();                                    // also: every thread is done reading the stage
         if (t < 32 && j + kHizStages < nMine)
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             s1[t] = v;
             const int gx = bx * 4 + ax, gy = by * 4 + ay;
             if (gx < hw1 && gy < hh1)
-                h1[gy * hw1 + gx] = v;
+                hiz_store<PEERS>(h1 + gy * hw1 + gx, v, hp);
         }
         __syncthreads();
         if (t < 4)
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
             s2[t] = v;
             const int gx = bx * 2 + ax, gy = by * 2 + ay;
             if (gx < hw2 && gy < hh2)
-                h2[gy * hw2 + gx] = v;
+                hiz_store<PEERS>(h2 + gy * hw2 + gx, v, hp);
             if (t == 0)
             {
                 // level 3 from the four level-2 values of this thread's neighbours: recomputed from s1 to save a barrier
@@ -288,11 +291,31 @@ __global__ void __launch_bounds__(kHizThreads) batch_hiz_tma_kernel(BatchParams 
                     mn = fminf(mn, s1[i].x);
                     mx = fmaxf(mx, s1[i].y);
                 }
-                h3[by * hw3 + bx] = make_float2(mn, mx);
+                hiz_store<PEERS>(h3 + by * hw3 + bx, make_float2(mn, mx), hp);
             }
         }
     }
-    tl_end(bp, kTlHizEnd);
+    if (!PEERS)
+    {
+        tl_end(bp, kTlHizEnd);
+        return;
+    }
+    // every tile is out (system-scope fence per thread); the last CTA raises this rank's word in every arena
+    __threadfence_system();
+    __shared__ int sLast;
+    __syncthreads();
+    if (t == 0)
+        sLast = atomicAdd(hp.hdr + 129, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!sLast)
+        return;
+    __threadfence_system();
+    if (t == 0)
+        hp.hdr[129] = 0u;
+    if (t < hp.world)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hp.flag[t]), "r"(hp.step) : "memory");
+    if (t == 0)
+        reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(hp.hdr) + 2048)[9 + 2 * hp.stamp_slot] = global_timer_ns();
 }
 
 // Emit the unit of brick b of chunk (x, y, z): `active` lanes hold one brick each. Free-space frames can only carve: the brick must
@@ -887,6 +910,11 @@ __device__ __forceinline__ void batch_snapshot(const BatchParams &bp, const Devi
     volatile int *dst = reinterpret_cast<volatile int *>(h);
     for (int i = t; i < (int)(sizeof(HostBatchSnapshot) / 4); i += blockDim.x)
         dst[i] = src[i];
+    // the counters of this staging set start from zero in the batch after next (nobody else is running: this is the last CTA)
+    __syncthreads();
+    int *cz = reinterpret_cast<int *>(bp.bctr);
+    for (int i = t; i < (int)(sizeof(BatchCounters) / 4); i += blockDim.x)
+        cz[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1824,17 +1852,21 @@ static cudaError_t launch_batch_variant(BatchParams bp, const DeviceMap &map, co
     }
     host_launch_lap(0);
     const int hizFirst = info.hizCount > 0 ? info.hizFirst : 0, hizCount = info.hizCount > 0 ? info.hizCount : bp.K;
-    if (info.hizTma)
+    if (info.skipHiz)
+    {
+        // the pyramids of this step were built rank by rank and have arrived through the exchange arenas
+    }
+    else if (info.hizTma)
     {
         static bool attr = false;
         if (!attr)
         {
-            if ((e = cudaFuncSetAttribute(batch_hiz_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHizSmem)) != cudaSuccess)
+            if ((e = cudaFuncSetAttribute(batch_hiz_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHizSmem)) != cudaSuccess)
                 return e;
             attr = true;
         }
         const int nItems = tiles * hizCount;
-        batch_hiz_tma_kernel<<<std::min(nItems, 148 * 4), kHizThreads, kHizSmem, bs.prep>>>(bp, tilesX, tiles, nItems, hizFirst);
+        batch_hiz_tma_kernel<false><<<std::min(nItems, 148 * 4), kHizThreads, kHizSmem, bs.prep>>>(bp, tilesX, tiles, nItems, hizFirst, HizPeers{});
     }
     else
         batch_hiz_kernel<<<dim3(tiles, hizCount), 256, 0, bs.prep>>>(bp, map, tilesX, hizFirst);
@@ -1895,6 +1927,24 @@ static cudaError_t launch_batch_cs(const BatchParams &bp, const DeviceMap &map, 
                              : launch_batch_variant<CS, true, false>(bp, map, info, evt, bs, phases);
     return info.perPixel ? launch_batch_variant<CS, false, true>(bp, map, info, evt, bs, phases)
                          : launch_batch_variant<CS, false, false>(bp, map, info, evt, bs, phases);
+}
+
+cudaError_t launch_hiz_sharded(int first, int count, const HizPeers &hp, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(batch_hiz_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHizSmem);
+        if (e != cudaSuccess)
+            return e;
+        attr = true;
+    }
+    const int tilesX = (hp.W + 63) / 64, tiles = tilesX * ((hp.H + 63) / 64);
+    const int nItems = tiles * count;
+    // beside the brick kernel of an earlier step only the SMs that kernel leaves idle are free: a small grid is enough, the
+    // kernel has a whole step of slack
+    batch_hiz_tma_kernel<true><<<std::min(nItems, 148 * 2), kHizThreads, kHizSmem, st>>>(BatchParams{}, tilesX, tiles, nItems, first, hp);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)

@@ -138,6 +138,7 @@ struct BatchLaunchInfo
     int (*afterHiz)(void *);        // called right after the Hi-Z kernel has been enqueued on the prepare stream (or nullptr)
     void *afterHizCtx;
     bool hizTma;                    // Hi-Z by the TMA bulk-copy kernel (float depth, constant truncator, aligned rows)
+    bool skipHiz;                   // the pyramids of this step arrive through the exchange arenas (launch_hiz_sharded on every rank)
     bool fastBricks;                // every frame satisfies the preconditions of batch_bricks_fast_kernel (brick_frames is filled)
     const BrickFrames *brickFrames; // host pointer; copied into the kernel's parameter block
 };
@@ -147,6 +148,30 @@ struct BatchLaunchInfo
 // the copies on the copy stream). pack != prep (device frames, prep == main): forked from `main` with `fork`.
 // CHS_HOST_PROFILE: laps inside launch_batch (capi.cu); i < 0 restarts the clock
 void host_launch_lap(int i);
+
+// Sharded Hi-Z of a distributed step (peer-memory exchange): a rank builds the pyramids of the frames IT ingests and stores every
+// tile into the exchange arena of every rank; its last CTA then raises the rank's "arrived" word everywhere.
+constexpr int kMaxPeersDev = 16;
+struct HizPeers
+{
+    long long delta[kMaxPeersDev];  // byte distance from this rank's arena to rank d's, as mapped here (0 for the rank itself)
+    unsigned *flag[kMaxPeersDev];   // this rank's arrived word in rank d's arena
+    unsigned *hdr;                  // this rank's arena header: ticket word [129], stamps at byte 2048
+    int world, rank;
+    unsigned step;
+    int stamp_slot;                 // which pair of stamps (the step's staging set)
+    // what the kernel needs of the frames, by value (it runs before the step's frame table is on the device): frame f's image is
+    // depth0 + f * npx, level l of its pyramid hiz0 + f * tiles_per_frame + level_off[l]
+    const float *depth0;
+    float2 *hiz0;
+    long long npx, tiles_per_frame;
+    int level_off[4], hizW[4], hizH[4];
+    int W, H, carve;
+    float cutoff, trunc, diag, carve_dist;
+};
+
+// Sharded Hi-Z (see HizPeers): pyramids of the frames [first, first + count) of the table `frames`, on stream st.
+cudaError_t launch_hiz_sharded(int first, int count, const HizPeers &hp, cudaStream_t st);
 
 struct BatchStreams
 {
