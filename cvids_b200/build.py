@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libchisel_b200.so")
-SOURCES = ["capi.cu", "integrate.cu", "integrate_batch.cu", "mesh.cu"]
+SOURCES = ["capi.cu", "integrate.cu", "integrate_batch_half.cu", "integrate_batch_quarter.cu", "mesh.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

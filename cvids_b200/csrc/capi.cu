@@ -161,7 +161,7 @@ struct chs_map
     long long knownChunks = 0, knownDirty = 0;
     HostSnapshot lastFrame{};
     bool haveFrame = false;
-    // fused multi-frame path (integrate_batch.cu)
+    // fused multi-frame path (integrate_batch_impl.cuh)
     // Two staging sets, used alternately: while the kernels of batch i read set i & 1 on the map's stream, the H2D copies and
     // the prepare kernel of batch i + 1 fill the other set on the copy stream.
     struct BatchSet
@@ -984,7 +984,7 @@ static int world_any_mm(chs_map *m, bool *anyMm);
 
 // ---------------------------------------------------------------------------------------------------------
 // chs_integrate_batch: n consecutive frames of one sensor stream (same image size, intrinsics and integrator). Sub-batches of
-// up to kMaxBatch frames go through the fused kernels (integrate_batch.cu); the map afterwards is bit-identical to n calls of
+// up to kMaxBatch frames go through the fused kernels (integrate_batch_impl.cuh); the map afterwards is bit-identical to n calls of
 // chs_integrate_depth[_color] in order. Frames whose colour camera differs from the depth camera are integrated one by one.
 // CHS_HOST_PROFILE=1: where the host time of a fused batch call goes (printed per process at exit)
 static double g_launchLapNs[12] = {};
@@ -1309,7 +1309,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
             hp.trunc = fps[0].trunc_param;
             hp.diag = fps[0].diag;
             hp.carve_dist = fps[0].carve_dist;
-            CHS_CUDA(launch_hiz_sharded(locFirst, locEnd - locFirst, hp, m->pushStream));
+            CHS_CUDA(half::launch_hiz_sharded(locFirst, locEnd - locFirst, hp, m->pushStream));
         }
         CHS_CUDA(cudaMemcpyAsync(bs.dFrames, slot, sizeof(FrameParams) * K, cudaMemcpyHostToDevice, cs));
     }
@@ -1376,7 +1376,7 @@ static int integrate_batch_fused(chs_map *m, const chs_integrator *integ, int K,
         info.hizTma = tma;
     }
     hs.lap(1);
-    // the fast brick kernel's per-frame constants and its preconditions (integrate_batch.cu: batch_bricks_fast_kernel)
+    // the fast brick kernel's per-frame constants and its preconditions (integrate_batch_impl.cuh: batch_bricks_fast_kernel)
     BrickFrames brickFrames;
     info.fastBricks = !perPixel && cam->width < (1 << 22) && cam->height < (1 << 22) && std::getenv("CHS_NO_FAST_BRICKS") == nullptr;
     for (int f = 0; f < K && info.fastBricks; f++)
@@ -2807,7 +2807,7 @@ int chs_selftest_arithmetic(int64_t div_pairs, int64_t out[4])
     unsigned long long *d = nullptr;
     CHS_CUDA(cudaMalloc((void **)&d, 4 * sizeof(unsigned long long)));
     CHS_CUDA(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
-    CHS_CUDA(launch_selftest_arithmetic(d, (unsigned long long)div_pairs, nullptr));
+    CHS_CUDA(half::launch_selftest_arithmetic(d, (unsigned long long)div_pairs, nullptr));
     unsigned long long h[4];
     CHS_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(d);

@@ -1,4 +1,4 @@
-// integrate_batch.cu -- fused multi-frame TSDF integration (sm_100a): K <= 16 consecutive frames in ONE pass over the map.
+// integrate_batch_impl.cuh -- fused multi-frame TSDF integration (sm_100a): K <= 16 consecutive frames in ONE pass over the map.
 //
 // Why this is exact. ProjectionIntegrator::Integrate[Color] (OC ProjectionIntegrator.h:51-183) updates every voxel from
 // that voxel's own state and the frame alone; chunk creation / garbage collection (Chisel.h:76-110, :133-207) depends only
@@ -32,7 +32,17 @@
 #include "kernels.h"
 #include "tma.cuh"
 
+#ifndef CHS_BATCH_VARIANT
+#error "compiled through integrate_batch_half.cu / integrate_batch_quarter.cu, which choose the task size of the brick kernels"
+#endif
+
 namespace chs
+{
+// Two builds of this file live in the library, in namespaces of their own: `half` (half-brick tasks, 8 voxels per lane, 128
+// threads x 4 CTAs/SM) for depth-only batches and `quarter` (quarter-brick tasks, 4 voxels per lane, 256 threads x 2 CTAs/SM) for
+// colour batches. Measured on B200: depth-only 67 us (half) vs 84 us (quarter) per 16-frame step of configs[4]; colour 80 us
+// (quarter) vs 100 us (half, 120 bytes of spills per thread) per 10-frame step of configs[1]. capi.cu picks per batch.
+namespace CHS_BATCH_VARIANT
 {
 
 static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams is copied word-wise into shared memory");
@@ -1957,4 +1967,5 @@ cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const Batc
     }
 }
 
+} // namespace CHS_BATCH_VARIANT
 } // namespace chs

@@ -18,7 +18,7 @@ cudaError_t frame_graph_launch(FrameGraph *fg, const FrameParams &fp, const Devi
                                bool profiling, cudaEvent_t *evt, cudaStream_t st);
 float host_truncation(int kind, float param, float depth);
 
-// ---- fused multi-frame integration (integrate_batch.cu) ----
+// ---- fused multi-frame integration (integrate_batch_impl.cuh) ----
 // K <= kMaxBatch consecutive frames in one pass: every voxel of the map is independent of every other voxel, so applying
 // frames f0 < f1 < ... to a voxel while its state sits in registers gives the same bits as K separate passes.
 constexpr int kMaxBatch = 16;
@@ -171,7 +171,10 @@ struct HizPeers
 };
 
 // Sharded Hi-Z (see HizPeers): pyramids of the frames [first, first + count) of the table `frames`, on stream st.
+namespace half
+{
 cudaError_t launch_hiz_sharded(int first, int count, const HizPeers &hp, cudaStream_t st);
+}
 
 struct BatchStreams
 {
@@ -180,10 +183,25 @@ struct BatchStreams
 };
 // events (profiling): [0] start, [1] after the Hi-Z kernel (both on prep), [2] = [7] after candidates, [3] after bricks (on main)
 // phases: bit 0 = prepare + candidates, bit 1 = bricks (3 = the whole batch; the host may size the pool between the two)
+// integrate_batch_impl.cuh is built twice (half-brick tasks for depth-only batches, quarter-brick tasks for colour batches)
+namespace half
+{
 cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases);
+}
+namespace quarter
+{
+cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases);
+}
+inline cudaError_t launch_batch(const BatchParams &bp, const DeviceMap &map, const BatchLaunchInfo &info, cudaEvent_t *evt, const BatchStreams &bs, int phases)
+{
+    return info.colorPath ? quarter::launch_batch(bp, map, info, evt, bs, phases) : half::launch_batch(bp, map, info, evt, bs, phases);
+}
 
 // dCounters[4] (zeroed): rcp mismatches, rcp tested, div mismatches, div tested
+namespace half
+{
 cudaError_t launch_selftest_arithmetic(unsigned long long *dCounters, unsigned long long divPairs, cudaStream_t st);
+}
 
 // table maintenance (capi.cu)
 void launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st);

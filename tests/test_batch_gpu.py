@@ -1,4 +1,4 @@
-"""GPU suite for the fused multi-frame path (chs_integrate_batch, cvids_b200/csrc/integrate_batch.cu): K frames in one pass
+"""GPU suite for the fused multi-frame path (chs_integrate_batch, cvids_b200/csrc/integrate_batch_impl.cuh): K frames in one pass
 must leave the map, the dirty set, the meshes and the per-frame counters bit-identical to K single-frame integrations -- checked
 against the CPU oracle (which integrates frame by frame, like the reference) and against the single-frame CUDA path."""
 import numpy as np
