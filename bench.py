@@ -6,16 +6,21 @@
 
 Headline workload, at every N (config.workload): BASELINE.json configs[4] -- the scaling-sweep config: 8 agents, 640x480 depth
 frames of the analytic room, 2 cm voxels, 16^3 chunks, truncation 4 voxels, carving on, all fused into ONE map. One STEP =
-the eight frames of one time step (one per agent, arrival order = agent order) in one chs_integrate_batch[_distributed] call.
+the frames of --time-steps-per-step (default 2) consecutive time steps, one frame per agent each (16 frames, arrival order =
+time step, then agent) in one chs_integrate_batch[_distributed] call: the fused kernels take up to 16 frames.
 N > 1: one process per GPU; the chunk-ID hash space is partitioned (owner = chs_owner(id) % N); rank r ingests the frames of
-agents [r*8/N, (r+1)*8/N), the library all-gathers them over NVLink (NCCL, in place, on its copy stream) and every rank
-integrates the chunks it owns. Same total work at every N => "scaling": "strong".
+agents [r*8/N, (r+1)*8/N) and PUSHES them into the exchange arenas of all ranks over NVLink (peer memory mapped through CUDA
+IPC inside the library, flag words instead of a collective; NCCL all-gather as fallback), every rank integrates the chunks it
+owns. Same total work at every N => "scaling": "strong".
 
 Metric: TSDF voxel updates per second (GVox/s; a "voxel update" is one DistVoxel::Integrate, SURVEY.md 8(d)), frames/s alongside.
   value     inputs resident in HBM on their ingest ranks; W warm-up steps from an empty map, then EXACTLY K steps enqueued back to
             back, bracketed by barrier + synchronize and timed with CUDA events on the map's stream; max over ranks. No L2 flush:
             the frame stream of the timed region is larger than L2 (config.l2 says so), the map working set stays cached as it
-            does in a live stream. Median of --passes passes (each from a fresh map); clocks are sampled across all of them.
+            does in a live stream. Median of --passes passes (each from a fresh map, after one untimed rehearsal pass); clocks
+            are sampled across all of them. The chunk pool is pre-sized (--pool-chunks) so that no growth lands in a timed pass.
+  config.rank0_device_timeline_us  medians over the steps of a pass in which the kernels stamp %globaltimer themselves
+            (chs_set_profiling(map, 2) / chs_get_device_timeline): kernel spans, gaps and overlap of the product path.
   e2e       the same call fed from pinned HOST frames (H2D inside the call, arguments marshalled inside the timed region) plus the
             D2H read of every step's per-frame counters (chs_wait_batch of the previous step: depth-2 pipeline), wall clock.
   roofline  the dominant kernel (the fused brick kernel): B_int of SURVEY.md 8(d) summed over the step's frames / the kernel's

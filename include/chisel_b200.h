@@ -217,9 +217,10 @@ int chs_comm_attach(chs_map *map, void *nccl_comm);         /* or: adopt the cal
 int chs_comm_destroy(chs_map *map);
 /* One step of n_total <= 16 frames (n_total % world == 0), e.g. the frames of all agents of one time step, in arrival order.
  * frames[0 .. n_total): poses of ALL frames; image pointers only for the frames this rank ingests,
- * [rank * n_total / world, (rank + 1) * n_total / world) (the other entries' pointers are ignored). The images are all-gathered
- * over NVLink into the batch staging set on the copy stream (beside the kernels of the previous step) and integrated as one
- * fused batch, every rank updating the chunks it owns: the union of the ranks' maps equals the single-GPU map of
+ * [rank * n_total / world, (rank + 1) * n_total / world) (the other entries' pointers are ignored). Every rank PUSHES its images
+ * over NVLink into exchange arenas of all ranks (peer memory mapped through CUDA IPC at the first call; flag words instead of a
+ * collective; NCCL all-gather where IPC is not available or with CHS_NCCL_EXCHANGE=1), a step ahead of the kernels that read
+ * them, and the step is integrated as one fused batch, every rank updating the chunks it owns: the union of the ranks' maps equals the single-GPU map of
  * chs_integrate_batch on the same frames. Colour camera and pose must equal the depth ones; constant / computed truncators only. */
 int chs_integrate_batch_distributed(chs_map *map, const chs_integrator *integ, int n_total, const chs_frame *frames, int mem,
                                     const chs_camera *cam, int channels, const chs_camera *color_cam);
