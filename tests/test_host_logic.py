@@ -163,3 +163,44 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
         assert int(got["%s sizeof" % name]) == C.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, "%s.%s" % (name, field)
+
+
+def test_timeline_names_match_the_header_and_the_kernels():
+    """chs_get_device_timeline: the header's stamp count, the kernels' enum and the Python names agree."""
+    hdr = open(os.path.join(ROOT, "include", "chisel_b200.h")).read()
+    n = int(re.search(r"#define CHS_TIMELINE_STAMPS (\d+)", hdr).group(1))
+    kern = open(os.path.join(ROOT, "cvids_b200", "csrc", "kernels.h")).read()
+    enum = re.search(r"enum TimelineStamp\s*\{(.*?)\}", kern, flags=re.S).group(1)
+    names = [x for x in re.findall(r"\b(kT[A-Za-z]+)\b", re.sub(r"//.*", "", enum))]
+    assert names[-1] == "kTimelineStamps" and len(names) - 1 == n
+    assert len(capi.Chisel.TIMELINE) == n
+    assert [x[3:].lower() for x in names[:-1]] == [x.replace("_", "") for x in capi.Chisel.TIMELINE]
+
+
+def test_both_builds_of_the_fused_kernels_are_in_the_library():
+    """integrate_batch_impl.cuh is compiled twice (half-brick tasks for depth-only batches, quarter-brick tasks for colour
+    batches); both launchers and both fast brick kernels must be there, for sm_100a."""
+    import subprocess
+    syms = subprocess.run(["nm", "-C", capi.LIB_PATH], capture_output=True, text=True).stdout
+    for ns in ("half", "quarter"):
+        assert "chs::%s::launch_batch(" % ns in syms, ns
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-res-usage", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert re.search(r"4half24batch_bricks_fast_kernel", out) and re.search(r"7quarter24batch_bricks_fast_kernel", out)
+    assert re.search(r"peer_push_kernel", out) and re.search(r"peer_wait_kernel", out)
+
+
+def test_bench_timeline_summary():
+    """bench.py's reading of the device timeline: medians in microseconds, gaps between consecutive steps, missing stamps."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    def step(t0, push=True):
+        return {"push_start": t0 - 90000 if push else 0, "push_end": t0 - 30000 if push else 0, "wait_end": t0 - 1000 if push else 0,
+                "hiz_start": t0, "hiz_end": t0 + 12000, "cand_start": t0 + 15000, "cand_end": t0 + 35000,
+                "bricks_start": t0 + 36000, "bricks_end": t0 + 90000}
+    s = bench.summarize_timeline([step(1000000 + 100000 * i) for i in range(5)])
+    assert s["step"] == 100.0 and s["hiz"] == 12.0 and s["candidates"] == 20.0 and s["bricks"] == 54.0
+    assert s["gap_bricks_to_next_hiz"] == 10.0 and s["gap_candidates_to_bricks"] == 1.0 and s["push"] == 60.0 and s["push_end_to_hiz_start"] == 30.0
+    s = bench.summarize_timeline([step(1000000 + 100000 * i, push=False) for i in range(3)])
+    assert s["push"] is None and s["arrival_to_hiz_start"] is None and len(s["steps"]) == 2
