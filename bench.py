@@ -23,6 +23,7 @@ Metric: TSDF voxel updates per second (GVox/s; a "voxel update" is one DistVoxel
             (chs_set_profiling(map, 2) / chs_get_device_timeline): kernel spans, gaps and overlap of the product path.
   e2e       the same call fed from pinned HOST frames (H2D inside the call, arguments marshalled inside the timed region) plus the
             D2H read of every step's per-frame counters (chs_wait_batch of the previous step: depth-2 pipeline), wall clock.
+  e2e_depth_mm (N = 1)  the e2e leg with 16UC1 millimetre depth (the sensor's encoding; converted on the device): half the PCIe bytes.
   roofline  the dominant kernel (the fused brick kernel): B_int of SURVEY.md 8(d) summed over the step's frames / the kernel's
             duration from CUDA events recorded by the library around it, on its stream, averaged over the timed steps of a
             separate profiling pass; peak = MEASURED_PEAKS.json. `traffic` from the committed ncu capture of the same command.
@@ -593,6 +594,40 @@ def run_multi_agent(B: Bench, args):
         m.comm_destroy()
     m.close()
 
+    # ---------------- e2e with the sensor's own encoding: 16UC1 millimetres (ROS), converted on the device (N = 1) ----------
+    # chisel_ros receives depth as uint16 millimetres and converts on the host (CR Conversions.h:141-152); chs_frame.depth_mm moves
+    # half the bytes over PCIe. The stream is the headline's quantised to millimetres, so its update count is its own. A failure
+    # of this side leg never costs the headline line.
+    e2e_mm = None
+    if world == 1:
+        try:
+            h_mm = torch.empty((T, per, H, W), dtype=torch.uint16).pin_memory()
+            mm_np = h_mm.numpy()
+            for t in range(T):
+                for j in range(per):
+                    mm_np[t, j] = np.clip(np.nan_to_num(frames[t][j][0], nan=0.0) * 1000.0, 0, 65535).astype(np.uint16)
+            m = B.new_map(cfg)
+            for t in range(warm):
+                m.integrate_batch(integ, [mm_np[t, j] for j in range(per)], poses[t], camv, host_async=True)
+            m.synchronize()
+            t0 = time.perf_counter()
+            upd_mm, prev = 0, None
+            for t in range(warm, T):
+                m.integrate_batch(integ, [mm_np[t, j] for j in range(per)], poses[t], camv, host_async=True)
+                tkt = m.last_batch_ticket()
+                if prev is not None:
+                    upd_mm += sum(st["n_upd"] for st in m.wait_batch(prev))
+                prev = tkt
+            upd_mm += sum(st["n_upd"] for st in m.wait_batch(prev))
+            t_mm = time.perf_counter() - t0
+            m.close()
+            e2e_mm = {"value": upd_mm / t_mm / 1e9, "unit": UNIT, "frames_per_s": steps * F / t_mm, "ms_per_step": 1000.0 * t_mm / steps,
+                      "h2d_bytes_per_step": 2 * npx * F, "h2d_gbs": 2 * npx * F * steps / t_mm / 1e9,
+                      "what": "the e2e leg with 16UC1 millimetre depth (chs_frame.depth_mm, converted on the device as CR Conversions.h:141-152 does on the "
+                              "host): half the PCIe bytes; the headline stream quantised to millimetres"}
+        except Exception as exc:                                      # noqa: BLE001
+            e2e_mm = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     t_e2e = B.max_over_ranks([t_e2e])[0]
     upd_total, upd_e2e_total, chunks_total = B.sum_over_ranks([float(upd), float(upd_e2e), float(total_chunks)])
     ksum = B.max_over_ranks([tk["integrate"], tk["prepare"], tk["candidates"]])
@@ -635,7 +670,9 @@ def run_multi_agent(B: Bench, args):
                 "rank0_host_us_per_step": {"in_the_call_incl_marshalling": 1e6 * host_call / steps, "waiting_for_the_previous_step": 1e6 * host_wait / steps},
                 "timing": "wall clock, max over ranks; per step chs_integrate_batch%s(pinned host frames, CHS_MEM_HOST_ASYNC; arguments marshalled inside the "
                           "timed region), then chs_wait_batch of the PREVIOUS step's counters (depth-2 pipeline)" % ("_distributed" if world > 1 else "")},
-        "gpu_launches": 3 * steps,
+        "e2e_depth_mm": e2e_mm,
+        # Hi-Z, candidates, bricks per step; N > 1: plus the push kernel and the arrival wait of the frame exchange
+        "gpu_launches": (3 if world == 1 else 5) * steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "batch_bricks_fast_kernel<16,0,0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
