@@ -211,58 +211,90 @@ def state_equal(a, b):
     return bad
 
 
+class CpuArm:
+    """Reference CPU OpenChisel on the host cores, frame by frame from an empty map: oracle/_ref (the unmodified reference, as-is
+    threading) when built, else the single-threaded C port. N_upd of a frame comes from an untimed pass of the C port."""
+
+    def __init__(self, cfg):
+        from oracle import pyoracle
+        self.cfg = cfg
+        self.use_ref = pyoracle.ref_available()
+        self.ref = make_cpu(cfg, True)
+        self.counter = make_cpu(cfg, False) if self.use_ref else None
+        cores = os.cpu_count() or 1
+        self.host_cores = cores
+        self.cores = (min(16, cores) if cfg.color else 1) if self.use_ref else 1      # Chisel.h:150 (colour: 16 threads) / :71-72 (depth: one)
+        self.kind = "reference" if self.use_ref else "port"
+
+    def frame(self, fr):
+        """-> (seconds of the timed implementation, voxel updates of the frame)"""
+        t0 = time.perf_counter()
+        cpu_integrate(self.ref, self.cfg, fr, as_is=True)
+        dt = time.perf_counter() - t0
+        if self.counter is not None:
+            cpu_integrate(self.counter, self.cfg, fr)
+            return dt, self.counter.frame_counters()["n_upd"]
+        return dt, self.ref.frame_counters()["n_upd"]
+
+
 def cpu_arm(cfg, frames, warm, budget_s):
-    """Reference CPU OpenChisel on the host cores over `frames` (in order, from an empty map); the first `warm` are untimed.
-    oracle/_ref (the unmodified reference, as-is threading) when built, else the single-threaded C port."""
-    from oracle import pyoracle
-    use_ref = pyoracle.ref_available()
-    ref = make_cpu(cfg, True)
-    counter = make_cpu(cfg, False) if use_ref else None     # untimed: counts N_upd of the same frames
+    """`frames` in order from an empty map, the first `warm` untimed, until the wall-clock budget is used up."""
+    arm = CpuArm(cfg)
     t_total, upd, done = 0.0, 0, 0
     t_begin = time.perf_counter()
     for i, fr in enumerate(frames):
-        t0 = time.perf_counter()
-        cpu_integrate(ref, cfg, fr, as_is=True)
-        dt = time.perf_counter() - t0
-        if counter is not None:
-            cpu_integrate(counter, cfg, fr)
-            n = counter.frame_counters()["n_upd"]
-        else:
-            n = ref.frame_counters()["n_upd"]
+        dt, n = arm.frame(fr)
         if i >= warm:
             t_total += dt
             upd += n
             done += 1
             if time.perf_counter() - t_begin > budget_s:
                 break
-    cores = os.cpu_count() or 1
-    used = (min(16, cores) if cfg.color else 1) if use_ref else 1      # Chisel.h:150 (colour: 16 threads) / :71-72 (depth: one)
-    return dict(value=upd / t_total / 1e9 if t_total else 0.0, fps=done / t_total if t_total else 0.0, kind="reference" if use_ref else "port",
-                cores=used, host_cores=cores, frames_done=done, seconds=t_total, updates=upd)
+    return dict(value=upd / t_total / 1e9 if t_total else 0.0, fps=done / t_total if t_total else 0.0, kind=arm.kind,
+                cores=arm.cores, host_cores=arm.host_cores, frames_done=done, seconds=t_total, updates=upd)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same workload and step."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same workload, metric and
+    unit. EXACTLY --steps timed steps after --warmup untimed ones; a step of this arm is a BOUNDED SAMPLE of the workload: n
+    consecutive frames of the same arrival-ordered stream (from the empty map), n chosen from the cost of the first frame so that
+    the whole run fits --cpu-budget seconds of wall clock (the GPU arm's step is the 16 frames of two time steps)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    warm_t, steps_t = args.warmup, args.steps
-    frames = []
-    t_build = time.perf_counter()
-    for t in range(warm_t + steps_t):
-        frames += step_frames(CFG, t)
-        if time.perf_counter() - t_build > 120:
-            break
-    r = cpu_arm(CFG, frames, warm_t * AGENTS * TS, budget_s=args.cpu_budget)
-    steps_done = r["frames_done"] / (AGENTS * TS)
+    K, Wm, full = max(1, args.steps), max(0, args.warmup), AGENTS * TS
+    arm = CpuArm(CFG)
+
+    def stream():
+        t = 0
+        while True:
+            for fr in step_frames(CFG, t):
+                yield fr
+            t += 1
+    src = stream()
+    # calibration: the first frame of the stream (it is also the first frame of the run, timed or not as the step layout says)
+    w0 = time.perf_counter()
+    first = arm.frame(next(src))
+    wall0 = time.perf_counter() - w0
+    n = int(min(full, max(1, args.cpu_budget / (1.7 * wall0 * (K + Wm)))))           # later frames see a fuller map: factor 1.7
+    t_total, upd, idx = 0.0, 0, 0
+    for step in range(Wm + K):
+        for _ in range(n):
+            dt, nu = first if idx == 0 else arm.frame(next(src))
+            idx += 1
+            if step >= Wm:
+                t_total += dt
+                upd += nu
+    value = upd / t_total / 1e9 if t_total else 0.0
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / max(steps_done, 1e-9), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_step": AGENTS * TS, "frames_per_s": r["fps"],
-        "config": {"workload": WORKLOAD % TS},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_cores": r["host_cores"], "kind": r["kind"],
-                         "threads": "1: the reference's depth-only path is serial (Chisel.h:71-72)" if r["kind"] == "reference" else "1 (C port)",
-                         "sample": "%d frames after %d warm-up frames of the same stream, whole frames, %.1f s" % (r["frames_done"], warm_t * AGENTS * TS, r["seconds"])},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": Wm, "ms_per_step": 1000.0 * t_total / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_step": n, "frames_per_s": K * n / t_total if t_total else 0.0,
+        "config": {"workload": WORKLOAD % TS, "reference_step": "a bounded sample: %d consecutive frames of the same stream per step (the GPU arm: %d)" % (n, full)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "host_cores": arm.host_cores, "kind": arm.kind,
+                         "threads": "1: the reference's depth-only path is serial (Chisel.h:71-72)" if arm.kind == "reference" else "1 (C port)",
+                         "sample": "%d timed steps of %d consecutive frames after %d warm-up steps, the same stream from an empty map, whole frames, %.1f s"
+                                   % (K, n, Wm, t_total)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
